@@ -1,0 +1,1471 @@
+// b200_bfv.cu — CUDA kernels (sm_100a), device context and the layer-1 C ABI (include/b200_bfv.h).
+//
+// One process drives one GPU.  All work is enqueued on the caller's stream; temporaries come from the
+// stream-ordered allocator (cudaMallocAsync), so back-to-back calls never synchronise with the host.
+// There is deliberately no CPU execution path in this library: if CUDA is unavailable every entry point
+// returns B200_E_CUDA.
+#include "../../include/b200_bfv.h"
+#include "bfv_body.cuh"
+#include "host_ctx.h"
+#include "ntt_body.cuh"
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#ifdef B200_EMU_HEADER
+// Test-only build (tests/emu): the same sources compiled by g++ against a sequential CPU stand-in for
+// the CUDA runtime, used by the CPU test-suite to check index math and orchestration without a GPU.
+// The product library is never built this way and the package loader refuses to load such a build.
+#include B200_EMU_HEADER
+#else
+#include <cuda_runtime.h>
+#define B200_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#endif
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using b200::BfvHostContext;
+using b200::LevelHost;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg)
+{
+    g_err = msg;
+    return code;
+}
+#define CU_TRY(expr)                                                                                                   \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        cudaError_t _e = (expr);                                                                                       \
+        if (_e != cudaSuccess)                                                                                         \
+            return fail(B200_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));                              \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------------------
+template <bool FWD, int NT>
+__global__ void __launch_bounds__(NT) ntt_kernel(const NttJob job)
+{
+#ifdef B200_EMU_HEADER
+    u64 *ntt_sm = (u64 *)emu_shared;
+#else
+    extern __shared__ u64 ntt_sm[];
+#endif
+    ntt_block_body<FWD>(job, (long long)blockIdx.x, ntt_sm, (int)threadIdx.x, (int)blockDim.x);
+}
+
+#define GLOBAL_IDX() ((long long)blockIdx.x * blockDim.x + threadIdx.x)
+
+template <int K>
+__global__ void lift_kernel(const LevelDev L, const u64 *a, int sa, const u64 *b, int sb, u64 *ext, long long n,
+                            long long total)
+{
+    const long long idx = GLOBAL_IDX();
+    if (idx >= total)
+        return;
+    const int P = sa + sb;
+    const long long c = idx % n;
+    const long long t = idx / n;
+    const int p = (int)(t % P);
+    const long long item = t / P;
+    const int R = K + L.nBsk;
+    const u64 *src = p < sa ? a + (item * sa + p) * K * n : b + (item * sb + (p - sa)) * K * n;
+    u64 *dst = ext + ((item * P + p) * R + K) * n;
+    lift_coeff<K>(L, src, dst, n, c);
+}
+
+// rows: residue rows r in [0,R): r<K -> q[r], else bsk[r-K]
+__global__ void tensor_kernel(const LevelDev L, const u64 *ext, int sa, int sb, u64 *D, long long n, long long total,
+                              int square)
+{
+    const long long idx = GLOBAL_IDX();
+    if (idx >= total)
+        return;
+    const int R = L.k + L.nBsk;
+    const long long c = idx % n;
+    const long long t = idx / n;
+    const int r = (int)(t % R);
+    const long long item = t / R;
+    const PrimeDev P = ld_prime(r < L.k ? &L.q[r] : &L.bsk[r - L.k]);
+    const int Pn = square ? sa : sa + sb;
+    const int Dn = square ? 3 : sa + sb - 1;
+    const u64 *A = ext + ((item * Pn) * R + r) * n;
+    u64 *Dp = D + ((item * Dn) * R + r) * n;
+    if (square)
+        square_coeff(P, A, R * n, Dp, R * n, c);
+    else
+        tensor_coeff(P, A, R * n, sa, A + (long long)sa * R * n, R * n, sb, Dp, R * n, c);
+}
+
+template <int K>
+__global__ void scale_kernel(const LevelDev L, const u64 *D, int Dn, u64 *dst0, int split, u64 *dst1, long long n,
+                             long long total)
+{
+    const long long idx = GLOBAL_IDX();
+    if (idx >= total)
+        return;
+    const int R = K + L.nBsk;
+    const long long c = idx % n;
+    const long long t = idx / n;
+    const int m = (int)(t % Dn);
+    const long long item = t / Dn;
+    const u64 *src = D + ((item * Dn + m) * R) * n;
+    u64 *dst = m < split ? dst0 + ((item * split + m) * K) * n : dst1 + ((item * (Dn - split) + (m - split)) * K) * n;
+    scale_coeff<K>(L, src, dst, n, c);
+}
+
+template <int K>
+__global__ void ksmac_kernel(const PrimeDev *primes, int special_idx, int key_rows, const u64 *ks1, const u64 *key,
+                             u64 *ks2, long long n, long long total)
+{
+    const long long idx = GLOBAL_IDX();
+    if (idx >= total)
+        return;
+    const long long c = idx % n;
+    const long long t = idx / n;
+    const int I = (int)(t % (K + 1));
+    const long long item = t / (K + 1);
+    const int prime_idx = I < K ? I : special_idx;
+    const int key_res = I < K ? I : key_rows - 1;
+    const PrimeDev P = ld_prime(&primes[prime_idx]);
+    const u64 *ops = ks1 + ((item * (K + 1) + I) * K) * n;
+    const u64 *kp = key + (long long)key_res * n;
+    u64 *o0 = ks2 + ((item * 2 + 0) * (K + 1) + I) * n;
+    u64 *o1 = ks2 + ((item * 2 + 1) * (K + 1) + I) * n;
+    ksmac_coeff<K>(P, ops, n, kp, 2LL * key_rows * n, (long long)key_rows * n, o0, o1, c);
+}
+
+template <int K>
+__global__ void ksmoddown_kernel(const PrimeDev *primes, int special_idx, const u64 *inv_qsp, const u64 *ks2,
+                                 const u64 *base0, long long base0_stride, const u64 *base1, long long base1_stride,
+                                 u64 *dst, long long dst_item_stride, long long n, long long total)
+{
+    const long long idx = GLOBAL_IDX();
+    if (idx >= total)
+        return;
+    const long long c = idx % n;
+    const long long t = idx / n;
+    const int comp = (int)(t & 1);
+    const long long item = t >> 1;
+    const PrimeDev SP = ld_prime(&primes[special_idx]);
+    const u64 *acc = ks2 + ((item * 2 + comp) * (K + 1)) * n;
+    const u64 *base = comp == 0 ? (base0 ? base0 + item * base0_stride : nullptr)
+                                : (base1 ? base1 + item * base1_stride : nullptr);
+    u64 *d = dst + item * dst_item_stride + (long long)comp * K * n;
+    ksmoddown_coeff<K>(primes, SP, inv_qsp, acc, n, base, d, c);
+}
+
+template <int K>
+__global__ void modswitch_kernel(const PrimeDev *primes, const u64 *inv_qlast, const u64 *src, u64 *dst, long long n,
+                                 long long total)
+{
+    const long long idx = GLOBAL_IDX();
+    if (idx >= total)
+        return;
+    const long long c = idx % n;
+    const long long poly = idx / n;
+    modswitch_coeff<K>(primes, inv_qlast, src + poly * K * n, n, dst + poly * (K - 1) * n, c);
+}
+
+// out0 <- sigma(c0) (into dst poly 0), tmp <- sigma(c1)
+__global__ void galois_kernel(const PrimeDev *primes, int k, const u64 *in2, u64 *out2, u64 *tmp, int logn, u32 g,
+                              long long total)
+{
+    const long long idx = GLOBAL_IDX();
+    if (idx >= total)
+        return;
+    const long long n = 1LL << logn;
+    const long long c = idx & (n - 1);
+    const long long t = idx >> logn;
+    const int r = (int)(t % k);
+    const long long u = t / k;
+    const int poly = (int)(u & 1);
+    const long long item = u >> 1;
+    const u64 p = __ldg(&primes[r].p);
+    const u64 *src = in2 + ((item * 2 + poly) * k + r) * n;
+    u64 *dst = poly == 0 ? out2 + ((item * 2) * k + r) * n : tmp + (item * k + r) * n;
+    galois_coeff(p, src, dst, logn, g, c);
+}
+
+// mode 0: add, 1: sub, 2: negate (b unused)
+__global__ void addsub_kernel(const PrimeDev *primes, int k, const u64 *a, const u64 *b, u64 *out, int logn, int mode,
+                              long long total)
+{
+    const long long idx = GLOBAL_IDX();
+    if (idx >= total)
+        return;
+    const int r = (int)((idx >> logn) % k);
+    const u64 p = __ldg(&primes[r].p);
+    const u64 x = a[idx];
+    u64 v;
+    if (mode == 0)
+        v = add_mod(x, b[idx], p);
+    else if (mode == 1)
+        v = sub_mod(x, b[idx], p);
+    else
+        v = neg_mod(x, p);
+    out[idx] = v;
+}
+
+// dyadic out[item][poly][r][c] = x * y[(item % pb)][r][c] mod q_r   (x, y canonical)
+__global__ void dyadic_plain_kernel(const PrimeDev *primes, int k, int size, const u64 *x, const u64 *y, long long pb,
+                                    u64 *out, int logn, long long total)
+{
+    const long long idx = GLOBAL_IDX();
+    if (idx >= total)
+        return;
+    const long long n = 1LL << logn;
+    const long long c = idx & (n - 1);
+    const long long t = idx >> logn;
+    const int r = (int)(t % k);
+    const long long u = t / k;
+    const long long item = u / size;
+    const PrimeDev P = ld_prime(&primes[r]);
+    const u64 yv = y[((item % pb) * k + r) * n + c];
+    u64 lo, hi;
+    mul128(x[idx], yv, lo, hi);
+    out[idx] = barrett128(lo, hi, P.p, P.r0, P.r1);
+}
+
+__global__ void plain_lift_kernel(const LevelDev L, const u64 *plain, u64 *out, int logn, long long total)
+{
+    const long long idx = GLOBAL_IDX();
+    if (idx >= total)
+        return;
+    const long long n = 1LL << logn;
+    const long long c = idx & (n - 1);
+    const long long t = idx >> logn;
+    const int r = (int)(t % L.k);
+    const long long item = t / L.k;
+    const PrimeDev Q = ld_prime(&L.q[r]);
+    out[idx] = plain_lift(L, Q, r, plain[item * n + c]);
+}
+
+// c0 +/- scaled plaintext; other polys copied.  sign: 0 add, 1 sub
+__global__ void addsub_plain_kernel(const LevelDev L, int size, const u64 *a, const u64 *plain, long long pb, u64 *out,
+                                    int logn, int sign, long long total)
+{
+    const long long idx = GLOBAL_IDX();
+    if (idx >= total)
+        return;
+    const long long n = 1LL << logn;
+    const long long c = idx & (n - 1);
+    const long long t = idx >> logn;
+    const int r = (int)(t % L.k);
+    const long long u = t / L.k;
+    const int poly = (int)(u % size);
+    const long long item = u / size;
+    u64 v = a[idx];
+    if (poly == 0)
+    {
+        const PrimeDev Q = ld_prime(&L.q[r]);
+        const u64 s = plain_scaled(L, Q, r, plain[(item % pb) * n + c]);
+        v = sign ? sub_mod(v, s, Q.p) : add_mod(v, s, Q.p);
+    }
+    out[idx] = v;
+}
+
+// acc[item][r][c] = sum_{j>=1} X[item][j-1][r][c] * s[j-1][r][c] mod q_r
+__global__ void dot_sk_kernel(const PrimeDev *primes, int k, int terms, const u64 *X, const u64 *sk, u64 *acc, int logn,
+                              long long total)
+{
+    const long long idx = GLOBAL_IDX();
+    if (idx >= total)
+        return;
+    const long long n = 1LL << logn;
+    const long long c = idx & (n - 1);
+    const long long t = idx >> logn;
+    const int r = (int)(t % k);
+    const long long item = t / k;
+    const PrimeDev P = ld_prime(&primes[r]);
+    u64 lo = 0, hi = 0;
+    for (int j = 0; j < terms; j++)
+        mac128(X[((item * terms + j) * k + r) * n + c], sk[((long long)j * k + r) * n + c], lo, hi);
+    acc[idx] = barrett128(lo, hi, P.p, P.r0, P.r1);
+}
+
+template <int K>
+__global__ void decrypt_kernel(const LevelDev L, int size, const u64 *ct, u64 *phase /*in: dot, scratch*/, u64 *plain,
+                               long long n, long long total)
+{
+    const long long idx = GLOBAL_IDX();
+    if (idx >= total)
+        return;
+    const long long c = idx % n;
+    const long long item = idx / n;
+    u64 *ph = phase + item * K * n;
+    const u64 *c0 = ct + item * size * K * n;
+#pragma unroll
+    for (int i = 0; i < K; i++)
+        ph[i * n + c] = add_mod(ph[i * n + c], c0[i * n + c], __ldg(&L.q[i].p));
+    plain[item * n + c] = decrypt_coeff<K>(L, ph, n, c);
+}
+
+__global__ void transparent_kernel(const u64 *ct, long long item_words, long long skip_words, u32 *flags)
+{
+    const long long item = blockIdx.y;
+    const u64 *p = ct + item * item_words + skip_words;
+    const long long cnt = item_words - skip_words;
+    bool nz = false;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += (long long)gridDim.x * blockDim.x)
+        nz |= p[i] != 0;
+    if (__syncthreads_or(nz) && threadIdx.x == 0)
+        flags[item] = 0;
+}
+
+__global__ void fill_u32_kernel(u32 *p, u32 v, long long total)
+{
+    const long long idx = GLOBAL_IDX();
+    if (idx < total)
+        p[idx] = v;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------------------
+struct JobDesc
+{
+    int slots = 0;
+    int *d_prime = nullptr;
+    long long *d_src = nullptr;
+    long long *d_dst = nullptr;
+};
+
+struct b200_ctx
+{
+    std::unique_ptr<BfvHostContext> host;
+    int device = 0;
+    int sm_count = 0;
+    size_t n = 0;
+    int logn = 0;
+    std::vector<void *> allocations; // everything freed at destroy
+    NttPrime *d_ntt_primes = nullptr;
+    PrimeDev *d_primes = nullptr;       // [all primes] key primes first
+    std::vector<LevelDev> levels;       // device pointers inside
+    std::vector<const u64 *> d_inv_qlast; // per level
+    const u64 *d_inv_qsp = nullptr;     // key level's inv_qlast: q_sp^-1 mod q_i
+    int npass = 0;
+    int pass_L[8];
+    std::map<std::string, JobDesc> jobs;
+    std::mutex mu;
+    std::atomic<uint64_t> launches{ 0 };
+    cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
+    int ntt_threads = 256;
+    size_t ntt_smem = 0;
+};
+
+template <class T>
+static int upload(b200_ctx *ctx, const std::vector<T> &v, T **out)
+{
+    void *d = nullptr;
+    size_t bytes = std::max<size_t>(v.size() * sizeof(T), 8);
+    CU_TRY(cudaMalloc(&d, bytes));
+    ctx->allocations.push_back(d);
+    if (!v.empty())
+        CU_TRY(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = (T *)d;
+    return 0;
+}
+#define UP(vec, ptr)                                                                                                   \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        int _rc = upload(ctx, vec, ptr);                                                                               \
+        if (_rc)                                                                                                       \
+            return _rc;                                                                                                \
+    } while (0)
+
+static std::vector<u64> flat(const std::vector<b200::Shoup> &v)
+{
+    std::vector<u64> o;
+    for (auto &s : v)
+    {
+        o.push_back(s.w);
+        o.push_back(s.wq);
+    }
+    return o;
+}
+static PrimeDev prime_dev(const b200::Modulus &m)
+{
+    PrimeDev p;
+    p.p = m.p;
+    p.r0 = m.r0;
+    p.r1 = m.r1;
+    return p;
+}
+
+static int build_device(b200_ctx *ctx)
+{
+    BfvHostContext &H = *ctx->host;
+    const size_t n = H.n;
+    // twiddle tables + per-prime descriptors
+    std::vector<NttPrime> np(H.primes.size());
+    std::vector<PrimeDev> pd(H.primes.size());
+    for (size_t i = 0; i < H.primes.size(); i++)
+    {
+        auto &P = H.primes[i];
+        u64 *dfwd = nullptr, *dinv = nullptr;
+        UP(P.fwd, &dfwd);
+        UP(P.inv, &dinv);
+        np[i].p = P.mod.p;
+        np[i].ratio1 = P.mod.r1;
+        np[i].inv_n = P.inv_n.w;
+        np[i].inv_n_q = P.inv_n.wq;
+        np[i].inv_n_w = P.inv_n_w.w;
+        np[i].inv_n_w_q = P.inv_n_w.wq;
+        np[i].fwd = dfwd;
+        np[i].inv = dinv;
+        pd[i] = prime_dev(P.mod);
+    }
+    UP(np, &ctx->d_ntt_primes);
+    UP(pd, &ctx->d_primes);
+    for (auto &Lh : H.levels)
+    {
+        LevelDev L;
+        memset(&L, 0, sizeof(L));
+        L.k = Lh.k;
+        L.nB = Lh.nB;
+        L.nBsk = Lh.nBsk;
+        L.q = ctx->d_primes; // q_idx is always the prefix 0..k-1
+        std::vector<PrimeDev> bsk;
+        for (int idx : Lh.bsk_idx)
+            bsk.push_back(pd[idx]);
+        PrimeDev *dbsk = nullptr;
+        UP(bsk, &dbsk);
+        L.bsk = dbsk;
+        L.m_sk = H.primes[H.aux0].mod.p;
+        L.t = H.t;
+        L.t_mod = prime_dev(H.t_mod);
+        L.gamma = pd[Lh.gamma_idx];
+        u64 *d = nullptr;
+#define UPF(field, vec)                                                                                                \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        std::vector<u64> _v = vec;                                                                                     \
+        UP(_v, &d);                                                                                                    \
+        L.field = d;                                                                                                   \
+    } while (0)
+        UPF(lift_c, flat(Lh.lift_c));
+        UPF(lift_mat, Lh.lift_mat);
+        UPF(lift_mt, Lh.lift_mt);
+        UPF(lift_qm, Lh.lift_qm);
+        L.neg_inv_q_mod_mt = Lh.neg_inv_q_mod_mt;
+        UPF(scale_c, flat(Lh.scale_c));
+        UPF(scale_tq, Lh.scale_tq);
+        UPF(scale_mat, Lh.scale_mat);
+        UPF(sk_c, flat(Lh.sk_c));
+        UPF(sk_mat_q, Lh.sk_mat_q);
+        UPF(sk_mat_msk, Lh.sk_mat_msk);
+        UPF(sk_prod_b_q, Lh.sk_prod_b_q);
+        L.sk_inv_b_msk = Lh.sk_inv_b_msk;
+        UPF(inv_qlast, flat(Lh.inv_qlast));
+        UPF(delta, Lh.delta);
+        UPF(plain_inc, Lh.plain_upper_half_inc);
+        L.q_mod_t = Lh.q_mod_t;
+        L.plain_thr = Lh.plain_upper_half_threshold;
+        UPF(dec_c, flat(Lh.dec_c));
+        UPF(dec_mat_t, Lh.dec_mat_t);
+        UPF(dec_mat_g, Lh.dec_mat_g);
+        L.inv_gamma_mod_t = Lh.inv_gamma_mod_t;
+#undef UPF
+        ctx->levels.push_back(L);
+    }
+    ctx->d_inv_qsp = ctx->levels[0].inv_qlast;
+    (void)n;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// launch helpers
+// ---------------------------------------------------------------------------------------------------------
+struct Scratch
+{
+    cudaStream_t s;
+    std::vector<void *> ptrs;
+    explicit Scratch(cudaStream_t st) : s(st) {}
+    int get(size_t words, u64 **out)
+    {
+        void *p = nullptr;
+        cudaError_t e = cudaMallocAsync(&p, std::max<size_t>(words, 1) * sizeof(u64), s);
+        if (e != cudaSuccess)
+            return fail(B200_E_NOMEM, std::string("cudaMallocAsync: ") + cudaGetErrorString(e));
+        ptrs.push_back(p);
+        *out = (u64 *)p;
+        return 0;
+    }
+    ~Scratch()
+    {
+        for (void *p : ptrs)
+            cudaFreeAsync(p, s);
+    }
+};
+
+static inline unsigned blocks_for(long long total, int bs) { return (unsigned)((total + bs - 1) / bs); }
+
+static int get_job(b200_ctx *ctx, const std::string &key, const std::vector<int> &prime, const std::vector<long long> &src,
+                   const std::vector<long long> &dst, JobDesc *out)
+{
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    auto it = ctx->jobs.find(key);
+    if (it != ctx->jobs.end())
+    {
+        *out = it->second;
+        return 0;
+    }
+    JobDesc j;
+    j.slots = (int)prime.size();
+    UP(prime, &j.d_prime);
+    UP(src, &j.d_src);
+    UP(dst, &j.d_dst);
+    ctx->jobs[key] = j;
+    *out = j;
+    return 0;
+}
+
+template <bool FWD>
+static int launch_ntt(b200_ctx *ctx, const JobDesc &jd, const u64 *src, long long src_stride, u64 *dst, long long dst_stride,
+                      long long items, int reduce_input, cudaStream_t s)
+{
+    if (items == 0 || jd.slots == 0)
+        return 0;
+    NttJob job;
+    job.logn = ctx->logn;
+    job.slots = jd.slots;
+    job.slot_prime = jd.d_prime;
+    job.slot_src = jd.d_src;
+    job.slot_dst = jd.d_dst;
+    job.src_item_stride = src_stride;
+    job.dst_item_stride = dst_stride;
+    job.src = src;
+    job.dst = dst;
+    job.primes = ctx->d_ntt_primes;
+    job.reduce_input = reduce_input;
+    job.npass = ctx->npass;
+    for (int i = 0; i < 8; i++)
+        job.pass_L[i] = ctx->pass_L[i];
+    const long long blocks = items * jd.slots;
+    if (blocks > 0x7fffffffLL)
+        return fail(B200_E_INVALID, "batch too large for one NTT launch");
+    void (*kfn)(const NttJob) = ctx->ntt_threads == 512   ? ntt_kernel<FWD, 512>
+                                : ctx->ntt_threads == 256 ? ntt_kernel<FWD, 256>
+                                                          : ntt_kernel<FWD, 64>;
+    B200_LAUNCH(kfn, (unsigned)blocks, ctx->ntt_threads, ctx->ntt_smem, s, job);
+    ctx->launches++;
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+#define DISPATCH_K(kval, ...)                                                                                         \
+    switch (kval)                                                                                                      \
+    {                                                                                                                  \
+    case 1: { constexpr int KK = 1; __VA_ARGS__; } break;                                                                     \
+    case 2: { constexpr int KK = 2; __VA_ARGS__; } break;                                                                     \
+    case 3: { constexpr int KK = 3; __VA_ARGS__; } break;                                                                     \
+    case 4: { constexpr int KK = 4; __VA_ARGS__; } break;                                                                     \
+    case 5: { constexpr int KK = 5; __VA_ARGS__; } break;                                                                     \
+    case 6: { constexpr int KK = 6; __VA_ARGS__; } break;                                                                     \
+    case 7: { constexpr int KK = 7; __VA_ARGS__; } break;                                                                     \
+    case 8: { constexpr int KK = 8; __VA_ARGS__; } break;                                                                     \
+    case 9: { constexpr int KK = 9; __VA_ARGS__; } break;                                                                     \
+    case 10: { constexpr int KK = 10; __VA_ARGS__; } break;                                                                   \
+    case 11: { constexpr int KK = 11; __VA_ARGS__; } break;                                                                   \
+    case 12: { constexpr int KK = 12; __VA_ARGS__; } break;                                                                   \
+    case 13: { constexpr int KK = 13; __VA_ARGS__; } break;                                                                   \
+    case 14: { constexpr int KK = 14; __VA_ARGS__; } break;                                                                   \
+    case 15: { constexpr int KK = 15; __VA_ARGS__; } break;                                                                   \
+    case 16: { constexpr int KK = 16; __VA_ARGS__; } break;                                                                   \
+    default: return fail(B200_E_INVALID, "unsupported residue count (max 16 data residues)");                          \
+    }
+
+static const int EB = 256; // element-wise block size
+
+static int check_level(b200_ctx *ctx, int level)
+{
+    if (!ctx)
+        return fail(B200_E_NULL, "null context");
+    if (level < 0 || level >= (int)ctx->levels.size())
+        return fail(B200_E_INVALID, "level out of range");
+    return 0;
+}
+
+// slots over a dense [items][slots][n] slab with per-slot prime
+static int dense_job(b200_ctx *ctx, const std::string &key, const std::vector<int> &prime, JobDesc *jd)
+{
+    std::vector<long long> off(prime.size());
+    for (size_t i = 0; i < prime.size(); i++)
+        off[i] = (long long)i * (long long)ctx->n;
+    return get_job(ctx, key, prime, off, off, jd);
+}
+
+static std::vector<int> row_primes(b200_ctx *ctx, int level, bool with_bsk)
+{
+    const LevelHost &Lh = ctx->host->levels[level];
+    std::vector<int> r(Lh.q_idx);
+    if (with_bsk)
+        r.insert(r.end(), Lh.bsk_idx.begin(), Lh.bsk_idx.end());
+    return r;
+}
+
+// ---- multiply core: writes polys [0,split) to dst0 and [split,Dn) to dst1 ----
+static int multiply_core(b200_ctx *ctx, int level, const u64 *a, int sa, const u64 *b, int sb, bool square, u64 *dst0,
+                         int split, u64 *dst1, long long batch, cudaStream_t s)
+{
+    const LevelDev &L = ctx->levels[level];
+    const LevelHost &Lh = ctx->host->levels[level];
+    const long long n = (long long)ctx->n;
+    const int k = L.k, R = k + L.nBsk;
+    const int P = square ? sa : sa + sb;
+    const int Dn = square ? 3 : sa + sb - 1;
+    Scratch scr(s);
+    u64 *ext = nullptr, *D = nullptr;
+    int rc;
+    if ((rc = scr.get((size_t)batch * P * R * n, &ext)))
+        return rc;
+    if ((rc = scr.get((size_t)batch * Dn * R * n, &D)))
+        return rc;
+    // (1)-(2) lift to Bsk
+    {
+        const long long total = batch * P * n;
+        DISPATCH_K(k, B200_LAUNCH(lift_kernel<KK>, blocks_for(total, EB), EB, 0, s, L, a, sa, square ? a : b, square ? 0 : sb, ext, n,
+                                                                           total));
+        ctx->launches++;
+    }
+    // (3) forward NTTs: q rows straight from the inputs, Bsk rows in place
+    for (int which = 0; which < (square ? 1 : 2); which++)
+    {
+        const int sz = which == 0 ? sa : sb;
+        const int p0 = which == 0 ? 0 : sa;
+        std::vector<int> prime;
+        std::vector<long long> so, dof;
+        for (int p = 0; p < sz; p++)
+            for (int r = 0; r < k; r++)
+            {
+                prime.push_back(Lh.q_idx[r]);
+                so.push_back(((long long)p * k + r) * n);
+                dof.push_back(((long long)(p0 + p) * R + r) * n);
+            }
+        JobDesc jd;
+        std::string key = "mulq:" + std::to_string(level) + ":" + std::to_string(sz) + ":" + std::to_string(p0) + ":" +
+                          std::to_string(P);
+        if ((rc = get_job(ctx, key, prime, so, dof, &jd)))
+            return rc;
+        if ((rc = launch_ntt<true>(ctx, jd, which == 0 ? a : b, (long long)sz * k * n, ext, (long long)P * R * n, batch, 0, s)))
+            return rc;
+    }
+    {
+        std::vector<int> prime;
+        std::vector<long long> off;
+        for (int p = 0; p < P; p++)
+            for (int j = 0; j < L.nBsk; j++)
+            {
+                prime.push_back(Lh.bsk_idx[j]);
+                off.push_back(((long long)p * R + k + j) * n);
+            }
+        JobDesc jd;
+        if ((rc = get_job(ctx, "mulbsk:" + std::to_string(level) + ":" + std::to_string(P), prime, off, off, &jd)))
+            return rc;
+        if ((rc = launch_ntt<true>(ctx, jd, ext, (long long)P * R * n, ext, (long long)P * R * n, batch, 0, s)))
+            return rc;
+    }
+    // (4) tensor
+    {
+        const long long total = batch * R * n;
+        B200_LAUNCH(tensor_kernel, blocks_for(total, EB), EB, 0, s, L, ext, sa, sb, D, n, total, square ? 1 : 0);
+        ctx->launches++;
+    }
+    // (5) inverse NTTs
+    {
+        std::vector<int> rows = row_primes(ctx, level, true), prime;
+        for (int m = 0; m < Dn; m++)
+            prime.insert(prime.end(), rows.begin(), rows.end());
+        JobDesc jd;
+        if ((rc = dense_job(ctx, "muld:" + std::to_string(level) + ":" + std::to_string(Dn), prime, &jd)))
+            return rc;
+        if ((rc = launch_ntt<false>(ctx, jd, D, (long long)Dn * R * n, D, (long long)Dn * R * n, batch, 0, s)))
+            return rc;
+    }
+    // (6)-(8) scale
+    {
+        const long long total = batch * Dn * n;
+        DISPATCH_K(k, B200_LAUNCH(scale_kernel<KK>, blocks_for(total, EB), EB, 0, s, L, D, Dn, dst0, split, dst1, n, total));
+        ctx->launches++;
+    }
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+// ---- key switch core: target d (k rows per item, stride d_stride), key list; dst_c = base_c + moddown(acc_c) ----
+static int keyswitch_core(b200_ctx *ctx, int level, const u64 *d, long long d_stride, const u64 *key, const u64 *base0,
+                          long long base0_stride, const u64 *base1, long long base1_stride, u64 *dst,
+                          long long dst_stride, long long batch, cudaStream_t s)
+{
+    if (!ctx->host->using_keyswitching || level < 1)
+        return fail(B200_E_LOGIC, "keyswitching is not supported by the context");
+    const LevelDev &L = ctx->levels[level];
+    const LevelHost &Lh = ctx->host->levels[level];
+    const long long n = (long long)ctx->n;
+    const int k = L.k;
+    const int Kkey = ctx->host->K;
+    const int special = Kkey - 1;
+    Scratch scr(s);
+    u64 *ks1 = nullptr, *ks2 = nullptr;
+    int rc;
+    if ((rc = scr.get((size_t)batch * (k + 1) * k * n, &ks1)))
+        return rc;
+    if ((rc = scr.get((size_t)batch * 2 * (k + 1) * n, &ks2)))
+        return rc;
+    {
+        std::vector<int> prime;
+        std::vector<long long> so, dof;
+        for (int I = 0; I <= k; I++)
+            for (int J = 0; J < k; J++)
+            {
+                prime.push_back(I < k ? Lh.q_idx[I] : special);
+                so.push_back((long long)J * n);
+                dof.push_back(((long long)I * k + J) * n);
+            }
+        JobDesc jd;
+        if ((rc = get_job(ctx, "ks1:" + std::to_string(level), prime, so, dof, &jd)))
+            return rc;
+        if ((rc = launch_ntt<true>(ctx, jd, d, d_stride, ks1, (long long)(k + 1) * k * n, batch, 1, s)))
+            return rc;
+    }
+    {
+        const long long total = batch * (k + 1) * n;
+        DISPATCH_K(k, B200_LAUNCH(ksmac_kernel<KK>, blocks_for(total, EB), EB, 0, s, ctx->d_primes, special, Kkey, ks1, key, ks2, n,
+                                                                            total));
+        ctx->launches++;
+    }
+    {
+        std::vector<int> prime;
+        for (int comp = 0; comp < 2; comp++)
+            for (int I = 0; I <= k; I++)
+                prime.push_back(I < k ? Lh.q_idx[I] : special);
+        JobDesc jd;
+        if ((rc = dense_job(ctx, "ks2:" + std::to_string(level), prime, &jd)))
+            return rc;
+        if ((rc = launch_ntt<false>(ctx, jd, ks2, 2LL * (k + 1) * n, ks2, 2LL * (k + 1) * n, batch, 0, s)))
+            return rc;
+    }
+    {
+        const long long total = batch * 2 * n;
+        DISPATCH_K(k, B200_LAUNCH(ksmoddown_kernel<KK>, blocks_for(total, EB), EB, 0, s, ctx->d_primes, special, ctx->d_inv_qsp, ks2,
+                                                                                base0, base0_stride, base1, base1_stride,
+                                                                                dst, dst_stride, n, total));
+        ctx->launches++;
+    }
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char *b200_last_error(void) { return g_err.c_str(); }
+
+int b200_device_count(void)
+{
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess)
+        return 0;
+    return c;
+}
+
+int b200_ctx_create(uint64_t n, const uint64_t *coeff_modulus, uint64_t count, uint64_t plain_modulus, int device,
+                    b200_ctx **out)
+{
+    if (!coeff_modulus || !out)
+        return fail(B200_E_NULL, "null argument");
+    *out = nullptr;
+    std::unique_ptr<b200_ctx> ctx(new b200_ctx());
+    try
+    {
+        std::vector<b200::u64> mods(coeff_modulus, coeff_modulus + count);
+        ctx->host.reset(new BfvHostContext((size_t)n, mods, plain_modulus));
+    }
+    catch (const std::invalid_argument &e)
+    {
+        return fail(B200_E_INVALID, e.what());
+    }
+    catch (const std::logic_error &e)
+    {
+        return fail(B200_E_LOGIC, e.what());
+    }
+    catch (const std::exception &e)
+    {
+        return fail(B200_E_INVALID, e.what());
+    }
+    ctx->n = ctx->host->n;
+    ctx->logn = ctx->host->logn;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(B200_E_CUDA, "no CUDA device available: the B200 backend has no CPU fallback");
+    if (device < 0 || device >= ndev)
+        return fail(B200_E_INVALID, "device index out of range");
+    CU_TRY(cudaSetDevice(device));
+    ctx->device = device;
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    // NTT launch configuration
+    ctx->npass = ntt_schedule(ctx->logn, ctx->pass_L);
+    ctx->ntt_smem = (size_t)ntt_smem_words((int)ctx->n) * sizeof(u64);
+    if (ctx->ntt_smem > (size_t)prop.sharedMemPerBlockOptin)
+        return fail(B200_E_INVALID, "poly_modulus_degree too large for the single-CTA NTT (max 16384 in this build)");
+    ctx->ntt_threads = ctx->n >= 16384 ? 512 : (ctx->n >= 1024 ? 256 : 64);
+    CU_TRY(cudaFuncSetAttribute(ntt_kernel<true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
+    CU_TRY(cudaFuncSetAttribute(ntt_kernel<false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
+    CU_TRY(cudaFuncSetAttribute(ntt_kernel<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
+    CU_TRY(cudaFuncSetAttribute(ntt_kernel<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
+    CU_TRY(cudaFuncSetAttribute(ntt_kernel<true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
+    CU_TRY(cudaFuncSetAttribute(ntt_kernel<false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
+    // keep freed scratch cached in the pool instead of returning it to the OS
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess)
+    {
+        unsigned long long thr = ~0ULL;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    int rc = build_device(ctx.get());
+    if (rc)
+        return rc;
+    CU_TRY(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
+    CU_TRY(cudaStreamCreateWithFlags(&ctx->s_comp, cudaStreamNonBlocking));
+    CU_TRY(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
+    CU_TRY(cudaDeviceSynchronize());
+    *out = ctx.release();
+    return 0;
+}
+
+void b200_ctx_destroy(b200_ctx *ctx)
+{
+    if (!ctx)
+        return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (void *p : ctx->allocations)
+        cudaFree(p);
+    if (ctx->s_h2d)
+        cudaStreamDestroy(ctx->s_h2d);
+    if (ctx->s_comp)
+        cudaStreamDestroy(ctx->s_comp);
+    if (ctx->s_d2h)
+        cudaStreamDestroy(ctx->s_d2h);
+    delete ctx;
+}
+
+int b200_ctx_info(const b200_ctx *ctx, b200_info *out)
+{
+    if (!ctx || !out)
+        return fail(B200_E_NULL, "null argument");
+    out->n = ctx->n;
+    out->plain_modulus = ctx->host->t;
+    out->key_primes = ctx->host->K;
+    out->levels = (int)ctx->host->levels.size();
+    out->first_level = ctx->host->first_level();
+    out->using_batching = ctx->host->using_batching;
+    out->device = ctx->device;
+    out->sm_count = ctx->sm_count;
+    return 0;
+}
+
+int b200_ctx_level_info(const b200_ctx *ctx, int level, b200_level_info *out)
+{
+    if (!ctx || !out)
+        return fail(B200_E_NULL, "null argument");
+    if (level < 0 || level >= (int)ctx->host->levels.size())
+        return fail(B200_E_INVALID, "level out of range");
+    const LevelHost &L = ctx->host->levels[level];
+    memset(out, 0, sizeof(*out));
+    out->k = L.k;
+    out->nB = L.nB;
+    out->nBsk = L.nBsk;
+    memcpy(out->parms_id, L.parms_id, sizeof(L.parms_id));
+    out->m_sk = ctx->host->primes[ctx->host->aux0].mod.p;
+    out->gamma = ctx->host->primes[L.gamma_idx].mod.p;
+    for (int i = 0; i < L.k && i < 64; i++)
+    {
+        out->q[i] = ctx->host->primes[L.q_idx[i]].mod.p;
+        out->roots[i] = ctx->host->primes[L.q_idx[i]].root;
+        out->delta[i] = L.delta[i];
+    }
+    for (int j = 0; j < L.nBsk && j < 66; j++)
+        out->bsk[j] = ctx->host->primes[L.bsk_idx[j]].mod.p;
+    out->q_mod_t = L.q_mod_t;
+    return 0;
+}
+
+int b200_galois_elt_from_step(const b200_ctx *ctx, int steps, uint32_t *elt)
+{
+    if (!ctx || !elt)
+        return fail(B200_E_NULL, "null argument");
+    try
+    {
+        *elt = ctx->host->galois_elt_from_step(steps);
+    }
+    catch (const std::exception &e)
+    {
+        return fail(B200_E_INVALID, e.what());
+    }
+    return 0;
+}
+
+int b200_malloc(b200_ctx *ctx, size_t bytes, void **dptr)
+{
+    if (!ctx || !dptr)
+        return fail(B200_E_NULL, "null argument");
+    CU_TRY(cudaSetDevice(ctx->device));
+    CU_TRY(cudaMalloc(dptr, bytes ? bytes : 8));
+    return 0;
+}
+int b200_free(b200_ctx *ctx, void *dptr)
+{
+    if (!ctx)
+        return fail(B200_E_NULL, "null argument");
+    CU_TRY(cudaFree(dptr));
+    return 0;
+}
+int b200_malloc_host(size_t bytes, void **hptr)
+{
+    if (!hptr)
+        return fail(B200_E_NULL, "null argument");
+    CU_TRY(cudaMallocHost(hptr, bytes ? bytes : 8));
+    return 0;
+}
+int b200_free_host(void *hptr)
+{
+    CU_TRY(cudaFreeHost(hptr));
+    return 0;
+}
+int b200_memcpy_h2d(b200_ctx *ctx, void *dst, const void *src, size_t bytes, void *stream)
+{
+    if (!ctx)
+        return fail(B200_E_NULL, "null argument");
+    CU_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return 0;
+}
+int b200_memcpy_d2h(b200_ctx *ctx, void *dst, const void *src, size_t bytes, void *stream)
+{
+    if (!ctx)
+        return fail(B200_E_NULL, "null argument");
+    CU_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return 0;
+}
+int b200_memcpy_d2d(b200_ctx *ctx, void *dst, const void *src, size_t bytes, void *stream)
+{
+    if (!ctx)
+        return fail(B200_E_NULL, "null argument");
+    CU_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return 0;
+}
+int b200_stream_synchronize(b200_ctx *ctx, void *stream)
+{
+    if (!ctx)
+        return fail(B200_E_NULL, "null argument");
+    CU_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    return 0;
+}
+
+uint64_t b200_launch_count(const b200_ctx *ctx) { return ctx ? ctx->launches.load() : 0; }
+
+// ---- NTT ----
+static int ntt_slab(b200_ctx *ctx, int level, u64 *data, uint64_t items, void *stream, bool fwd)
+{
+    int rc = check_level(ctx, level);
+    if (rc)
+        return rc;
+    if (!data)
+        return fail(B200_E_NULL, "null data");
+    JobDesc jd;
+    if ((rc = dense_job(ctx, "slab:" + std::to_string(level), row_primes(ctx, level, false), &jd)))
+        return rc;
+    const long long stride = (long long)ctx->levels[level].k * (long long)ctx->n;
+    if (fwd)
+        return launch_ntt<true>(ctx, jd, data, stride, data, stride, (long long)items, 0, (cudaStream_t)stream);
+    return launch_ntt<false>(ctx, jd, data, stride, data, stride, (long long)items, 0, (cudaStream_t)stream);
+}
+int b200_ntt_forward(b200_ctx *ctx, int level, uint64_t *data, uint64_t items, void *stream)
+{
+    return ntt_slab(ctx, level, (u64 *)data, items, stream, true);
+}
+int b200_ntt_inverse(b200_ctx *ctx, int level, uint64_t *data, uint64_t items, void *stream)
+{
+    return ntt_slab(ctx, level, (u64 *)data, items, stream, false);
+}
+
+// ---- add / sub / negate ----
+static int addsub(b200_ctx *ctx, int level, const u64 *a, const u64 *b, u64 *out, int size, uint64_t batch, void *stream,
+                  int mode)
+{
+    int rc = check_level(ctx, level);
+    if (rc)
+        return rc;
+    if (!a || !out || (mode != 2 && !b))
+        return fail(B200_E_NULL, "null ciphertext pointer");
+    if (size < 1)
+        return fail(B200_E_INVALID, "size");
+    const LevelDev &L = ctx->levels[level];
+    const long long total = (long long)batch * size * L.k * (long long)ctx->n;
+    if (total == 0)
+        return 0;
+    B200_LAUNCH(addsub_kernel, blocks_for(total, EB), EB, 0, (cudaStream_t)stream, ctx->d_primes, L.k, a, b, out, ctx->logn, mode,
+                                                                         total);
+    ctx->launches++;
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+int b200_add(b200_ctx *ctx, int level, const uint64_t *a, const uint64_t *b, uint64_t *out, int size, uint64_t batch,
+             void *stream)
+{
+    return addsub(ctx, level, (const u64 *)a, (const u64 *)b, (u64 *)out, size, batch, stream, 0);
+}
+int b200_sub(b200_ctx *ctx, int level, const uint64_t *a, const uint64_t *b, uint64_t *out, int size, uint64_t batch,
+             void *stream)
+{
+    return addsub(ctx, level, (const u64 *)a, (const u64 *)b, (u64 *)out, size, batch, stream, 1);
+}
+int b200_negate(b200_ctx *ctx, int level, const uint64_t *a, uint64_t *out, int size, uint64_t batch, void *stream)
+{
+    return addsub(ctx, level, (const u64 *)a, nullptr, (u64 *)out, size, batch, stream, 2);
+}
+
+// ---- multiply / square ----
+int b200_multiply(b200_ctx *ctx, int level, const uint64_t *a, int sa, const uint64_t *b, int sb, uint64_t *out,
+                  uint64_t batch, void *stream)
+{
+    int rc = check_level(ctx, level);
+    if (rc)
+        return rc;
+    if (!a || !b || !out)
+        return fail(B200_E_NULL, "null ciphertext pointer");
+    if (sa < 1 || sb < 1 || sa > 4 || sb > 4)
+        return fail(B200_E_INVALID, "ciphertext sizes must be in [1,4] (destination size <= 7)");
+    if (batch == 0)
+        return 0;
+    CU_TRY(cudaSetDevice(ctx->device));
+    const int Dn = sa + sb - 1;
+    return multiply_core(ctx, level, (const u64 *)a, sa, (const u64 *)b, sb, false, (u64 *)out, Dn, nullptr,
+                         (long long)batch, (cudaStream_t)stream);
+}
+
+int b200_square(b200_ctx *ctx, int level, const uint64_t *a, uint64_t *out, uint64_t batch, void *stream)
+{
+    int rc = check_level(ctx, level);
+    if (rc)
+        return rc;
+    if (!a || !out)
+        return fail(B200_E_NULL, "null ciphertext pointer");
+    if (batch == 0)
+        return 0;
+    CU_TRY(cudaSetDevice(ctx->device));
+    return multiply_core(ctx, level, (const u64 *)a, 2, nullptr, 0, true, (u64 *)out, 3, nullptr, (long long)batch,
+                         (cudaStream_t)stream);
+}
+
+int b200_relinearize(b200_ctx *ctx, int level, const uint64_t *in3, const uint64_t *relin_key, uint64_t *out2,
+                     uint64_t batch, void *stream)
+{
+    int rc = check_level(ctx, level);
+    if (rc)
+        return rc;
+    if (!in3 || !relin_key || !out2)
+        return fail(B200_E_NULL, "null pointer");
+    if (batch == 0)
+        return 0;
+    if ((const void *)in3 == (const void *)out2 && batch != 1)
+        return fail(B200_E_INVALID, "in-place relinearize is only defined for batch == 1");
+    CU_TRY(cudaSetDevice(ctx->device));
+    const long long n = (long long)ctx->n;
+    const int k = ctx->levels[level].k;
+    const u64 *c = (const u64 *)in3;
+    return keyswitch_core(ctx, level, c + 2LL * k * n, 3LL * k * n, (const u64 *)relin_key, c, 3LL * k * n, c + (long long)k * n,
+                          3LL * k * n, (u64 *)out2, 2LL * k * n, (long long)batch, (cudaStream_t)stream);
+}
+
+int b200_multiply_relin(b200_ctx *ctx, int level, const uint64_t *a, const uint64_t *b, const uint64_t *relin_key,
+                        uint64_t *out2, uint64_t batch, void *stream)
+{
+    int rc = check_level(ctx, level);
+    if (rc)
+        return rc;
+    if (!a || !b || !relin_key || !out2)
+        return fail(B200_E_NULL, "null pointer");
+    if (batch == 0)
+        return 0;
+    CU_TRY(cudaSetDevice(ctx->device));
+    const long long n = (long long)ctx->n;
+    const int k = ctx->levels[level].k;
+    cudaStream_t s = (cudaStream_t)stream;
+    Scratch scr(s);
+    u64 *c2 = nullptr;
+    if ((rc = scr.get((size_t)batch * k * n, &c2)))
+        return rc;
+    // c0,c1 go straight into out2; c2 into scratch
+    if ((rc = multiply_core(ctx, level, (const u64 *)a, 2, (const u64 *)b, 2, false, (u64 *)out2, 2, c2, (long long)batch, s)))
+        return rc;
+    u64 *o = (u64 *)out2;
+    return keyswitch_core(ctx, level, c2, (long long)k * n, (const u64 *)relin_key, o, 2LL * k * n, o + (long long)k * n,
+                          2LL * k * n, o, 2LL * k * n, (long long)batch, s);
+}
+
+int b200_apply_galois(b200_ctx *ctx, int level, const uint64_t *in2, uint32_t galois_elt, const uint64_t *galois_key,
+                      uint64_t *out2, uint64_t batch, void *stream)
+{
+    int rc = check_level(ctx, level);
+    if (rc)
+        return rc;
+    if (!in2 || !galois_key || !out2)
+        return fail(B200_E_NULL, "null pointer");
+    if (!(galois_elt & 1) || galois_elt >= 2 * ctx->n)
+        return fail(B200_E_INVALID, "Galois element is not valid");
+    if ((const void *)in2 == (const void *)out2)
+        return fail(B200_E_INVALID, "apply_galois cannot run in place at this layer");
+    if (batch == 0)
+        return 0;
+    CU_TRY(cudaSetDevice(ctx->device));
+    const long long n = (long long)ctx->n;
+    const LevelDev &L = ctx->levels[level];
+    const int k = L.k;
+    cudaStream_t s = (cudaStream_t)stream;
+    Scratch scr(s);
+    u64 *tmp = nullptr;
+    if ((rc = scr.get((size_t)batch * k * n, &tmp)))
+        return rc;
+    const long long total = (long long)batch * 2 * k * n;
+    B200_LAUNCH(galois_kernel, blocks_for(total, EB), EB, 0, s, ctx->d_primes, k, (const u64 *)in2, (u64 *)out2, tmp, ctx->logn,
+                                                       galois_elt, total);
+    ctx->launches++;
+    u64 *o = (u64 *)out2;
+    return keyswitch_core(ctx, level, tmp, (long long)k * n, (const u64 *)galois_key, o, 2LL * k * n, nullptr, 0, o,
+                          2LL * k * n, (long long)batch, s);
+}
+
+int b200_multiply_plain(b200_ctx *ctx, int level, const uint64_t *a, int size, const uint64_t *plain, uint64_t pb,
+                        uint64_t *out, uint64_t batch, void *stream)
+{
+    int rc = check_level(ctx, level);
+    if (rc)
+        return rc;
+    if (!a || !plain || !out)
+        return fail(B200_E_NULL, "null pointer");
+    if (size < 1 || (pb != 1 && pb != batch))
+        return fail(B200_E_INVALID, "size / plain_batch");
+    if (batch == 0)
+        return 0;
+    CU_TRY(cudaSetDevice(ctx->device));
+    const long long n = (long long)ctx->n;
+    const LevelDev &L = ctx->levels[level];
+    const int k = L.k;
+    cudaStream_t s = (cudaStream_t)stream;
+    Scratch scr(s);
+    u64 *pl = nullptr;
+    if ((rc = scr.get((size_t)pb * k * n, &pl)))
+        return rc;
+    {
+        const long long total = (long long)pb * k * n;
+        B200_LAUNCH(plain_lift_kernel, blocks_for(total, EB), EB, 0, s, L, (const u64 *)plain, pl, ctx->logn, total);
+        ctx->launches++;
+    }
+    JobDesc jd;
+    if ((rc = dense_job(ctx, "slab:" + std::to_string(level), row_primes(ctx, level, false), &jd)))
+        return rc;
+    if ((rc = launch_ntt<true>(ctx, jd, pl, (long long)k * n, pl, (long long)k * n, (long long)pb, 0, s)))
+        return rc;
+    // ct polys: forward (out of place), dyadic, inverse
+    if ((rc = launch_ntt<true>(ctx, jd, (const u64 *)a, (long long)k * n, (u64 *)out, (long long)k * n, (long long)batch * size, 0,
+                               s)))
+        return rc;
+    {
+        const long long total = (long long)batch * size * k * n;
+        B200_LAUNCH(dyadic_plain_kernel, blocks_for(total, EB), EB, 0, s, ctx->d_primes, k, size, (const u64 *)out, pl, (long long)pb,
+                                                                 (u64 *)out, ctx->logn, total);
+        ctx->launches++;
+    }
+    if ((rc = launch_ntt<false>(ctx, jd, (const u64 *)out, (long long)k * n, (u64 *)out, (long long)k * n,
+                                (long long)batch * size, 0, s)))
+        return rc;
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+static int addsub_plain(b200_ctx *ctx, int level, const u64 *a, int size, const u64 *plain, uint64_t pb, u64 *out,
+                        uint64_t batch, void *stream, int sign)
+{
+    int rc = check_level(ctx, level);
+    if (rc)
+        return rc;
+    if (!a || !plain || !out)
+        return fail(B200_E_NULL, "null pointer");
+    if (size < 1 || (pb != 1 && pb != batch))
+        return fail(B200_E_INVALID, "size / plain_batch");
+    if (batch == 0)
+        return 0;
+    const LevelDev &L = ctx->levels[level];
+    const long long total = (long long)batch * size * L.k * (long long)ctx->n;
+    B200_LAUNCH(addsub_plain_kernel, blocks_for(total, EB), EB, 0, (cudaStream_t)stream, L, size, a, plain, (long long)pb, out,
+                                                                               ctx->logn, sign, total);
+    ctx->launches++;
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+int b200_add_plain(b200_ctx *ctx, int level, const uint64_t *a, int size, const uint64_t *plain, uint64_t pb, uint64_t *out,
+                   uint64_t batch, void *stream)
+{
+    return addsub_plain(ctx, level, (const u64 *)a, size, (const u64 *)plain, pb, (u64 *)out, batch, stream, 0);
+}
+int b200_sub_plain(b200_ctx *ctx, int level, const uint64_t *a, int size, const uint64_t *plain, uint64_t pb, uint64_t *out,
+                   uint64_t batch, void *stream)
+{
+    return addsub_plain(ctx, level, (const u64 *)a, size, (const u64 *)plain, pb, (u64 *)out, batch, stream, 1);
+}
+
+int b200_mod_switch_to_next(b200_ctx *ctx, int level, const uint64_t *a, int size, uint64_t *out, uint64_t batch,
+                            void *stream)
+{
+    int rc = check_level(ctx, level);
+    if (rc)
+        return rc;
+    if (!a || !out)
+        return fail(B200_E_NULL, "null pointer");
+    const LevelDev &L = ctx->levels[level];
+    if (L.k < 2 || level + 1 >= (int)ctx->levels.size())
+        return fail(B200_E_INVALID, "end of modulus switching chain reached");
+    if (batch == 0)
+        return 0;
+    const long long n = (long long)ctx->n;
+    const long long total = (long long)batch * size * n;
+    DISPATCH_K(L.k, B200_LAUNCH(modswitch_kernel<KK>, blocks_for(total, EB), EB, 0, (cudaStream_t)stream, 
+                        ctx->d_primes, L.inv_qlast, (const u64 *)a, (u64 *)out, n, total));
+    ctx->launches++;
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+int b200_decrypt(b200_ctx *ctx, int level, const uint64_t *ct, int size, const uint64_t *sk_powers_ntt, uint64_t *plain_out,
+                 uint64_t batch, void *stream)
+{
+    int rc = check_level(ctx, level);
+    if (rc)
+        return rc;
+    if (!ct || !sk_powers_ntt || !plain_out)
+        return fail(B200_E_NULL, "null pointer");
+    if (size < 2)
+        return fail(B200_E_INVALID, "ciphertext size must be >= 2");
+    if (batch == 0)
+        return 0;
+    CU_TRY(cudaSetDevice(ctx->device));
+    const long long n = (long long)ctx->n;
+    const LevelDev &L = ctx->levels[level];
+    const LevelHost &Lh = ctx->host->levels[level];
+    const int k = L.k, terms = size - 1;
+    cudaStream_t s = (cudaStream_t)stream;
+    Scratch scr(s);
+    u64 *X = nullptr, *acc = nullptr;
+    if ((rc = scr.get((size_t)batch * terms * k * n, &X)))
+        return rc;
+    if ((rc = scr.get((size_t)batch * k * n, &acc)))
+        return rc;
+    {
+        std::vector<int> prime;
+        std::vector<long long> so, dof;
+        for (int j = 0; j < terms; j++)
+            for (int r = 0; r < k; r++)
+            {
+                prime.push_back(Lh.q_idx[r]);
+                so.push_back(((long long)(j + 1) * k + r) * n);
+                dof.push_back(((long long)j * k + r) * n);
+            }
+        JobDesc jd;
+        if ((rc = get_job(ctx, "dec:" + std::to_string(level) + ":" + std::to_string(size), prime, so, dof, &jd)))
+            return rc;
+        if ((rc = launch_ntt<true>(ctx, jd, (const u64 *)ct, (long long)size * k * n, X, (long long)terms * k * n,
+                                   (long long)batch, 0, s)))
+            return rc;
+    }
+    {
+        const long long total = (long long)batch * k * n;
+        B200_LAUNCH(dot_sk_kernel, blocks_for(total, EB), EB, 0, s, ctx->d_primes, k, terms, X, (const u64 *)sk_powers_ntt, acc,
+                                                           ctx->logn, total);
+        ctx->launches++;
+    }
+    JobDesc jd;
+    if ((rc = dense_job(ctx, "slab:" + std::to_string(level), row_primes(ctx, level, false), &jd)))
+        return rc;
+    if ((rc = launch_ntt<false>(ctx, jd, acc, (long long)k * n, acc, (long long)k * n, (long long)batch, 0, s)))
+        return rc;
+    {
+        const long long total = (long long)batch * n;
+        DISPATCH_K(k, B200_LAUNCH(decrypt_kernel<KK>, blocks_for(total, EB), EB, 0, s, L, size, (const u64 *)ct, acc,
+                                                                              (u64 *)plain_out, n, total));
+        ctx->launches++;
+    }
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+int b200_is_transparent(b200_ctx *ctx, int level, const uint64_t *ct, int size, uint32_t *flags_out, uint64_t batch,
+                        void *stream)
+{
+    int rc = check_level(ctx, level);
+    if (rc)
+        return rc;
+    if (!ct || !flags_out)
+        return fail(B200_E_NULL, "null pointer");
+    if (batch == 0)
+        return 0;
+    const long long n = (long long)ctx->n;
+    const int k = ctx->levels[level].k;
+    cudaStream_t s = (cudaStream_t)stream;
+    B200_LAUNCH(fill_u32_kernel, blocks_for((long long)batch, EB), EB, 0, s, flags_out, 1u, (long long)batch);
+    ctx->launches++;
+    if (size >= 2)
+    {
+        dim3 grid(8, (unsigned)batch);
+        B200_LAUNCH(transparent_kernel, grid, 256, 0, s, (const u64 *)ct, (long long)size * k * n, (long long)k * n, flags_out);
+        ctx->launches++;
+    }
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+// ---- host-buffer variants ----
+int b200_multiply_relin_host(b200_ctx *ctx, int level, const uint64_t *a_host, const uint64_t *b_host,
+                             const uint64_t *relin_key_dev, uint64_t *out_host, uint64_t batch)
+{
+    int rc = check_level(ctx, level);
+    if (rc)
+        return rc;
+    if (!a_host || !b_host || !relin_key_dev || !out_host)
+        return fail(B200_E_NULL, "null pointer");
+    if (batch == 0)
+        return 0;
+    CU_TRY(cudaSetDevice(ctx->device));
+    const long long n = (long long)ctx->n;
+    const int k = ctx->levels[level].k;
+    const size_t ct_words = (size_t)2 * k * n;
+    const char *env = getenv("B200_HOST_CHUNK");
+    long long chunk = env ? atoll(env) : 64;
+    if (chunk < 1)
+        chunk = 1;
+    if ((uint64_t)chunk > batch)
+        chunk = (long long)batch;
+    const int NBUF = 3;
+    u64 *da[NBUF], *db[NBUF], *dout[NBUF];
+    cudaEvent_t ev_in[NBUF], ev_comp[NBUF], ev_out[NBUF];
+    for (int i = 0; i < NBUF; i++)
+    {
+        CU_TRY(cudaMalloc((void **)&da[i], chunk * ct_words * sizeof(u64)));
+        CU_TRY(cudaMalloc((void **)&db[i], chunk * ct_words * sizeof(u64)));
+        CU_TRY(cudaMalloc((void **)&dout[i], chunk * ct_words * sizeof(u64)));
+        CU_TRY(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&ev_comp[i], cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming));
+    }
+    int it = 0;
+    rc = 0;
+    for (uint64_t off = 0; off < batch && rc == 0; off += (uint64_t)chunk, it++)
+    {
+        const int sl = it % NBUF;
+        const long long cnt = (long long)std::min<uint64_t>((uint64_t)chunk, batch - off);
+        const size_t bytes = (size_t)cnt * ct_words * sizeof(u64);
+        if (it >= NBUF)
+            cudaStreamWaitEvent(ctx->s_h2d, ev_out[sl], 0); // slot free once its previous output left
+        cudaMemcpyAsync(da[sl], a_host + off * ct_words, bytes, cudaMemcpyHostToDevice, ctx->s_h2d);
+        cudaMemcpyAsync(db[sl], b_host + off * ct_words, bytes, cudaMemcpyHostToDevice, ctx->s_h2d);
+        cudaEventRecord(ev_in[sl], ctx->s_h2d);
+        cudaStreamWaitEvent(ctx->s_comp, ev_in[sl], 0);
+        rc = b200_multiply_relin(ctx, level, (const uint64_t *)da[sl], (const uint64_t *)db[sl], relin_key_dev, (uint64_t *)dout[sl],
+                                 (uint64_t)cnt, ctx->s_comp);
+        cudaEventRecord(ev_comp[sl], ctx->s_comp);
+        cudaStreamWaitEvent(ctx->s_d2h, ev_comp[sl], 0);
+        cudaMemcpyAsync(out_host + off * ct_words, dout[sl], bytes, cudaMemcpyDeviceToHost, ctx->s_d2h);
+        cudaEventRecord(ev_out[sl], ctx->s_d2h);
+    }
+    cudaError_t e1 = cudaStreamSynchronize(ctx->s_h2d);
+    cudaError_t e2 = cudaStreamSynchronize(ctx->s_comp);
+    cudaError_t e3 = cudaStreamSynchronize(ctx->s_d2h);
+    for (int i = 0; i < NBUF; i++)
+    {
+        cudaFree(da[i]);
+        cudaFree(db[i]);
+        cudaFree(dout[i]);
+        cudaEventDestroy(ev_in[i]);
+        cudaEventDestroy(ev_comp[i]);
+        cudaEventDestroy(ev_out[i]);
+    }
+    if (rc)
+        return rc;
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
+        return fail(B200_E_CUDA, std::string("host pipeline: ") +
+                                     cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
+    return 0;
+}
+
+int b200_ntt_roundtrip_host(b200_ctx *ctx, int level, const uint64_t *in_host, uint64_t *out_host, uint64_t items)
+{
+    int rc = check_level(ctx, level);
+    if (rc)
+        return rc;
+    if (!in_host || !out_host)
+        return fail(B200_E_NULL, "null pointer");
+    if (items == 0)
+        return 0;
+    CU_TRY(cudaSetDevice(ctx->device));
+    const size_t words = (size_t)ctx->levels[level].k * ctx->n;
+    long long chunk = 256;
+    if ((uint64_t)chunk > items)
+        chunk = (long long)items;
+    const int NBUF = 3;
+    u64 *d[NBUF];
+    cudaEvent_t ev_in[NBUF], ev_comp[NBUF], ev_out[NBUF];
+    for (int i = 0; i < NBUF; i++)
+    {
+        CU_TRY(cudaMalloc((void **)&d[i], chunk * words * sizeof(u64)));
+        CU_TRY(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&ev_comp[i], cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming));
+    }
+    int it = 0;
+    rc = 0;
+    for (uint64_t off = 0; off < items && rc == 0; off += (uint64_t)chunk, it++)
+    {
+        const int sl = it % NBUF;
+        const long long cnt = (long long)std::min<uint64_t>((uint64_t)chunk, items - off);
+        const size_t bytes = (size_t)cnt * words * sizeof(u64);
+        if (it >= NBUF)
+            cudaStreamWaitEvent(ctx->s_h2d, ev_out[sl], 0);
+        cudaMemcpyAsync(d[sl], in_host + off * words, bytes, cudaMemcpyHostToDevice, ctx->s_h2d);
+        cudaEventRecord(ev_in[sl], ctx->s_h2d);
+        cudaStreamWaitEvent(ctx->s_comp, ev_in[sl], 0);
+        rc = b200_ntt_forward(ctx, level, (uint64_t *)d[sl], (uint64_t)cnt, ctx->s_comp);
+        if (!rc)
+            rc = b200_ntt_inverse(ctx, level, (uint64_t *)d[sl], (uint64_t)cnt, ctx->s_comp);
+        cudaEventRecord(ev_comp[sl], ctx->s_comp);
+        cudaStreamWaitEvent(ctx->s_d2h, ev_comp[sl], 0);
+        cudaMemcpyAsync(out_host + off * words, d[sl], bytes, cudaMemcpyDeviceToHost, ctx->s_d2h);
+        cudaEventRecord(ev_out[sl], ctx->s_d2h);
+    }
+    cudaError_t e1 = cudaStreamSynchronize(ctx->s_h2d);
+    cudaError_t e2 = cudaStreamSynchronize(ctx->s_comp);
+    cudaError_t e3 = cudaStreamSynchronize(ctx->s_d2h);
+    for (int i = 0; i < NBUF; i++)
+    {
+        cudaFree(d[i]);
+        cudaEventDestroy(ev_in[i]);
+        cudaEventDestroy(ev_comp[i]);
+        cudaEventDestroy(ev_out[i]);
+    }
+    if (rc)
+        return rc;
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
+        return fail(B200_E_CUDA, "host pipeline failed");
+    return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,297 @@
+// ntt_body.cuh — batched negacyclic NTT / INTT over one residue polynomial per CTA.
+//
+// Observable contract = the reference's (S/util/ntt.cpp:393-474, S/util/dwthandler.h:94-356):
+//   forward : natural-order input  -> bit-reversed-order output,  out[i] = sum_j in[j] * psi^((2*bitrev(i)+1) j)
+//   inverse : exact inverse including n^-1
+// psi = minimal primitive 2n-th root (host_ctx.cpp).  The internal schedule is our own: the polynomial
+// lives in shared memory (padded, conflict-free), and each pass does 3 or 4 butterfly stages in
+// registers (radix-8 / radix-16 groups) before the next block-wide exchange.  Butterflies are
+// Harvey-lazy ([0,4p) forward, [0,2p) inverse) with Shoup twiddles (w, floor(w*2^64/p)).
+//
+// Twiddle tables (device, per prime):  fwd[idx] = psi^bitrev(idx) for idx in [1,n)  (same indexing as the
+// reference's root_powers), inv[idx] = fwd[idx]^-1 (our own layout: the inverse of the forward twiddle of
+// the same butterfly group), each stored as 2 words {w, wq}.
+//
+// The bodies are __host__ __device__ and written as strided loops over work items with B200_SYNC()
+// between phases, so tests/emu can execute a CTA sequentially (tid=0,nthreads=1) on the CPU.
+#pragma once
+#include "modarith.cuh"
+
+#if defined(__CUDA_ARCH__)
+#define B200_SYNC() __syncthreads()
+#else
+#define B200_SYNC() ((void)0)
+#endif
+
+struct NttPrime
+{
+    u64 p;
+    u64 ratio1;        // floor(2^64/p) (Barrett, single word)
+    u64 inv_n, inv_n_q;      // n^-1 mod p and its Shoup quotient
+    u64 inv_n_w, inv_n_w_q;  // n^-1 * inv[1] mod p (last inverse stage folded) and its Shoup quotient
+    const u64 *fwd;    // [2n] words
+    const u64 *inv;    // [2n] words
+};
+
+// One launch = `items` x `slots` residue polynomials.
+struct NttJob
+{
+    int logn;
+    int slots;                 // residue polynomials per item
+    const int *slot_prime;     // [slots] index into primes[]
+    const long long *slot_src; // [slots] source offset (words) inside an item
+    const long long *slot_dst; // [slots] destination offset (words) inside an item
+    long long src_item_stride; // words
+    long long dst_item_stride; // words
+    const u64 *src;
+    u64 *dst;
+    const NttPrime *primes;
+    int reduce_input;          // 1: inputs are arbitrary 64-bit words -> Barrett to [0,p) on load
+    int npass;                 // forward pass schedule (host: ntt_schedule); inverse runs it mirrored
+    int pass_L[8];
+};
+
+B200_HD int ntt_pad(int e) { return e + (e >> 4); }
+B200_HD int ntt_smem_words(int n) { return n + (n >> 4); }
+
+// pass schedules: stages per pass for the forward transform (the inverse uses the mirror image).
+// Rule: the last forward pass is radix-16 so that the pass before it has sub-stride >= 16 (conflict-free).
+inline int ntt_schedule(int logn, int *passes)
+{
+    int np = 0;
+    int rem = logn;
+    // number of radix-16 passes a, radix-8 passes b with 4a+3b = logn where possible
+    int a = 0, b = 0;
+    for (a = (rem >= 4 ? 1 : 0); a <= rem / 4; a++)
+        if ((rem - 4 * a) % 3 == 0)
+            break;
+    if (a > rem / 4)
+    { // not representable with a>=1 (logn in {1,2,3,5,6,9}): fall back to a greedy split
+        int r = rem;
+        while (r > 0)
+        {
+            int L = r >= 4 && r != 5 && r != 6 ? 4 : (r >= 3 ? 3 : r);
+            passes[np++] = L;
+            r -= L;
+        }
+        // order ascending so larger radices come last
+        for (int i = 0; i < np; i++)
+            for (int j = i + 1; j < np; j++)
+                if (passes[j] < passes[i])
+                {
+                    int t = passes[i];
+                    passes[i] = passes[j];
+                    passes[j] = t;
+                }
+        return np;
+    }
+    // prefer more radix-16 passes when both decompositions exist (fewer exchanges)
+    while (rem - 4 * (a + 3) >= 0 && (rem - 4 * (a + 3)) % 3 == 0)
+        a += 3;
+    b = (rem - 4 * a) / 3;
+    for (int i = 0; i < b; i++)
+        passes[np++] = 3;
+    for (int i = 0; i < a; i++)
+        passes[np++] = 4;
+    return np;
+}
+
+// ---- forward: Cooley-Tukey group of 2^L elements, L stages -------------------------------------------
+template <int L>
+B200_HD void ntt_fwd_group(u64 *sm, int g, int logs /*log2 sub-stride*/, int M /*groups at first stage*/,
+                           const u64 *__restrict__ tw, u64 p)
+{
+    constexpr int R = 1 << L;
+    const int s = 1 << logs;
+    const int i = g >> logs;
+    const int o = g & (s - 1);
+    const int base = (i << (logs + L)) + o;
+    const u64 two_p = p << 1;
+    u64 x[R];
+#pragma unroll
+    for (int j = 0; j < R; j++)
+        x[j] = sm[ntt_pad(base + (j << logs))];
+#pragma unroll
+    for (int l = 0; l < L; l++)
+    {
+        const int half = 1 << (L - 1 - l);
+        const int tw_base = (M << l) + (i << l);
+#pragma unroll
+        for (int grp = 0; grp < (1 << l); grp++)
+        {
+            const int idx = tw_base + grp;
+#if defined(__CUDA_ARCH__)
+            const ulonglong2 t2 = __ldg(reinterpret_cast<const ulonglong2 *>(tw) + idx);
+            const u64 w = t2.x, wq = t2.y;
+#else
+            const u64 w = tw[2 * idx], wq = tw[2 * idx + 1];
+#endif
+#pragma unroll
+            for (int jj = 0; jj < half; jj++)
+            {
+                const int j = grp * 2 * half + jj;
+                u64 X = x[j];
+                X = X >= two_p ? X - two_p : X;
+                const u64 T = shoup_mul_lazy(x[j + half], w, wq, p);
+                x[j] = X + T;
+                x[j + half] = X - T + two_p;
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < R; j++)
+        sm[ntt_pad(base + (j << logs))] = x[j];
+}
+
+// ---- inverse: Gentleman-Sande group of 2^L elements, L stages (gap grows) -----------------------------
+// `last` marks the pass containing the final stage (m = 1), where n^-1 is folded in.
+template <int L>
+B200_HD void ntt_inv_group(u64 *sm, int g, int logs, int logn, const u64 *__restrict__ tw, const NttPrime &P,
+                           bool last)
+{
+    constexpr int R = 1 << L;
+    const int s = 1 << logs;
+    const int i = g >> logs;
+    const int o = g & (s - 1);
+    const int base = (i << (logs + L)) + o;
+    const u64 p = P.p, two_p = p << 1;
+    u64 x[R];
+#pragma unroll
+    for (int j = 0; j < R; j++)
+        x[j] = sm[ntt_pad(base + (j << logs))];
+#pragma unroll
+    for (int l = 0; l < L; l++)
+    {
+        const int half = 1 << l;
+        // global gap G = s*2^l, m = n/(2G) groups at this stage
+        const int m = 1 << (logn - 1 - logs - l);
+        const int tw_base = m + (i << (L - l - 1));
+        const bool fold = last && (l == L - 1);
+#pragma unroll
+        for (int grp = 0; grp < (R >> (l + 1)); grp++)
+        {
+            const int idx = tw_base + grp;
+            u64 w, wq;
+            if (fold)
+            {
+                w = P.inv_n_w;
+                wq = P.inv_n_w_q;
+            }
+            else
+            {
+#if defined(__CUDA_ARCH__)
+                const ulonglong2 t2 = __ldg(reinterpret_cast<const ulonglong2 *>(tw) + idx);
+                w = t2.x;
+                wq = t2.y;
+#else
+                w = tw[2 * idx];
+                wq = tw[2 * idx + 1];
+#endif
+            }
+#pragma unroll
+            for (int jj = 0; jj < half; jj++)
+            {
+                const int j = grp * 2 * half + jj;
+                const u64 X = x[j], Y = x[j + half];
+                u64 U = X + Y;
+                U = U >= two_p ? U - two_p : U;
+                const u64 V = shoup_mul_lazy(X - Y + two_p, w, wq, p);
+                x[j] = fold ? shoup_mul_lazy(U, P.inv_n, P.inv_n_q, p) : U;
+                x[j + half] = V;
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < R; j++)
+        sm[ntt_pad(base + (j << logs))] = x[j];
+}
+
+template <bool FWD, int L>
+B200_HD void ntt_pass(u64 *sm, int n, int logs, int logn, int M, const NttPrime &P, bool last, int tid, int nthreads)
+{
+    const int ngroups = n >> L;
+    for (int g = tid; g < ngroups; g += nthreads)
+    {
+        if (FWD)
+            ntt_fwd_group<L>(sm, g, logs, M, P.fwd, P.p);
+        else
+            ntt_inv_group<L>(sm, g, logs, logn, P.inv, P, last);
+    }
+}
+
+template <bool FWD>
+B200_HD void ntt_pass_dispatch(int L, u64 *sm, int n, int logs, int logn, int M, const NttPrime &P, bool last, int tid,
+                               int nthreads)
+{
+    switch (L)
+    {
+    case 1: ntt_pass<FWD, 1>(sm, n, logs, logn, M, P, last, tid, nthreads); break;
+    case 2: ntt_pass<FWD, 2>(sm, n, logs, logn, M, P, last, tid, nthreads); break;
+    case 3: ntt_pass<FWD, 3>(sm, n, logs, logn, M, P, last, tid, nthreads); break;
+    default: ntt_pass<FWD, 4>(sm, n, logs, logn, M, P, last, tid, nthreads); break;
+    }
+}
+
+// One CTA: transform residue polynomial `block` of the job. sm holds ntt_smem_words(n) words.
+template <bool FWD>
+B200_HD void ntt_block_body(const NttJob &job, long long block, u64 *sm, int tid, int nthreads)
+{
+    const int logn = job.logn;
+    const int n = 1 << logn;
+    const long long item = block / job.slots;
+    const int slot = (int)(block - item * job.slots);
+    const NttPrime P = job.primes[job.slot_prime[slot]];
+    const u64 *src = job.src + item * job.src_item_stride + job.slot_src[slot];
+    u64 *dst = job.dst + item * job.dst_item_stride + job.slot_dst[slot];
+    const u64 p = P.p;
+
+    for (int e = tid; e < n; e += nthreads)
+    {
+        u64 v = src[e];
+        if (job.reduce_input)
+            v = barrett64(v, p, P.ratio1);
+        sm[ntt_pad(e)] = v;
+    }
+    B200_SYNC();
+
+    const int np = job.npass;
+    if (FWD)
+    {
+        int done = 0; // stages completed
+        for (int pi = 0; pi < np; pi++)
+        {
+            const int L = job.pass_L[pi];
+            const int M = 1 << done;
+            const int logs = logn - done - L;
+            ntt_pass_dispatch<true>(L, sm, n, logs, logn, M, P, false, tid, nthreads);
+            B200_SYNC();
+            done += L;
+        }
+        const u64 two_p = p << 1;
+        for (int e = tid; e < n; e += nthreads)
+        {
+            u64 v = sm[ntt_pad(e)];
+            v = v >= two_p ? v - two_p : v;
+            v = v >= p ? v - p : v;
+            dst[e] = v;
+        }
+    }
+    else
+    {
+        int logs = 0;
+        for (int pi = np - 1; pi >= 0; pi--)
+        {
+            const int L = job.pass_L[pi];
+            const bool last = (pi == 0);
+            ntt_pass_dispatch<false>(L, sm, n, logs, logn, 0, P, last, tid, nthreads);
+            B200_SYNC();
+            logs += L;
+        }
+        for (int e = tid; e < n; e += nthreads)
+        {
+            u64 v = sm[ntt_pad(e)];
+            v = v >= p ? v - p : v;
+            dst[e] = v;
+        }
+    }
+}

@@ -1,0 +1,236 @@
+"""Word-for-word parity checks of the B200 path against the unmodified reference (shared by CPU-emu and GPU tests)."""
+import numpy as np
+
+from refseal import RefContext, appendix_b_inputs
+from sunscreen_b200.lib import B200Context
+
+
+class Pair:
+    """Same parameters instantiated on the reference and on the B200 library."""
+
+    def __init__(self, be, n, moduli, t):
+        self.be = be
+        self.n, self.moduli, self.t = n, list(moduli), t
+        self.ref = RefContext(n, moduli, t)
+        self.ctx = B200Context(n, moduli, t, lib=be.lib)
+        self.k = self.ctx.k()
+        self.inp = appendix_b_inputs(n, self.moduli, t)
+
+    def dev(self, arr):
+        return self.be.to_dev(arr)
+
+    def host(self, x):
+        return self.be.to_host(x)
+
+    def out(self, *shape):
+        return self.be.empty(shape)
+
+
+def rand_ct(rng, moduli, k, n, size=2, batch=None):
+    shape = (size, k, n) if batch is None else (batch, size, k, n)
+    out = np.empty(shape, dtype=np.uint64)
+    for i in range(k):
+        out[..., i, :] = rng.integers(0, moduli[i], size=shape[:-2] + (n,), dtype=np.uint64)
+    return out
+
+
+def rand_ksk(rng, moduli, k, n):
+    K = len(moduli)
+    out = np.empty((k, 2, K, n), dtype=np.uint64)
+    for i in range(K):
+        out[:, :, i, :] = rng.integers(0, moduli[i], size=(k, 2, n), dtype=np.uint64)
+    return out
+
+
+def eq(got, exp, what):
+    got = np.asarray(got).reshape(-1)
+    exp = np.asarray(exp).reshape(-1)
+    assert got.shape == exp.shape, f"{what}: shape {got.shape} vs {exp.shape}"
+    if not np.array_equal(got, exp):
+        bad = np.flatnonzero(got != exp)
+        raise AssertionError(f"{what}: {bad.size} of {got.size} words differ; first at {bad[:4]}: "
+                             f"{got[bad[:4]]} vs {exp[bad[:4]]}")
+
+
+def check_context(P):
+    li = P.ctx.level_info(P.ctx.first_level)
+    ri = P.ref.rns_info()
+    assert li["parms_id"] == list(P.ref.first_parms_id)
+    assert P.ctx.level_info(0)["parms_id"] == list(P.ref.key_parms_id)
+    assert li["bsk"] == ri["bsk_primes"] and li["m_sk"] == ri["m_sk"] and li["gamma"] == ri["gamma"]
+    assert (li["nB"], li["nBsk"]) == (ri["B"], ri["Bsk"])
+    pi = P.ref.plain_info()
+    assert li["delta"] == pi["delta"]
+    assert li["q_mod_t"] == pi["upper_half_increment"][0] % P.t or li["q_mod_t"] == pi["upper_half_increment"][0]
+    for q, r in zip(li["q"], li["roots"]):
+        assert P.ref.ref.ntt_root(q, P.n) == r
+
+
+def check_ntt(P, items=3, seed=1):
+    rng = np.random.default_rng(seed)
+    x = rand_ct(rng, P.moduli, P.k, P.n, size=1, batch=items)[:, 0]
+    x[0, :, :8] = 0
+    x[0, 0, 0] = 1  # delta -> all-ones spectrum
+    d = P.dev(x)
+    P.ctx.ntt_forward(d, items)
+    got = P.host(d)
+    exp = np.stack([np.stack([P.ref.ref.ntt_forward(P.moduli[i], x[b, i]) for i in range(P.k)]) for b in range(items)])
+    eq(got, exp, "ntt_forward")
+    P.ctx.ntt_inverse(d, items)
+    eq(P.host(d), x, "ntt round trip")
+    # inverse alone against the reference
+    d2 = P.dev(exp)
+    P.ctx.ntt_inverse(d2, items)
+    eq(P.host(d2), x, "ntt_inverse")
+
+
+def check_elementwise(P):
+    a, b = P.inp["a"], P.inp["b"]
+    ra, rb = P.ref.new_ct(a), P.ref.new_ct(b)
+    da, db = P.dev(a), P.dev(b)
+    o = P.out(2, P.k, P.n)
+    P.ctx.add(da, db, o, 2, 1)
+    eq(P.host(o), P.ref.ct_words(P.ref.add(ra, rb)), "add")
+    P.ctx.sub(da, db, o, 2, 1)
+    eq(P.host(o), P.ref.ct_words(P.ref.sub(ra, rb)), "sub")
+    P.ctx.negate(da, o, 2, 1)
+    eq(P.host(o), P.ref.ct_words(P.ref.negate(ra)), "negate")
+    # zero stays zero under negate
+    z = np.zeros_like(a)
+    P.ctx.negate(P.dev(z), o, 2, 1)
+    eq(P.host(o), z, "negate(0)")
+
+
+def check_multiply(P, with_sizes=True):
+    a, b = P.inp["a"], P.inp["b"]
+    ra, rb = P.ref.new_ct(a), P.ref.new_ct(b)
+    da, db = P.dev(a), P.dev(b)
+    o3 = P.out(3, P.k, P.n)
+    P.ctx.multiply(da, 2, db, 2, o3, 1)
+    rm = P.ref.multiply(ra, rb)
+    m3 = P.ref.ct_words(rm)
+    eq(P.host(o3), m3, "multiply(2,2)")
+    P.ctx.square(da, o3, 1)
+    eq(P.host(o3), P.ref.ct_words(P.ref.square(ra)), "square")
+    if with_sizes:
+        # (3,2) -> 4 : the general K x L convolution loop (S/evaluator.cpp:497-541)
+        o4 = P.out(4, P.k, P.n)
+        P.ctx.multiply(P.dev(m3), 3, db, 2, o4, 1)
+        eq(P.host(o4), P.ref.ct_words(P.ref.multiply(rm, rb)), "multiply(3,2)")
+    return m3, rm
+
+
+def check_relin(P, m3=None, rm=None):
+    if m3 is None:
+        ra, rb = P.ref.new_ct(P.inp["a"]), P.ref.new_ct(P.inp["b"])
+        rm = P.ref.multiply(ra, rb)
+        m3 = P.ref.ct_words(rm)
+    rlk = P.ref.new_ksk({0: P.inp["rlk"]})
+    exp = P.ref.ct_words(P.ref.relinearize(rm, rlk))
+    dk = P.dev(P.inp["rlk"])
+    o2 = P.out(2, P.k, P.n)
+    P.ctx.relinearize(P.dev(m3), dk, o2, 1)
+    eq(P.host(o2), exp, "relinearize")
+    o2b = P.out(2, P.k, P.n)
+    P.ctx.multiply_relin(P.dev(P.inp["a"]), P.dev(P.inp["b"]), dk, o2b, 1)
+    eq(P.host(o2b), exp, "multiply_relin")
+    return exp
+
+
+def check_galois(P):
+    n = P.n
+    a = P.inp["a"]
+    ra = P.ref.new_ct(a)
+    glk = P.ref.new_ksk({(3 - 1) // 2: P.inp["glk3"], (2 * n - 1 - 1) // 2: P.inp["glkc"]})
+    da = P.dev(a)
+    o2 = P.out(2, P.k, P.n)
+    assert P.ctx.galois_elt_from_step(1) == 3 and P.ctx.galois_elt_from_step(0) == 2 * n - 1
+    P.ctx.apply_galois(da, 3, P.dev(P.inp["glk3"]), o2, 1)
+    eq(P.host(o2), P.ref.ct_words(P.ref.rotate_rows(ra, 1, glk)), "rotate_rows(1)")
+    P.ctx.apply_galois(da, 2 * n - 1, P.dev(P.inp["glkc"]), o2, 1)
+    eq(P.host(o2), P.ref.ct_words(P.ref.rotate_columns(ra, glk)), "rotate_columns")
+
+
+def check_plain(P):
+    a, p = P.inp["a"], P.inp["p"]
+    ra, rp = P.ref.new_ct(a), P.ref.new_pt(p)
+    da, dp = P.dev(a), P.dev(p)
+    o2 = P.out(2, P.k, P.n)
+    P.ctx.multiply_plain(da, 2, dp, 1, o2, 1)
+    eq(P.host(o2), P.ref.ct_words(P.ref.multiply_plain(ra, rp)), "multiply_plain")
+    P.ctx.add_plain(da, 2, dp, 1, o2, 1)
+    eq(P.host(o2), P.ref.ct_words(P.ref.add_plain(ra, rp)), "add_plain")
+    P.ctx.sub_plain(da, 2, dp, 1, o2, 1)
+    eq(P.host(o2), P.ref.ct_words(P.ref.sub_plain(ra, rp)), "sub_plain")
+    # monomial plaintext (the reference takes its fast path, S/evaluator.cpp:1885-1933): same words expected
+    mono = np.zeros(P.n, dtype=np.uint64)
+    mono[5] = 7
+    rm = P.ref.new_pt(mono[:6])
+    P.ctx.multiply_plain(da, 2, P.dev(mono), 1, o2, 1)
+    eq(P.host(o2), P.ref.ct_words(P.ref.multiply_plain(ra, rm)), "multiply_plain(monomial)")
+
+
+def check_modswitch(P):
+    a = P.inp["a"]
+    if P.k < 2:
+        return
+    ra = P.ref.new_ct(a)
+    o = P.out(2, P.k - 1, P.n)
+    P.ctx.mod_switch_to_next(P.dev(a), 2, o, 1)
+    eq(P.host(o), P.ref.ct_words(P.ref.mod_switch_to_next(ra)), "mod_switch_to_next")
+
+
+def check_batch(P, batch=3, seed=7):
+    """Distinct items in one launch: strides / item indexing."""
+    rng = np.random.default_rng(seed)
+    A = rand_ct(rng, P.moduli, P.k, P.n, batch=batch)
+    B = rand_ct(rng, P.moduli, P.k, P.n, batch=batch)
+    key = rand_ksk(rng, P.moduli, P.k, P.n)
+    rlk = P.ref.new_ksk({0: key})
+    glk = P.ref.new_ksk({1: key})
+    dA, dB, dK = P.dev(A), P.dev(B), P.dev(key)
+    o2 = P.out(batch, 2, P.k, P.n)
+    o3 = P.out(batch, 3, P.k, P.n)
+    P.ctx.multiply(dA, 2, dB, 2, o3, batch)
+    got3 = P.host(o3)
+    P.ctx.multiply_relin(dA, dB, dK, o2, batch)
+    got2 = P.host(o2)
+    og = P.out(batch, 2, P.k, P.n)
+    P.ctx.apply_galois(dA, 3, dK, og, batch)
+    gotg = P.host(og)
+    for i in range(batch):
+        ra, rb = P.ref.new_ct(A[i]), P.ref.new_ct(B[i])
+        rm = P.ref.multiply(ra, rb)
+        eq(got3[i], P.ref.ct_words(rm), f"batch multiply item {i}")
+        eq(got2[i], P.ref.ct_words(P.ref.relinearize(rm, rlk)), f"batch multiply_relin item {i}")
+        if P.ctx.using_batching:
+            eq(gotg[i], P.ref.ct_words(P.ref.rotate_rows(ra, 1, glk)), f"batch rotate item {i}")
+        for h in (ra, rb, rm):
+            P.ref.free_ct(h)
+
+
+def check_encrypted_roundtrip(P, seed=3):
+    """Real keys + fresh encryptions from the reference; B200 multiply+relin output decrypts (on the reference
+    AND through b200_decrypt) to the slot-wise product, and equals the reference's ciphertext word for word."""
+    rng = np.random.default_rng(seed)
+    R = P.ref
+    kg = R.keygen()
+    sk, pk, rk = R.secret_key(kg), R.public_key(kg), R.relin_keys(kg)
+    enc, dec = R.encryptor(pk), R.decryptor(sk)
+    be_ = R.batch_encoder()
+    v1 = rng.integers(0, P.t, size=P.n, dtype=np.uint64)
+    v2 = rng.integers(0, P.t, size=P.n, dtype=np.uint64)
+    c1, c2 = R.encrypt(enc, R.batch_encode(be_, v1)), R.encrypt(enc, R.batch_encode(be_, v2))
+    w1, w2 = R.ct_words(c1), R.ct_words(c2)
+    key = R.ksk_words(rk)[0]
+    exp_ct = R.relinearize(R.multiply(c1, c2), rk)
+    o2 = P.out(2, P.k, P.n)
+    P.ctx.multiply_relin(P.dev(w1), P.dev(w2), P.dev(key), o2, 1)
+    got = P.host(o2)
+    eq(got, R.ct_words(exp_ct), "multiply_relin on real ciphertexts")
+    back = R.new_ct(got.reshape(2, P.k, P.n))
+    assert R.noise_budget(dec, back) > 0
+    vals = R.batch_decode(be_, R.decrypt(dec, back))
+    expect = (v1.astype(object) * v2.astype(object)) % P.t
+    assert np.array_equal(vals.astype(object), expect)
+    return dict(dec=dec, sk=sk, ct=got, expect_plain=R.pt_coeffs(R.decrypt(dec, back)))

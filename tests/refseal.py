@@ -51,8 +51,15 @@ def splitmix64_words(count, modulus, state):
 
 def fnv1a64(words):
     """FNV-1a-64 over the little-endian bytes of a u64 array."""
+    w = np.ascontiguousarray(words, dtype="<u8").reshape(-1)
+    so = os.path.join(_ROOT, "oracle", "_ref", "libbfv_oracle.so")
+    if os.path.exists(so):
+        lib = C.CDLL(so)
+        lib.orc_fnv1a64.restype = u64
+        lib.orc_fnv1a64.argtypes = [vp, C.c_size_t]
+        return int(lib.orc_fnv1a64(w.ctypes.data, w.size))
     h = 0xCBF29CE484222325
-    data = np.ascontiguousarray(words, dtype="<u8").tobytes()
+    data = w.tobytes()
     # pure-python loop is too slow for MBs; process with a small C-like loop via int ops on memoryview chunks
     prime = 0x100000001B3
     mask = 0xFFFFFFFFFFFFFFFF
