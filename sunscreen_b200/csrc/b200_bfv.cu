@@ -8,6 +8,7 @@
 #include "bfv_body.cuh"
 #include "host_ctx.h"
 #include "ntt_body.cuh"
+#include "ntt_fp_body.cuh"
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -55,7 +56,37 @@ __global__ void __launch_bounds__(NT) ntt_kernel(const NttJob job)
 #else
     extern __shared__ u64 ntt_sm[];
 #endif
-    ntt_block_body<FWD>(job, (long long)blockIdx.x, ntt_sm, (int)threadIdx.x, (int)blockDim.x);
+    const long long block = (long long)blockIdx.x;
+    const long long item = block / job.slots;
+    const int slot = (int)(block - item * job.slots);
+    const int pidx = job.slot_prime[slot];
+    if (job.fprimes[pidx].enabled)
+    {
+        const u64 *src = job.src + item * job.src_item_stride + job.slot_src[slot];
+        u64 *dst = job.dst + item * job.dst_item_stride + job.slot_dst[slot];
+        ntt_fp_block_body<FWD>(job, job.fprimes[pidx], job.primes[pidx], src, dst, reinterpret_cast<double *>(ntt_sm),
+                               (int)threadIdx.x, (int)blockDim.x);
+    }
+    else
+        ntt_block_body<FWD>(job, block, ntt_sm, (int)threadIdx.x, (int)blockDim.x);
+}
+
+// FP64-only statically scheduled kernel (all slots of the job use FP-capable primes)
+template <int LOGN, bool FWD, int NT>
+__global__ void __launch_bounds__(NT, (LOGN <= 13 ? (NT <= 256 ? 3 : 2) : 1)) ntt_fp_kernel(const NttJob job)
+{
+#ifndef B200_EMU_HEADER
+    extern __shared__ u64 ntt_sm[];
+    const long long block = (long long)blockIdx.x;
+    const long long item = block / job.slots;
+    const int slot = (int)(block - item * job.slots);
+    const int pidx = job.slot_prime[slot];
+    const NttPrimeFp PF = job.fprimes[pidx];
+    const NttPrime PI_ = job.primes[pidx];
+    const u64 *src = job.src + item * job.src_item_stride + job.slot_src[slot];
+    u64 *dst = job.dst + item * job.dst_item_stride + job.slot_dst[slot];
+    NttFpStaticPass<LOGN, NT, FWD, 0>::run(job, PF, PI_, src, dst, reinterpret_cast<double *>(ntt_sm), (int)threadIdx.x);
+#endif
 }
 
 #define GLOBAL_IDX() ((long long)blockIdx.x * blockDim.x + threadIdx.x)
@@ -330,6 +361,7 @@ __global__ void fill_u32_kernel(u32 *p, u32 v, long long total)
 struct JobDesc
 {
     int slots = 0;
+    bool all_fp = false; // every slot's prime takes the FP64 path
     int *d_prime = nullptr;
     long long *d_src = nullptr;
     long long *d_dst = nullptr;
@@ -344,6 +376,8 @@ struct b200_ctx
     int logn = 0;
     std::vector<void *> allocations; // everything freed at destroy
     NttPrime *d_ntt_primes = nullptr;
+    NttPrimeFp *d_fp_primes = nullptr;
+    bool fp_enabled = false;
     PrimeDev *d_primes = nullptr;       // [all primes] key primes first
     std::vector<LevelDev> levels;       // device pointers inside
     std::vector<const u64 *> d_inv_qlast; // per level
@@ -422,6 +456,88 @@ static int build_device(b200_ctx *ctx)
     }
     UP(np, &ctx->d_ntt_primes);
     UP(pd, &ctx->d_primes);
+    {
+        // FP64 fast path descriptors + magnitude bookkeeping (see ntt_fp_body.cuh).  All intermediates must stay
+        // below 2^51; a forward stage adds < p to the bound, an inverse stage doubles it.
+        const bool no_fp = std::getenv("B200_NO_FP64_NTT") != nullptr;
+        ctx->fp_enabled = !no_fp;
+        std::vector<NttPrimeFp> fp(H.primes.size());
+        const double LIMIT = 2251799813685248.0; // 2^51
+        for (size_t i = 0; i < H.primes.size(); i++)
+        {
+            auto &P = H.primes[i];
+            memset(&fp[i], 0, sizeof(NttPrimeFp));
+            if (!P.fp || no_fp)
+                continue;
+            double *dfwd = nullptr, *dinv = nullptr;
+            UP(P.dfwd, &dfwd);
+            UP(P.dinv, &dinv);
+            const double p = (double)P.mod.p;
+            fp[i].p = p;
+            fp[i].pinv = 1.0 / p;
+            fp[i].inv_n[0] = P.inv_n_d[0];
+            fp[i].inv_n[1] = P.inv_n_d[1];
+            fp[i].inv_n_w[0] = P.inv_n_w_d[0];
+            fp[i].inv_n_w[1] = P.inv_n_w_d[1];
+            fp[i].fwd = dfwd;
+            fp[i].inv = dinv;
+            fp[i].enabled = 1;
+            if (ctx->logn >= 4)
+            { // transposed tables for the sub-stride-1 radix-16 pass (lanes read consecutive entries)
+                const int n16 = (int)(n >> 4), lg = ctx->logn;
+                std::vector<double> f16((size_t)15 * n16 * 2), i16((size_t)15 * n16 * 2);
+                for (int g = 0; g < n16; g++)
+                    for (int l = 0; l < 4; l++)
+                    {
+                        for (int grp = 0; grp < (1 << l); grp++)
+                        { // forward: M = n/16 groups at the first stage of the pass
+                            const size_t idx = ((size_t)n16 << l) + ((size_t)g << l) + grp;
+                            const size_t slot = (size_t)((1 << l) - 1 + grp) * n16 + g;
+                            f16[2 * slot] = P.dfwd[2 * idx];
+                            f16[2 * slot + 1] = P.dfwd[2 * idx + 1];
+                        }
+                        for (int grp = 0; grp < (8 >> l); grp++)
+                        { // inverse: stage l has m = n/2 >> l groups
+                            const size_t idx = ((size_t)1 << (lg - 1 - l)) + ((size_t)g << (3 - l)) + grp;
+                            const size_t slot = (size_t)(16 - (16 >> l) + grp) * n16 + g;
+                            i16[2 * slot] = P.dinv[2 * idx];
+                            i16[2 * slot + 1] = P.dinv[2 * idx + 1];
+                        }
+                    }
+                double *d16 = nullptr;
+                UP(f16, &d16);
+                fp[i].fwd16 = d16;
+                UP(i16, &d16);
+                fp[i].inv16 = d16;
+            }
+            double B = p;
+            for (int pi = 0; pi < ctx->npass; pi++)
+            {
+                const int L = ctx->pass_L[pi];
+                if (B + L * p >= LIMIT)
+                {
+                    fp[i].renorm_fwd |= 1u << pi;
+                    B = 0.51 * p;
+                }
+                B += L * p;
+            }
+            B = p;
+            int step = 0;
+            for (int pi = ctx->npass - 1; pi >= 0; pi--, step++)
+            {
+                const int L = ctx->pass_L[pi];
+                if (B * (double)(1 << L) >= LIMIT)
+                {
+                    fp[i].renorm_inv |= 1u << step;
+                    B = 0.51 * p;
+                }
+                B *= (double)(1 << L);
+                if (B >= LIMIT)
+                    return fail(B200_E_LOGIC, "internal: FP64 NTT bound analysis failed");
+            }
+        }
+        UP(fp, &ctx->d_fp_primes);
+    }
     for (auto &Lh : H.levels)
     {
         LevelDev L;
@@ -517,6 +633,9 @@ static int get_job(b200_ctx *ctx, const std::string &key, const std::vector<int>
     }
     JobDesc j;
     j.slots = (int)prime.size();
+    j.all_fp = ctx->fp_enabled;
+    for (int pi : prime)
+        j.all_fp = j.all_fp && ctx->host->primes[pi].fp;
     UP(prime, &j.d_prime);
     UP(src, &j.d_src);
     UP(dst, &j.d_dst);
@@ -542,6 +661,7 @@ static int launch_ntt(b200_ctx *ctx, const JobDesc &jd, const u64 *src, long lon
     job.src = src;
     job.dst = dst;
     job.primes = ctx->d_ntt_primes;
+    job.fprimes = ctx->d_fp_primes;
     job.reduce_input = reduce_input;
     job.npass = ctx->npass;
     for (int i = 0; i < 8; i++)
@@ -549,6 +669,20 @@ static int launch_ntt(b200_ctx *ctx, const JobDesc &jd, const u64 *src, long lon
     const long long blocks = items * jd.slots;
     if (blocks > 0x7fffffffLL)
         return fail(B200_E_INVALID, "batch too large for one NTT launch");
+#ifndef B200_EMU_HEADER
+    if (jd.all_fp && ctx->logn >= 12 && ctx->logn <= 14 && !std::getenv("B200_NO_STATIC_NTT"))
+    {
+        static const int nt13 = std::getenv("B200_NTT_NT") ? atoi(std::getenv("B200_NTT_NT")) : 256;
+        void (*sfn)(const NttJob) = ctx->logn == 12   ? ntt_fp_kernel<12, FWD, 256>
+                                    : ctx->logn == 13 ? (nt13 == 256 ? ntt_fp_kernel<13, FWD, 256> : ntt_fp_kernel<13, FWD, 512>)
+                                                      : ntt_fp_kernel<14, FWD, 1024>;
+        const int nt = ctx->logn == 12 ? 256 : ctx->logn == 13 ? (nt13 == 256 ? 256 : 512) : 1024;
+        B200_LAUNCH(sfn, (unsigned)blocks, nt, ctx->ntt_smem, s, job);
+        ctx->launches++;
+        CU_TRY(cudaGetLastError());
+        return 0;
+    }
+#endif
     void (*kfn)(const NttJob) = ctx->ntt_threads == 512   ? ntt_kernel<FWD, 512>
                                 : ctx->ntt_threads == 256 ? ntt_kernel<FWD, 256>
                                                           : ntt_kernel<FWD, 64>;
@@ -819,6 +953,16 @@ int b200_ctx_create(uint64_t n, const uint64_t *coeff_modulus, uint64_t count, u
     if (ctx->ntt_smem > (size_t)prop.sharedMemPerBlockOptin)
         return fail(B200_E_INVALID, "poly_modulus_degree too large for the single-CTA NTT (max 16384 in this build)");
     ctx->ntt_threads = ctx->n >= 16384 ? 512 : (ctx->n >= 1024 ? 256 : 64);
+#ifndef B200_EMU_HEADER
+#define SET_SMEM(fn)                                                                                                   \
+    CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));   \
+    CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    SET_SMEM((ntt_fp_kernel<12, true, 256>)) SET_SMEM((ntt_fp_kernel<12, false, 256>))
+    SET_SMEM((ntt_fp_kernel<13, true, 512>)) SET_SMEM((ntt_fp_kernel<13, false, 512>))
+    SET_SMEM((ntt_fp_kernel<13, true, 256>)) SET_SMEM((ntt_fp_kernel<13, false, 256>))
+    SET_SMEM((ntt_fp_kernel<14, true, 1024>)) SET_SMEM((ntt_fp_kernel<14, false, 1024>))
+#undef SET_SMEM
+#endif
     CU_TRY(cudaFuncSetAttribute(ntt_kernel<true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
     CU_TRY(cudaFuncSetAttribute(ntt_kernel<false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
     CU_TRY(cudaFuncSetAttribute(ntt_kernel<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));

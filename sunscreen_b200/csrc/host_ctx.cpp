@@ -1,6 +1,7 @@
 // host_ctx.cpp — see host_ctx.h. Product code (host), no CUDA, no dependency on oracle/.
 #include "host_ctx.h"
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace b200
@@ -340,7 +341,7 @@ void compute_parms_id(size_t n, const std::vector<u64> &moduli, u64 t, u64 out[4
 // ------------------------------------------------------------------------------------------------
 // tables
 // ------------------------------------------------------------------------------------------------
-static NttPrimeHost make_ntt_prime(u64 p, int logn)
+static NttPrimeHost make_ntt_prime(u64 p, int logn, bool allow_fp = true)
 {
     NttPrimeHost P;
     P.mod = Modulus(p);
@@ -382,6 +383,24 @@ static NttPrimeHost make_ntt_prime(u64 p, int logn)
     u64 inv_n = inv_mod((u64)n % p, p);
     P.inv_n = P.mod.shoup(inv_n);
     P.inv_n_w = P.mod.shoup(P.mod.mul(inv_n, n > 1 ? ipw[1] : 1));
+    P.fp = P.mod.bits <= FP_PRIME_BITS && allow_fp;
+    if (P.fp)
+    {
+        const double pd = (double)p;
+        P.dfwd.resize(2 * n);
+        P.dinv.resize(2 * n);
+        for (size_t i = 0; i < n; i++)
+        {
+            P.dfwd[2 * i] = (double)pw[i];
+            P.dfwd[2 * i + 1] = (double)pw[i] / pd;
+            P.dinv[2 * i] = (double)ipw[i];
+            P.dinv[2 * i + 1] = (double)ipw[i] / pd;
+        }
+        P.inv_n_d[0] = (double)P.inv_n.w;
+        P.inv_n_d[1] = (double)P.inv_n.w / pd;
+        P.inv_n_w_d[0] = (double)P.inv_n_w.w;
+        P.inv_n_w_d[1] = (double)P.inv_n_w.w / pd;
+    }
     return P;
 }
 
@@ -425,11 +444,33 @@ BfvHostContext::BfvHostContext(size_t poly_modulus_degree, const std::vector<u64
         using_batching = true;
     }
 
-    // aux primes: m_sk, gamma, then B (enough for the largest level: |B| <= K+1)
+    // Auxiliary BEHZ base: m_sk, gamma, then B.
+    // The reference takes the largest 61-bit primes == 1 mod 2n (S/util/rns.cpp:634-644).  The result of
+    // bfv_multiply does not depend on WHICH auxiliary primes are used, only on their product being large enough
+    // (t * n * K * Q * (1+rho)^2 < prod(B) * m_sk, the reference's own condition, rns.cpp:617-624): every
+    // approximation error in the BEHZ chain (the q-overflows of the two fast base conversions) is a function of
+    // the base-q residues alone, and the Shenoy-Kumaresan step is exact.  So when every user prime fits the FP64
+    // NTT path we pick 47-bit auxiliary primes instead, so that the Bsk transforms take the same fast path;
+    // gamma (decryption only, never transformed) stays the reference's.
     aux0 = K;
-    std::vector<u64> aux = get_primes(2 * (u64)n, 61, (size_t)K + 3);
-    for (u64 a : aux)
-        primes.push_back(make_ntt_prime(a, logn));
+    bool all_fp = std::getenv("B200_FORCE_AUX61") == nullptr;
+    for (int i = 0; i < K; i++)
+        all_fp = all_fp && primes[i].fp;
+    aux_bits = all_fp ? FP_PRIME_BITS : 61;
+    const std::vector<u64> ref_aux = get_primes(2 * (u64)n, 61, 2);
+    // enough 47-bit primes for the largest level: bits(prod(B) * m_sk) >= 33 + bits(t) + bits(Q)
+    size_t aux_count = (size_t)K + 3;
+    if (all_fp)
+    {
+        BigUInt Qall(1);
+        for (int i = 0; i < K; i++)
+            Qall.mul(coeff_modulus[i]);
+        aux_count = (size_t)((33 + t_mod.bits + Qall.bit_length()) * 100 / 4690 + 3);
+    }
+    std::vector<u64> aux = get_primes(2 * (u64)n, aux_bits, aux_count);
+    aux[1] = ref_aux[1]; // gamma: the reference's second 61-bit prime
+    for (size_t i = 0; i < aux.size(); i++)
+        primes.push_back(make_ntt_prime(aux[i], logn));
     const u64 m_sk = aux[0], gamma = aux[1];
     const u64 mt = u64(1) << 32;
 
@@ -451,10 +492,21 @@ BfvHostContext::BfvHostContext(size_t poly_modulus_degree, const std::vector<u64
         for (u64 v : q)
             Q.mul(v);
         L.total_bits = Q.bit_length();
-        L.nB = k;
-        if (32 + t_mod.bits + L.total_bits >= 61 * k + 61)
-            L.nB++;
+        if (aux_bits == 61)
+        { // the reference's rule (S/util/rns.cpp:617-624)
+            L.nB = k;
+            if (32 + t_mod.bits + L.total_bits >= 61 * k + 61)
+                L.nB++;
+        }
+        else
+        { // same inequality, solved for 47-bit primes (each contributes > 46.9 bits)
+            int need = 33 + t_mod.bits + L.total_bits;
+            int cnt = (need * 100 + 4689) / 4690;
+            L.nB = std::max(1, cnt - 1);
+        }
         L.nBsk = L.nB + 1;
+        if ((size_t)L.nB + 2 > aux.size())
+            throw std::logic_error("internal: auxiliary base too small");
         std::vector<u64> B(aux.begin() + 2, aux.begin() + 2 + L.nB);
         for (int b = 0; b < L.nB; b++)
             L.bsk_idx.push_back(aux0 + 2 + b);

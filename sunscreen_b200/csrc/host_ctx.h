@@ -64,7 +64,17 @@ struct NttPrimeHost
     u64 root = 0; // minimal primitive 2n-th root
     Shoup inv_n, inv_n_w;
     std::vector<u64> fwd, inv;
+    // FP64 fast path (primes < 2^FP_PRIME_BITS): the same twiddles as exact integer-valued doubles {w, w/p}
+    bool fp = false;
+    std::vector<double> dfwd, dinv; // [2n]
+    double inv_n_d[2] = { 0, 0 }, inv_n_w_d[2] = { 0, 0 };
+    unsigned renorm_inv_mask = 0;   // bit i: renormalise the inputs of inverse pass i (see ntt_fp_body.cuh)
+    unsigned renorm_fwd_mask = 0;
 };
+
+// Largest prime size (bits) the FP64 NTT path accepts; also the size of the auxiliary BEHZ primes we pick
+// when every user prime qualifies.
+static const int FP_PRIME_BITS = 47;
 
 // One level of the modulus chain (mirrors ContextData + RNSTool for that level).
 // Index conventions: q_idx / bsk_idx / gamma_idx index into BfvHostContext::primes.
@@ -117,6 +127,7 @@ struct BfvHostContext
     std::vector<NttPrimeHost> primes; // key primes [0,K), then aux primes: m_sk, gamma, B...
     int K = 0;                        // key-level prime count
     int aux0 = 0;                     // index of m_sk; gamma = aux0+1; B_i = aux0+2+i
+    int aux_bits = 61;                // 61 = the reference's aux base; 47 = FP64-friendly base (same results)
     std::vector<LevelHost> levels;    // levels[0] = key level, levels[1] = first data level, ...
     bool using_keyswitching = false;  // K > 1
     bool using_batching = false;      // t prime and t == 1 mod 2n

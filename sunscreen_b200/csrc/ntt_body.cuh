@@ -33,6 +33,8 @@ struct NttPrime
     const u64 *inv;    // [2n] words
 };
 
+struct NttPrimeFp; // ntt_fp_body.cuh
+
 // One launch = `items` x `slots` residue polynomials.
 struct NttJob
 {
@@ -46,6 +48,7 @@ struct NttJob
     const u64 *src;
     u64 *dst;
     const NttPrime *primes;
+    const NttPrimeFp *fprimes; // FP64 fast-path descriptors, same indexing as primes[]
     int reduce_input;          // 1: inputs are arbitrary 64-bit words -> Barrett to [0,p) on load
     int npass;                 // forward pass schedule (host: ntt_schedule); inverse runs it mirrored
     int pass_L[8];

@@ -1,0 +1,357 @@
+// ntt_fp_body.cuh — the FP64-pipe negacyclic NTT / INTT for primes below 2^47 (B200-specific fast path).
+//
+// Why: on B200 (sm_100a) the 64-bit integer butterfly is bound by IMAD.WIDE.U32, which issues at only ~25
+// lanes/clk/SM (measured, tools/ubench.cu), while DFMA/DMUL/DADD issue at 64 lanes/clk/SM.  A modular
+// multiplication by a precomputed twiddle can be done EXACTLY in 6 double-precision operations:
+//     h = y*w (rounded)            l = fma(y, w, -h)        (h + l == y*w exactly)
+//     q = rint(y * (w/p))          (magic-number rounding: fma(y, wp, 1.5*2^52) - 1.5*2^52)
+//     r = fma(-q, p, h) + l        (== y*w - q*p exactly: an integer of magnitude < p)
+// All values are integer-valued doubles in a signed lazy range; every operation above is exact as long as
+// |y| < 2^51 and p < 2^47, so the transform computes the same residues as the integer path — the outputs are
+// reduced to the canonical [0,p) before they leave the kernel and are bit-identical to the reference's
+// ntt_negacyclic_harvey / inverse_ntt_negacyclic_harvey (S/util/ntt.cpp:393-474).
+//
+// Schedule: identical pass structure to ntt_body.cuh (radix-8/16 groups, padded shared memory), except that
+// the FIRST pass reads its group straight from global memory (u64 -> double) and the LAST pass writes its
+// group straight to global memory (double -> canonical u64), saving two shared-memory round trips.
+// Magnitude bookkeeping (host, b200_bfv.cu:fp_renorm_masks): a forward butterfly adds < p to the bound, an
+// inverse butterfly doubles it on the sum path; whenever a pass would exceed 2^50 its inputs are first
+// renormalised (x -= rint(x/p)*p, 3 DP ops).
+#pragma once
+#include "ntt_body.cuh"
+
+#if defined(__CUDA_ARCH__)
+#define B200_DMUL(a, b) __dmul_rn((a), (b))
+#define B200_DADD(a, b) __dadd_rn((a), (b))
+#define B200_DFMA(a, b, c) __fma_rn((a), (b), (c))
+#else
+#include <cmath>
+// host (tests/emu): built with -ffp-contract=off so these stay separate IEEE operations
+#define B200_DMUL(a, b) ((a) * (b))
+#define B200_DADD(a, b) ((a) + (b))
+#define B200_DFMA(a, b, c) std::fma((a), (b), (c))
+#endif
+
+#define B200_MAGIC 6755399441055744.0   /* 1.5 * 2^52 */
+#define B200_TWO52 4503599627370496.0   /* 2^52 */
+
+struct NttPrimeFp
+{
+    double p, pinv;
+    double inv_n[2], inv_n_w[2]; // {w, w/p}
+    const double *fwd;           // [2n] {w, w/p}
+    const double *inv;
+    const double *fwd16;         // transposed twiddles of the sub-stride-1 radix-16 pass: [15][n/16] {w, w/p}
+    const double *inv16;
+    unsigned renorm_fwd, renorm_inv; // bit i: renormalise inputs of pass i (pass order of the respective transform)
+    int enabled;
+};
+
+B200_HD double fp_mulmod(double y, double w, double wp, double p)
+{
+    const double h = B200_DMUL(y, w);
+    const double l = B200_DFMA(y, w, -h);
+    const double q = B200_DADD(B200_DFMA(y, wp, B200_MAGIC), -B200_MAGIC);
+    return B200_DADD(B200_DFMA(-q, p, h), l);
+}
+B200_HD double fp_renorm(double x, double p, double pinv)
+{
+    const double q = B200_DADD(B200_DFMA(x, pinv, B200_MAGIC), -B200_MAGIC);
+    return B200_DFMA(-q, p, x);
+}
+// any lazy value -> canonical [0,p) as u64
+B200_HD u64 fp_to_canonical(double x, double p, double pinv)
+{
+    double r = fp_renorm(x, p, pinv); // |r| <= p/2 + 1
+    r = r < 0.0 ? B200_DADD(r, p) : r;
+#if defined(__CUDA_ARCH__)
+    return (u64)__double_as_longlong(r + B200_TWO52) & 0x000FFFFFFFFFFFFFULL; // exact: 0 <= r < 2^47
+#else
+    return (u64)(long long)r;
+#endif
+}
+B200_HD double fp_from_u64(u64 v) // exact for v < 2^52
+{
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double((long long)(v | 0x4330000000000000ULL)) - B200_TWO52;
+#else
+    return (double)v;
+#endif
+}
+
+B200_HD void fp_load_tw(const double *__restrict__ tw, int idx, double &w, double &wp)
+{
+#if defined(__CUDA_ARCH__)
+    const double2 t2 = __ldg(reinterpret_cast<const double2 *>(tw) + idx);
+    w = t2.x;
+    wp = t2.y;
+#else
+    w = tw[2 * idx];
+    wp = tw[2 * idx + 1];
+#endif
+}
+
+// one butterfly stage `l` of a radix-2^L group (compile-time stage index so everything stays in registers)
+template <int L, int l, bool FWD, bool TW16>
+B200_HD void fp_stage(double (&x)[1 << L], const double *__restrict__ tw, int g, int i, int logs, int logn, int M, int n16,
+                      const NttPrimeFp &P, bool last_inv)
+{
+    constexpr int R = 1 << L;
+    const double p = P.p;
+    if (FWD)
+    {
+        constexpr int half = 1 << (L - 1 - l);
+        const int tw_base = (M << l) + (i << l);
+#pragma unroll
+        for (int grp = 0; grp < (1 << l); grp++)
+        {
+            const int idx = TW16 ? (((1 << l) - 1 + grp) * n16 + g) : (tw_base + grp);
+            double w, wp;
+            fp_load_tw(tw, idx, w, wp);
+#pragma unroll
+            for (int jj = 0; jj < half; jj++)
+            {
+                const int j = grp * 2 * half + jj;
+                const double T = fp_mulmod(x[j + half], w, wp, p);
+                const double X = x[j];
+                x[j] = B200_DADD(X, T);
+                x[j + half] = B200_DADD(X, -T);
+            }
+        }
+    }
+    else
+    {
+        constexpr int half = 1 << l;
+        const int m = 1 << (logn - 1 - logs - l);
+        const int tw_base = m + (i << (L - l - 1));
+        const bool fold = last_inv && (l == L - 1);
+#pragma unroll
+        for (int grp = 0; grp < (R >> (l + 1)); grp++)
+        {
+            // TW16 slots (L == 4): l=0 -> 0..7, l=1 -> 8..11, l=2 -> 12..13, l=3 -> 14
+            const int idx = TW16 ? ((16 - (16 >> l) + grp) * n16 + g) : (tw_base + grp);
+            double w, wp;
+            if (fold)
+            {
+                w = P.inv_n_w[0];
+                wp = P.inv_n_w[1];
+            }
+            else
+                fp_load_tw(tw, idx, w, wp);
+#pragma unroll
+            for (int jj = 0; jj < half; jj++)
+            {
+                const int j = grp * 2 * half + jj;
+                const double X = x[j], Y = x[j + half];
+                const double U = B200_DADD(X, Y);
+                x[j + half] = fp_mulmod(B200_DADD(X, -Y), w, wp, p);
+                x[j] = fold ? fp_mulmod(U, P.inv_n[0], P.inv_n[1], p) : U;
+            }
+        }
+    }
+}
+
+template <int L, bool FWD, bool SRC_GLOBAL, bool DST_GLOBAL, bool TW16 = false>
+B200_HD void ntt_fp_group(double *sm, const u64 *__restrict__ gsrc, u64 *__restrict__ gdst, int g, int logs, int logn, int M,
+                          const NttPrimeFp &P, bool renorm, bool last_inv, bool reduce_input, u64 pint, u64 ratio1)
+{
+    constexpr int R = 1 << L;
+    const int s = 1 << logs;
+    const int i = g >> logs;
+    const int o = g & (s - 1);
+    const int base = (i << (logs + L)) + o;
+    const double p = P.p;
+    double x[R];
+#pragma unroll
+    for (int j = 0; j < R; j++)
+    {
+        if (SRC_GLOBAL)
+        {
+            u64 v = gsrc[base + (j << logs)];
+            if (reduce_input)
+                v = barrett64(v, pint, ratio1);
+            x[j] = fp_from_u64(v);
+        }
+        else
+            x[j] = sm[ntt_pad(base + (j << logs))];
+        if (renorm)
+            x[j] = fp_renorm(x[j], p, P.pinv);
+    }
+    const double *__restrict__ tw = TW16 ? (FWD ? P.fwd16 : P.inv16) : (FWD ? P.fwd : P.inv);
+    const int n16 = 1 << (logn - 4); // groups of the radix-16 pass (TW16 layout: [slot][group])
+    fp_stage<L, 0, FWD, TW16>(x, tw, g, i, logs, logn, M, n16, P, last_inv);
+    if constexpr (L > 1)
+        fp_stage<L, 1, FWD, TW16>(x, tw, g, i, logs, logn, M, n16, P, last_inv);
+    if constexpr (L > 2)
+        fp_stage<L, 2, FWD, TW16>(x, tw, g, i, logs, logn, M, n16, P, last_inv);
+    if constexpr (L > 3)
+        fp_stage<L, 3, FWD, TW16>(x, tw, g, i, logs, logn, M, n16, P, last_inv);
+#pragma unroll
+    for (int j = 0; j < R; j++)
+    {
+        if (DST_GLOBAL)
+            gdst[base + (j << logs)] = fp_to_canonical(x[j], p, P.pinv);
+        else
+            sm[ntt_pad(base + (j << logs))] = x[j];
+    }
+}
+
+template <int L, bool FWD, bool SG, bool DG>
+B200_HD void ntt_fp_pass(double *sm, const u64 *gsrc, u64 *gdst, int n, int logs, int logn, int M, const NttPrimeFp &P,
+                         bool renorm, bool last_inv, bool reduce_input, u64 pint, u64 ratio1, int tid, int nthreads)
+{
+    const int ngroups = n >> L;
+    for (int g = tid; g < ngroups; g += nthreads)
+        ntt_fp_group<L, FWD, SG, DG>(sm, gsrc, gdst, g, logs, logn, M, P, renorm, last_inv, reduce_input, pint, ratio1);
+}
+
+template <bool FWD, bool SG, bool DG>
+B200_HD void ntt_fp_pass_dispatch(int L, double *sm, const u64 *gsrc, u64 *gdst, int n, int logs, int logn, int M,
+                                  const NttPrimeFp &P, bool renorm, bool last_inv, bool reduce_input, u64 pint, u64 ratio1,
+                                  int tid, int nthreads)
+{
+    switch (L)
+    {
+    case 1: ntt_fp_pass<1, FWD, SG, DG>(sm, gsrc, gdst, n, logs, logn, M, P, renorm, last_inv, reduce_input, pint, ratio1, tid, nthreads); break;
+    case 2: ntt_fp_pass<2, FWD, SG, DG>(sm, gsrc, gdst, n, logs, logn, M, P, renorm, last_inv, reduce_input, pint, ratio1, tid, nthreads); break;
+    case 3: ntt_fp_pass<3, FWD, SG, DG>(sm, gsrc, gdst, n, logs, logn, M, P, renorm, last_inv, reduce_input, pint, ratio1, tid, nthreads); break;
+    default: ntt_fp_pass<4, FWD, SG, DG>(sm, gsrc, gdst, n, logs, logn, M, P, renorm, last_inv, reduce_input, pint, ratio1, tid, nthreads); break;
+    }
+}
+
+// One CTA: FP64 transform of one residue polynomial. `smd` holds ntt_smem_words(n) doubles.
+template <bool FWD>
+B200_HD void ntt_fp_block_body(const NttJob &job, const NttPrimeFp &P, const NttPrime &PI, const u64 *src, u64 *dst, double *smd,
+                               int tid, int nthreads)
+{
+    const int logn = job.logn;
+    const int n = 1 << logn;
+    const int np = job.npass;
+    const bool red = job.reduce_input != 0;
+    if (FWD)
+    {
+        int done = 0;
+        for (int pi = 0; pi < np; pi++)
+        {
+            const int L = job.pass_L[pi];
+            const int M = 1 << done;
+            const int logs = logn - done - L;
+            const bool rn = (P.renorm_fwd >> pi) & 1;
+            const bool first = pi == 0, last = pi == np - 1;
+            if (first && last)
+                ntt_fp_pass_dispatch<true, true, true>(L, smd, src, dst, n, logs, logn, M, P, rn, false, red, PI.p, PI.ratio1, tid, nthreads);
+            else if (first)
+                ntt_fp_pass_dispatch<true, true, false>(L, smd, src, dst, n, logs, logn, M, P, rn, false, red, PI.p, PI.ratio1, tid, nthreads);
+            else if (last)
+                ntt_fp_pass_dispatch<true, false, true>(L, smd, src, dst, n, logs, logn, M, P, rn, false, false, 0, 0, tid, nthreads);
+            else
+                ntt_fp_pass_dispatch<true, false, false>(L, smd, src, dst, n, logs, logn, M, P, rn, false, false, 0, 0, tid, nthreads);
+            B200_SYNC();
+            done += L;
+        }
+    }
+    else
+    {
+        int logs = 0;
+        int step = 0;
+        for (int pi = np - 1; pi >= 0; pi--, step++)
+        {
+            const int L = job.pass_L[pi];
+            const bool rn = (P.renorm_inv >> step) & 1;
+            const bool first = step == 0, last = pi == 0;
+            if (first && last)
+                ntt_fp_pass_dispatch<false, true, true>(L, smd, src, dst, n, logs, logn, 0, P, rn, true, red, PI.p, PI.ratio1, tid, nthreads);
+            else if (first)
+                ntt_fp_pass_dispatch<false, true, false>(L, smd, src, dst, n, logs, logn, 0, P, rn, false, red, PI.p, PI.ratio1, tid, nthreads);
+            else if (last)
+                ntt_fp_pass_dispatch<false, false, true>(L, smd, src, dst, n, logs, logn, 0, P, rn, true, false, 0, 0, tid, nthreads);
+            else
+                ntt_fp_pass_dispatch<false, false, false>(L, smd, src, dst, n, logs, logn, 0, P, rn, false, false, 0, 0, tid, nthreads);
+            B200_SYNC();
+            logs += L;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Statically scheduled variant (device fast path): compile-time pass schedule and thread count, group loops
+// fully unrolled so that all global loads of the first pass are issued before the first butterfly.
+// Same group routine as above (which the CPU emulation tests cover); only the control flow is specialised.
+// ---------------------------------------------------------------------------------------------------------
+#if defined(__CUDACC__)
+template <int LOGN> struct NttSched;
+template <> struct NttSched<12> { static constexpr int NP = 3; static constexpr int L0 = 4, L1 = 4, L2 = 4, L3 = 0; };
+template <> struct NttSched<13> { static constexpr int NP = 4; static constexpr int L0 = 3, L1 = 3, L2 = 3, L3 = 4; };
+template <> struct NttSched<14> { static constexpr int NP = 4; static constexpr int L0 = 3, L1 = 3, L2 = 4, L3 = 4; };
+
+template <int LOGN, int PI> struct NttSchedL
+{
+    static constexpr int value = PI == 0 ? NttSched<LOGN>::L0 : PI == 1 ? NttSched<LOGN>::L1 : PI == 2 ? NttSched<LOGN>::L2 : NttSched<LOGN>::L3;
+};
+template <int LOGN, int PI> struct NttSchedDone // stages completed before forward pass PI
+{
+    static constexpr int value = NttSchedDone<LOGN, PI - 1>::value + NttSchedL<LOGN, PI - 1>::value;
+};
+template <int LOGN> struct NttSchedDone<LOGN, 0> { static constexpr int value = 0; };
+
+template <int LOGN, int NT, bool FWD, int STEP /*0..NP-1 in execution order*/>
+struct NttFpStaticPass
+{
+    static __device__ __forceinline__ void run(const NttJob &job, const NttPrimeFp &P, const NttPrime &PI_, const u64 *src, u64 *dst,
+                                               double *smd, int tid)
+    {
+#if defined(__CUDA_ARCH__)
+        constexpr int N = 1 << LOGN;
+        constexpr int NP = NttSched<LOGN>::NP;
+        constexpr int PIDX = FWD ? STEP : NP - 1 - STEP;       // index into the forward schedule
+        constexpr int L = NttSchedL<LOGN, PIDX>::value;
+        constexpr int DONE = NttSchedDone<LOGN, PIDX>::value;  // forward stages before this pass
+        constexpr int LOGS = LOGN - DONE - L;                  // log2 sub-stride (same for the mirrored inverse pass)
+        constexpr int M = 1 << DONE;
+        // Direct global I/O only where consecutive lanes touch consecutive words (large sub-stride).  The
+        // sub-stride-1 pass would make every lane touch its own 128-byte line (32 L1 wavefronts per request), so
+        // its global side is staged through shared memory with coalesced copies instead.
+        constexpr bool EDGE_IN = STEP == 0, EDGE_OUT = STEP == NP - 1;
+        constexpr bool SG = EDGE_IN && LOGS >= 5, DG = EDGE_OUT && LOGS >= 5;
+        constexpr bool TW16 = (L == 4 && LOGS == 0);
+        constexpr int NGROUPS = N >> L;
+        constexpr int ITERS = (NGROUPS + NT - 1) / NT;
+        const bool rn = ((FWD ? P.renorm_fwd : P.renorm_inv) >> STEP) & 1;
+        const bool red = EDGE_IN && job.reduce_input != 0;
+        if (EDGE_IN && !SG)
+        { // coalesced copy-in: u64 -> double
+#pragma unroll
+            for (int it = 0; it < N / NT; it++)
+            {
+                const int e = tid + it * NT;
+                u64 v = src[e];
+                if (red)
+                    v = barrett64(v, PI_.p, PI_.ratio1);
+                smd[ntt_pad(e)] = fp_from_u64(v);
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int it = 0; it < ITERS; it++)
+        {
+            const int g = tid + it * NT;
+            if (NGROUPS % NT == 0 || g < NGROUPS)
+                ntt_fp_group<L, FWD, SG, DG, TW16>(smd, src, dst, g, LOGS, LOGN, M, P, rn, !FWD && EDGE_OUT, SG && red, PI_.p,
+                                                   PI_.ratio1);
+        }
+        __syncthreads();
+        if (EDGE_OUT && !DG)
+        { // coalesced copy-out: lazy double -> canonical u64
+#pragma unroll
+            for (int it = 0; it < N / NT; it++)
+            {
+                const int e = tid + it * NT;
+                dst[e] = fp_to_canonical(smd[ntt_pad(e)], P.p, P.pinv);
+            }
+        }
+        if (STEP + 1 < NP)
+            NttFpStaticPass<LOGN, NT, FWD, (STEP + 1 < NP ? STEP + 1 : STEP)>::run(job, P, PI_, src, dst, smd, tid);
+#endif
+    }
+};
+#endif // __CUDACC__

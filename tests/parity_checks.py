@@ -57,8 +57,17 @@ def check_context(P):
     ri = P.ref.rns_info()
     assert li["parms_id"] == list(P.ref.first_parms_id)
     assert P.ctx.level_info(0)["parms_id"] == list(P.ref.key_parms_id)
-    assert li["bsk"] == ri["bsk_primes"] and li["m_sk"] == ri["m_sk"] and li["gamma"] == ri["gamma"]
-    assert (li["nB"], li["nBsk"]) == (ri["B"], ri["Bsk"])
+    assert li["gamma"] == ri["gamma"]
+    if li["m_sk"] == ri["m_sk"]:
+        # the reference's own auxiliary base (61-bit primes)
+        assert li["bsk"] == ri["bsk_primes"] and (li["nB"], li["nBsk"]) == (ri["B"], ri["Bsk"])
+    else:
+        # FP64-friendly auxiliary base: 47-bit NTT primes with at least the reference's dynamic range condition
+        # 32 + bits(t) + bits(Q) < bits(prod(B) * m_sk)   (S/util/rns.cpp:617-624); results are base-independent.
+        import math
+        assert all(p < (1 << 47) and p % (2 * P.n) == 1 for p in li["bsk"]) and len(set(li["bsk"])) == len(li["bsk"])
+        Q = math.prod(li["q"])
+        assert math.prod(li["bsk"]).bit_length() > 32 + P.t.bit_length() + Q.bit_length()
     pi = P.ref.plain_info()
     assert li["delta"] == pi["delta"]
     assert li["q_mod_t"] == pi["upper_half_increment"][0] % P.t or li["q_mod_t"] == pi["upper_half_increment"][0]
