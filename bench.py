@@ -44,6 +44,7 @@ class ClockSampler:
 
     def __init__(self, index=0):
         self.samples = []
+        self.mark = 0
         self.proc = None
         self.index = index
 
@@ -51,7 +52,7 @@ class ClockSampler:
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "25",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -68,7 +69,7 @@ class ClockSampler:
         time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons = [], 0, set()
-        for s in self.samples:
+        for s in self.samples[max(self.mark - 1, 0):]:
             f = [x.strip() for x in s.split(",")]
             if len(f) < 6:
                 continue
@@ -108,31 +109,41 @@ def cpu_reference_rate(threads, iters, warmup=2):
 
 
 def run_reference(args):
+    """The reference's own CPU implementation (oracle/_ref) on all host cores; one step = a bounded sample."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import numpy as np
+    import refseal
     cores = os.cpu_count() or 1
-    iters = 24
-    for _ in range(max(args.warmup, 0)):
-        cpu_reference_rate(cores, 4, warmup=1)
-    t0 = time.perf_counter()
-    total_ops = 0
+    iters = 16  # per thread per step: cores*16 multiply+relinearize per step
+    R = refseal.RefContext(N_POLY, MODULI, PLAIN)
+    rng = np.random.default_rng(0)
+    k = 4
+    w = np.empty((2, 2, k, N_POLY), dtype=np.uint64)
+    key = np.empty((k, 2, 5, N_POLY), dtype=np.uint64)
+    for i in range(k):
+        w[:, :, i, :] = rng.integers(0, MODULI[i], size=(2, 2, N_POLY), dtype=np.uint64)
+    for i in range(5):
+        key[:, :, i, :] = rng.integers(0, MODULI[i], size=(k, 2, N_POLY), dtype=np.uint64)
+    a, b, rlk = R.new_ct(w[0]), R.new_ct(w[1]), R.new_ksk({0: key})
+    for _ in range(max(args.warmup, 1)):
+        R.time_mul_relin(a, b, rlk, cores, 4, 1)
+    secs = 0.0
     for _ in range(args.steps):
-        rate, secs = cpu_reference_rate(cores, iters)
-        total_ops += cores * iters
-    # rate from the timed inner regions only (context creation excluded)
-    rate, secs = cpu_reference_rate(cores, iters)
-    wall = time.perf_counter() - t0
+        secs += R.time_mul_relin(a, b, rlk, cores, iters, 0)
+    rate = args.steps * cores * iters / secs
     line = {
         "metric": "ciphertext mul+relin/sec", "value": rate, "unit": "ops/s", "impl": "reference", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * secs, "higher_is_better": True,
+        "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": 1000.0 * secs / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": "Evaluator::multiply + relinearize, n=8192, BFVDefault 218-bit chain (k=4 + special)",
-                   "batch_per_step": cores * iters, "parallelism": f"{cores} host threads, one memory pool each"},
+        "config": {"workload": "Evaluator::multiply + relinearize, n=8192, BFVDefault 218-bit chain (k=4 + special), "
+                               f"bounded sample of {cores * iters} ct pairs per step", "batch_per_step": cores * iters,
+                   "parallelism": f"{cores} host threads, one memory pool each (oracle/_ref = unmodified reference)"},
         "cpu_baseline": {"value": rate, "unit": "ops/s", "cores": cores, "kind": "reference",
-                         "sample": f"{cores} threads x {iters} multiply+relinearize_inplace, uniform-random ciphertext words"},
+                         "sample": f"{args.steps} steps x {cores} threads x {iters} multiply+relinearize_inplace, "
+                                   "uniform-random ciphertext words"},
         "e2e": {"value": rate, "unit": "ops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "wall_s": wall,
     }
     print(json.dumps(line))
 
@@ -193,12 +204,18 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()  # nvidia-smi needs ~0.2 s to come up: start it before the warm-up
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    # keep the GPU under the same load until the sampler is producing lines, then time
+    t_wait = time.time()
+    while rank == 0 and not sampler.samples and time.time() - t_wait < 3.0:
+        step()
+        torch.cuda.synchronize()
+    sampler.mark = len(sampler.samples)
     l0 = ctx.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()

@@ -106,7 +106,10 @@ __global__ void lift_kernel(const LevelDev L, const u64 *a, int sa, const u64 *b
     const int R = K + L.nBsk;
     const u64 *src = p < sa ? a + (item * sa + p) * K * n : b + (item * sb + (p - sa)) * K * n;
     u64 *dst = ext + ((item * P + p) * R + K) * n;
-    lift_coeff<K>(L, src, dst, n, c);
+    if (L.fp)
+        lift_coeff_fp<K>(L, src, dst, n, c);
+    else
+        lift_coeff<K>(L, src, dst, n, c);
 }
 
 // rows: residue rows r in [0,R): r<K -> q[r], else bsk[r-K]
@@ -126,6 +129,16 @@ __global__ void tensor_kernel(const LevelDev L, const u64 *ext, int sa, int sb, 
     const int Dn = square ? 3 : sa + sb - 1;
     const u64 *A = ext + ((item * Pn) * R + r) * n;
     u64 *Dp = D + ((item * Dn) * R + r) * n;
+    if (L.fp)
+    {
+        const double *pd = r < L.k ? &L.dq[2 * r] : &L.dbsk[2 * (r - L.k)];
+        const double p = __ldg(pd), pinv = __ldg(pd + 1);
+        if (square)
+            square_coeff_fp(p, pinv, A, R * n, Dp, R * n, c);
+        else
+            tensor_coeff_fp(p, pinv, A, R * n, sa, A + (long long)sa * R * n, R * n, sb, Dp, R * n, c);
+        return;
+    }
     if (square)
         square_coeff(P, A, R * n, Dp, R * n, c);
     else
@@ -146,12 +159,15 @@ __global__ void scale_kernel(const LevelDev L, const u64 *D, int Dn, u64 *dst0, 
     const long long item = t / Dn;
     const u64 *src = D + ((item * Dn + m) * R) * n;
     u64 *dst = m < split ? dst0 + ((item * split + m) * K) * n : dst1 + ((item * (Dn - split) + (m - split)) * K) * n;
-    scale_coeff<K>(L, src, dst, n, c);
+    if (L.fp)
+        scale_coeff_fp<K>(L, src, dst, n, c);
+    else
+        scale_coeff<K>(L, src, dst, n, c);
 }
 
 template <int K>
-__global__ void ksmac_kernel(const PrimeDev *primes, int special_idx, int key_rows, const u64 *ks1, const u64 *key,
-                             u64 *ks2, long long n, long long total)
+__global__ void ksmac_kernel(const PrimeDev *primes, const NttPrimeFp *fprimes, int use_fp, int special_idx, int key_rows,
+                             const u64 *ks1, const u64 *key, u64 *ks2, long long n, long long total)
 {
     const long long idx = GLOBAL_IDX();
     if (idx >= total)
@@ -167,6 +183,12 @@ __global__ void ksmac_kernel(const PrimeDev *primes, int special_idx, int key_ro
     const u64 *kp = key + (long long)key_res * n;
     u64 *o0 = ks2 + ((item * 2 + 0) * (K + 1) + I) * n;
     u64 *o1 = ks2 + ((item * 2 + 1) * (K + 1) + I) * n;
+    if (use_fp)
+    {
+        const double p = __ldg(&fprimes[prime_idx].p), pinv = __ldg(&fprimes[prime_idx].pinv);
+        ksmac_coeff_fp<K>(p, pinv, ops, n, kp, 2LL * key_rows * n, (long long)key_rows * n, o0, o1, c);
+        return;
+    }
     ksmac_coeff<K>(P, ops, n, kp, 2LL * key_rows * n, (long long)key_rows * n, o0, o1, c);
 }
 
@@ -388,6 +410,12 @@ struct b200_ctx
     std::mutex mu;
     std::atomic<uint64_t> launches{ 0 };
     cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
+    // staging ring of the *_host entry points (allocated on first use, reused afterwards)
+    static const int NBUF = 3;
+    u64 *hp_a[NBUF] = { nullptr, nullptr, nullptr }, *hp_b[NBUF] = { nullptr, nullptr, nullptr }, *hp_o[NBUF] = { nullptr, nullptr, nullptr };
+    cudaEvent_t hp_in[NBUF], hp_comp[NBUF], hp_out[NBUF];
+    size_t hp_words = 0;
+    std::mutex hp_mu;
     int ntt_threads = 256;
     size_t ntt_smem = 0;
 };
@@ -582,6 +610,78 @@ static int build_device(b200_ctx *ctx)
         UPF(plain_inc, Lh.plain_upper_half_inc);
         L.q_mod_t = Lh.q_mod_t;
         L.plain_thr = Lh.plain_upper_half_threshold;
+        {
+            bool lfp = ctx->fp_enabled && H.aux_bits == b200::FP_PRIME_BITS;
+            for (int idx : Lh.q_idx)
+                lfp = lfp && H.primes[idx].fp;
+            for (int idx : Lh.bsk_idx)
+                lfp = lfp && H.primes[idx].fp;
+            L.fp = lfp ? 1 : 0;
+            if (lfp)
+            {
+                std::vector<double> qd, bd;
+                std::vector<u64> qv, bv;
+                for (int idx : Lh.q_idx)
+                    qv.push_back(H.primes[idx].mod.p);
+                for (int idx : Lh.bsk_idx)
+                    bv.push_back(H.primes[idx].mod.p);
+                auto primes_d = [](const std::vector<u64> &v) {
+                    std::vector<double> o;
+                    for (u64 p : v)
+                    {
+                        o.push_back((double)p);
+                        o.push_back(1.0 / (double)p);
+                    }
+                    return o;
+                };
+                // {w, w/p} with p = target[row] (rows of `cols` entries)
+                auto pairs = [](const std::vector<u64> &w, const std::vector<u64> &target, int cols) {
+                    std::vector<double> o;
+                    for (size_t i = 0; i < w.size(); i++)
+                    {
+                        const double p = (double)target[i / (size_t)cols];
+                        o.push_back((double)w[i]);
+                        o.push_back((double)w[i] / p);
+                    }
+                    return o;
+                };
+                auto shoup_w = [](const std::vector<b200::Shoup> &v) {
+                    std::vector<u64> o;
+                    for (auto &s : v)
+                        o.push_back(s.w);
+                    return o;
+                };
+                double *dd = nullptr;
+#define UPD(field, vec)                                                                                                \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        std::vector<double> _v = vec;                                                                                  \
+        UP(_v, &dd);                                                                                                   \
+        L.field = dd;                                                                                                  \
+    } while (0)
+                const int k = Lh.k, nB = Lh.nB;
+                UPD(dq, primes_d(qv));
+                UPD(dbsk, primes_d(bv));
+                UPD(dlift_c, pairs(shoup_w(Lh.lift_c), qv, 1));
+                UPD(dlift_mat, pairs(Lh.lift_mat, bv, k));
+                UPD(dlift_qm, pairs(Lh.lift_qm, bv, 1));
+                UPD(dscale_c, pairs(shoup_w(Lh.scale_c), qv, 1));
+                UPD(dscale_tq, pairs(Lh.scale_tq, bv, 1));
+                UPD(dscale_mat, pairs(Lh.scale_mat, bv, k));
+                UPD(dsk_c, pairs(shoup_w(Lh.sk_c), bv, 1));
+                UPD(dsk_mat_q, pairs(Lh.sk_mat_q, qv, nB));
+                std::vector<u64> msk_t(1, bv[nB]);
+                UPD(dsk_mat_msk, pairs(Lh.sk_mat_msk, msk_t, nB > 0 ? nB : 1));
+                UPD(dsk_prod_b_q, pairs(Lh.sk_prod_b_q, qv, 1));
+                std::vector<u64> negpb;
+                for (int i = 0; i < k; i++)
+                    negpb.push_back((qv[i] - Lh.sk_prod_b_q[i]) % qv[i]);
+                UPD(dsk_negprod_b_q, pairs(negpb, qv, 1));
+                L.dsk_inv_b_msk[0] = (double)Lh.sk_inv_b_msk;
+                L.dsk_inv_b_msk[1] = (double)Lh.sk_inv_b_msk / (double)bv[nB];
+#undef UPD
+            }
+        }
         UPF(dec_c, flat(Lh.dec_c));
         UPF(dec_mat_t, Lh.dec_mat_t);
         UPF(dec_mat_g, Lh.dec_mat_g);
@@ -869,7 +969,7 @@ static int keyswitch_core(b200_ctx *ctx, int level, const u64 *d, long long d_st
     }
     {
         const long long total = batch * (k + 1) * n;
-        DISPATCH_K(k, B200_LAUNCH(ksmac_kernel<KK>, blocks_for(total, EB), EB, 0, s, ctx->d_primes, special, Kkey, ks1, key, ks2, n,
+        DISPATCH_K(k, B200_LAUNCH(ksmac_kernel<KK>, blocks_for(total, EB), EB, 0, s, ctx->d_primes, ctx->d_fp_primes, (int)(L.fp != 0), special, Kkey, ks1, key, ks2, n,
                                                                             total));
         ctx->launches++;
     }
@@ -995,6 +1095,16 @@ void b200_ctx_destroy(b200_ctx *ctx)
     cudaDeviceSynchronize();
     for (void *p : ctx->allocations)
         cudaFree(p);
+    for (int i = 0; i < b200_ctx::NBUF; i++)
+        if (ctx->hp_a[i])
+        {
+            cudaFree(ctx->hp_a[i]);
+            cudaFree(ctx->hp_b[i]);
+            cudaFree(ctx->hp_o[i]);
+            cudaEventDestroy(ctx->hp_in[i]);
+            cudaEventDestroy(ctx->hp_comp[i]);
+            cudaEventDestroy(ctx->hp_out[i]);
+        }
     if (ctx->s_h2d)
         cudaStreamDestroy(ctx->s_h2d);
     if (ctx->s_comp)
@@ -1479,6 +1589,32 @@ int b200_is_transparent(b200_ctx *ctx, int level, const uint64_t *ct, int size, 
 }
 
 // ---- host-buffer variants ----
+static int host_ring(b200_ctx *ctx, size_t words_per_slot)
+{
+    if (ctx->hp_words >= words_per_slot)
+        return 0;
+    for (int i = 0; i < b200_ctx::NBUF; i++)
+    {
+        if (ctx->hp_a[i])
+        {
+            cudaFree(ctx->hp_a[i]);
+            cudaFree(ctx->hp_b[i]);
+            cudaFree(ctx->hp_o[i]);
+        }
+        else
+        {
+            CU_TRY(cudaEventCreateWithFlags(&ctx->hp_in[i], cudaEventDisableTiming));
+            CU_TRY(cudaEventCreateWithFlags(&ctx->hp_comp[i], cudaEventDisableTiming));
+            CU_TRY(cudaEventCreateWithFlags(&ctx->hp_out[i], cudaEventDisableTiming));
+        }
+        CU_TRY(cudaMalloc((void **)&ctx->hp_a[i], words_per_slot * sizeof(u64)));
+        CU_TRY(cudaMalloc((void **)&ctx->hp_b[i], words_per_slot * sizeof(u64)));
+        CU_TRY(cudaMalloc((void **)&ctx->hp_o[i], words_per_slot * sizeof(u64)));
+    }
+    ctx->hp_words = words_per_slot;
+    return 0;
+}
+
 int b200_multiply_relin_host(b200_ctx *ctx, int level, const uint64_t *a_host, const uint64_t *b_host,
                              const uint64_t *relin_key_dev, uint64_t *out_host, uint64_t batch)
 {
@@ -1490,6 +1626,7 @@ int b200_multiply_relin_host(b200_ctx *ctx, int level, const uint64_t *a_host, c
     if (batch == 0)
         return 0;
     CU_TRY(cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> lk(ctx->hp_mu);
     const long long n = (long long)ctx->n;
     const int k = ctx->levels[level].k;
     const size_t ct_words = (size_t)2 * k * n;
@@ -1499,50 +1636,31 @@ int b200_multiply_relin_host(b200_ctx *ctx, int level, const uint64_t *a_host, c
         chunk = 1;
     if ((uint64_t)chunk > batch)
         chunk = (long long)batch;
-    const int NBUF = 3;
-    u64 *da[NBUF], *db[NBUF], *dout[NBUF];
-    cudaEvent_t ev_in[NBUF], ev_comp[NBUF], ev_out[NBUF];
-    for (int i = 0; i < NBUF; i++)
-    {
-        CU_TRY(cudaMalloc((void **)&da[i], chunk * ct_words * sizeof(u64)));
-        CU_TRY(cudaMalloc((void **)&db[i], chunk * ct_words * sizeof(u64)));
-        CU_TRY(cudaMalloc((void **)&dout[i], chunk * ct_words * sizeof(u64)));
-        CU_TRY(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
-        CU_TRY(cudaEventCreateWithFlags(&ev_comp[i], cudaEventDisableTiming));
-        CU_TRY(cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming));
-    }
+    if ((rc = host_ring(ctx, (size_t)chunk * ct_words)))
+        return rc;
+    const int NBUF = b200_ctx::NBUF;
     int it = 0;
-    rc = 0;
     for (uint64_t off = 0; off < batch && rc == 0; off += (uint64_t)chunk, it++)
     {
         const int sl = it % NBUF;
         const long long cnt = (long long)std::min<uint64_t>((uint64_t)chunk, batch - off);
         const size_t bytes = (size_t)cnt * ct_words * sizeof(u64);
         if (it >= NBUF)
-            cudaStreamWaitEvent(ctx->s_h2d, ev_out[sl], 0); // slot free once its previous output left
-        cudaMemcpyAsync(da[sl], a_host + off * ct_words, bytes, cudaMemcpyHostToDevice, ctx->s_h2d);
-        cudaMemcpyAsync(db[sl], b_host + off * ct_words, bytes, cudaMemcpyHostToDevice, ctx->s_h2d);
-        cudaEventRecord(ev_in[sl], ctx->s_h2d);
-        cudaStreamWaitEvent(ctx->s_comp, ev_in[sl], 0);
-        rc = b200_multiply_relin(ctx, level, (const uint64_t *)da[sl], (const uint64_t *)db[sl], relin_key_dev, (uint64_t *)dout[sl],
-                                 (uint64_t)cnt, ctx->s_comp);
-        cudaEventRecord(ev_comp[sl], ctx->s_comp);
-        cudaStreamWaitEvent(ctx->s_d2h, ev_comp[sl], 0);
-        cudaMemcpyAsync(out_host + off * ct_words, dout[sl], bytes, cudaMemcpyDeviceToHost, ctx->s_d2h);
-        cudaEventRecord(ev_out[sl], ctx->s_d2h);
+            cudaStreamWaitEvent(ctx->s_h2d, ctx->hp_out[sl], 0); // slot free once its previous output left
+        cudaMemcpyAsync(ctx->hp_a[sl], a_host + off * ct_words, bytes, cudaMemcpyHostToDevice, ctx->s_h2d);
+        cudaMemcpyAsync(ctx->hp_b[sl], b_host + off * ct_words, bytes, cudaMemcpyHostToDevice, ctx->s_h2d);
+        cudaEventRecord(ctx->hp_in[sl], ctx->s_h2d);
+        cudaStreamWaitEvent(ctx->s_comp, ctx->hp_in[sl], 0);
+        rc = b200_multiply_relin(ctx, level, (const uint64_t *)ctx->hp_a[sl], (const uint64_t *)ctx->hp_b[sl], relin_key_dev,
+                                 (uint64_t *)ctx->hp_o[sl], (uint64_t)cnt, ctx->s_comp);
+        cudaEventRecord(ctx->hp_comp[sl], ctx->s_comp);
+        cudaStreamWaitEvent(ctx->s_d2h, ctx->hp_comp[sl], 0);
+        cudaMemcpyAsync(out_host + off * ct_words, ctx->hp_o[sl], bytes, cudaMemcpyDeviceToHost, ctx->s_d2h);
+        cudaEventRecord(ctx->hp_out[sl], ctx->s_d2h);
     }
     cudaError_t e1 = cudaStreamSynchronize(ctx->s_h2d);
     cudaError_t e2 = cudaStreamSynchronize(ctx->s_comp);
     cudaError_t e3 = cudaStreamSynchronize(ctx->s_d2h);
-    for (int i = 0; i < NBUF; i++)
-    {
-        cudaFree(da[i]);
-        cudaFree(db[i]);
-        cudaFree(dout[i]);
-        cudaEventDestroy(ev_in[i]);
-        cudaEventDestroy(ev_comp[i]);
-        cudaEventDestroy(ev_out[i]);
-    }
     if (rc)
         return rc;
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
@@ -1561,50 +1679,36 @@ int b200_ntt_roundtrip_host(b200_ctx *ctx, int level, const uint64_t *in_host, u
     if (items == 0)
         return 0;
     CU_TRY(cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> lk(ctx->hp_mu);
     const size_t words = (size_t)ctx->levels[level].k * ctx->n;
-    long long chunk = 256;
+    long long chunk = 512;
     if ((uint64_t)chunk > items)
         chunk = (long long)items;
-    const int NBUF = 3;
-    u64 *d[NBUF];
-    cudaEvent_t ev_in[NBUF], ev_comp[NBUF], ev_out[NBUF];
-    for (int i = 0; i < NBUF; i++)
-    {
-        CU_TRY(cudaMalloc((void **)&d[i], chunk * words * sizeof(u64)));
-        CU_TRY(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
-        CU_TRY(cudaEventCreateWithFlags(&ev_comp[i], cudaEventDisableTiming));
-        CU_TRY(cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming));
-    }
+    if ((rc = host_ring(ctx, (size_t)chunk * words)))
+        return rc;
+    const int NBUF = b200_ctx::NBUF;
     int it = 0;
-    rc = 0;
     for (uint64_t off = 0; off < items && rc == 0; off += (uint64_t)chunk, it++)
     {
         const int sl = it % NBUF;
         const long long cnt = (long long)std::min<uint64_t>((uint64_t)chunk, items - off);
         const size_t bytes = (size_t)cnt * words * sizeof(u64);
         if (it >= NBUF)
-            cudaStreamWaitEvent(ctx->s_h2d, ev_out[sl], 0);
-        cudaMemcpyAsync(d[sl], in_host + off * words, bytes, cudaMemcpyHostToDevice, ctx->s_h2d);
-        cudaEventRecord(ev_in[sl], ctx->s_h2d);
-        cudaStreamWaitEvent(ctx->s_comp, ev_in[sl], 0);
-        rc = b200_ntt_forward(ctx, level, (uint64_t *)d[sl], (uint64_t)cnt, ctx->s_comp);
+            cudaStreamWaitEvent(ctx->s_h2d, ctx->hp_out[sl], 0);
+        cudaMemcpyAsync(ctx->hp_a[sl], in_host + off * words, bytes, cudaMemcpyHostToDevice, ctx->s_h2d);
+        cudaEventRecord(ctx->hp_in[sl], ctx->s_h2d);
+        cudaStreamWaitEvent(ctx->s_comp, ctx->hp_in[sl], 0);
+        rc = b200_ntt_forward(ctx, level, (uint64_t *)ctx->hp_a[sl], (uint64_t)cnt, ctx->s_comp);
         if (!rc)
-            rc = b200_ntt_inverse(ctx, level, (uint64_t *)d[sl], (uint64_t)cnt, ctx->s_comp);
-        cudaEventRecord(ev_comp[sl], ctx->s_comp);
-        cudaStreamWaitEvent(ctx->s_d2h, ev_comp[sl], 0);
-        cudaMemcpyAsync(out_host + off * words, d[sl], bytes, cudaMemcpyDeviceToHost, ctx->s_d2h);
-        cudaEventRecord(ev_out[sl], ctx->s_d2h);
+            rc = b200_ntt_inverse(ctx, level, (uint64_t *)ctx->hp_a[sl], (uint64_t)cnt, ctx->s_comp);
+        cudaEventRecord(ctx->hp_comp[sl], ctx->s_comp);
+        cudaStreamWaitEvent(ctx->s_d2h, ctx->hp_comp[sl], 0);
+        cudaMemcpyAsync(out_host + off * words, ctx->hp_a[sl], bytes, cudaMemcpyDeviceToHost, ctx->s_d2h);
+        cudaEventRecord(ctx->hp_out[sl], ctx->s_d2h);
     }
     cudaError_t e1 = cudaStreamSynchronize(ctx->s_h2d);
     cudaError_t e2 = cudaStreamSynchronize(ctx->s_comp);
     cudaError_t e3 = cudaStreamSynchronize(ctx->s_d2h);
-    for (int i = 0; i < NBUF; i++)
-    {
-        cudaFree(d[i]);
-        cudaEventDestroy(ev_in[i]);
-        cudaEventDestroy(ev_comp[i]);
-        cudaEventDestroy(ev_out[i]);
-    }
     if (rc)
         return rc;
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)

@@ -16,6 +16,7 @@
 //   plain ops = multiply_add_plain_with_scaling_variant / plain lift      S/util/scalingvariant.cpp:69-188, S/evaluator.cpp:1939-1968
 #pragma once
 #include "modarith.cuh"
+#include "ntt_fp_body.cuh"
 
 #define B200_MAXK 16 // data residues per level (the reference's chain tops out at 15 data + 1 special for n=32768)
 
@@ -54,6 +55,14 @@ struct LevelDev
     const u64 *delta;      // [k]
     const u64 *plain_inc;  // [k]
     u64 q_mod_t, plain_thr;
+    // FP64 fast path (every prime of the level and of the aux base is below 2^47): the same constants as
+    // integer-valued doubles, each entry {w, w/p_target}; primes as {p, 1/p}
+    int fp;
+    const double *dq;        // [2k]     {q_i, 1/q_i}
+    const double *dbsk;      // [2nBsk]  {p_j, 1/p_j}
+    const double *dlift_c, *dlift_mat, *dlift_qm;
+    const double *dscale_c, *dscale_tq, *dscale_mat, *dsk_c, *dsk_mat_q, *dsk_mat_msk, *dsk_prod_b_q, *dsk_negprod_b_q;
+    double dsk_inv_b_msk[2];
     // decrypt
     const u64 *dec_c;      // [2k]
     const u64 *dec_mat_t;  // [k]
@@ -391,4 +400,171 @@ B200_HD u64 decrypt_coeff(const LevelDev &L, const u64 *__restrict__ src, long l
         m = barrett128(lo, hi, T.p, T.r0, T.r1);
     }
     return m;
+}
+
+
+// =========================================================================================================
+// FP64-pipe variants (B200: DFMA issues 2.5x faster than IMAD.WIDE; see ntt_fp_body.cuh for the exactness
+// argument).  Same mathematics, same canonical outputs; used when LevelDev::fp is set.
+// =========================================================================================================
+B200_HD double fp_canon(double r, double p) // (-p, p) -> [0, p)
+{
+    return r < 0.0 ? B200_DADD(r, p) : r;
+}
+// general product a*b mod p for canonical a, b (no precomputed quotient): result in (-p, p)
+B200_HD double fp_mulmod2(double a, double b, double p, double pinv)
+{
+    const double h = B200_DMUL(a, b);
+    const double l = B200_DFMA(a, b, -h);
+    const double q = B200_DADD(B200_DFMA(h, pinv, B200_MAGIC), -B200_MAGIC);
+    return B200_DADD(B200_DFMA(-q, p, h), l);
+}
+B200_HD u64 fp_to_u64(double r) // exact for 0 <= r < 2^52
+{
+#if defined(__CUDA_ARCH__)
+    return (u64)__double_as_longlong(r + B200_TWO52) & 0x000FFFFFFFFFFFFFULL;
+#else
+    return (u64)(long long)r;
+#endif
+}
+B200_HD double ldd(const double *p) { return B200_LDG(p); }
+
+template <int K>
+B200_HD void lift_coeff_fp(const LevelDev &L, const u64 *__restrict__ src, u64 *__restrict__ dst, long long n, long long c)
+{
+    double y[K];
+    u64 ymt = 0;
+#pragma unroll
+    for (int i = 0; i < K; i++)
+    {
+        const double q = ldd(&L.dq[2 * i]);
+        y[i] = fp_canon(fp_mulmod(fp_from_u64(src[i * n + c]), ldd(&L.dlift_c[2 * i]), ldd(&L.dlift_c[2 * i + 1]), q), q);
+        ymt += fp_to_u64(y[i]) * B200_LDG(&L.lift_mt[i]);
+    }
+    const u64 r = ((ymt & 0xffffffffULL) * L.neg_inv_q_mod_mt) & 0xffffffffULL;
+    // centred representative of r (exact small integer)
+    const double rc = (r >= 0x80000000ULL) ? -(double)(0x100000000ULL - r) : (double)r;
+#pragma unroll
+    for (int j = 0; j < K + 2; j++)
+    {
+        if (j < L.nBsk)
+        {
+            const double p = ldd(&L.dbsk[2 * j]), pinv = ldd(&L.dbsk[2 * j + 1]);
+            double acc = fp_mulmod(rc, ldd(&L.dlift_qm[2 * j]), ldd(&L.dlift_qm[2 * j + 1]), p);
+#pragma unroll
+            for (int i = 0; i < K; i++)
+                acc = B200_DADD(acc, fp_mulmod(y[i], ldd(&L.dlift_mat[2 * (j * K + i)]), ldd(&L.dlift_mat[2 * (j * K + i) + 1]), p));
+            dst[j * n + c] = fp_to_canonical(acc, p, pinv);
+        }
+    }
+}
+
+B200_HD void tensor_coeff_fp(double p, double pinv, const u64 *__restrict__ A, long long a_poly_stride, int sa,
+                             const u64 *__restrict__ B, long long b_poly_stride, int sb, u64 *__restrict__ D,
+                             long long d_poly_stride, long long c)
+{
+    double a[4], b[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+    {
+        a[r] = r < sa ? fp_from_u64(A[r * a_poly_stride + c]) : 0.0;
+        b[r] = r < sb ? fp_from_u64(B[r * b_poly_stride + c]) : 0.0;
+    }
+#pragma unroll
+    for (int m = 0; m < 7; m++)
+    {
+        if (m < sa + sb - 1)
+        {
+            double acc = 0.0;
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+            {
+                const int s = m - r;
+                if (s >= 0 && s < 4 && r < sa && s < sb)
+                    acc = B200_DADD(acc, fp_mulmod2(a[r], b[s], p, pinv));
+            }
+            D[m * d_poly_stride + c] = fp_to_canonical(acc, p, pinv);
+        }
+    }
+}
+
+B200_HD void square_coeff_fp(double p, double pinv, const u64 *__restrict__ A, long long a_poly_stride, u64 *__restrict__ D,
+                             long long d_poly_stride, long long c)
+{
+    const double a0 = fp_from_u64(A[c]), a1 = fp_from_u64(A[a_poly_stride + c]);
+    D[c] = fp_to_canonical(fp_mulmod2(a0, a0, p, pinv), p, pinv);
+    const double x = fp_mulmod2(a0, a1, p, pinv);
+    D[d_poly_stride + c] = fp_to_canonical(B200_DADD(x, x), p, pinv);
+    D[2 * d_poly_stride + c] = fp_to_canonical(fp_mulmod2(a1, a1, p, pinv), p, pinv);
+}
+
+template <int K>
+B200_HD void scale_coeff_fp(const LevelDev &L, const u64 *__restrict__ src, u64 *__restrict__ dst, long long n, long long c)
+{
+    double y[K];
+#pragma unroll
+    for (int i = 0; i < K; i++)
+    {
+        const double q = ldd(&L.dq[2 * i]);
+        y[i] = fp_canon(fp_mulmod(fp_from_u64(src[i * n + c]), ldd(&L.dscale_c[2 * i]), ldd(&L.dscale_c[2 * i + 1]), q), q);
+    }
+    double yb[K + 1];
+    double w_sk = 0.0;
+#pragma unroll
+    for (int j = 0; j < K + 2; j++)
+    {
+        if (j < L.nBsk)
+        {
+            const double p = ldd(&L.dbsk[2 * j]), pinv = ldd(&L.dbsk[2 * j + 1]);
+            double acc = fp_mulmod(fp_from_u64(src[(K + j) * n + c]), ldd(&L.dscale_tq[2 * j]), ldd(&L.dscale_tq[2 * j + 1]), p);
+#pragma unroll
+            for (int i = 0; i < K; i++)
+                acc = B200_DADD(acc, fp_mulmod(y[i], ldd(&L.dscale_mat[2 * (j * K + i)]), ldd(&L.dscale_mat[2 * (j * K + i) + 1]), p));
+            // canonical w_j
+            double w = fp_renorm(acc, p, pinv);
+            w = fp_canon(w, p);
+            if (j < L.nB)
+                yb[j < K + 1 ? j : 0] = fp_canon(fp_mulmod(w, ldd(&L.dsk_c[2 * j]), ldd(&L.dsk_c[2 * j + 1]), p), p);
+            else
+                w_sk = w;
+        }
+    }
+    const double ms = ldd(&L.dbsk[2 * L.nB]), msinv = ldd(&L.dbsk[2 * L.nB + 1]);
+    double alpha = fp_mulmod(-w_sk, L.dsk_inv_b_msk[0], L.dsk_inv_b_msk[1], ms);
+#pragma unroll
+    for (int b = 0; b < K + 1; b++)
+        if (b < L.nB)
+            alpha = B200_DADD(alpha, fp_mulmod(yb[b], ldd(&L.dsk_mat_msk[2 * b]), ldd(&L.dsk_mat_msk[2 * b + 1]), ms));
+    alpha = fp_canon(fp_renorm(alpha, ms, msinv), ms);
+    const bool neg = alpha > B200_DMUL(ms, 0.5); // m_sk odd: alpha > floor(m_sk/2)  <=>  alpha > m_sk/2
+    const double mag = neg ? B200_DADD(ms, -alpha) : alpha;
+#pragma unroll
+    for (int i = 0; i < K; i++)
+    {
+        const double q = ldd(&L.dq[2 * i]), qinv = ldd(&L.dq[2 * i + 1]);
+        const double *pb = neg ? &L.dsk_prod_b_q[2 * i] : &L.dsk_negprod_b_q[2 * i];
+        double acc = fp_mulmod(mag, ldd(pb), ldd(pb + 1), q);
+#pragma unroll
+        for (int b = 0; b < K + 1; b++)
+            if (b < L.nB)
+                acc = B200_DADD(acc, fp_mulmod(yb[b], ldd(&L.dsk_mat_q[2 * (i * L.nB + b)]), ldd(&L.dsk_mat_q[2 * (i * L.nB + b) + 1]), q));
+        dst[i * n + c] = fp_to_canonical(acc, q, qinv);
+    }
+}
+
+template <int K>
+B200_HD void ksmac_coeff_fp(double p, double pinv, const u64 *__restrict__ ops, long long op_stride, const u64 *__restrict__ key,
+                            long long key_j_stride, long long key_comp_stride, u64 *__restrict__ out0, u64 *__restrict__ out1,
+                            long long c)
+{
+    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+    for (int J = 0; J < K; J++)
+    {
+        const double x = fp_from_u64(ops[J * op_stride + c]);
+        a0 = B200_DADD(a0, fp_mulmod2(x, fp_from_u64(B200_LDG(&key[J * key_j_stride + c])), p, pinv));
+        a1 = B200_DADD(a1, fp_mulmod2(x, fp_from_u64(B200_LDG(&key[J * key_j_stride + key_comp_stride + c])), p, pinv));
+    }
+    out0[c] = fp_to_canonical(a0, p, pinv);
+    out1[c] = fp_to_canonical(a1, p, pinv);
 }

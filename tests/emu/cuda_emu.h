@@ -54,6 +54,7 @@ inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, int) { *e = nullptr;
 inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return 0; }
 inline cudaError_t cudaEventDestroy(cudaEvent_t) { return 0; }
 inline unsigned long long __ldg(const unsigned long long *p) { return *p; }
+inline double __ldg(const double *p) { return *p; }
 inline int __syncthreads_or(int v) { return v; }
 
 template <class F>
