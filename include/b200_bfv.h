@@ -120,6 +120,9 @@ int b200_mod_switch_to_next(b200_ctx *ctx, int level, const uint64_t *a, int siz
 /* ct (size polys) . secret-key powers (NTT form, [size-1][k][n]) -> plaintext coefficients [batch][n] mod t */
 int b200_decrypt(b200_ctx *ctx, int level, const uint64_t *ct, int size, const uint64_t *sk_powers_ntt, uint64_t *plain_out,
                  uint64_t batch, void *stream);
+/* phase = c0 + sum_j c_j * s^j in coefficient form: [batch][k][n] (Decryptor::dot_product_ct_sk_array, S/decryptor.cpp:340-422) */
+int b200_ct_sk_phase(b200_ctx *ctx, int level, const uint64_t *ct, int size, const uint64_t *sk_powers_ntt, uint64_t *phase_out,
+                     uint64_t batch, void *stream);
 /* any-nonzero test over polys [1, size) of each item (transparent-ciphertext guard, S/ciphertext.h:451-456);
    flags_out: device array [batch] of 0/1 ("is transparent") */
 int b200_is_transparent(b200_ctx *ctx, int level, const uint64_t *ct, int size, uint32_t *flags_out, uint64_t batch,

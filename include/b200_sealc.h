@@ -1,0 +1,179 @@
+/* b200_sealc.h — layer-2 C ABI: the SEAL C export names that Sunscreen's `seal_fhe` crate binds to
+ * (seal_fhe/build.rs:157-180 allow-list, seal_fhe/bindgen_wrapper.h), re-implemented over the B200 backend.
+ *
+ * Same calling convention as the reference's S/c/defines.h:26-56: every function returns an HRESULT in a
+ * `long`, objects are opaque `void*` handles created by *_Create* and released by *_Destroy, out-parameters are
+ * pointers.  Error mapping follows S/c/evaluator.cpp:58-80: NULL handle -> E_POINTER, what the reference throws
+ * as std::invalid_argument -> E_INVALIDARG, std::logic_error -> COR_E_INVALIDOPERATION.
+ *
+ * Ciphertexts live in GPU memory; the host mirror is materialised lazily by the accessors that read words
+ * (Ciphertext_GetDataAt*, B200_Ciphertext_GetWords).  Evaluator calls are re-entrant (one internal stream per
+ * SEALContext, enqueue under a mutex), matching the reference's thread-safety contract for the rayon DAG
+ * executor (sunscreen_runtime/src/run.rs:415-469).
+ *
+ * Covered in this round: parameter objects, SEALContext, Ciphertext/Plaintext/PublicKey/SecretKey/KSwitchKeys data
+ * objects, the whole BFV Evaluator surface seal_fhe uses, and Decryptor (decrypt + invariant noise budget).
+ * KeyGenerator / Encryptor / BatchEncoder / Save-Load / PolynomialArray are "next" rows (SURVEY.md §8(a) row E and
+ * §8(f)): keys and fresh ciphertexts produced by the reference are imported through the data-object accessors.
+ * B200_* names are extensions (bulk word access, batching) that the reference does not have.
+ */
+#ifndef B200_SEALC_H
+#define B200_SEALC_H
+#include <stdbool.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef SEAL_C_FUNC
+#define SEAL_C_FUNC long
+#endif
+
+/* HRESULT values (S/c/defines.h:29-41) */
+#define B200_S_OK 0L
+#define B200_E_POINTER_HR 0x80004003L
+#define B200_E_INVALIDARG_HR 0x80070057L
+#define B200_E_OUTOFMEMORY_HR 0x8007000EL
+#define B200_E_UNEXPECTED_HR 0x8000FFFFL
+#define B200_COR_E_INVALIDOPERATION_HR 0x80131509L
+#define B200_ERROR_INVALID_INDEX_HR 0x80070585L /* HRESULT_FROM_WIN32(ERROR_INVALID_INDEX) */
+
+/* ---- Modulus / CoeffModulus (S/c/modulus.h) ---- */
+SEAL_C_FUNC Modulus_Create1(uint64_t value, void **small_modulus);
+SEAL_C_FUNC Modulus_Create2(void *copy, void **small_modulus);
+SEAL_C_FUNC Modulus_Destroy(void *thisptr);
+SEAL_C_FUNC Modulus_Value(void *thisptr, uint64_t *value);
+SEAL_C_FUNC Modulus_BitCount(void *thisptr, int *bit_count);
+SEAL_C_FUNC CoeffModulus_MaxBitCount(uint64_t poly_modulus_degree, int sec_level, int *bit_count);
+SEAL_C_FUNC CoeffModulus_BFVDefault(uint64_t poly_modulus_degree, int sec_level, uint64_t *length, void **coeffs);
+
+/* ---- EncryptionParameters (S/c/encryptionparameters.h) ---- */
+SEAL_C_FUNC EncParams_Create1(uint8_t scheme, void **enc_params);
+SEAL_C_FUNC EncParams_Destroy(void *thisptr);
+SEAL_C_FUNC EncParams_GetPolyModulusDegree(void *thisptr, uint64_t *degree);
+SEAL_C_FUNC EncParams_SetPolyModulusDegree(void *thisptr, uint64_t degree);
+SEAL_C_FUNC EncParams_GetCoeffModulus(void *thisptr, uint64_t *length, void **coeffs);
+SEAL_C_FUNC EncParams_SetCoeffModulus(void *thisptr, uint64_t length, void **coeffs);
+SEAL_C_FUNC EncParams_GetScheme(void *thisptr, uint8_t *scheme);
+SEAL_C_FUNC EncParams_GetParmsId(void *thisptr, uint64_t *parms_id);
+SEAL_C_FUNC EncParams_GetPlainModulus(void *thisptr, void **plain_modulus);
+SEAL_C_FUNC EncParams_SetPlainModulus1(void *thisptr, void *modulus);
+SEAL_C_FUNC EncParams_SetPlainModulus2(void *thisptr, uint64_t plain_modulus);
+
+/* ---- SEALContext (S/c/sealcontext.h) ---- */
+SEAL_C_FUNC SEALContext_Create(void *encryptionParams, bool expand_mod_chain, int sec_level, void **context);
+SEAL_C_FUNC SEALContext_Destroy(void *thisptr);
+SEAL_C_FUNC SEALContext_KeyParmsId(void *thisptr, uint64_t *parms_id);
+SEAL_C_FUNC SEALContext_FirstParmsId(void *thisptr, uint64_t *parms_id);
+SEAL_C_FUNC SEALContext_LastParmsId(void *thisptr, uint64_t *parms_id);
+SEAL_C_FUNC SEALContext_ParametersSet(void *thisptr, bool *params_set);
+SEAL_C_FUNC SEALContext_UsingKeyswitching(void *thisptr, bool *using_keyswitching);
+
+/* ---- Ciphertext (S/c/ciphertext.h) ---- */
+SEAL_C_FUNC Ciphertext_Create1(void *pool, void **cipher);
+SEAL_C_FUNC Ciphertext_Create2(void *copy, void **cipher);
+SEAL_C_FUNC Ciphertext_Set(void *thisptr, void *assign);
+SEAL_C_FUNC Ciphertext_Destroy(void *thisptr);
+SEAL_C_FUNC Ciphertext_Size(void *thisptr, uint64_t *size);
+SEAL_C_FUNC Ciphertext_PolyModulusDegree(void *thisptr, uint64_t *poly_modulus_degree);
+SEAL_C_FUNC Ciphertext_CoeffModulusSize(void *thisptr, uint64_t *coeff_modulus_size);
+SEAL_C_FUNC Ciphertext_ParmsId(void *thisptr, uint64_t *parms_id);
+SEAL_C_FUNC Ciphertext_SetParmsId(void *thisptr, uint64_t *parms_id);
+SEAL_C_FUNC Ciphertext_Resize1(void *thisptr, void *context, uint64_t *parms_id, uint64_t size);
+SEAL_C_FUNC Ciphertext_GetDataAt1(void *thisptr, uint64_t index, uint64_t *data);
+SEAL_C_FUNC Ciphertext_GetDataAt2(void *thisptr, uint64_t poly_index, uint64_t coeff_index, uint64_t *data);
+SEAL_C_FUNC Ciphertext_SetDataAt(void *thisptr, uint64_t index, uint64_t value);
+SEAL_C_FUNC Ciphertext_IsNTTForm(void *thisptr, bool *is_ntt_form);
+SEAL_C_FUNC Ciphertext_SetIsNTTForm(void *thisptr, bool is_ntt_form);
+SEAL_C_FUNC Ciphertext_Scale(void *thisptr, double *scale);
+SEAL_C_FUNC Ciphertext_IsTransparent(void *thisptr, bool *result);
+
+/* ---- Plaintext (S/c/plaintext.h) ---- */
+SEAL_C_FUNC Plaintext_Create1(void *memoryPoolHandle, void **plaintext);
+SEAL_C_FUNC Plaintext_Create2(uint64_t coeffCount, void *memoryPoolHandle, void **plaintext);
+SEAL_C_FUNC Plaintext_Create5(void *copy, void **plaintext);
+SEAL_C_FUNC Plaintext_Destroy(void *thisptr);
+SEAL_C_FUNC Plaintext_CoeffCount(void *thisptr, uint64_t *coeff_count);
+SEAL_C_FUNC Plaintext_CoeffAt(void *thisptr, uint64_t index, uint64_t *coeff);
+SEAL_C_FUNC Plaintext_SetCoeffAt(void *thisptr, uint64_t index, uint64_t value);
+SEAL_C_FUNC Plaintext_Resize(void *thisptr, uint64_t coeff_count);
+SEAL_C_FUNC Plaintext_IsNTTForm(void *thisptr, bool *is_ntt_form);
+SEAL_C_FUNC Plaintext_IsZero(void *thisptr, bool *is_zero);
+
+/* ---- PublicKey / SecretKey (S/c/publickey.h, secretkey.h) ---- */
+SEAL_C_FUNC PublicKey_Create1(void **public_key);
+SEAL_C_FUNC PublicKey_Create2(void *copy, void **public_key);
+SEAL_C_FUNC PublicKey_Data(void *thisptr, void **data);
+SEAL_C_FUNC PublicKey_ParmsId(void *thisptr, uint64_t *parms_id);
+SEAL_C_FUNC PublicKey_Destroy(void *thisptr);
+SEAL_C_FUNC SecretKey_Create1(void **secret_key);
+SEAL_C_FUNC SecretKey_Create2(void *copy, void **secret_key);
+SEAL_C_FUNC SecretKey_Data(void *thisptr, void **data);
+SEAL_C_FUNC SecretKey_ParmsId(void *thisptr, uint64_t *parms_id);
+SEAL_C_FUNC SecretKey_Destroy(void *thisptr);
+
+/* ---- KSwitchKeys / RelinKeys / GaloisKeys (S/c/kswitchkeys.h, relinkeys.h, galoiskeys.h) ---- */
+SEAL_C_FUNC KSwitchKeys_Create1(void **kswitch_keys);
+SEAL_C_FUNC KSwitchKeys_Create2(void *copy, void **kswitch_keys);
+SEAL_C_FUNC KSwitchKeys_Destroy(void *thisptr);
+SEAL_C_FUNC KSwitchKeys_Size(void *thisptr, uint64_t *size);
+SEAL_C_FUNC KSwitchKeys_RawSize(void *thisptr, uint64_t *key_count);
+SEAL_C_FUNC KSwitchKeys_GetKeyList(void *thisptr, uint64_t index, uint64_t *count, void **key_list);
+SEAL_C_FUNC KSwitchKeys_ClearDataAndReserve(void *thisptr, uint64_t size);
+SEAL_C_FUNC KSwitchKeys_AddKeyList(void *thisptr, uint64_t count, void **key_list);
+SEAL_C_FUNC KSwitchKeys_GetParmsId(void *thisptr, uint64_t *parms_id);
+SEAL_C_FUNC KSwitchKeys_SetParmsId(void *thisptr, uint64_t *parms_id);
+SEAL_C_FUNC RelinKeys_GetIndex(uint64_t key_power, uint64_t *index);
+SEAL_C_FUNC GaloisKeys_GetIndex(uint32_t galois_elt, uint64_t *index);
+
+/* ---- Evaluator (S/c/evaluator.h:16-79) ---- */
+SEAL_C_FUNC Evaluator_Create(void *context, void **evaluator);
+SEAL_C_FUNC Evaluator_Destroy(void *thisptr);
+SEAL_C_FUNC Evaluator_Negate(void *thisptr, void *encrypted, void *destination);
+SEAL_C_FUNC Evaluator_Add(void *thisptr, void *encrypted1, void *encrypted2, void *destination);
+SEAL_C_FUNC Evaluator_AddMany(void *thisptr, uint64_t count, void **encrypteds, void *destination);
+SEAL_C_FUNC Evaluator_AddPlain(void *thisptr, void *encrypted, void *plain, void *destination);
+SEAL_C_FUNC Evaluator_Sub(void *thisptr, void *encrypted1, void *encrypted2, void *destination);
+SEAL_C_FUNC Evaluator_SubPlain(void *thisptr, void *encrypted, void *plain, void *destination);
+SEAL_C_FUNC Evaluator_Multiply(void *thisptr, void *encrypted1, void *encrypted2, void *destination, void *pool);
+SEAL_C_FUNC Evaluator_MultiplyMany(void *thisptr, uint64_t count, void **encrypteds, void *relin_keys, void *destination,
+                                   void *pool);
+SEAL_C_FUNC Evaluator_MultiplyPlain(void *thisptr, void *encrypted, void *plain, void *destination, void *pool);
+SEAL_C_FUNC Evaluator_Square(void *thisptr, void *encrypted, void *destination, void *pool);
+SEAL_C_FUNC Evaluator_Relinearize(void *thisptr, void *encrypted, void *relinKeys, void *destination, void *pool);
+SEAL_C_FUNC Evaluator_ModSwitchToNext1(void *thisptr, void *encrypted, void *destination, void *pool);
+SEAL_C_FUNC Evaluator_Exponentiate(void *thisptr, void *encrypted, uint64_t exponent, void *relin_keys, void *destination,
+                                   void *pool);
+SEAL_C_FUNC Evaluator_ApplyGalois(void *thisptr, void *encrypted, uint32_t galois_elt, void *galois_keys, void *destination,
+                                  void *pool);
+SEAL_C_FUNC Evaluator_RotateRows(void *thisptr, void *encrypted, int steps, void *galoisKeys, void *destination, void *pool);
+SEAL_C_FUNC Evaluator_RotateColumns(void *thisptr, void *encrypted, void *galois_keys, void *destination, void *pool);
+SEAL_C_FUNC Evaluator_ContextUsingKeyswitching(void *thisptr, bool *using_keyswitching);
+
+/* ---- Decryptor (S/c/decryptor.h) ---- */
+SEAL_C_FUNC Decryptor_Create(void *context, void *secret_key, void **decryptor);
+SEAL_C_FUNC Decryptor_Destroy(void *thisptr);
+SEAL_C_FUNC Decryptor_Decrypt(void *thisptr, void *encrypted, void *destination);
+SEAL_C_FUNC Decryptor_InvariantNoiseBudget(void *thisptr, void *encrypted, int *invariant_noise_budget);
+
+/* ---- extensions (not in the reference) ---- */
+/* bulk word access: the reference only offers word-at-a-time accessors */
+SEAL_C_FUNC B200_Ciphertext_SetWords(void *thisptr, void *context, uint64_t *parms_id, uint64_t size, bool is_ntt_form,
+                                     const uint64_t *words);
+SEAL_C_FUNC B200_Ciphertext_GetWords(void *thisptr, uint64_t *words, uint64_t capacity_words);
+SEAL_C_FUNC B200_Plaintext_SetCoeffs(void *thisptr, uint64_t count, const uint64_t *coeffs);
+/* Key list `index` <- `decomp` size-2 key-level NTT-form ciphertexts given as one flat word array */
+SEAL_C_FUNC B200_KSwitchKeys_SetKeyWords(void *thisptr, void *context, uint64_t index, uint64_t decomp, const uint64_t *words);
+/* SecretKey <- key-level NTT-form words [K][n] */
+SEAL_C_FUNC B200_SecretKey_SetWords(void *thisptr, void *context, const uint64_t *words);
+/* wait until every enqueued operation of this context has finished */
+SEAL_C_FUNC B200_SEALContext_Synchronize(void *context);
+/* multiply + relinearize over `count` independent pairs in one launch sequence (DAG-level batching seam) */
+SEAL_C_FUNC B200_Evaluator_MultiplyRelinBatch(void *thisptr, uint64_t count, void **encrypteds1, void **encrypteds2,
+                                              void *relin_keys, void **destinations);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

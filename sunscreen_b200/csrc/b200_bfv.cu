@@ -358,6 +358,21 @@ __global__ void decrypt_kernel(const LevelDev L, int size, const u64 *ct, u64 *p
     plain[item * n + c] = decrypt_coeff<K>(L, ph, n, c);
 }
 
+template <int K>
+__global__ void phase_add_kernel(const PrimeDev *primes, int size, const u64 *ct, u64 *phase, long long n, long long total)
+{
+    const long long idx = GLOBAL_IDX();
+    if (idx >= total)
+        return;
+    const long long c = idx % n;
+    const long long item = idx / n;
+    u64 *ph = phase + item * K * n;
+    const u64 *c0 = ct + item * size * K * n;
+#pragma unroll
+    for (int i = 0; i < K; i++)
+        ph[i * n + c] = add_mod(ph[i * n + c], c0[i * n + c], __ldg(&primes[i].p));
+}
+
 __global__ void transparent_kernel(const u64 *ct, long long item_words, long long skip_words, u32 *flags)
 {
     const long long item = blockIdx.y;
@@ -1557,6 +1572,68 @@ int b200_decrypt(b200_ctx *ctx, int level, const uint64_t *ct, int size, const u
         const long long total = (long long)batch * n;
         DISPATCH_K(k, B200_LAUNCH(decrypt_kernel<KK>, blocks_for(total, EB), EB, 0, s, L, size, (const u64 *)ct, acc,
                                                                               (u64 *)plain_out, n, total));
+        ctx->launches++;
+    }
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+// phase = c0 + sum_{j>=1} c_j * s^j  (coefficient form, canonical), [batch][k][n]
+int b200_ct_sk_phase(b200_ctx *ctx, int level, const uint64_t *ct, int size, const uint64_t *sk_powers_ntt, uint64_t *phase_out,
+                     uint64_t batch, void *stream)
+{
+    int rc = check_level(ctx, level);
+    if (rc)
+        return rc;
+    if (!ct || !sk_powers_ntt || !phase_out)
+        return fail(B200_E_NULL, "null pointer");
+    if (size < 2)
+        return fail(B200_E_INVALID, "ciphertext size must be >= 2");
+    if (batch == 0)
+        return 0;
+    CU_TRY(cudaSetDevice(ctx->device));
+    const long long n = (long long)ctx->n;
+    const LevelDev &L = ctx->levels[level];
+    const LevelHost &Lh = ctx->host->levels[level];
+    const int k = L.k, terms = size - 1;
+    cudaStream_t s = (cudaStream_t)stream;
+    Scratch scr(s);
+    u64 *X = nullptr;
+    u64 *acc = (u64 *)phase_out;
+    if ((rc = scr.get((size_t)batch * terms * k * n, &X)))
+        return rc;
+    {
+        std::vector<int> prime;
+        std::vector<long long> so, dof;
+        for (int j = 0; j < terms; j++)
+            for (int r = 0; r < k; r++)
+            {
+                prime.push_back(Lh.q_idx[r]);
+                so.push_back(((long long)(j + 1) * k + r) * n);
+                dof.push_back(((long long)j * k + r) * n);
+            }
+        JobDesc jd;
+        if ((rc = get_job(ctx, "dec:" + std::to_string(level) + ":" + std::to_string(size), prime, so, dof, &jd)))
+            return rc;
+        if ((rc = launch_ntt<true>(ctx, jd, (const u64 *)ct, (long long)size * k * n, X, (long long)terms * k * n,
+                                   (long long)batch, 0, s)))
+            return rc;
+    }
+    {
+        const long long total = (long long)batch * k * n;
+        B200_LAUNCH(dot_sk_kernel, blocks_for(total, EB), EB, 0, s, ctx->d_primes, k, terms, X, (const u64 *)sk_powers_ntt, acc,
+                    ctx->logn, total);
+        ctx->launches++;
+    }
+    JobDesc jd;
+    if ((rc = dense_job(ctx, "slab:" + std::to_string(level), row_primes(ctx, level, false), &jd)))
+        return rc;
+    if ((rc = launch_ntt<false>(ctx, jd, acc, (long long)k * n, acc, (long long)k * n, (long long)batch, 0, s)))
+        return rc;
+    {
+        const long long total = (long long)batch * n;
+        DISPATCH_K(k, B200_LAUNCH(phase_add_kernel<KK>, blocks_for(total, EB), EB, 0, s, ctx->d_primes, size, (const u64 *)ct, acc, n,
+                                  total));
         ctx->launches++;
     }
     CU_TRY(cudaGetLastError());

@@ -1,0 +1,2056 @@
+// sealc_api.cpp — layer-2 C ABI (include/b200_sealc.h): SEAL's C export names over the B200 backend.
+//
+// Mirrors the behaviour (argument meaning, ownership, HRESULTs, validation order) of the reference's C export
+// layer S/c/*.cpp and of the C++ methods it forwards to, for the BFV path that seal_fhe uses:
+//   Evaluator_*      S/c/evaluator.cpp:31-700  -> S/evaluator.cpp (negate/add/sub/multiply/square/relinearize/
+//                    mod_switch/multiply_plain/add_plain/sub_plain/apply_galois/rotate)
+//   Ciphertext_*     S/c/ciphertext.cpp        -> S/ciphertext.h:337-715
+//   KSwitchKeys_*    S/c/kswitchkeys.cpp       -> S/kswitchkeys.h:340
+//   SEALContext_*    S/c/sealcontext.cpp       -> S/context.cpp:135-522
+// No arithmetic happens here: every operation is a call into the layer-1 functions of b200_bfv.cu.
+#include "../../include/b200_bfv.h"
+#include "../../include/b200_sealc.h"
+#include "host_ctx.h"
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <vector>
+
+namespace
+{
+typedef uint64_t u64;
+typedef std::array<u64, 4> ParmsId;
+const ParmsId kZeroId = { { 0, 0, 0, 0 } };
+
+const long S_OK_ = 0L;
+const long E_POINTER_ = (long)0x80004003L;
+const long E_INVALIDARG_ = (long)0x80070057L;
+const long E_OUTOFMEMORY_ = (long)0x8007000EL;
+const long E_UNEXPECTED_ = (long)0x8000FFFFL;
+const long COR_E_INVALIDOPERATION_ = (long)0x80131509L;
+const long ERROR_INVALID_INDEX_ = (long)0x80070585L;
+
+struct InvalidArg : std::runtime_error { using std::runtime_error::runtime_error; };
+struct LogicErr : std::runtime_error { using std::runtime_error::runtime_error; };
+
+struct Modulus_ { u64 value = 0; };
+
+struct EncParams_
+{
+    uint8_t scheme = 1; // bfv
+    u64 n = 0;
+    std::vector<u64> coeff;
+    u64 plain = 0;
+};
+
+// BFV default coefficient moduli for 128-bit security (values of S/util/globals.cpp:23-71) and the HE-standard
+// total bit bounds (S/util/hestdparms.h).
+const u64 kDefault1024[] = { 0x7e00001 };
+const u64 kDefault2048[] = { 0x3fffffff000001 };
+const u64 kDefault4096[] = { 0xffffee001, 0xffffc4001, 0x1ffffe0001 };
+const u64 kDefault8192[] = { 0x7fffffd8001, 0x7fffffc8001, 0xfffffffc001, 0xffffff6c001, 0xfffffebc001 };
+const u64 kDefault16384[] = { 0xfffffffd8001, 0xfffffffa0001, 0xfffffff00001, 0x1fffffff68001, 0x1fffffff50001,
+                              0x1ffffffee8001, 0x1ffffffea0001, 0x1ffffffe88001, 0x1ffffffe48001 };
+const u64 kDefault32768[] = { 0x7fffffffe90001, 0x7fffffffbf0001, 0x7fffffffbd0001, 0x7fffffffba0001, 0x7fffffffaa0001,
+                              0x7fffffffa50001, 0x7fffffff9f0001, 0x7fffffff7e0001, 0x7fffffff770001, 0x7fffffff380001,
+                              0x7fffffff330001, 0x7fffffff2d0001, 0x7fffffff170001, 0x7fffffff150001, 0x7ffffffef00001,
+                              0xfffffffff70001 };
+int max_bits_tc128(u64 n)
+{
+    switch (n)
+    {
+    case 1024: return 27;
+    case 2048: return 54;
+    case 4096: return 109;
+    case 8192: return 218;
+    case 16384: return 438;
+    case 32768: return 881;
+    default: return 0;
+    }
+}
+int max_bits(u64 n, int sec)
+{
+    if (sec == 128)
+        return max_bits_tc128(n);
+    if (sec == 192)
+    {
+        switch (n) { case 1024: return 19; case 2048: return 37; case 4096: return 75; case 8192: return 152;
+                     case 16384: return 305; case 32768: return 611; default: return 0; }
+    }
+    if (sec == 256)
+    {
+        switch (n) { case 1024: return 14; case 2048: return 29; case 4096: return 58; case 8192: return 118;
+                     case 16384: return 237; case 32768: return 476; default: return 0; }
+    }
+    return 0;
+}
+
+struct Context_
+{
+    EncParams_ parms;
+    bool parameters_set = false;
+    bool using_keyswitching = false;
+    bool using_batching = false;
+    b200_ctx *dev = nullptr;
+    int levels = 0, first_level = 0;
+    std::vector<ParmsId> ids; // per level
+    std::vector<int> level_k;
+    std::mutex mu;            // serialises enqueue on the context's stream (the legacy default stream)
+    bool check_transparent = true;
+    ~Context_()
+    {
+        if (dev)
+            b200_ctx_destroy(dev);
+    }
+    int level_of(const ParmsId &id) const
+    {
+        for (int i = 0; i < (int)ids.size(); i++)
+            if (ids[i] == id)
+                return i;
+        return -1;
+    }
+};
+
+void dev_check(int rc)
+{
+    if (rc == 0)
+        return;
+    if (rc == B200_E_INVALID)
+        throw InvalidArg(b200_last_error());
+    if (rc == B200_E_LOGIC)
+        throw LogicErr(b200_last_error());
+    if (rc == B200_E_NOMEM)
+        throw std::bad_alloc();
+    throw std::runtime_error(b200_last_error());
+}
+
+// Ciphertext: device-resident words with a lazily materialised host mirror.
+struct Ciphertext_
+{
+    ParmsId parms_id = kZeroId;
+    bool is_ntt_form = false;
+    u64 size = 0, n = 0, k = 0;
+    double scale = 1.0;
+    u64 correction_factor = 1;
+    Context_ *ctx = nullptr; // owner of the device buffer (set once data exists)
+    mutable std::vector<u64> host;
+    mutable bool host_valid = true;
+    u64 *dev = nullptr;
+    size_t dev_words = 0;
+    bool dev_valid = false;
+
+    size_t words() const { return (size_t)(size * n * k); }
+    ~Ciphertext_() { release_dev(); }
+    void release_dev()
+    {
+        if (dev && ctx && ctx->dev)
+            b200_free(ctx->dev, dev);
+        dev = nullptr;
+        dev_words = 0;
+        dev_valid = false;
+    }
+    void ensure_dev_capacity(Context_ *c)
+    {
+        if (ctx != c || dev_words < words() || !dev)
+        {
+            release_dev();
+            ctx = c;
+            void *p = nullptr;
+            dev_check(b200_malloc(c->dev, std::max<size_t>(words(), 1) * sizeof(u64), &p));
+            dev = (u64 *)p;
+            dev_words = words();
+        }
+    }
+    // make the device copy current (upload the host mirror if that is the valid one)
+    const u64 *dev_ptr(Context_ *c)
+    {
+        if (!dev_valid || ctx != c)
+        {
+            if (!host_valid)
+                sync_host();
+            ensure_dev_capacity(c);
+            if (words())
+                dev_check(b200_memcpy_h2d(c->dev, dev, host.data(), words() * sizeof(u64), nullptr));
+            dev_check(b200_stream_synchronize(c->dev, nullptr));
+            dev_valid = true;
+        }
+        return dev;
+    }
+    void sync_host() const
+    {
+        if (host_valid)
+            return;
+        host.resize(words());
+        if (words() && dev && ctx)
+        {
+            dev_check(b200_memcpy_d2h(ctx->dev, host.data(), dev, words() * sizeof(u64), nullptr));
+            dev_check(b200_stream_synchronize(ctx->dev, nullptr));
+        }
+        host_valid = true;
+    }
+    // prepare as an output of shape (size, k) for context c; contents undefined, device copy becomes the valid one
+    u64 *prepare_output(Context_ *c, const ParmsId &id, u64 new_size, u64 new_k)
+    {
+        parms_id = id;
+        size = new_size;
+        k = new_k;
+        n = c->parms.n;
+        is_ntt_form = false;
+        scale = 1.0;
+        correction_factor = 1;
+        ensure_dev_capacity(c);
+        dev_valid = true;
+        host_valid = false;
+        return dev;
+    }
+    void assign(const Ciphertext_ &o)
+    {
+        if (this == &o)
+            return;
+        o.sync_host();
+        release_dev();
+        parms_id = o.parms_id;
+        is_ntt_form = o.is_ntt_form;
+        size = o.size;
+        n = o.n;
+        k = o.k;
+        scale = o.scale;
+        correction_factor = o.correction_factor;
+        ctx = o.ctx;
+        host = o.host;
+        host_valid = true;
+    }
+};
+
+struct Plaintext_
+{
+    ParmsId parms_id = kZeroId;
+    std::vector<u64> coeffs;
+    double scale = 1.0;
+};
+
+struct PublicKey_ { Ciphertext_ data; };
+struct SecretKey_ { Plaintext_ data; };
+
+struct KSwitchKeys_
+{
+    ParmsId parms_id = kZeroId;
+    std::vector<std::vector<PublicKey_ *>> keys; // owned
+    // device cache of flattened key lists
+    struct Flat { u64 *dev = nullptr; Context_ *ctx = nullptr; };
+    std::vector<Flat> flat;
+    ~KSwitchKeys_() { clear(); }
+    void clear()
+    {
+        for (auto &l : keys)
+            for (auto *p : l)
+                delete p;
+        keys.clear();
+        drop_flat();
+    }
+    void drop_flat()
+    {
+        for (auto &f : flat)
+            if (f.dev && f.ctx && f.ctx->dev)
+                b200_free(f.ctx->dev, f.dev);
+        flat.clear();
+    }
+    const u64 *flat_dev(Context_ *c, size_t index, int decomp)
+    {
+        if (flat.size() <= index)
+            flat.resize(index + 1);
+        Flat &f = flat[index];
+        if (f.dev && f.ctx == c)
+            return f.dev;
+        const size_t K = c->parms.coeff.size(), n = c->parms.n;
+        const size_t per = 2 * K * n;
+        std::vector<u64> buf(per * decomp);
+        for (int j = 0; j < decomp; j++)
+        {
+            Ciphertext_ &ct = keys[index][j]->data;
+            ct.sync_host();
+            if (ct.words() != per)
+                throw InvalidArg("kswitch_keys is not valid for encryption parameters");
+            std::memcpy(buf.data() + per * j, ct.host.data(), per * sizeof(u64));
+        }
+        void *p = nullptr;
+        dev_check(b200_malloc(c->dev, buf.size() * sizeof(u64), &p));
+        dev_check(b200_memcpy_h2d(c->dev, p, buf.data(), buf.size() * sizeof(u64), nullptr));
+        dev_check(b200_stream_synchronize(c->dev, nullptr));
+        f.dev = (u64 *)p;
+        f.ctx = c;
+        return f.dev;
+    }
+};
+
+struct Evaluator_ { Context_ *ctx; };
+
+struct Decryptor_
+{
+    Context_ *ctx;
+    std::vector<u64> sk; // key level NTT form [K][n]
+    // device cache: powers s^1..s^m packed per (level, terms)
+    struct Pow { int level, terms; u64 *dev; };
+    std::vector<Pow> cache;
+    ~Decryptor_()
+    {
+        for (auto &p : cache)
+            if (p.dev)
+                b200_free(ctx->dev, p.dev);
+    }
+    const u64 *powers(int level, int terms)
+    {
+        for (auto &p : cache)
+            if (p.level == level && p.terms == terms)
+                return p.dev;
+        const size_t n = ctx->parms.n;
+        const int k = ctx->level_k[level];
+        std::vector<u64> buf((size_t)terms * k * n);
+        for (int r = 0; r < k; r++)
+        {
+            const u64 q = ctx->parms.coeff[r];
+            const u64 *s1 = sk.data() + (size_t)r * n;
+            for (size_t c = 0; c < n; c++)
+            {
+                u64 cur = s1[c];
+                for (int j = 0; j < terms; j++)
+                {
+                    buf[((size_t)j * k + r) * n + c] = cur;
+                    cur = (u64)((unsigned __int128)cur * s1[c] % q);
+                }
+            }
+        }
+        void *p = nullptr;
+        dev_check(b200_malloc(ctx->dev, buf.size() * sizeof(u64), &p));
+        dev_check(b200_memcpy_h2d(ctx->dev, p, buf.data(), buf.size() * sizeof(u64), nullptr));
+        dev_check(b200_stream_synchronize(ctx->dev, nullptr));
+        cache.push_back({ level, terms, (u64 *)p });
+        return (u64 *)p;
+    }
+};
+
+template <class F>
+long guard(F f)
+{
+    try
+    {
+        f();
+        return S_OK_;
+    }
+    catch (const InvalidArg &)
+    {
+        return E_INVALIDARG_;
+    }
+    catch (const std::invalid_argument &)
+    {
+        return E_INVALIDARG_;
+    }
+    catch (const LogicErr &)
+    {
+        return COR_E_INVALIDOPERATION_;
+    }
+    catch (const std::logic_error &)
+    {
+        return COR_E_INVALIDOPERATION_;
+    }
+    catch (const std::bad_alloc &)
+    {
+        return E_OUTOFMEMORY_;
+    }
+    catch (...)
+    {
+        return E_UNEXPECTED_;
+    }
+}
+
+#define NULLRET(p)                                                                                                     \
+    if (!(p))                                                                                                          \
+    return E_POINTER_
+
+// is_metadata_valid_for (S/valcheck.cpp:67-112): known data-level parms_id, matching shape
+int data_level(Context_ *c, const Ciphertext_ &ct, const char *what)
+{
+    int lv = c->level_of(ct.parms_id);
+    if (lv < 0 || (lv == 0 && c->first_level == 1) || ct.n != c->parms.n || (int)ct.k != c->level_k[lv] || ct.size < 2 || ct.size > 6)
+        throw InvalidArg(what);
+    return lv;
+}
+
+void transparent_guard(Context_ *c, int level, Ciphertext_ &dst)
+{
+    if (!c->check_transparent)
+        return;
+    // SEAL_THROW_ON_TRANSPARENT_CIPHERTEXT (seal_fhe/build.rs:37-42): "result ciphertext is transparent"
+    void *flag = nullptr;
+    dev_check(b200_malloc(c->dev, 8, &flag));
+    uint32_t h = 0;
+    int rc = b200_is_transparent(c->dev, level, dst.dev, (int)dst.size, (uint32_t *)flag, 1, nullptr);
+    if (!rc)
+        rc = b200_memcpy_d2h(c->dev, &h, flag, 4, nullptr);
+    if (!rc)
+        rc = b200_stream_synchronize(c->dev, nullptr);
+    b200_free(c->dev, flag);
+    dev_check(rc);
+    if (h)
+        throw LogicErr("result ciphertext is transparent");
+}
+
+// run `body(dst_ptr)` writing to `dst`; when dst aliases an input, go through a temporary
+template <class F>
+void with_output(Context_ *c, Ciphertext_ &dst, std::initializer_list<const Ciphertext_ *> inputs, const ParmsId &id, u64 size,
+                 u64 k, F body)
+{
+    bool alias = false;
+    for (auto *in : inputs)
+        alias = alias || in == &dst;
+    if (!alias)
+    {
+        body(dst.prepare_output(c, id, size, k));
+        return;
+    }
+    Ciphertext_ tmp;
+    body(tmp.prepare_output(c, id, size, k));
+    // move tmp's buffer into dst
+    dst.release_dev();
+    dst.parms_id = id;
+    dst.size = size;
+    dst.k = k;
+    dst.n = c->parms.n;
+    dst.is_ntt_form = false;
+    dst.scale = 1.0;
+    dst.ctx = c;
+    dst.dev = tmp.dev;
+    dst.dev_words = tmp.dev_words;
+    dst.dev_valid = true;
+    dst.host_valid = false;
+    tmp.dev = nullptr;
+    tmp.dev_words = 0;
+}
+
+void check_same(const Ciphertext_ &a, const Ciphertext_ &b)
+{
+    if (a.parms_id != b.parms_id)
+        throw InvalidArg("encrypted1 and encrypted2 parameter mismatch");
+    if (a.is_ntt_form != b.is_ntt_form)
+        throw InvalidArg("NTT form mismatch");
+    if (a.scale != b.scale)
+        throw InvalidArg("scale mismatch");
+}
+
+void op_addsub(Context_ *c, Ciphertext_ &a, Ciphertext_ &b, Ciphertext_ &dst, int mode)
+{
+    std::lock_guard<std::mutex> lk(c->mu);
+    int lv = data_level(c, a, "encrypted1 is not valid for encryption parameters");
+    data_level(c, b, "encrypted2 is not valid for encryption parameters");
+    check_same(a, b);
+    const u64 k = a.k, n = a.n;
+    const u64 mx = std::max(a.size, b.size), mn = std::min(a.size, b.size);
+    const u64 *pa = a.dev_ptr(c), *pb = b.dev_ptr(c);
+    with_output(c, dst, { &a, &b }, a.parms_id, mx, k, [&](u64 *out) {
+        dev_check((mode == 0 ? b200_add : b200_sub)(c->dev, lv, pa, pb, out, (int)mn, 1, nullptr));
+        if (a.size > mn) // tail polys copied from the larger operand
+            dev_check(b200_memcpy_d2d(c->dev, out + mn * k * n, pa + mn * k * n, (a.size - mn) * k * n * sizeof(u64), nullptr));
+        else if (b.size > mn)
+        {
+            if (mode == 0)
+                dev_check(b200_memcpy_d2d(c->dev, out + mn * k * n, pb + mn * k * n, (b.size - mn) * k * n * sizeof(u64), nullptr));
+            else
+                dev_check(b200_negate(c->dev, lv, pb + mn * k * n, out + mn * k * n, (int)(b.size - mn), 1, nullptr));
+        }
+    });
+    dst.is_ntt_form = a.is_ntt_form;
+    transparent_guard(c, lv, dst);
+}
+
+void op_multiply(Context_ *c, Ciphertext_ &a, Ciphertext_ &b, Ciphertext_ &dst, bool square)
+{
+    std::lock_guard<std::mutex> lk(c->mu);
+    int lv = data_level(c, a, "encrypted1 is not valid for encryption parameters");
+    if (!square)
+    {
+        data_level(c, b, "encrypted2 is not valid for encryption parameters");
+        if (a.parms_id != b.parms_id)
+            throw InvalidArg("encrypted1 and encrypted2 parameter mismatch");
+    }
+    if (a.is_ntt_form || (!square && b.is_ntt_form))
+        throw InvalidArg("encrypted1 or encrypted2 cannot be in NTT form");
+    const u64 k = a.k;
+    const u64 *pa = a.dev_ptr(c), *pb = square ? pa : b.dev_ptr(c);
+    if (square && a.size != 2)
+    { // the reference falls back to multiply for sizes other than 2 (S/evaluator.cpp:880-884)
+        square = false;
+        pb = pa;
+    }
+    const u64 sb = square ? a.size : (&a == &b ? a.size : b.size);
+    const u64 ds = square ? 3 : a.size + sb - 1;
+    if (a.size > 4 || sb > 4)
+        throw LogicErr("invalid parameters");
+    with_output(c, dst, { &a, &b }, a.parms_id, ds, k, [&](u64 *out) {
+        if (square)
+            dev_check(b200_square(c->dev, lv, pa, out, 1, nullptr));
+        else
+            dev_check(b200_multiply(c->dev, lv, pa, (int)a.size, pb, (int)sb, out, 1, nullptr));
+    });
+    transparent_guard(c, lv, dst);
+}
+
+void check_keys(Context_ *c, KSwitchKeys_ &keys, size_t index)
+{
+    if (!c->using_keyswitching)
+        throw LogicErr("keyswitching is not supported by the context");
+    if (keys.parms_id != c->ids[0])
+        throw InvalidArg("parameter mismatch");
+    if (index >= keys.keys.size() || keys.keys[index].empty())
+        throw InvalidArg("key not present");
+}
+
+void op_relinearize(Context_ *c, Ciphertext_ &a, KSwitchKeys_ &keys, Ciphertext_ &dst)
+{
+    std::lock_guard<std::mutex> lk(c->mu);
+    int lv = data_level(c, a, "encrypted is not valid for encryption parameters");
+    if (keys.parms_id != c->ids[0])
+        throw InvalidArg("relin_keys is not valid for encryption parameters");
+    if (a.is_ntt_form)
+        throw InvalidArg("BFV encrypted cannot be in NTT form");
+    const u64 k = a.k, n = a.n;
+    if (a.size == 2)
+    { // nothing to do (S/evaluator.cpp:1131-1135)
+        dst.assign(a);
+        return;
+    }
+    if (keys.keys.size() < a.size - 2)
+        throw InvalidArg("not enough relinearization keys");
+    const u64 *pa = a.dev_ptr(c);
+    with_output(c, dst, { &a }, a.parms_id, 2, k, [&](u64 *out) {
+        if (a.size == 3)
+        {
+            check_keys(c, keys, 0);
+            const u64 *key = keys.flat_dev(c, 0, (int)k);
+            dev_check(b200_relinearize(c->dev, lv, pa, key, out, 1, nullptr));
+            return;
+        }
+        // size > 3: peel polynomials from the top, key index = power - 2 (S/evaluator.cpp:1143-1151)
+        void *tmp = nullptr;
+        dev_check(b200_malloc(c->dev, 3 * k * n * sizeof(u64), &tmp));
+        u64 *t3 = (u64 *)tmp;
+        dev_check(b200_memcpy_d2d(c->dev, out, pa, 2 * k * n * sizeof(u64), nullptr));
+        int rc = 0;
+        for (u64 s = a.size - 1; s >= 2 && !rc; s--)
+        {
+            check_keys(c, keys, s - 2);
+            const u64 *key = keys.flat_dev(c, s - 2, (int)k);
+            rc = b200_memcpy_d2d(c->dev, t3, out, 2 * k * n * sizeof(u64), nullptr);
+            if (!rc)
+                rc = b200_memcpy_d2d(c->dev, t3 + 2 * k * n, pa + s * k * n, k * n * sizeof(u64), nullptr);
+            if (!rc)
+                rc = b200_relinearize(c->dev, lv, t3, key, out, 1, nullptr);
+        }
+        b200_stream_synchronize(c->dev, nullptr);
+        b200_free(c->dev, tmp);
+        dev_check(rc);
+    });
+    transparent_guard(c, lv, dst);
+}
+
+void op_galois(Context_ *c, Ciphertext_ &a, uint32_t elt, KSwitchKeys_ &keys, Ciphertext_ &dst)
+{
+    // caller holds c->mu
+    int lv = data_level(c, a, "encrypted is not valid for encryption parameters");
+    if (keys.parms_id != c->ids[0])
+        throw InvalidArg("galois_keys is not valid for encryption parameters");
+    if (!(elt & 1) || elt >= 2 * c->parms.n)
+        throw InvalidArg("Galois element is not valid");
+    if (a.size > 2)
+        throw InvalidArg("encrypted size must be 2");
+    const size_t index = (elt - 1) >> 1;
+    if (index >= keys.keys.size() || keys.keys[index].empty())
+        throw InvalidArg("Galois key not present");
+    check_keys(c, keys, index);
+    const u64 *pa = a.dev_ptr(c);
+    const u64 *key = keys.flat_dev(c, index, (int)a.k);
+    with_output(c, dst, { &a }, a.parms_id, 2, a.k, [&](u64 *out) {
+        dev_check(b200_apply_galois(c->dev, lv, pa, elt, key, out, 1, nullptr));
+    });
+    transparent_guard(c, lv, dst);
+}
+
+// naf of an integer (S/util/numth.h: naf) — signed powers of two, least significant first
+std::vector<int> naf(int value)
+{
+    std::vector<int> res;
+    bool sign = value < 0;
+    value = std::abs(value);
+    for (int i = 0; value; i++)
+    {
+        int zi = (value & 1) ? 2 - (value & 3) : 0;
+        value = (value - zi) >> 1;
+        if (zi)
+            res.push_back((sign ? -zi : zi) * (1 << i));
+    }
+    return res;
+}
+
+void op_rotate(Context_ *c, Ciphertext_ &a, int steps, KSwitchKeys_ &keys, Ciphertext_ &dst)
+{
+    // rotate_internal (S/evaluator.cpp:2325-2380)
+    if (!c->using_batching)
+        throw LogicErr("encryption parameters do not support batching");
+    if (keys.parms_id != c->ids[0])
+        throw InvalidArg("galois_keys is not valid for encryption parameters");
+    if (steps == 0)
+    {
+        dst.assign(a);
+        return;
+    }
+    const size_t n = c->parms.n;
+    uint32_t elt = 0;
+    if (b200_galois_elt_from_step(c->dev, steps, &elt))
+        throw InvalidArg("step count too large");
+    auto has = [&](uint32_t e) {
+        size_t idx = (e - 1) >> 1;
+        return idx < keys.keys.size() && !keys.keys[idx].empty();
+    };
+    if (has(elt))
+    {
+        op_galois(c, a, elt, keys, dst);
+        return;
+    }
+    std::vector<int> parts = naf(steps);
+    if (parts.size() == 1)
+        throw InvalidArg("Galois key not present");
+    Ciphertext_ cur;
+    cur.assign(a);
+    for (int st : parts)
+    {
+        if ((size_t)std::abs(st) == (n >> 1))
+            continue; // a rotation by the full row is the identity
+        uint32_t e = 0;
+        if (b200_galois_elt_from_step(c->dev, st, &e))
+            throw InvalidArg("step count too large");
+        Ciphertext_ nxt;
+        op_galois(c, cur, e, keys, nxt);
+        cur.assign(nxt);
+    }
+    dst.assign(cur);
+}
+
+std::vector<u64> padded_plain(Context_ *c, const Plaintext_ &p)
+{
+    if (p.parms_id != kZeroId)
+        throw InvalidArg("plain is not valid for encryption parameters");
+    if (p.coeffs.size() > c->parms.n)
+        throw InvalidArg("plain is not valid for encryption parameters");
+    std::vector<u64> v(c->parms.n, 0);
+    for (size_t i = 0; i < p.coeffs.size(); i++)
+    {
+        if (p.coeffs[i] >= c->parms.plain)
+            throw InvalidArg("plain is not valid for encryption parameters");
+        v[i] = p.coeffs[i];
+    }
+    return v;
+}
+
+void op_plain(Context_ *c, Ciphertext_ &a, const Plaintext_ &p, Ciphertext_ &dst, int which /*0 add 1 sub 2 mul*/)
+{
+    std::lock_guard<std::mutex> lk(c->mu);
+    int lv = data_level(c, a, "encrypted is not valid for encryption parameters");
+    if (a.is_ntt_form)
+        throw InvalidArg("BFV encrypted cannot be in NTT form");
+    std::vector<u64> pv = padded_plain(c, p);
+    if (which == 2)
+    {
+        bool zero = true;
+        for (u64 x : pv)
+            zero = zero && x == 0;
+        if (zero && c->check_transparent)
+            throw LogicErr("result ciphertext is transparent");
+    }
+    void *dp = nullptr;
+    dev_check(b200_malloc(c->dev, pv.size() * sizeof(u64), &dp));
+    int rc = b200_memcpy_h2d(c->dev, dp, pv.data(), pv.size() * sizeof(u64), nullptr);
+    const u64 *pa = a.dev_ptr(c);
+    try
+    {
+        dev_check(rc);
+        with_output(c, dst, { &a }, a.parms_id, a.size, a.k, [&](u64 *out) {
+            if (which == 0)
+                dev_check(b200_add_plain(c->dev, lv, pa, (int)a.size, (const u64 *)dp, 1, out, 1, nullptr));
+            else if (which == 1)
+                dev_check(b200_sub_plain(c->dev, lv, pa, (int)a.size, (const u64 *)dp, 1, out, 1, nullptr));
+            else
+                dev_check(b200_multiply_plain(c->dev, lv, pa, (int)a.size, (const u64 *)dp, 1, out, 1, nullptr));
+        });
+        b200_stream_synchronize(c->dev, nullptr);
+    }
+    catch (...)
+    {
+        b200_stream_synchronize(c->dev, nullptr);
+        b200_free(c->dev, dp);
+        throw;
+    }
+    b200_free(c->dev, dp);
+    transparent_guard(c, lv, dst);
+}
+
+} // namespace
+
+extern "C" {
+
+// ---------------------------------------------------------------------------------------------------------
+// Modulus / CoeffModulus
+// ---------------------------------------------------------------------------------------------------------
+long Modulus_Create1(uint64_t value, void **out)
+{
+    NULLRET(out);
+    if (value == 1 || (value >> 61))
+        return E_INVALIDARG_; // Modulus::set_value: "value can be at most 61 bits and cannot be 1"
+    auto *m = new Modulus_();
+    m->value = value;
+    *out = m;
+    return S_OK_;
+}
+long Modulus_Create2(void *copy, void **out)
+{
+    NULLRET(copy);
+    NULLRET(out);
+    *out = new Modulus_(*(Modulus_ *)copy);
+    return S_OK_;
+}
+long Modulus_Destroy(void *p)
+{
+    NULLRET(p);
+    delete (Modulus_ *)p;
+    return S_OK_;
+}
+long Modulus_Value(void *p, uint64_t *v)
+{
+    NULLRET(p);
+    NULLRET(v);
+    *v = ((Modulus_ *)p)->value;
+    return S_OK_;
+}
+long Modulus_BitCount(void *p, int *b)
+{
+    NULLRET(p);
+    NULLRET(b);
+    u64 v = ((Modulus_ *)p)->value;
+    *b = v ? 64 - __builtin_clzll(v) : 0;
+    return S_OK_;
+}
+long CoeffModulus_MaxBitCount(uint64_t n, int sec, int *bits)
+{
+    NULLRET(bits);
+    *bits = sec == 0 ? 2147483647 : max_bits(n, sec);
+    return S_OK_;
+}
+long CoeffModulus_BFVDefault(uint64_t n, int sec, uint64_t *length, void **coeffs)
+{
+    NULLRET(length);
+    const u64 *tab = nullptr;
+    size_t cnt = 0;
+    if (sec != 128)
+        return E_INVALIDARG_; // only the tc128 tables are carried (all Sunscreen uses: sunscreen/src/params.rs:137)
+#define TAB(N)                                                                                                         \
+    case N:                                                                                                            \
+        tab = kDefault##N;                                                                                             \
+        cnt = sizeof(kDefault##N) / sizeof(u64);                                                                       \
+        break;
+    switch (n)
+    {
+        TAB(1024) TAB(2048) TAB(4096) TAB(8192) TAB(16384) TAB(32768)
+    default:
+        return E_INVALIDARG_;
+    }
+#undef TAB
+    *length = cnt;
+    if (!coeffs)
+        return S_OK_; // size query (S/c/modulus.cpp: BuildModulusPointers)
+    for (size_t i = 0; i < cnt; i++)
+    {
+        auto *m = new Modulus_();
+        m->value = tab[i];
+        coeffs[i] = m;
+    }
+    return S_OK_;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// EncryptionParameters
+// ---------------------------------------------------------------------------------------------------------
+long EncParams_Create1(uint8_t scheme, void **out)
+{
+    NULLRET(out);
+    if (scheme != 1)
+        return E_INVALIDARG_; // only BFV is built by Sunscreen (seal_fhe/src/lib.rs:11-13)
+    auto *p = new EncParams_();
+    p->scheme = scheme;
+    *out = p;
+    return S_OK_;
+}
+long EncParams_Destroy(void *p)
+{
+    NULLRET(p);
+    delete (EncParams_ *)p;
+    return S_OK_;
+}
+long EncParams_GetPolyModulusDegree(void *p, uint64_t *d)
+{
+    NULLRET(p);
+    NULLRET(d);
+    *d = ((EncParams_ *)p)->n;
+    return S_OK_;
+}
+long EncParams_SetPolyModulusDegree(void *p, uint64_t d)
+{
+    NULLRET(p);
+    ((EncParams_ *)p)->n = d;
+    return S_OK_;
+}
+long EncParams_GetCoeffModulus(void *p, uint64_t *length, void **coeffs)
+{
+    NULLRET(p);
+    NULLRET(length);
+    auto *e = (EncParams_ *)p;
+    *length = e->coeff.size();
+    if (!coeffs)
+        return S_OK_;
+    for (size_t i = 0; i < e->coeff.size(); i++)
+    {
+        auto *m = new Modulus_();
+        m->value = e->coeff[i];
+        coeffs[i] = m;
+    }
+    return S_OK_;
+}
+long EncParams_SetCoeffModulus(void *p, uint64_t length, void **coeffs)
+{
+    NULLRET(p);
+    NULLRET(coeffs);
+    auto *e = (EncParams_ *)p;
+    if (length < 1 || length > 64)
+        return E_INVALIDARG_;
+    std::vector<u64> v;
+    for (uint64_t i = 0; i < length; i++)
+    {
+        NULLRET(coeffs[i]);
+        u64 q = ((Modulus_ *)coeffs[i])->value;
+        int bits = q ? 64 - __builtin_clzll(q) : 0;
+        if (bits > 60 || bits < 2)
+            return E_INVALIDARG_; // "coeff_modulus is invalid" (S/encryptionparams.h:209-225)
+        v.push_back(q);
+    }
+    e->coeff = v;
+    return S_OK_;
+}
+long EncParams_GetScheme(void *p, uint8_t *s)
+{
+    NULLRET(p);
+    NULLRET(s);
+    *s = ((EncParams_ *)p)->scheme;
+    return S_OK_;
+}
+long EncParams_GetParmsId(void *p, uint64_t *id)
+{
+    NULLRET(p);
+    NULLRET(id);
+    auto *e = (EncParams_ *)p;
+    std::vector<b200::u64> mods(e->coeff.begin(), e->coeff.end());
+    b200::u64 out[4];
+    b200::compute_parms_id((size_t)e->n, mods, e->plain, out);
+    std::copy_n(out, 4, id);
+    return S_OK_;
+}
+long EncParams_GetPlainModulus(void *p, void **m)
+{
+    NULLRET(p);
+    NULLRET(m);
+    auto *mm = new Modulus_();
+    mm->value = ((EncParams_ *)p)->plain;
+    *m = mm;
+    return S_OK_;
+}
+long EncParams_SetPlainModulus1(void *p, void *m)
+{
+    NULLRET(p);
+    NULLRET(m);
+    ((EncParams_ *)p)->plain = ((Modulus_ *)m)->value;
+    return S_OK_;
+}
+long EncParams_SetPlainModulus2(void *p, uint64_t v)
+{
+    NULLRET(p);
+    if (v == 1 || (v >> 61))
+        return E_INVALIDARG_;
+    ((EncParams_ *)p)->plain = v;
+    return S_OK_;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// SEALContext
+// ---------------------------------------------------------------------------------------------------------
+long SEALContext_Create(void *parms, bool /*expand_mod_chain*/, int sec_level, void **out)
+{
+    NULLRET(parms);
+    NULLRET(out);
+    if (sec_level != 0 && sec_level != 128 && sec_level != 192 && sec_level != 256)
+        return E_INVALIDARG_;
+    auto *e = (EncParams_ *)parms;
+    std::unique_ptr<Context_> c(new Context_());
+    c->parms = *e;
+    const char *nt = getenv("B200_SKIP_TRANSPARENT_CHECK");
+    c->check_transparent = !(nt && nt[0] == '1');
+    // validation (S/context.cpp:135-420): anything failing leaves parameters_set = false, it is not an error here
+    bool ok = e->n >= 2 && e->n <= 131072 && !(e->n & (e->n - 1)) && !e->coeff.empty() && e->plain >= 2;
+    if (ok)
+    {
+        int total = 0;
+        {
+            b200::BigUInt Q(1);
+            for (u64 q : e->coeff)
+                Q.mul(q);
+            total = Q.bit_length();
+        }
+        if (sec_level != 0 && total > max_bits(e->n, sec_level))
+            ok = false;
+        for (size_t i = 0; i < e->coeff.size() && ok; i++)
+        {
+            if ((e->coeff[i] - 1) % (2 * e->n))
+                ok = false;
+            if (e->plain >= e->coeff[i] && e->coeff.size() == 1)
+                ok = false;
+            if (std::__gcd(e->plain, e->coeff[i]) != 1)
+                ok = false;
+        }
+    }
+    if (ok)
+    {
+        const char *dv = getenv("B200_DEVICE");
+        int device = dv ? atoi(dv) : 0;
+        b200_ctx *dev = nullptr;
+        int rc = b200_ctx_create(e->n, e->coeff.data(), e->coeff.size(), e->plain, device, &dev);
+        if (rc == B200_E_CUDA || rc == B200_E_NOMEM)
+            return E_UNEXPECTED_; // no CPU fallback: the backend cannot exist without its GPU
+        if (rc)
+            ok = false;
+        else
+        {
+            c->dev = dev;
+            b200_info info;
+            b200_ctx_info(dev, &info);
+            c->levels = info.levels;
+            c->first_level = info.first_level;
+            c->using_keyswitching = e->coeff.size() > 1;
+            c->using_batching = info.using_batching != 0;
+            for (int l = 0; l < info.levels; l++)
+            {
+                b200_level_info li;
+                b200_ctx_level_info(dev, l, &li);
+                ParmsId id;
+                std::copy_n(li.parms_id, 4, id.begin());
+                c->ids.push_back(id);
+                c->level_k.push_back(li.k);
+            }
+        }
+    }
+    c->parameters_set = ok;
+    *out = c.release();
+    return S_OK_;
+}
+long SEALContext_Destroy(void *p)
+{
+    NULLRET(p);
+    delete (Context_ *)p;
+    return S_OK_;
+}
+static long ctx_id(void *p, uint64_t *out, int which)
+{
+    NULLRET(p);
+    NULLRET(out);
+    auto *c = (Context_ *)p;
+    if (!c->parameters_set)
+    {
+        std::fill_n(out, 4, 0);
+        return S_OK_;
+    }
+    int lv = which == 0 ? 0 : which == 1 ? c->first_level : c->levels - 1;
+    std::copy_n(c->ids[lv].begin(), 4, out);
+    return S_OK_;
+}
+long SEALContext_KeyParmsId(void *p, uint64_t *o) { return ctx_id(p, o, 0); }
+long SEALContext_FirstParmsId(void *p, uint64_t *o) { return ctx_id(p, o, 1); }
+long SEALContext_LastParmsId(void *p, uint64_t *o) { return ctx_id(p, o, 2); }
+long SEALContext_ParametersSet(void *p, bool *b)
+{
+    NULLRET(p);
+    NULLRET(b);
+    *b = ((Context_ *)p)->parameters_set;
+    return S_OK_;
+}
+long SEALContext_UsingKeyswitching(void *p, bool *b)
+{
+    NULLRET(p);
+    NULLRET(b);
+    *b = ((Context_ *)p)->using_keyswitching;
+    return S_OK_;
+}
+long B200_SEALContext_Synchronize(void *p)
+{
+    NULLRET(p);
+    auto *c = (Context_ *)p;
+    return guard([&] {
+        if (c->dev)
+            dev_check(b200_stream_synchronize(c->dev, nullptr));
+    });
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Ciphertext
+// ---------------------------------------------------------------------------------------------------------
+long Ciphertext_Create1(void * /*pool*/, void **out)
+{
+    NULLRET(out);
+    *out = new Ciphertext_();
+    return S_OK_;
+}
+long Ciphertext_Create2(void *copy, void **out)
+{
+    NULLRET(copy);
+    NULLRET(out);
+    auto *c = new Ciphertext_();
+    long hr = guard([&] { c->assign(*(Ciphertext_ *)copy); });
+    if (hr)
+    {
+        delete c;
+        return hr;
+    }
+    *out = c;
+    return S_OK_;
+}
+long Ciphertext_Set(void *p, void *assign)
+{
+    NULLRET(p);
+    NULLRET(assign);
+    return guard([&] { ((Ciphertext_ *)p)->assign(*(Ciphertext_ *)assign); });
+}
+long Ciphertext_Destroy(void *p)
+{
+    NULLRET(p);
+    delete (Ciphertext_ *)p;
+    return S_OK_;
+}
+long Ciphertext_Size(void *p, uint64_t *s)
+{
+    NULLRET(p);
+    NULLRET(s);
+    *s = ((Ciphertext_ *)p)->size;
+    return S_OK_;
+}
+long Ciphertext_PolyModulusDegree(void *p, uint64_t *s)
+{
+    NULLRET(p);
+    NULLRET(s);
+    *s = ((Ciphertext_ *)p)->n;
+    return S_OK_;
+}
+long Ciphertext_CoeffModulusSize(void *p, uint64_t *s)
+{
+    NULLRET(p);
+    NULLRET(s);
+    *s = ((Ciphertext_ *)p)->k;
+    return S_OK_;
+}
+long Ciphertext_ParmsId(void *p, uint64_t *id)
+{
+    NULLRET(p);
+    NULLRET(id);
+    std::copy_n(((Ciphertext_ *)p)->parms_id.begin(), 4, id);
+    return S_OK_;
+}
+long Ciphertext_SetParmsId(void *p, uint64_t *id)
+{
+    NULLRET(p);
+    NULLRET(id);
+    std::copy_n(id, 4, ((Ciphertext_ *)p)->parms_id.begin());
+    return S_OK_;
+}
+long Ciphertext_Resize1(void *p, void *context, uint64_t *parms_id, uint64_t size)
+{
+    NULLRET(p);
+    NULLRET(context);
+    NULLRET(parms_id);
+    auto *ct = (Ciphertext_ *)p;
+    auto *c = (Context_ *)context;
+    return guard([&] {
+        if (!c->parameters_set)
+            throw InvalidArg("encryption parameters are not set correctly");
+        ParmsId id;
+        std::copy_n(parms_id, 4, id.begin());
+        int lv = c->level_of(id);
+        if (lv < 0)
+            throw InvalidArg("parms_id is not valid for encryption parameters");
+        if ((size < 2 && size != 0) || size > 6)
+            throw InvalidArg("invalid size");
+        ct->sync_host();
+        std::vector<u64> old = ct->host;
+        const u64 ok = ct->k, on = ct->n, os = ct->size;
+        ct->release_dev();
+        ct->parms_id = id;
+        ct->size = size;
+        ct->k = c->level_k[lv];
+        ct->n = c->parms.n;
+        ct->ctx = c;
+        ct->host.assign(ct->words(), 0);
+        if (ok == ct->k && on == ct->n) // same shape per polynomial: existing polynomials are kept (DynArray::resize)
+            std::copy_n(old.begin(), std::min(old.size(), ct->host.size()), ct->host.begin());
+        (void)os;
+        ct->host_valid = true;
+    });
+}
+long Ciphertext_GetDataAt1(void *p, uint64_t index, uint64_t *data)
+{
+    NULLRET(p);
+    NULLRET(data);
+    auto *ct = (Ciphertext_ *)p;
+    long hr = guard([&] { ct->sync_host(); });
+    if (hr)
+        return hr;
+    if (index >= ct->host.size())
+        return ERROR_INVALID_INDEX_;
+    *data = ct->host[index];
+    return S_OK_;
+}
+long Ciphertext_GetDataAt2(void *p, uint64_t poly, uint64_t coeff, uint64_t *data)
+{
+    NULLRET(p);
+    NULLRET(data);
+    auto *ct = (Ciphertext_ *)p;
+    if (poly >= ct->size || coeff >= ct->k * ct->n)
+        return ERROR_INVALID_INDEX_;
+    return Ciphertext_GetDataAt1(p, poly * ct->k * ct->n + coeff, data);
+}
+long Ciphertext_SetDataAt(void *p, uint64_t index, uint64_t value)
+{
+    NULLRET(p);
+    auto *ct = (Ciphertext_ *)p;
+    long hr = guard([&] { ct->sync_host(); });
+    if (hr)
+        return hr;
+    if (index >= ct->host.size())
+        return ERROR_INVALID_INDEX_;
+    ct->host[index] = value;
+    ct->dev_valid = false;
+    return S_OK_;
+}
+long Ciphertext_IsNTTForm(void *p, bool *b)
+{
+    NULLRET(p);
+    NULLRET(b);
+    *b = ((Ciphertext_ *)p)->is_ntt_form;
+    return S_OK_;
+}
+long Ciphertext_SetIsNTTForm(void *p, bool b)
+{
+    NULLRET(p);
+    ((Ciphertext_ *)p)->is_ntt_form = b;
+    return S_OK_;
+}
+long Ciphertext_Scale(void *p, double *s)
+{
+    NULLRET(p);
+    NULLRET(s);
+    *s = ((Ciphertext_ *)p)->scale;
+    return S_OK_;
+}
+long Ciphertext_IsTransparent(void *p, bool *r)
+{
+    NULLRET(p);
+    NULLRET(r);
+    auto *ct = (Ciphertext_ *)p;
+    return guard([&] {
+        // (!size || size < 2) || all polys from index 1 are zero (S/ciphertext.h:451-456)
+        if (ct->size < 2)
+        {
+            *r = true;
+            return;
+        }
+        ct->sync_host();
+        bool nz = false;
+        for (size_t i = (size_t)(ct->k * ct->n); i < ct->host.size() && !nz; i++)
+            nz = ct->host[i] != 0;
+        *r = !nz;
+    });
+}
+long B200_Ciphertext_SetWords(void *p, void *context, uint64_t *parms_id, uint64_t size, bool ntt, const uint64_t *words)
+{
+    NULLRET(words);
+    long hr = Ciphertext_Resize1(p, context, parms_id, size);
+    if (hr)
+        return hr;
+    auto *ct = (Ciphertext_ *)p;
+    std::memcpy(ct->host.data(), words, ct->words() * sizeof(u64));
+    ct->is_ntt_form = ntt;
+    ct->dev_valid = false;
+    return S_OK_;
+}
+long B200_Ciphertext_GetWords(void *p, uint64_t *words, uint64_t cap)
+{
+    NULLRET(p);
+    NULLRET(words);
+    auto *ct = (Ciphertext_ *)p;
+    long hr = guard([&] { ct->sync_host(); });
+    if (hr)
+        return hr;
+    if (cap < ct->host.size())
+        return E_INVALIDARG_;
+    std::memcpy(words, ct->host.data(), ct->host.size() * sizeof(u64));
+    return S_OK_;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Plaintext
+// ---------------------------------------------------------------------------------------------------------
+long Plaintext_Create1(void *, void **out)
+{
+    NULLRET(out);
+    *out = new Plaintext_();
+    return S_OK_;
+}
+long Plaintext_Create2(uint64_t count, void *, void **out)
+{
+    NULLRET(out);
+    auto *p = new Plaintext_();
+    p->coeffs.assign(count, 0);
+    *out = p;
+    return S_OK_;
+}
+long Plaintext_Create5(void *copy, void **out)
+{
+    NULLRET(copy);
+    NULLRET(out);
+    *out = new Plaintext_(*(Plaintext_ *)copy);
+    return S_OK_;
+}
+long Plaintext_Destroy(void *p)
+{
+    NULLRET(p);
+    delete (Plaintext_ *)p;
+    return S_OK_;
+}
+long Plaintext_CoeffCount(void *p, uint64_t *c)
+{
+    NULLRET(p);
+    NULLRET(c);
+    *c = ((Plaintext_ *)p)->coeffs.size();
+    return S_OK_;
+}
+long Plaintext_CoeffAt(void *p, uint64_t i, uint64_t *c)
+{
+    NULLRET(p);
+    NULLRET(c);
+    auto *pl = (Plaintext_ *)p;
+    if (i >= pl->coeffs.size())
+        return ERROR_INVALID_INDEX_;
+    *c = pl->coeffs[i];
+    return S_OK_;
+}
+long Plaintext_SetCoeffAt(void *p, uint64_t i, uint64_t v)
+{
+    NULLRET(p);
+    auto *pl = (Plaintext_ *)p;
+    if (i >= pl->coeffs.size())
+        return ERROR_INVALID_INDEX_;
+    pl->coeffs[i] = v;
+    return S_OK_;
+}
+long Plaintext_Resize(void *p, uint64_t c)
+{
+    NULLRET(p);
+    auto *pl = (Plaintext_ *)p;
+    if (pl->parms_id != kZeroId)
+        return COR_E_INVALIDOPERATION_; // "cannot resize an NTT transformed Plaintext"
+    pl->coeffs.resize(c, 0);
+    return S_OK_;
+}
+long Plaintext_IsNTTForm(void *p, bool *b)
+{
+    NULLRET(p);
+    NULLRET(b);
+    *b = ((Plaintext_ *)p)->parms_id != kZeroId;
+    return S_OK_;
+}
+long Plaintext_IsZero(void *p, bool *b)
+{
+    NULLRET(p);
+    NULLRET(b);
+    auto *pl = (Plaintext_ *)p;
+    *b = std::all_of(pl->coeffs.begin(), pl->coeffs.end(), [](u64 x) { return x == 0; });
+    return S_OK_;
+}
+long B200_Plaintext_SetCoeffs(void *p, uint64_t count, const uint64_t *coeffs)
+{
+    NULLRET(p);
+    if (count)
+        NULLRET(coeffs);
+    ((Plaintext_ *)p)->coeffs.assign(coeffs, coeffs + count);
+    return S_OK_;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// PublicKey / SecretKey
+// ---------------------------------------------------------------------------------------------------------
+long PublicKey_Create1(void **out)
+{
+    NULLRET(out);
+    *out = new PublicKey_();
+    return S_OK_;
+}
+long PublicKey_Create2(void *copy, void **out)
+{
+    NULLRET(copy);
+    NULLRET(out);
+    auto *k = new PublicKey_();
+    long hr = guard([&] { k->data.assign(((PublicKey_ *)copy)->data); });
+    if (hr)
+    {
+        delete k;
+        return hr;
+    }
+    *out = k;
+    return S_OK_;
+}
+long PublicKey_Data(void *p, void **data)
+{
+    NULLRET(p);
+    NULLRET(data);
+    *data = &((PublicKey_ *)p)->data; // a view owned by the key, like the reference (S/c/publickey.cpp)
+    return S_OK_;
+}
+long PublicKey_ParmsId(void *p, uint64_t *id)
+{
+    NULLRET(p);
+    NULLRET(id);
+    std::copy_n(((PublicKey_ *)p)->data.parms_id.begin(), 4, id);
+    return S_OK_;
+}
+long PublicKey_Destroy(void *p)
+{
+    NULLRET(p);
+    delete (PublicKey_ *)p;
+    return S_OK_;
+}
+long SecretKey_Create1(void **out)
+{
+    NULLRET(out);
+    *out = new SecretKey_();
+    return S_OK_;
+}
+long SecretKey_Create2(void *copy, void **out)
+{
+    NULLRET(copy);
+    NULLRET(out);
+    *out = new SecretKey_(*(SecretKey_ *)copy);
+    return S_OK_;
+}
+long SecretKey_Data(void *p, void **data)
+{
+    NULLRET(p);
+    NULLRET(data);
+    *data = &((SecretKey_ *)p)->data;
+    return S_OK_;
+}
+long SecretKey_ParmsId(void *p, uint64_t *id)
+{
+    NULLRET(p);
+    NULLRET(id);
+    std::copy_n(((SecretKey_ *)p)->data.parms_id.begin(), 4, id);
+    return S_OK_;
+}
+long SecretKey_Destroy(void *p)
+{
+    NULLRET(p);
+    delete (SecretKey_ *)p;
+    return S_OK_;
+}
+long B200_SecretKey_SetWords(void *p, void *context, const uint64_t *words)
+{
+    NULLRET(p);
+    NULLRET(context);
+    NULLRET(words);
+    auto *c = (Context_ *)context;
+    if (!c->parameters_set)
+        return E_INVALIDARG_;
+    auto *sk = (SecretKey_ *)p;
+    sk->data.coeffs.assign(words, words + c->parms.coeff.size() * c->parms.n);
+    sk->data.parms_id = c->ids[0];
+    return S_OK_;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// KSwitchKeys
+// ---------------------------------------------------------------------------------------------------------
+long KSwitchKeys_Create1(void **out)
+{
+    NULLRET(out);
+    *out = new KSwitchKeys_();
+    return S_OK_;
+}
+long KSwitchKeys_Create2(void *copy, void **out)
+{
+    NULLRET(copy);
+    NULLRET(out);
+    auto *src = (KSwitchKeys_ *)copy;
+    auto *k = new KSwitchKeys_();
+    long hr = guard([&] {
+        k->parms_id = src->parms_id;
+        for (auto &l : src->keys)
+        {
+            k->keys.emplace_back();
+            for (auto *pk : l)
+            {
+                auto *n = new PublicKey_();
+                n->data.assign(pk->data);
+                k->keys.back().push_back(n);
+            }
+        }
+    });
+    if (hr)
+    {
+        delete k;
+        return hr;
+    }
+    *out = k;
+    return S_OK_;
+}
+long KSwitchKeys_Destroy(void *p)
+{
+    NULLRET(p);
+    delete (KSwitchKeys_ *)p;
+    return S_OK_;
+}
+long KSwitchKeys_Size(void *p, uint64_t *s)
+{
+    NULLRET(p);
+    NULLRET(s);
+    auto *k = (KSwitchKeys_ *)p;
+    *s = (uint64_t)std::count_if(k->keys.begin(), k->keys.end(), [](const std::vector<PublicKey_ *> &v) { return !v.empty(); });
+    return S_OK_;
+}
+long KSwitchKeys_RawSize(void *p, uint64_t *s)
+{
+    NULLRET(p);
+    NULLRET(s);
+    *s = ((KSwitchKeys_ *)p)->keys.size();
+    return S_OK_;
+}
+long KSwitchKeys_GetKeyList(void *p, uint64_t index, uint64_t *count, void **list)
+{
+    NULLRET(p);
+    NULLRET(count);
+    auto *k = (KSwitchKeys_ *)p;
+    if (index >= k->keys.size())
+        return ERROR_INVALID_INDEX_;
+    *count = k->keys[index].size();
+    if (!list)
+        return S_OK_;
+    for (size_t i = 0; i < k->keys[index].size(); i++)
+    { // copies owned by the caller (S/c/kswitchkeys.cpp: GetKeyFromVector)
+        auto *n = new PublicKey_();
+        n->data.assign(k->keys[index][i]->data);
+        list[i] = n;
+    }
+    return S_OK_;
+}
+long KSwitchKeys_ClearDataAndReserve(void *p, uint64_t size)
+{
+    NULLRET(p);
+    auto *k = (KSwitchKeys_ *)p;
+    k->clear();
+    k->keys.reserve(size);
+    return S_OK_;
+}
+long KSwitchKeys_AddKeyList(void *p, uint64_t count, void **list)
+{
+    NULLRET(p);
+    NULLRET(list);
+    auto *k = (KSwitchKeys_ *)p;
+    return guard([&] {
+        k->keys.emplace_back();
+        for (uint64_t i = 0; i < count; i++)
+        {
+            auto *n = new PublicKey_();
+            n->data.assign(((PublicKey_ *)list[i])->data);
+            k->keys.back().push_back(n);
+        }
+        k->drop_flat();
+    });
+}
+long KSwitchKeys_GetParmsId(void *p, uint64_t *id)
+{
+    NULLRET(p);
+    NULLRET(id);
+    std::copy_n(((KSwitchKeys_ *)p)->parms_id.begin(), 4, id);
+    return S_OK_;
+}
+long KSwitchKeys_SetParmsId(void *p, uint64_t *id)
+{
+    NULLRET(p);
+    NULLRET(id);
+    std::copy_n(id, 4, ((KSwitchKeys_ *)p)->parms_id.begin());
+    return S_OK_;
+}
+long RelinKeys_GetIndex(uint64_t key_power, uint64_t *index)
+{
+    NULLRET(index);
+    if (key_power < 2)
+        return E_INVALIDARG_;
+    *index = key_power - 2;
+    return S_OK_;
+}
+long GaloisKeys_GetIndex(uint32_t elt, uint64_t *index)
+{
+    NULLRET(index);
+    if (!(elt & 1) || elt < 3)
+        return E_INVALIDARG_; // GaloisTool::GetIndexFromElt (S/util/galois.h:139-147)
+    *index = (elt - 1) >> 1;
+    return S_OK_;
+}
+long B200_KSwitchKeys_SetKeyWords(void *p, void *context, uint64_t index, uint64_t decomp, const uint64_t *words)
+{
+    NULLRET(p);
+    NULLRET(context);
+    NULLRET(words);
+    auto *k = (KSwitchKeys_ *)p;
+    auto *c = (Context_ *)context;
+    return guard([&] {
+        if (!c->parameters_set)
+            throw InvalidArg("encryption parameters are not set correctly");
+        if (k->keys.size() <= index)
+            k->keys.resize(index + 1);
+        for (auto *pk : k->keys[index])
+            delete pk;
+        k->keys[index].clear();
+        const size_t K = c->parms.coeff.size(), n = c->parms.n, per = 2 * K * n;
+        for (uint64_t j = 0; j < decomp; j++)
+        {
+            auto *pk = new PublicKey_();
+            pk->data.parms_id = c->ids[0];
+            pk->data.size = 2;
+            pk->data.k = K;
+            pk->data.n = n;
+            pk->data.is_ntt_form = true;
+            pk->data.host.assign(words + per * j, words + per * (j + 1));
+            pk->data.host_valid = true;
+            k->keys[index].push_back(pk);
+        }
+        k->parms_id = c->ids[0];
+        k->drop_flat();
+    });
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Evaluator
+// ---------------------------------------------------------------------------------------------------------
+long Evaluator_Create(void *context, void **out)
+{
+    NULLRET(context);
+    NULLRET(out);
+    auto *c = (Context_ *)context;
+    if (!c->parameters_set)
+        return E_INVALIDARG_; // "encryption parameters are not set correctly" (S/evaluator.cpp:66-71)
+    auto *e = new Evaluator_();
+    e->ctx = c;
+    *out = e;
+    return S_OK_;
+}
+long Evaluator_Destroy(void *p)
+{
+    NULLRET(p);
+    delete (Evaluator_ *)p;
+    return S_OK_;
+}
+long Evaluator_ContextUsingKeyswitching(void *p, bool *b)
+{
+    NULLRET(p);
+    NULLRET(b);
+    *b = ((Evaluator_ *)p)->ctx->using_keyswitching;
+    return S_OK_;
+}
+long Evaluator_Negate(void *p, void *enc, void *dst)
+{
+    NULLRET(p);
+    NULLRET(enc);
+    NULLRET(dst);
+    auto *c = ((Evaluator_ *)p)->ctx;
+    auto &a = *(Ciphertext_ *)enc;
+    auto &d = *(Ciphertext_ *)dst;
+    return guard([&] {
+        std::lock_guard<std::mutex> lk(c->mu);
+        int lv = data_level(c, a, "encrypted is not valid for encryption parameters");
+        const u64 *pa = a.dev_ptr(c);
+        bool ntt = a.is_ntt_form;
+        with_output(c, d, { &a }, a.parms_id, a.size, a.k,
+                    [&](u64 *out) { dev_check(b200_negate(c->dev, lv, pa, out, (int)a.size, 1, nullptr)); });
+        d.is_ntt_form = ntt;
+        transparent_guard(c, lv, d);
+    });
+}
+long Evaluator_Add(void *p, void *a, void *b, void *dst)
+{
+    NULLRET(p);
+    NULLRET(a);
+    NULLRET(b);
+    NULLRET(dst);
+    return guard([&] { op_addsub(((Evaluator_ *)p)->ctx, *(Ciphertext_ *)a, *(Ciphertext_ *)b, *(Ciphertext_ *)dst, 0); });
+}
+long Evaluator_Sub(void *p, void *a, void *b, void *dst)
+{
+    NULLRET(p);
+    NULLRET(a);
+    NULLRET(b);
+    NULLRET(dst);
+    return guard([&] { op_addsub(((Evaluator_ *)p)->ctx, *(Ciphertext_ *)a, *(Ciphertext_ *)b, *(Ciphertext_ *)dst, 1); });
+}
+long Evaluator_AddMany(void *p, uint64_t count, void **encs, void *dst)
+{
+    NULLRET(p);
+    NULLRET(encs);
+    NULLRET(dst);
+    auto *c = ((Evaluator_ *)p)->ctx;
+    return guard([&] {
+        if (count == 0)
+            throw InvalidArg("encrypteds cannot be empty");
+        for (uint64_t i = 0; i < count; i++)
+            if (!encs[i] || encs[i] == dst)
+                throw InvalidArg("encrypteds must be different from destination");
+        // destination = encrypteds[0]; then add_inplace the rest in order (S/evaluator.cpp:319-350)
+        auto &d = *(Ciphertext_ *)dst;
+        d.assign(*(Ciphertext_ *)encs[0]);
+        for (uint64_t i = 1; i < count; i++)
+            op_addsub(c, d, *(Ciphertext_ *)encs[i], d, 0);
+    });
+}
+long Evaluator_Multiply(void *p, void *a, void *b, void *dst, void *)
+{
+    NULLRET(p);
+    NULLRET(a);
+    NULLRET(b);
+    NULLRET(dst);
+    return guard([&] { op_multiply(((Evaluator_ *)p)->ctx, *(Ciphertext_ *)a, *(Ciphertext_ *)b, *(Ciphertext_ *)dst, false); });
+}
+long Evaluator_Square(void *p, void *a, void *dst, void *)
+{
+    NULLRET(p);
+    NULLRET(a);
+    NULLRET(dst);
+    return guard([&] { op_multiply(((Evaluator_ *)p)->ctx, *(Ciphertext_ *)a, *(Ciphertext_ *)a, *(Ciphertext_ *)dst, true); });
+}
+long Evaluator_Relinearize(void *p, void *a, void *keys, void *dst, void *)
+{
+    NULLRET(p);
+    NULLRET(a);
+    NULLRET(keys);
+    NULLRET(dst);
+    return guard([&] { op_relinearize(((Evaluator_ *)p)->ctx, *(Ciphertext_ *)a, *(KSwitchKeys_ *)keys, *(Ciphertext_ *)dst); });
+}
+long Evaluator_MultiplyMany(void *p, uint64_t count, void **encs, void *relin_keys, void *dst, void *)
+{
+    NULLRET(p);
+    NULLRET(encs);
+    NULLRET(relin_keys);
+    NULLRET(dst);
+    auto *c = ((Evaluator_ *)p)->ctx;
+    auto &keys = *(KSwitchKeys_ *)relin_keys;
+    return guard([&] {
+        // Evaluator::multiply_many (S/evaluator.cpp:1535-1605): pairwise products appended to a work list
+        if (count == 0)
+            throw InvalidArg("encrypteds vector must not be empty");
+        for (uint64_t i = 0; i < count; i++)
+            if (!encs[i] || encs[i] == dst)
+                throw InvalidArg("encrypteds must be different from destination");
+        auto &d = *(Ciphertext_ *)dst;
+        if (count == 1)
+        {
+            d.assign(*(Ciphertext_ *)encs[0]);
+            return;
+        }
+        std::vector<std::unique_ptr<Ciphertext_>> prod;
+        auto mulrelin = [&](Ciphertext_ &x, Ciphertext_ &y, bool same) {
+            std::unique_ptr<Ciphertext_> t(new Ciphertext_()), r(new Ciphertext_());
+            op_multiply(c, x, same ? x : y, *t, same);
+            op_relinearize(c, *t, keys, *r);
+            prod.push_back(std::move(r));
+        };
+        for (uint64_t i = 0; i + 1 < count; i += 2)
+            mulrelin(*(Ciphertext_ *)encs[i], *(Ciphertext_ *)encs[i + 1], encs[i] == encs[i + 1]);
+        if (count & 1)
+        {
+            std::unique_ptr<Ciphertext_> t(new Ciphertext_());
+            t->assign(*(Ciphertext_ *)encs[count - 1]);
+            prod.push_back(std::move(t));
+        }
+        for (size_t i = 0; i + 1 < prod.size(); i += 2)
+            mulrelin(*prod[i], *prod[i + 1], false);
+        d.assign(*prod.back());
+    });
+}
+long Evaluator_Exponentiate(void *p, void *a, uint64_t exponent, void *relin_keys, void *dst, void *pool)
+{
+    NULLRET(p);
+    NULLRET(a);
+    NULLRET(relin_keys);
+    NULLRET(dst);
+    if (exponent == 0)
+        return E_INVALIDARG_;
+    if (exponent == 1)
+        return Ciphertext_Set(dst, a);
+    // exponentiate_inplace: multiply_many over `exponent` copies (S/evaluator.cpp:1607-1643); the copies are
+    // distinct objects there, so the square shortcut of multiply_many (same data pointer) does not trigger
+    std::vector<std::unique_ptr<Ciphertext_>> copies;
+    std::vector<void *> ptrs;
+    long hr = guard([&] {
+        for (uint64_t i = 0; i < exponent; i++)
+        {
+            copies.emplace_back(new Ciphertext_());
+            copies.back()->assign(*(Ciphertext_ *)a);
+            ptrs.push_back(copies.back().get());
+        }
+    });
+    if (hr)
+        return hr;
+    Ciphertext_ tmp;
+    hr = Evaluator_MultiplyMany(p, exponent, ptrs.data(), relin_keys, &tmp, pool);
+    if (hr)
+        return hr;
+    return Ciphertext_Set(dst, &tmp);
+}
+long Evaluator_ModSwitchToNext1(void *p, void *a, void *dst, void *)
+{
+    NULLRET(p);
+    NULLRET(a);
+    NULLRET(dst);
+    auto *c = ((Evaluator_ *)p)->ctx;
+    auto &x = *(Ciphertext_ *)a;
+    auto &d = *(Ciphertext_ *)dst;
+    return guard([&] {
+        std::lock_guard<std::mutex> lk(c->mu);
+        int lv = data_level(c, x, "encrypted is not valid for encryption parameters");
+        if (lv + 1 >= c->levels)
+            throw InvalidArg("end of modulus switching chain reached");
+        if (x.is_ntt_form)
+            throw InvalidArg("BFV encrypted cannot be in NTT form");
+        const u64 *px = x.dev_ptr(c);
+        with_output(c, d, { &x }, c->ids[lv + 1], x.size, x.k - 1,
+                    [&](u64 *out) { dev_check(b200_mod_switch_to_next(c->dev, lv, px, (int)x.size, out, 1, nullptr)); });
+        transparent_guard(c, lv + 1, d);
+    });
+}
+long Evaluator_AddPlain(void *p, void *a, void *pl, void *dst)
+{
+    NULLRET(p);
+    NULLRET(a);
+    NULLRET(pl);
+    NULLRET(dst);
+    return guard([&] { op_plain(((Evaluator_ *)p)->ctx, *(Ciphertext_ *)a, *(Plaintext_ *)pl, *(Ciphertext_ *)dst, 0); });
+}
+long Evaluator_SubPlain(void *p, void *a, void *pl, void *dst)
+{
+    NULLRET(p);
+    NULLRET(a);
+    NULLRET(pl);
+    NULLRET(dst);
+    return guard([&] { op_plain(((Evaluator_ *)p)->ctx, *(Ciphertext_ *)a, *(Plaintext_ *)pl, *(Ciphertext_ *)dst, 1); });
+}
+long Evaluator_MultiplyPlain(void *p, void *a, void *pl, void *dst, void *)
+{
+    NULLRET(p);
+    NULLRET(a);
+    NULLRET(pl);
+    NULLRET(dst);
+    return guard([&] { op_plain(((Evaluator_ *)p)->ctx, *(Ciphertext_ *)a, *(Plaintext_ *)pl, *(Ciphertext_ *)dst, 2); });
+}
+long Evaluator_ApplyGalois(void *p, void *a, uint32_t elt, void *keys, void *dst, void *)
+{
+    NULLRET(p);
+    NULLRET(a);
+    NULLRET(keys);
+    NULLRET(dst);
+    auto *c = ((Evaluator_ *)p)->ctx;
+    return guard([&] {
+        std::lock_guard<std::mutex> lk(c->mu);
+        op_galois(c, *(Ciphertext_ *)a, elt, *(KSwitchKeys_ *)keys, *(Ciphertext_ *)dst);
+    });
+}
+long Evaluator_RotateRows(void *p, void *a, int steps, void *keys, void *dst, void *)
+{
+    NULLRET(p);
+    NULLRET(a);
+    NULLRET(keys);
+    NULLRET(dst);
+    auto *c = ((Evaluator_ *)p)->ctx;
+    return guard([&] {
+        std::lock_guard<std::mutex> lk(c->mu);
+        op_rotate(c, *(Ciphertext_ *)a, steps, *(KSwitchKeys_ *)keys, *(Ciphertext_ *)dst);
+    });
+}
+long Evaluator_RotateColumns(void *p, void *a, void *keys, void *dst, void *)
+{
+    NULLRET(p);
+    NULLRET(a);
+    NULLRET(keys);
+    NULLRET(dst);
+    auto *c = ((Evaluator_ *)p)->ctx;
+    return guard([&] {
+        std::lock_guard<std::mutex> lk(c->mu);
+        if (!c->using_batching)
+            throw LogicErr("encryption parameters do not support batching");
+        op_galois(c, *(Ciphertext_ *)a, (uint32_t)(2 * c->parms.n - 1), *(KSwitchKeys_ *)keys, *(Ciphertext_ *)dst);
+    });
+}
+long B200_Evaluator_MultiplyRelinBatch(void *p, uint64_t count, void **e1, void **e2, void *relin_keys, void **dsts)
+{
+    NULLRET(p);
+    NULLRET(e1);
+    NULLRET(e2);
+    NULLRET(relin_keys);
+    NULLRET(dsts);
+    auto *c = ((Evaluator_ *)p)->ctx;
+    auto &keys = *(KSwitchKeys_ *)relin_keys;
+    return guard([&] {
+        if (count == 0)
+            return;
+        std::lock_guard<std::mutex> lk(c->mu);
+        auto &a0 = *(Ciphertext_ *)e1[0];
+        int lv = data_level(c, a0, "encrypted is not valid for encryption parameters");
+        const u64 k = a0.k, n = a0.n, w = 2 * k * n;
+        check_keys(c, keys, 0);
+        void *da = nullptr, *db = nullptr, *dout = nullptr;
+        dev_check(b200_malloc(c->dev, count * w * 8, &da));
+        dev_check(b200_malloc(c->dev, count * w * 8, &db));
+        dev_check(b200_malloc(c->dev, count * w * 8, &dout));
+        int rc = 0;
+        try
+        {
+            for (uint64_t i = 0; i < count; i++)
+            {
+                auto &a = *(Ciphertext_ *)e1[i];
+                auto &b = *(Ciphertext_ *)e2[i];
+                if (data_level(c, a, "encrypted1 is not valid") != lv || data_level(c, b, "encrypted2 is not valid") != lv ||
+                    a.size != 2 || b.size != 2 || a.is_ntt_form || b.is_ntt_form)
+                    throw InvalidArg("batch items must be size-2 ciphertexts at the same level");
+                dev_check(b200_memcpy_d2d(c->dev, (u64 *)da + i * w, a.dev_ptr(c), w * 8, nullptr));
+                dev_check(b200_memcpy_d2d(c->dev, (u64 *)db + i * w, b.dev_ptr(c), w * 8, nullptr));
+            }
+            dev_check(b200_multiply_relin(c->dev, lv, (u64 *)da, (u64 *)db, keys.flat_dev(c, 0, (int)k), (u64 *)dout, count, nullptr));
+            for (uint64_t i = 0; i < count; i++)
+            {
+                auto &d = *(Ciphertext_ *)dsts[i];
+                u64 *o = d.prepare_output(c, a0.parms_id, 2, k);
+                dev_check(b200_memcpy_d2d(c->dev, o, (u64 *)dout + i * w, w * 8, nullptr));
+            }
+        }
+        catch (...)
+        {
+            rc = 1;
+            b200_stream_synchronize(c->dev, nullptr);
+            b200_free(c->dev, da);
+            b200_free(c->dev, db);
+            b200_free(c->dev, dout);
+            throw;
+        }
+        (void)rc;
+        b200_stream_synchronize(c->dev, nullptr);
+        b200_free(c->dev, da);
+        b200_free(c->dev, db);
+        b200_free(c->dev, dout);
+    });
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Decryptor
+// ---------------------------------------------------------------------------------------------------------
+long Decryptor_Create(void *context, void *secret_key, void **out)
+{
+    NULLRET(context);
+    NULLRET(secret_key);
+    NULLRET(out);
+    auto *c = (Context_ *)context;
+    auto *sk = (SecretKey_ *)secret_key;
+    if (!c->parameters_set)
+        return E_INVALIDARG_;
+    if (sk->data.parms_id != c->ids[0] || sk->data.coeffs.size() != c->parms.coeff.size() * c->parms.n)
+        return E_INVALIDARG_; // "secret key is not valid for encryption parameters" (S/decryptor.cpp:54-77)
+    auto *d = new Decryptor_();
+    d->ctx = c;
+    d->sk = sk->data.coeffs;
+    *out = d;
+    return S_OK_;
+}
+long Decryptor_Destroy(void *p)
+{
+    NULLRET(p);
+    delete (Decryptor_ *)p;
+    return S_OK_;
+}
+long Decryptor_Decrypt(void *p, void *enc, void *dst)
+{
+    NULLRET(p);
+    NULLRET(enc);
+    NULLRET(dst);
+    auto *d = (Decryptor_ *)p;
+    auto *c = d->ctx;
+    auto &ct = *(Ciphertext_ *)enc;
+    auto &pl = *(Plaintext_ *)dst;
+    return guard([&] {
+        std::lock_guard<std::mutex> lk(c->mu);
+        int lv = data_level(c, ct, "encrypted is not valid for encryption parameters");
+        if (ct.is_ntt_form)
+            throw InvalidArg("encrypted cannot be in NTT form");
+        const size_t n = c->parms.n;
+        const u64 *pc = ct.dev_ptr(c);
+        const u64 *pw = d->powers(lv, (int)ct.size - 1);
+        void *dp = nullptr;
+        dev_check(b200_malloc(c->dev, n * 8, &dp));
+        std::vector<u64> out(n);
+        int rc = b200_decrypt(c->dev, lv, pc, (int)ct.size, pw, (u64 *)dp, 1, nullptr);
+        if (!rc)
+            rc = b200_memcpy_d2h(c->dev, out.data(), dp, n * 8, nullptr);
+        if (!rc)
+            rc = b200_stream_synchronize(c->dev, nullptr);
+        b200_free(c->dev, dp);
+        dev_check(rc);
+        // trim leading zero coefficients (S/decryptor.cpp:186-193)
+        size_t cnt = n;
+        while (cnt > 0 && out[cnt - 1] == 0)
+            cnt--;
+        pl.coeffs.assign(out.begin(), out.begin() + std::max<size_t>(cnt, 1));
+        pl.parms_id = kZeroId;
+        pl.scale = 1.0;
+    });
+}
+long Decryptor_InvariantNoiseBudget(void *p, void *enc, int *budget)
+{
+    NULLRET(p);
+    NULLRET(enc);
+    NULLRET(budget);
+    auto *d = (Decryptor_ *)p;
+    auto *c = d->ctx;
+    auto &ct = *(Ciphertext_ *)enc;
+    return guard([&] {
+        // Decryptor::invariant_noise_budget (S/decryptor.cpp:424-527): norm of t * (ct . sk) mod Q, centred
+        std::lock_guard<std::mutex> lk(c->mu);
+        int lv = data_level(c, ct, "encrypted is not valid for encryption parameters");
+        if (ct.is_ntt_form)
+            throw InvalidArg("encrypted cannot be in NTT form");
+        const size_t n = c->parms.n;
+        const int k = c->level_k[lv];
+        const u64 *pc = ct.dev_ptr(c);
+        const u64 *pw = d->powers(lv, (int)ct.size - 1);
+        void *dp = nullptr;
+        dev_check(b200_malloc(c->dev, (size_t)k * n * 8, &dp));
+        std::vector<u64> ph((size_t)k * n);
+        int rc = b200_ct_sk_phase(c->dev, lv, pc, (int)ct.size, pw, (u64 *)dp, 1, nullptr);
+        if (!rc)
+            rc = b200_memcpy_d2h(c->dev, ph.data(), dp, ph.size() * 8, nullptr);
+        if (!rc)
+            rc = b200_stream_synchronize(c->dev, nullptr);
+        b200_free(c->dev, dp);
+        dev_check(rc);
+        // CRT-compose each coefficient (Garner-free: sum_i [x_i * t * (Q/q_i)^-1]_{q_i} * (Q/q_i) mod Q) and take
+        // the infinity norm of the centred values.  Multi-precision on the host, like the reference.
+        typedef unsigned __int128 u128;
+        std::vector<u64> q(c->parms.coeff.begin(), c->parms.coeff.begin() + k);
+        b200::BigUInt Q(1);
+        for (u64 v : q)
+            Q.mul(v);
+        const size_t W = Q.w.size();
+        std::vector<std::vector<u64>> punc(k, std::vector<u64>(W, 0));
+        std::vector<u64> inv(k);
+        for (int i = 0; i < k; i++)
+        {
+            b200::BigUInt P(1);
+            u64 pm = 1;
+            for (int j = 0; j < k; j++)
+                if (j != i)
+                {
+                    P.mul(q[j]);
+                    pm = (u64)((u128)pm * (q[j] % q[i]) % q[i]);
+                }
+            std::copy(P.w.begin(), P.w.end(), punc[i].begin());
+            inv[i] = b200::inv_mod(pm, q[i]);
+        }
+        std::vector<u64> Qw(W + 1, 0), half(W + 1, 0);
+        std::copy(Q.w.begin(), Q.w.end(), Qw.begin());
+        { // half = (Q + 1) / 2 comparison threshold: value >= half  <=>  centred negative (poly_infty_norm_coeffmod)
+            std::vector<u64> tmp(Qw);
+            u64 carry = 1;
+            for (auto &x : tmp)
+            {
+                u64 s = x + carry;
+                carry = s < x;
+                x = s;
+            }
+            for (size_t i = 0; i < tmp.size(); i++)
+                half[i] = (tmp[i] >> 1) | (i + 1 < tmp.size() ? tmp[i + 1] << 63 : 0);
+        }
+        auto ge = [&](const std::vector<u64> &a, const std::vector<u64> &b) {
+            for (size_t i = a.size(); i-- > 0;)
+                if (a[i] != b[i])
+                    return a[i] > b[i];
+            return true;
+        };
+        auto sub = [&](std::vector<u64> &a, const std::vector<u64> &b) {
+            u64 borrow = 0;
+            for (size_t i = 0; i < a.size(); i++)
+            {
+                u64 bi = b[i] + borrow;
+                u64 nb = (bi < borrow) || (a[i] < bi);
+                a[i] -= bi;
+                borrow = nb;
+            }
+        };
+        std::vector<u64> norm(W + 1, 0);
+        const u64 t = c->parms.plain;
+        for (size_t cidx = 0; cidx < n; cidx++)
+        {
+            std::vector<u64> acc(W + 1, 0);
+            for (int i = 0; i < k; i++)
+            {
+                u64 x = (u64)((u128)ph[(size_t)i * n + cidx] * (t % q[i]) % q[i]);
+                u64 y = (u64)((u128)x * inv[i] % q[i]);
+                u64 carry = 0;
+                for (size_t w = 0; w < W; w++)
+                {
+                    u128 m = (u128)punc[i][w] * y + acc[w] + carry;
+                    acc[w] = (u64)m;
+                    carry = (u64)(m >> 64);
+                }
+                acc[W] += carry;
+                while (ge(acc, Qw))
+                    sub(acc, Qw);
+            }
+            if (ge(acc, half))
+            { // centred magnitude = Q - acc
+                std::vector<u64> m(Qw);
+                sub(m, acc);
+                acc = m;
+            }
+            if (ge(acc, norm))
+                norm = acc;
+        }
+        int nb = 0;
+        for (size_t i = norm.size(); i-- > 0;)
+            if (norm[i])
+            {
+                nb = (int)(64 * i + 64 - __builtin_clzll(norm[i]));
+                break;
+            }
+        *budget = std::max(0, Q.bit_length() - nb - 1);
+    });
+}
+
+} // extern "C"

@@ -78,5 +78,5 @@ inline void emu_launch(dim3 grid, dim3 block, size_t smem, bool single_thread, F
 }
 // kernels with shared memory (or block-wide votes) run as ONE thread per CTA; the rest thread by thread
 #define B200_LAUNCH(kernel, grid, block, smem, stream, ...)                                                            \
-    emu_launch(dim3(grid), dim3(block), (size_t)(smem), (smem) != 0 || sizeof(#kernel) == sizeof("transparent_kernel"), \
+    emu_launch(dim3(grid), dim3(block), (size_t)(smem), (smem) != 0 || std::strcmp(#kernel, "transparent_kernel") == 0, \
                [&]() { kernel(__VA_ARGS__); })

@@ -1,0 +1,25 @@
+"""SEAL-named ABI layer (include/b200_sealc.h) on the CPU emulation build: FFI call sequences of seal_fhe replayed
+against our library and the reference, every word / HRESULT compared."""
+import pytest
+
+import sealc_checks as sc
+from params import PARAMS
+from sealc_driver import Sealc
+
+
+@pytest.fixture(scope="module")
+def S(emu_lib):
+    return Sealc(emu_lib.lib)
+
+
+def test_simple_multiply_ffi_sequence(S, ref):
+    sc.simple_multiply_sequence(S, *PARAMS["n4096"])
+
+
+@pytest.mark.parametrize("name", ["n4096", "n8192"])
+def test_evaluator_surface(S, ref, name):
+    sc.evaluator_surface(S, *PARAMS[name])
+
+
+def test_error_codes(S, ref):
+    sc.error_codes(S, ref, *PARAMS["n4096"])

@@ -1,0 +1,55 @@
+"""SEAL-named ABI layer on the real CUDA library (pytest -m gpu): the same FFI sequences as test_sealc_emu.py."""
+import ctypes as C
+import os
+
+import pytest
+
+import sealc_checks as sc
+from params import PARAMS
+from sealc_driver import Sealc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def S():
+    from sunscreen_b200.lib import B200Lib
+    lib = B200Lib.default()
+    assert os.path.basename(lib.path) == "libb200bfv.so"
+    return Sealc(lib.lib)
+
+
+def test_simple_multiply_ffi_sequence(S, ref):
+    sc.simple_multiply_sequence(S, *PARAMS["n4096"])
+
+
+@pytest.mark.parametrize("name", ["n4096", "n8192", "n16384"])
+def test_evaluator_surface(S, ref, name):
+    sc.evaluator_surface(S, *PARAMS[name])
+
+
+def test_error_codes(S, ref):
+    sc.error_codes(S, ref, *PARAMS["n4096"])
+
+
+def test_batched_multiply_relin_seam(S, ref):
+    """B200_Evaluator_MultiplyRelinBatch == per-handle Evaluator_Multiply + Evaluator_Relinearize."""
+    import numpy as np
+    import refseal
+    n, moduli, t = PARAMS["n8192"]
+    O = S.context(n, moduli, t)
+    inp = refseal.appendix_b_inputs(n, moduli, t)
+    rng = np.random.default_rng(2)
+    rlk = O.new_ksk({0: inp["rlk"]})
+    As, Bs, exp = [], [], []
+    for i in range(4):
+        a = np.stack([rng.integers(0, moduli[r], size=(2, n), dtype=np.uint64) for r in range(O.k)], axis=1)
+        b = np.stack([rng.integers(0, moduli[r], size=(2, n), dtype=np.uint64) for r in range(O.k)], axis=1)
+        ha, hb = O.new_ct(a), O.new_ct(b)
+        As.append(ha); Bs.append(hb)
+        exp.append(O.ct_words(O.relinearize(O.multiply(ha, hb), rlk)))
+    dsts = [O._dst() for _ in range(4)]
+    vp = C.c_void_p
+    O.S.call("B200_Evaluator_MultiplyRelinBatch", O.ev, C.c_uint64(4), (vp * 4)(*As), (vp * 4)(*Bs), rlk, (vp * 4)(*dsts))
+    for d, e in zip(dsts, exp):
+        assert np.array_equal(O.ct_words(d), e)
