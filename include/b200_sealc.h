@@ -12,9 +12,10 @@
  * executor (sunscreen_runtime/src/run.rs:415-469).
  *
  * Covered in this round: parameter objects, SEALContext, Ciphertext/Plaintext/PublicKey/SecretKey/KSwitchKeys data
- * objects, the whole BFV Evaluator surface seal_fhe uses, and Decryptor (decrypt + invariant noise budget).
- * KeyGenerator / Encryptor / BatchEncoder / Save-Load / PolynomialArray are "next" rows (SURVEY.md §8(a) row E and
- * §8(f)): keys and fresh ciphertexts produced by the reference are imported through the data-object accessors.
+ * objects, the whole BFV Evaluator surface seal_fhe uses, Decryptor (decrypt + invariant noise budget), KeyGenerator
+ * and Encryptor (sampling on the host with the reference's PRNG stream, arithmetic on the GPU).
+ * BatchEncoder / Save-Load / PolynomialArray / the ReturnComponents encryption variants are "next" rows
+ * (SURVEY.md §8(f)).
  * B200_* names are extensions (bulk word access, batching) that the reference does not have.
  */
 #ifndef B200_SEALC_H
@@ -157,7 +158,28 @@ SEAL_C_FUNC Decryptor_Destroy(void *thisptr);
 SEAL_C_FUNC Decryptor_Decrypt(void *thisptr, void *encrypted, void *destination);
 SEAL_C_FUNC Decryptor_InvariantNoiseBudget(void *thisptr, void *encrypted, int *invariant_noise_budget);
 
+/* ---- KeyGenerator (S/c/keygenerator.h) : host-side sampling (the reference's Blake2xb stream), GPU arithmetic ---- */
+SEAL_C_FUNC KeyGenerator_Create1(void *context, void **key_generator);
+SEAL_C_FUNC KeyGenerator_Create2(void *context, void *secret_key, void **key_generator);
+SEAL_C_FUNC KeyGenerator_Destroy(void *thisptr);
+SEAL_C_FUNC KeyGenerator_SecretKey(void *thisptr, void **secret_key);
+SEAL_C_FUNC KeyGenerator_CreatePublicKey(void *thisptr, bool save_seed, void **public_key);
+SEAL_C_FUNC KeyGenerator_CreateRelinKeys(void *thisptr, bool save_seed, void **relin_keys);
+SEAL_C_FUNC KeyGenerator_CreateGaloisKeysFromElts(void *thisptr, uint64_t count, uint32_t *galois_elts, bool save_seed,
+                                                  void **galois_keys);
+SEAL_C_FUNC KeyGenerator_CreateGaloisKeysFromSteps(void *thisptr, uint64_t count, int *steps, bool save_seed, void **galois_keys);
+SEAL_C_FUNC KeyGenerator_CreateGaloisKeysAll(void *thisptr, bool save_seed, void **galois_keys);
+
+/* ---- Encryptor (S/c/encryptor.h) ---- */
+SEAL_C_FUNC Encryptor_Create(void *context, void *public_key, void *secret_key, void **encryptor);
+SEAL_C_FUNC Encryptor_Destroy(void *thisptr);
+SEAL_C_FUNC Encryptor_Encrypt(void *thisptr, void *plaintext, void *destination, void *pool_handle);
+SEAL_C_FUNC Encryptor_EncryptSymmetric(void *thisptr, void *plaintext, bool save_seed, void *destination, void *pool_handle);
+
 /* ---- extensions (not in the reference) ---- */
+/* deterministic pk-encryption from a 64-byte seed: the same random stream (and therefore the same ciphertext words)
+   as the reference's Encryptor_EncryptReturnComponentsSetSeed (S/c/encryptor.cpp:185-240) */
+SEAL_C_FUNC B200_Encryptor_EncryptSetSeed(void *thisptr, void *plaintext, const uint64_t *seed8, void *destination);
 /* bulk word access: the reference only offers word-at-a-time accessors */
 SEAL_C_FUNC B200_Ciphertext_SetWords(void *thisptr, void *context, uint64_t *parms_id, uint64_t size, bool is_ntt_form,
                                      const uint64_t *words);

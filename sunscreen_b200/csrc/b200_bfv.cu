@@ -78,8 +78,9 @@ __global__ void __launch_bounds__(NT, (LOGN <= 13 ? (NT <= 256 ? 3 : 2) : 1)) nt
 #ifndef B200_EMU_HEADER
     extern __shared__ u64 ntt_sm[];
     const long long block = (long long)blockIdx.x;
-    const long long item = block / job.slots;
-    const int slot = (int)(block - item * job.slots);
+    // slot-major order: CTAs that run at the same time work on the same prime, so the early-pass twiddles stay in L1
+    const int slot = job.slot_major ? (int)(block / job.items) : (int)(block % job.slots);
+    const long long item = job.slot_major ? block - (long long)slot * job.items : block / job.slots;
     const int pidx = job.slot_prime[slot];
     const NttPrimeFp PF = job.fprimes[pidx];
     const NttPrime PI_ = job.primes[pidx];
@@ -425,6 +426,12 @@ struct b200_ctx
     std::mutex mu;
     std::atomic<uint64_t> launches{ 0 };
     cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
+    // side streams for intra-call concurrency: sub-batches of one call run on different streams so that the
+    // FP64-bound NTT kernels of one overlap the HBM-bound element-wise kernels of another
+    static const int NSIDE = 4;
+    cudaStream_t s_side[NSIDE] = { nullptr, nullptr, nullptr, nullptr };
+    cudaEvent_t ev_fork = nullptr, ev_join[NSIDE] = { nullptr, nullptr, nullptr, nullptr };
+    int mr_split = 1;
     // staging ring of the *_host entry points (allocated on first use, reused afterwards)
     static const int NBUF = 3;
     u64 *hp_a[NBUF] = { nullptr, nullptr, nullptr }, *hp_b[NBUF] = { nullptr, nullptr, nullptr }, *hp_o[NBUF] = { nullptr, nullptr, nullptr };
@@ -778,6 +785,9 @@ static int launch_ntt(b200_ctx *ctx, const JobDesc &jd, const u64 *src, long lon
     job.primes = ctx->d_ntt_primes;
     job.fprimes = ctx->d_fp_primes;
     job.reduce_input = reduce_input;
+    job.items = items;
+    static const int slot_major = std::getenv("B200_NTT_ITEM_MAJOR") ? 0 : 1;
+    job.slot_major = slot_major;
     job.npass = ctx->npass;
     for (int i = 0; i < 8; i++)
         job.pass_L[i] = ctx->pass_L[i];
@@ -1097,6 +1107,14 @@ int b200_ctx_create(uint64_t n, const uint64_t *coeff_modulus, uint64_t count, u
     CU_TRY(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
     CU_TRY(cudaStreamCreateWithFlags(&ctx->s_comp, cudaStreamNonBlocking));
     CU_TRY(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < b200_ctx::NSIDE; i++)
+    {
+        CU_TRY(cudaStreamCreateWithFlags(&ctx->s_side[i], cudaStreamNonBlocking));
+        CU_TRY(cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming));
+    }
+    CU_TRY(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    if (const char *sp = getenv("B200_MR_SPLIT"))
+        ctx->mr_split = std::max(1, std::min((int)b200_ctx::NSIDE, atoi(sp)));
     CU_TRY(cudaDeviceSynchronize());
     *out = ctx.release();
     return 0;
@@ -1357,8 +1375,8 @@ int b200_relinearize(b200_ctx *ctx, int level, const uint64_t *in3, const uint64
                           3LL * k * n, (u64 *)out2, 2LL * k * n, (long long)batch, (cudaStream_t)stream);
 }
 
-int b200_multiply_relin(b200_ctx *ctx, int level, const uint64_t *a, const uint64_t *b, const uint64_t *relin_key,
-                        uint64_t *out2, uint64_t batch, void *stream)
+static int multiply_relin_one(b200_ctx *ctx, int level, const uint64_t *a, const uint64_t *b, const uint64_t *relin_key,
+                             uint64_t *out2, uint64_t batch, void *stream)
 {
     int rc = check_level(ctx, level);
     if (rc)
@@ -1381,6 +1399,31 @@ int b200_multiply_relin(b200_ctx *ctx, int level, const uint64_t *a, const uint6
     u64 *o = (u64 *)out2;
     return keyswitch_core(ctx, level, c2, (long long)k * n, (const u64 *)relin_key, o, 2LL * k * n, o + (long long)k * n,
                           2LL * k * n, o, 2LL * k * n, (long long)batch, s);
+}
+
+int b200_multiply_relin(b200_ctx *ctx, int level, const uint64_t *a, const uint64_t *b, const uint64_t *relin_key,
+                        uint64_t *out2, uint64_t batch, void *stream)
+{
+    int rc = check_level(ctx, level);
+    if (rc)
+        return rc;
+    const int parts = (ctx->mr_split > 1 && batch >= 64) ? ctx->mr_split : 1;
+    if (parts == 1)
+        return multiply_relin_one(ctx, level, a, b, relin_key, out2, batch, stream);
+    // fork: sub-batches on side streams, ordered after everything already enqueued on the caller's stream
+    CU_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t us = (cudaStream_t)stream;
+    const size_t w = (size_t)2 * ctx->levels[level].k * ctx->n;
+    CU_TRY(cudaEventRecord(ctx->ev_fork, us));
+    for (int p = 0; p < parts && !rc; p++)
+    {
+        const uint64_t lo = batch * p / parts, hi = batch * (p + 1) / parts;
+        CU_TRY(cudaStreamWaitEvent(ctx->s_side[p], ctx->ev_fork, 0));
+        rc = multiply_relin_one(ctx, level, a + lo * w, b + lo * w, relin_key, out2 + lo * w, hi - lo, ctx->s_side[p]);
+        CU_TRY(cudaEventRecord(ctx->ev_join[p], ctx->s_side[p]));
+        CU_TRY(cudaStreamWaitEvent(us, ctx->ev_join[p], 0));
+    }
+    return rc;
 }
 
 int b200_apply_galois(b200_ctx *ctx, int level, const uint64_t *in2, uint32_t galois_elt, const uint64_t *galois_key,
@@ -1459,6 +1502,29 @@ int b200_multiply_plain(b200_ctx *ctx, int level, const uint64_t *a, int size, c
     if ((rc = launch_ntt<false>(ctx, jd, (const u64 *)out, (long long)k * n, (u64 *)out, (long long)k * n,
                                 (long long)batch * size, 0, s)))
         return rc;
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+// out[item][poly][r][c] = x[item][poly][r][c] * y[item % y_batch][r][c] mod q_r  (dyadic_product_coeffmod,
+// S/util/polyarithsmallmod.cpp:226-284); any domain, canonical in/out
+int b200_dyadic_product(b200_ctx *ctx, int level, const uint64_t *x, int size, const uint64_t *y, uint64_t y_batch,
+                        uint64_t *out, uint64_t batch, void *stream)
+{
+    int rc = check_level(ctx, level);
+    if (rc)
+        return rc;
+    if (!x || !y || !out)
+        return fail(B200_E_NULL, "null pointer");
+    if (size < 1 || y_batch < 1)
+        return fail(B200_E_INVALID, "size / y_batch");
+    if (batch == 0)
+        return 0;
+    const int k = ctx->levels[level].k;
+    const long long total = (long long)batch * size * k * (long long)ctx->n;
+    B200_LAUNCH(dyadic_plain_kernel, blocks_for(total, EB), EB, 0, (cudaStream_t)stream, ctx->d_primes, k, size, (const u64 *)x,
+                (const u64 *)y, (long long)y_batch, (u64 *)out, ctx->logn, total);
+    ctx->launches++;
     CU_TRY(cudaGetLastError());
     return 0;
 }

@@ -50,6 +50,8 @@ struct NttJob
     const NttPrime *primes;
     const NttPrimeFp *fprimes; // FP64 fast-path descriptors, same indexing as primes[]
     int reduce_input;          // 1: inputs are arbitrary 64-bit words -> Barrett to [0,p) on load
+    long long items;           // number of items in this launch
+    int slot_major;            // block order (static FP kernel): 1 = all items of slot 0, then slot 1, ...
     int npass;                 // forward pass schedule (host: ntt_schedule); inverse runs it mirrored
     int pass_L[8];
 };

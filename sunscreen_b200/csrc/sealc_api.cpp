@@ -11,6 +11,7 @@
 #include "../../include/b200_bfv.h"
 #include "../../include/b200_sealc.h"
 #include "host_ctx.h"
+#include "sampling.h"
 #include <algorithm>
 #include <array>
 #include <cmath>
@@ -332,6 +333,100 @@ struct Decryptor_
         cache.push_back({ level, terms, (u64 *)p });
         return (u64 *)p;
     }
+};
+
+// ---- small device helpers for key generation / encryption (all arithmetic on the GPU through layer 1) ----
+struct DevBuf
+{
+    Context_ *c;
+    u64 *p = nullptr;
+    size_t words;
+    DevBuf(Context_ *ctx, size_t w) : c(ctx), words(w)
+    {
+        void *q = nullptr;
+        dev_check(b200_malloc(c->dev, std::max<size_t>(w, 1) * 8, &q));
+        p = (u64 *)q;
+    }
+    DevBuf(Context_ *ctx, const std::vector<u64> &h) : DevBuf(ctx, h.size()) { upload(h); }
+    ~DevBuf()
+    {
+        b200_stream_synchronize(c->dev, nullptr);
+        b200_free(c->dev, p);
+    }
+    void upload(const std::vector<u64> &h) { dev_check(b200_memcpy_h2d(c->dev, p, h.data(), h.size() * 8, nullptr)); }
+    std::vector<u64> download()
+    {
+        std::vector<u64> h(words);
+        dev_check(b200_memcpy_d2h(c->dev, h.data(), p, words * 8, nullptr));
+        dev_check(b200_stream_synchronize(c->dev, nullptr));
+        return h;
+    }
+    DevBuf(const DevBuf &) = delete;
+};
+
+// encrypt_zero_symmetric at the key level, NTT form, no seed saving (S/util/rlwe.cpp:312-459): returns [2][K][n]
+// c1 <- uniform (a fresh PRNG seeded from the bootstrap PRNG), c0 = -(s*c1 + e)
+std::vector<u64> encrypt_zero_symmetric_key_level(Context_ *c, const std::vector<u64> &sk, b200::Blake2xbPrng &bootstrap)
+{
+    const size_t n = c->parms.n, K = c->parms.coeff.size();
+    b200::PrngSeed pub;
+    bootstrap.generate(sizeof(pub), pub.data());
+    b200::Blake2xbPrng ct_prng(pub);
+    std::vector<u64> c1(K * n), noise(K * n);
+    b200::sample_poly_uniform(ct_prng, n, c->parms.coeff, c1.data());
+    b200::sample_poly_normal(bootstrap, n, c->parms.coeff, noise.data());
+    DevBuf d1(c, c1), de(c, noise), ds(c, sk), d0(c, K * n);
+    dev_check(b200_dyadic_product(c->dev, 0, ds.p, 1, d1.p, 1, d0.p, 1, nullptr)); // s (*) c1
+    dev_check(b200_ntt_forward(c->dev, 0, de.p, 1, nullptr));                      // NTT(e)
+    dev_check(b200_add(c->dev, 0, d0.p, de.p, d0.p, 1, 1, nullptr));
+    dev_check(b200_negate(c->dev, 0, d0.p, d0.p, 1, 1, nullptr));
+    std::vector<u64> out = d0.download();
+    out.insert(out.end(), c1.begin(), c1.end());
+    return out;
+}
+
+struct KeyGenerator_
+{
+    Context_ *ctx;
+    std::vector<u64> sk; // key level, NTT form [K][n]
+    // generate_one_kswitch_key (S/keygenerator.cpp:303-337): new_key = [K][n] NTT form
+    void one_kswitch_key(const std::vector<u64> &new_key, std::vector<PublicKey_ *> &dest)
+    {
+        Context_ *c = ctx;
+        const size_t n = c->parms.n, K = c->parms.coeff.size();
+        const int decomp = c->level_k[c->first_level];
+        const u64 qsp = c->parms.coeff.back();
+        b200::Blake2xbPrng bootstrap(b200::random_seed());
+        for (int J = 0; J < decomp; J++)
+        {
+            std::vector<u64> w = encrypt_zero_symmetric_key_level(c, sk, bootstrap);
+            const u64 qj = c->parms.coeff[J];
+            const u64 factor = qsp % qj;
+            for (size_t i = 0; i < n; i++)
+            { // c0[J] += factor * new_key[J]  (S/keygenerator.cpp:330-334)
+                u64 t = (u64)((unsigned __int128)new_key[(size_t)J * n + i] * factor % qj);
+                u64 &d = w[(size_t)J * n + i];
+                d = (u64)(((unsigned __int128)d + t) % qj);
+            }
+            auto *pk = new PublicKey_();
+            pk->data.parms_id = c->ids[0];
+            pk->data.size = 2;
+            pk->data.k = K;
+            pk->data.n = n;
+            pk->data.is_ntt_form = true;
+            pk->data.host = std::move(w);
+            pk->data.host_valid = true;
+            dest.push_back(pk);
+        }
+    }
+};
+
+struct Encryptor_
+{
+    Context_ *ctx;
+    bool has_pk = false, has_sk = false;
+    std::vector<u64> pk; // [2][K][n] NTT form, key level
+    std::vector<u64> sk; // [K][n]
 };
 
 template <class F>
@@ -2050,6 +2145,363 @@ long Decryptor_InvariantNoiseBudget(void *p, void *enc, int *budget)
                 break;
             }
         *budget = std::max(0, Q.bit_length() - nb - 1);
+    });
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// KeyGenerator (S/c/keygenerator.cpp -> S/keygenerator.cpp)
+// ---------------------------------------------------------------------------------------------------------
+long KeyGenerator_Create1(void *context, void **out)
+{
+    NULLRET(context);
+    NULLRET(out);
+    auto *c = (Context_ *)context;
+    if (!c->parameters_set)
+        return E_INVALIDARG_;
+    auto *kg = new KeyGenerator_();
+    kg->ctx = c;
+    long hr = guard([&] {
+        std::lock_guard<std::mutex> lk(c->mu);
+        const size_t n = c->parms.n, K = c->parms.coeff.size();
+        // generate_sk (S/keygenerator.cpp:57-92): ternary sample, then NTT at the key level
+        b200::Blake2xbPrng prng(b200::random_seed());
+        std::vector<u64> s(K * n);
+        b200::sample_poly_ternary(prng, n, c->parms.coeff, s.data());
+        DevBuf d(c, s);
+        dev_check(b200_ntt_forward(c->dev, 0, d.p, 1, nullptr));
+        kg->sk = d.download();
+    });
+    if (hr)
+    {
+        delete kg;
+        return hr;
+    }
+    *out = kg;
+    return S_OK_;
+}
+long KeyGenerator_Create2(void *context, void *secret_key, void **out)
+{
+    NULLRET(context);
+    NULLRET(secret_key);
+    NULLRET(out);
+    auto *c = (Context_ *)context;
+    auto *sk = (SecretKey_ *)secret_key;
+    if (!c->parameters_set || sk->data.parms_id != c->ids[0] || sk->data.coeffs.size() != c->parms.coeff.size() * c->parms.n)
+        return E_INVALIDARG_;
+    auto *kg = new KeyGenerator_();
+    kg->ctx = c;
+    kg->sk = sk->data.coeffs;
+    *out = kg;
+    return S_OK_;
+}
+long KeyGenerator_Destroy(void *p)
+{
+    NULLRET(p);
+    delete (KeyGenerator_ *)p;
+    return S_OK_;
+}
+long KeyGenerator_SecretKey(void *p, void **out)
+{
+    NULLRET(p);
+    NULLRET(out);
+    auto *kg = (KeyGenerator_ *)p;
+    auto *sk = new SecretKey_();
+    sk->data.coeffs = kg->sk;
+    sk->data.parms_id = kg->ctx->ids[0];
+    *out = sk;
+    return S_OK_;
+}
+long KeyGenerator_CreatePublicKey(void *p, bool /*save_seed*/, void **out)
+{
+    NULLRET(p);
+    NULLRET(out);
+    auto *kg = (KeyGenerator_ *)p;
+    auto *c = kg->ctx;
+    auto *pk = new PublicKey_();
+    long hr = guard([&] {
+        std::lock_guard<std::mutex> lk(c->mu);
+        b200::Blake2xbPrng bootstrap(b200::random_seed());
+        pk->data.host = encrypt_zero_symmetric_key_level(c, kg->sk, bootstrap); // generate_pk (S/keygenerator.cpp:94-122)
+        pk->data.host_valid = true;
+        pk->data.parms_id = c->ids[0];
+        pk->data.size = 2;
+        pk->data.k = c->parms.coeff.size();
+        pk->data.n = c->parms.n;
+        pk->data.is_ntt_form = true;
+    });
+    if (hr)
+    {
+        delete pk;
+        return hr;
+    }
+    *out = pk;
+    return S_OK_;
+}
+long KeyGenerator_CreateRelinKeys(void *p, bool /*save_seed*/, void **out)
+{
+    NULLRET(p);
+    NULLRET(out);
+    auto *kg = (KeyGenerator_ *)p;
+    auto *c = kg->ctx;
+    if (!c->using_keyswitching)
+        return COR_E_INVALIDOPERATION_;
+    auto *keys = new KSwitchKeys_();
+    long hr = guard([&] {
+        std::lock_guard<std::mutex> lk(c->mu);
+        const size_t n = c->parms.n, K = c->parms.coeff.size();
+        // s^2 in NTT form (compute_secret_key_array, S/keygenerator.cpp:245-300), then one key list (index 0)
+        DevBuf ds(c, kg->sk), d2(c, K * n);
+        dev_check(b200_dyadic_product(c->dev, 0, ds.p, 1, ds.p, 1, d2.p, 1, nullptr));
+        std::vector<u64> s2 = d2.download();
+        keys->keys.emplace_back();
+        kg->one_kswitch_key(s2, keys->keys[0]);
+        keys->parms_id = c->ids[0];
+    });
+    if (hr)
+    {
+        delete keys;
+        return hr;
+    }
+    *out = keys;
+    return S_OK_;
+}
+static long create_galois(KeyGenerator_ *kg, const std::vector<uint32_t> &elts, void **out)
+{
+    auto *c = kg->ctx;
+    if (!c->using_keyswitching)
+        return COR_E_INVALIDOPERATION_;
+    auto *keys = new KSwitchKeys_();
+    long hr = guard([&] {
+        std::lock_guard<std::mutex> lk(c->mu);
+        const size_t n = c->parms.n, K = c->parms.coeff.size();
+        int logn = 0;
+        while (((size_t)1 << logn) < n)
+            logn++;
+        keys->keys.resize(n);
+        for (uint32_t elt : elts)
+        {
+            if (!(elt & 1) || elt >= 2 * n)
+                throw InvalidArg("Galois element is not valid");
+            const size_t index = (elt - 1) >> 1;
+            if (!keys->keys[index].empty())
+                continue;
+            // apply_galois_ntt: a permutation of the NTT slots (S/util/galois.cpp:18-50,192-218)
+            std::vector<u64> rot(K * n);
+            for (size_t i = 0; i < n; i++)
+            {
+                const uint32_t rev = (uint32_t)b200::reverse_bits(n + i, logn + 1);
+                const u64 raw = (((u64)elt * rev) >> 1) & (n - 1);
+                const size_t src = (size_t)b200::reverse_bits(raw, logn);
+                for (size_t r = 0; r < K; r++)
+                    rot[r * n + i] = kg->sk[r * n + src];
+            }
+            kg->one_kswitch_key(rot, keys->keys[index]);
+        }
+        keys->parms_id = c->ids[0];
+    });
+    if (hr)
+    {
+        delete keys;
+        return hr;
+    }
+    *out = keys;
+    return S_OK_;
+}
+long KeyGenerator_CreateGaloisKeysFromElts(void *p, uint64_t count, uint32_t *elts, bool, void **out)
+{
+    NULLRET(p);
+    NULLRET(elts);
+    NULLRET(out);
+    return create_galois((KeyGenerator_ *)p, std::vector<uint32_t>(elts, elts + count), out);
+}
+long KeyGenerator_CreateGaloisKeysFromSteps(void *p, uint64_t count, int *steps, bool, void **out)
+{
+    NULLRET(p);
+    NULLRET(steps);
+    NULLRET(out);
+    auto *kg = (KeyGenerator_ *)p;
+    if (!kg->ctx->using_batching)
+        return COR_E_INVALIDOPERATION_;
+    std::vector<uint32_t> elts;
+    for (uint64_t i = 0; i < count; i++)
+    {
+        uint32_t e;
+        if (b200_galois_elt_from_step(kg->ctx->dev, steps[i], &e))
+            return E_INVALIDARG_;
+        elts.push_back(e);
+    }
+    return create_galois(kg, elts, out);
+}
+long KeyGenerator_CreateGaloisKeysAll(void *p, bool, void **out)
+{
+    NULLRET(p);
+    NULLRET(out);
+    auto *kg = (KeyGenerator_ *)p;
+    if (!kg->ctx->using_batching)
+        return COR_E_INVALIDOPERATION_;
+    // GaloisTool::get_elts_all (S/util/galois.cpp:106-131)
+    const uint32_t m = (uint32_t)(2 * kg->ctx->parms.n);
+    int logn = 0;
+    while (((size_t)1 << logn) < kg->ctx->parms.n)
+        logn++;
+    std::vector<uint32_t> elts{ m - 1 };
+    u64 pos = 3, neg = b200::inv_mod(3, m);
+    for (int i = 0; i < logn - 1; i++)
+    {
+        elts.push_back((uint32_t)pos);
+        pos = (pos * pos) & (m - 1);
+        elts.push_back((uint32_t)neg);
+        neg = (neg * neg) & (m - 1);
+    }
+    return create_galois(kg, elts, out);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Encryptor (S/c/encryptor.cpp -> S/encryptor.cpp:114-321)
+// ---------------------------------------------------------------------------------------------------------
+long Encryptor_Create(void *context, void *public_key, void *secret_key, void **out)
+{
+    NULLRET(context);
+    NULLRET(out);
+    auto *c = (Context_ *)context;
+    if (!c->parameters_set)
+        return E_INVALIDARG_;
+    auto *e = new Encryptor_();
+    e->ctx = c;
+    long hr = guard([&] {
+        const size_t words = c->parms.coeff.size() * c->parms.n;
+        if (public_key)
+        {
+            auto &d = ((PublicKey_ *)public_key)->data;
+            d.sync_host();
+            if (d.parms_id != c->ids[0] || d.host.size() != 2 * words)
+                throw InvalidArg("public key is not valid for encryption parameters");
+            e->pk = d.host;
+            e->has_pk = true;
+        }
+        if (secret_key)
+        {
+            auto &d = ((SecretKey_ *)secret_key)->data;
+            if (d.parms_id != c->ids[0] || d.coeffs.size() != words)
+                throw InvalidArg("secret key is not valid for encryption parameters");
+            e->sk = d.coeffs;
+            e->has_sk = true;
+        }
+    });
+    if (hr)
+    {
+        delete e;
+        return hr;
+    }
+    *out = e;
+    return S_OK_;
+}
+long Encryptor_Destroy(void *p)
+{
+    NULLRET(p);
+    delete (Encryptor_ *)p;
+    return S_OK_;
+}
+
+// pk encryption of `plain` with the given PRNG: encrypt_zero_asymmetric at the key level, divide-and-round by the
+// special prime, then add round(q m / t) (S/util/rlwe.cpp:193-310, S/encryptor.cpp:160-208,300-312)
+static void encrypt_asymmetric(Encryptor_ *e, const Plaintext_ &plain, b200::Blake2xbPrng &prng, Ciphertext_ &dst)
+{
+    Context_ *c = e->ctx;
+    if (!e->has_pk)
+        throw LogicErr("public key is not set");
+    std::vector<u64> pv = padded_plain(c, plain);
+    const size_t n = c->parms.n, K = c->parms.coeff.size();
+    const bool drop = c->first_level == 1; // a key level above the data level exists
+    std::vector<u64> u(K * n), e0(K * n), e1(K * n);
+    b200::sample_poly_ternary(prng, n, c->parms.coeff, u.data());
+    b200::sample_poly_normal(prng, n, c->parms.coeff, e0.data());
+    b200::sample_poly_normal(prng, n, c->parms.coeff, e1.data());
+    std::vector<u64> ee(e0);
+    ee.insert(ee.end(), e1.begin(), e1.end());
+    DevBuf du(c, u), dpk(c, e->pk), de(c, ee), dct(c, 2 * K * n), dpl(c, pv);
+    dev_check(b200_ntt_forward(c->dev, 0, du.p, 1, nullptr));
+    dev_check(b200_dyadic_product(c->dev, 0, dpk.p, 2, du.p, 1, dct.p, 1, nullptr)); // pk_j (*) NTT(u)
+    dev_check(b200_ntt_inverse(c->dev, 0, dct.p, 2, nullptr));                       // two polys = two slab items
+    dev_check(b200_add(c->dev, 0, dct.p, de.p, dct.p, 2, 1, nullptr));               // + e_j
+    const int lv = c->first_level;
+    u64 *out = dst.prepare_output(c, c->ids[lv], 2, c->level_k[lv]);
+    if (drop)
+    {
+        DevBuf tmp(c, 2 * (K - 1) * n);
+        dev_check(b200_mod_switch_to_next(c->dev, 0, dct.p, 2, tmp.p, 1, nullptr));
+        dev_check(b200_add_plain(c->dev, lv, tmp.p, 2, dpl.p, 1, out, 1, nullptr));
+    }
+    else
+        dev_check(b200_add_plain(c->dev, lv, dct.p, 2, dpl.p, 1, out, 1, nullptr));
+    dev_check(b200_stream_synchronize(c->dev, nullptr));
+}
+
+long Encryptor_Encrypt(void *p, void *plaintext, void *destination, void *)
+{
+    NULLRET(p);
+    NULLRET(plaintext);
+    NULLRET(destination);
+    auto *e = (Encryptor_ *)p;
+    return guard([&] {
+        std::lock_guard<std::mutex> lk(e->ctx->mu);
+        b200::Blake2xbPrng prng(b200::random_seed());
+        encrypt_asymmetric(e, *(Plaintext_ *)plaintext, prng, *(Ciphertext_ *)destination);
+    });
+}
+// deterministic variant: same stream as the reference's Encryptor_EncryptReturnComponentsSetSeed (S/c/encryptor.cpp:185-240)
+long B200_Encryptor_EncryptSetSeed(void *p, void *plaintext, const uint64_t *seed8, void *destination)
+{
+    NULLRET(p);
+    NULLRET(plaintext);
+    NULLRET(seed8);
+    NULLRET(destination);
+    auto *e = (Encryptor_ *)p;
+    return guard([&] {
+        std::lock_guard<std::mutex> lk(e->ctx->mu);
+        b200::PrngSeed sd;
+        std::copy_n(seed8, 8, sd.begin());
+        b200::Blake2xbPrng prng(sd);
+        encrypt_asymmetric(e, *(Plaintext_ *)plaintext, prng, *(Ciphertext_ *)destination);
+    });
+}
+long Encryptor_EncryptSymmetric(void *p, void *plaintext, bool /*save_seed*/, void *destination, void *)
+{
+    NULLRET(p);
+    NULLRET(plaintext);
+    NULLRET(destination);
+    auto *e = (Encryptor_ *)p;
+    auto *c = e->ctx;
+    return guard([&] {
+        std::lock_guard<std::mutex> lk(c->mu);
+        if (!e->has_sk)
+            throw LogicErr("secret key is not set");
+        std::vector<u64> pv = padded_plain(c, *(Plaintext_ *)plaintext);
+        // encrypt_zero_symmetric at the first data level, coefficient form (S/util/rlwe.cpp:312-459)
+        const int lv = c->first_level;
+        const size_t n = c->parms.n;
+        const int k = c->level_k[lv];
+        std::vector<u64> mods(c->parms.coeff.begin(), c->parms.coeff.begin() + k);
+        b200::Blake2xbPrng bootstrap(b200::random_seed());
+        b200::PrngSeed pub;
+        bootstrap.generate(sizeof(pub), pub.data());
+        b200::Blake2xbPrng ct_prng(pub);
+        std::vector<u64> c1((size_t)k * n), noise((size_t)k * n);
+        b200::sample_poly_uniform(ct_prng, n, mods, c1.data());
+        b200::sample_poly_normal(bootstrap, n, mods, noise.data());
+        std::vector<u64> skl(e->sk.begin(), e->sk.begin() + (size_t)k * n);
+        DevBuf d1(c, c1), de(c, noise), ds(c, skl), d0(c, (size_t)2 * k * n), dpl(c, pv);
+        // c0 = -(INTT(s (*) c1) + e); c1 is sampled in the NTT domain and converted back at the end
+        dev_check(b200_dyadic_product(c->dev, lv, ds.p, 1, d1.p, 1, d0.p, 1, nullptr));
+        dev_check(b200_ntt_inverse(c->dev, lv, d0.p, 1, nullptr));
+        dev_check(b200_add(c->dev, lv, d0.p, de.p, d0.p, 1, 1, nullptr));
+        dev_check(b200_negate(c->dev, lv, d0.p, d0.p, 1, 1, nullptr));
+        dev_check(b200_ntt_inverse(c->dev, lv, d1.p, 1, nullptr));
+        dev_check(b200_memcpy_d2d(c->dev, d0.p + (size_t)k * n, d1.p, (size_t)k * n * 8, nullptr));
+        auto &dst = *(Ciphertext_ *)destination;
+        u64 *out = dst.prepare_output(c, c->ids[lv], 2, k);
+        dev_check(b200_add_plain(c->dev, lv, d0.p, 2, dpl.p, 1, out, 1, nullptr));
+        dev_check(b200_stream_synchronize(c->dev, nullptr));
     });
 }
 

@@ -220,6 +220,16 @@ class RefContext:
             C.memmove(out.ctypes.data, R.lib.refshim_ct_data(h), out.nbytes)
         return out
 
+    def ct_words_any(self, h):
+        """Words of any ciphertext-shaped object (e.g. a public key at the key level)."""
+        R = self.ref
+        size, k = u64(), u64()
+        R.call("Ciphertext_Size", h, C.byref(size))
+        R.call("Ciphertext_CoeffModulusSize", h, C.byref(k))
+        out = np.empty((size.value, k.value, self.n), dtype=np.uint64)
+        C.memmove(out.ctypes.data, R.lib.refshim_ct_data(h), out.nbytes)
+        return out
+
     def free_ct(self, h):
         self.ref.call("Ciphertext_Destroy", h)
 

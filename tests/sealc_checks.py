@@ -125,3 +125,128 @@ def error_codes(S, R_lib, n, moduli, t):
     assert not bad.parameters_set
     ev = vp()
     assert S.rc("Evaluator_Create", bad.ctx, C.byref(ev)) == E_INVALIDARG
+
+
+def _ref_pk_words(R, pk):
+    h = vp()
+    R.ref.call("PublicKey_Data", pk, C.byref(h))
+    return R.ct_words_any(h)
+
+
+def seeded_encryption_parity(S, n, moduli, t):
+    """pk-encryption from a fixed 64-byte seed: our B200_Encryptor_EncryptSetSeed reproduces the reference's
+    Encryptor_EncryptReturnComponentsSetSeed ciphertext word for word (same Blake2xb stream, same samplers)."""
+    R = refseal.RefContext(n, moduli, t)
+    O = S.context(n, moduli, t)
+    kg = R.keygen()
+    pk = R.public_key(kg)
+    pkw = _ref_pk_words(R, pk)
+    enc_r = R.encryptor(pk)
+    # our Encryptor over the same public key words
+    opk = vp()
+    O.S.call("PublicKey_Create1", C.byref(opk))
+    opk_ct = vp()
+    O.S.call("PublicKey_Data", opk, C.byref(opk_ct))
+    w = np.ascontiguousarray(pkw, dtype=np.uint64)
+    O.S.call("B200_Ciphertext_SetWords", opk_ct, O.ctx, O.key_id, u64(2), C.c_bool(True), w.ctypes.data_as(C.POINTER(u64)))
+    enc_o = vp()
+    O.S.call("Encryptor_Create", O.ctx, opk, None, C.byref(enc_o))
+    rng = np.random.default_rng(4)
+    for trial, seed in enumerate(([0] * 8, [1, 2, 3, 4, 5, 6, 7, 8], list(rng.integers(0, 2**63, size=8)))):
+        msg = rng.integers(0, t, size=n if trial else 3, dtype=np.uint64)
+        seed_arr = (u64 * 8)(*[int(x) for x in seed])
+        # reference
+        rct = R.new_ct()
+        pa_u, pa_e, rem = vp(), vp(), vp()
+        R.ref.call("PolynomialArray_Create", None, C.byref(pa_u))
+        R.ref.call("PolynomialArray_Create", None, C.byref(pa_e))
+        R.ref.call("Plaintext_Create1", None, C.byref(rem))
+        R.ref.call("Encryptor_EncryptReturnComponentsSetSeed", enc_r, R.new_pt(msg), C.c_bool(False), rct, pa_u, pa_e, rem,
+                   seed_arr, None)
+        # ours
+        oct_ = O._dst()
+        O.S.call("B200_Encryptor_EncryptSetSeed", enc_o, O.new_pt(msg), seed_arr, oct_)
+        eq(O.ct_words(oct_), R.ct_words(rct), f"seeded encryption, trial {trial}")
+
+
+def keygen_interop(S, n, moduli, t):
+    """Keys made by OUR KeyGenerator (host sampling + GPU arithmetic) are valid keys for the REFERENCE: a ciphertext
+    encrypted by our Encryptor is multiplied / relinearized / rotated by the reference's Evaluator with our keys and
+    decrypted by the reference's Decryptor with our secret key — and the same through our own layer."""
+    R = refseal.RefContext(n, moduli, t)
+    O = S.context(n, moduli, t)
+    kg = vp()
+    O.S.call("KeyGenerator_Create1", O.ctx, C.byref(kg))
+    sk, pk, rlk = vp(), vp(), vp()
+    O.S.call("KeyGenerator_SecretKey", kg, C.byref(sk))
+    O.S.call("KeyGenerator_CreatePublicKey", kg, C.c_bool(False), C.byref(pk))
+    O.S.call("KeyGenerator_CreateRelinKeys", kg, C.c_bool(False), C.byref(rlk))
+    # secret key words -> reference SecretKey
+    skd = vp()
+    O.S.call("SecretKey_Data", sk, C.byref(skd))
+    skw = O.pt_coeffs(skd)
+    rsk = vp()
+    R.ref.call("SecretKey_Create1", C.byref(rsk))
+    rskd = vp()
+    R.ref.call("SecretKey_Data", rsk, C.byref(rskd))
+    R.ref.call("Plaintext_Resize", rskd, u64(skw.size))
+    C.memmove(R.ref.lib.refshim_pt_data(rskd), skw.ctypes.data, skw.nbytes)
+    R.ref.call("Plaintext_SetParmsId", rskd, R.key_parms_id)
+    rdec = R.decryptor(rsk)
+    # relin keys -> reference
+    cnt = u64()
+    O.S.call("KSwitchKeys_GetKeyList", rlk, u64(0), C.byref(cnt), None)
+    lst = (vp * cnt.value)()
+    O.S.call("KSwitchKeys_GetKeyList", rlk, u64(0), C.byref(cnt), lst)
+    words = []
+    for h in lst:
+        d = vp()
+        O.S.call("PublicKey_Data", vp(h), C.byref(d))
+        words.append(O.ct_words_key(d))
+    rrlk = R.new_ksk({0: np.stack(words)})
+    # encrypt with OUR encryptor (pk) and symmetric encryptor (sk)
+    enc = vp()
+    O.S.call("Encryptor_Create", O.ctx, pk, sk, C.byref(enc))
+    rng = np.random.default_rng(8)
+    m1 = rng.integers(0, t, size=n, dtype=np.uint64)
+    m2 = rng.integers(0, t, size=16, dtype=np.uint64)
+    c1, c2 = O._dst(), O._dst()
+    O.S.call("Encryptor_Encrypt", enc, O.new_pt(m1), c1, None)
+    O.S.call("Encryptor_EncryptSymmetric", enc, O.new_pt(m2), C.c_bool(False), c2, None)
+    r1, r2 = R.new_ct(O.ct_words(c1)), R.new_ct(O.ct_words(c2))
+    assert R.noise_budget(rdec, r1) > 20 and R.noise_budget(rdec, r2) > 20
+    eq(R.pt_coeffs(R.decrypt(rdec, r1)), m1[: np.flatnonzero(m1)[-1] + 1], "reference decrypts our pk-encryption")
+    eq(R.pt_coeffs(R.decrypt(rdec, r2)), m2[: np.flatnonzero(m2)[-1] + 1], "reference decrypts our sk-encryption")
+    # reference evaluator with OUR relin keys: (c1 * c2) relinearized decrypts to the negacyclic product mod t
+    rprod = R.relinearize(R.multiply(r1, r2), rrlk)
+    assert R.noise_budget(rdec, rprod) > 0
+    exp = np.zeros(n, dtype=object)
+    for i, a in enumerate(m2):
+        if a:
+            shifted = np.concatenate([-(m1[n - i:].astype(object)), m1[: n - i].astype(object)]) if i else m1.astype(object)
+            exp = (exp + int(a) * shifted) % t
+    got = R.pt_coeffs(R.decrypt(rdec, rprod)).astype(object)
+    full = np.zeros(n, dtype=object)
+    full[: got.size] = got
+    assert np.array_equal(full, exp % t), "product under our relinearization keys decrypts wrongly on the reference"
+    # and entirely inside our layer
+    odec = O.decryptor(skw)
+    oprod = O.relinearize(O.multiply(c1, c2), rlk)
+    eq(O.ct_words(oprod), R.ct_words(rprod), "our evaluator == reference evaluator on our keys")
+    got2 = np.zeros(n, dtype=object)
+    g = O.pt_coeffs(O.decrypt(odec, oprod)).astype(object)
+    got2[: g.size] = g
+    assert np.array_equal(got2, exp % t)
+    if t % (2 * n) == 1:
+        glk = vp()
+        steps = (C.c_int * 2)(1, -2)
+        O.S.call("KeyGenerator_CreateGaloisKeysFromSteps", kg, u64(2), steps, C.c_bool(False), C.byref(glk))
+        be_ = R.batch_encoder()
+        vals = rng.integers(0, t, size=n, dtype=np.uint64)
+        cv = O._dst()
+        O.S.call("Encryptor_Encrypt", enc, O.new_pt(R.pt_coeffs(R.batch_encode(be_, vals))), cv, None)
+        rot = O.rotate_rows(cv, 1, glk)
+        back = R.batch_decode(be_, R.decrypt(rdec, R.new_ct(O.ct_words(rot))))
+        half = n // 2
+        expect = np.concatenate([np.roll(vals[:half], -1), np.roll(vals[half:], -1)])
+        eq(back, expect, "rotate_rows(1) with our Galois keys")

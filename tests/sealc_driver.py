@@ -84,6 +84,10 @@ class SealcContext:
         self.S.call("B200_Ciphertext_GetWords", h, out.ctypes.data_as(C.POINTER(u64)), u64(out.size))
         return out
 
+    def ct_words_key(self, h):
+        """Words of a key-level ciphertext-shaped object (public key / key-switching key element)."""
+        return self.ct_words(h)
+
     def new_pt(self, coeffs):
         h = vp()
         c = np.ascontiguousarray(coeffs, dtype=np.uint64)

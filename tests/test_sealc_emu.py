@@ -23,3 +23,13 @@ def test_evaluator_surface(S, ref, name):
 
 def test_error_codes(S, ref):
     sc.error_codes(S, ref, *PARAMS["n4096"])
+
+
+@pytest.mark.parametrize("name", ["n4096", "n8192"])
+def test_seeded_encryption_matches_reference(S, ref, name):
+    sc.seeded_encryption_parity(S, *PARAMS[name])
+
+
+@pytest.mark.parametrize("name", ["n4096", "n8192"])
+def test_keygen_and_encryptor_interoperate_with_reference(S, ref, name):
+    sc.keygen_interop(S, *PARAMS[name])

@@ -53,3 +53,13 @@ def test_batched_multiply_relin_seam(S, ref):
     O.S.call("B200_Evaluator_MultiplyRelinBatch", O.ev, C.c_uint64(4), (vp * 4)(*As), (vp * 4)(*Bs), rlk, (vp * 4)(*dsts))
     for d, e in zip(dsts, exp):
         assert np.array_equal(O.ct_words(d), e)
+
+
+@pytest.mark.parametrize("name", ["n4096", "n8192"])
+def test_seeded_encryption_matches_reference(S, ref, name):
+    sc.seeded_encryption_parity(S, *PARAMS[name])
+
+
+@pytest.mark.parametrize("name", ["n4096", "n8192", "n16384"])
+def test_keygen_and_encryptor_interoperate_with_reference(S, ref, name):
+    sc.keygen_interop(S, *PARAMS[name])
