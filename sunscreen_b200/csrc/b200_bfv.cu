@@ -92,6 +92,16 @@ __global__ void __launch_bounds__(NT, (LOGN <= 13 ? (NT <= 256 ? 3 : 2) : 1)) nt
 
 #define GLOBAL_IDX() ((long long)blockIdx.x * blockDim.x + threadIdx.x)
 
+template <bool FWD>
+__global__ void ntt_outer_kernel(const NttJob job, long long total)
+{
+    const long long idx = GLOBAL_IDX();
+    if (idx >= total)
+        return;
+    const int halfn = 1 << (job.logn - 1);
+    ntt_outer_pair<FWD>(job, idx / halfn, (int)(idx % halfn));
+}
+
 template <int K>
 __global__ void lift_kernel(const LevelDev L, const u64 *a, int sa, const u64 *b, int sb, u64 *ext, long long n,
                             long long total)
@@ -440,6 +450,7 @@ struct b200_ctx
     std::mutex hp_mu;
     int ntt_threads = 256;
     size_t ntt_smem = 0;
+    int ntt_split = 0; // 1: n > 16384 -> two-level transform (ntt_outer_kernel + half-size sub-transforms)
 };
 
 template <class T>
@@ -509,7 +520,7 @@ static int build_device(b200_ctx *ctx)
     {
         // FP64 fast path descriptors + magnitude bookkeeping (see ntt_fp_body.cuh).  All intermediates must stay
         // below 2^51; a forward stage adds < p to the bound, an inverse stage doubles it.
-        const bool no_fp = std::getenv("B200_NO_FP64_NTT") != nullptr;
+        const bool no_fp = std::getenv("B200_NO_FP64_NTT") != nullptr || ctx->ntt_split;
         ctx->fp_enabled = !no_fp;
         std::vector<NttPrimeFp> fp(H.primes.size());
         const double LIMIT = 2251799813685248.0; // 2^51
@@ -788,10 +799,35 @@ static int launch_ntt(b200_ctx *ctx, const JobDesc &jd, const u64 *src, long lon
     job.items = items;
     static const int slot_major = std::getenv("B200_NTT_ITEM_MAJOR") ? 0 : 1;
     job.slot_major = slot_major;
+    job.split = ctx->ntt_split;
     job.npass = ctx->npass;
     for (int i = 0; i < 8; i++)
         job.pass_L[i] = ctx->pass_L[i];
-    const long long blocks = items * jd.slots;
+    const long long blocks = items * jd.slots * (ctx->ntt_split ? 2 : 1);
+    if (ctx->ntt_split)
+    {
+        // two-level transform: the stage over the whole polynomial runs in global memory, the halves in shared memory
+        const long long pairs = items * jd.slots * (long long)(ctx->n >> 1);
+        void (*kin)(const NttJob) = ctx->ntt_threads == 512 ? ntt_kernel<FWD, 512> : ntt_kernel<FWD, 256>;
+        if (FWD)
+        {
+            B200_LAUNCH(ntt_outer_kernel<true>, blocks_for(pairs, 256), 256, 0, s, job, pairs);
+            NttJob inner = job; // sub-transforms run in place on the destination
+            inner.src = job.dst;
+            inner.slot_src = job.slot_dst;
+            inner.src_item_stride = job.dst_item_stride;
+            inner.reduce_input = 0;
+            B200_LAUNCH(kin, (unsigned)blocks, ctx->ntt_threads, ctx->ntt_smem, s, inner);
+        }
+        else
+        {
+            B200_LAUNCH(kin, (unsigned)blocks, ctx->ntt_threads, ctx->ntt_smem, s, job);
+            B200_LAUNCH(ntt_outer_kernel<false>, blocks_for(pairs, 256), 256, 0, s, job, pairs);
+        }
+        ctx->launches += 2;
+        CU_TRY(cudaGetLastError());
+        return 0;
+    }
     if (blocks > 0x7fffffffLL)
         return fail(B200_E_INVALID, "batch too large for one NTT launch");
 #ifndef B200_EMU_HEADER
@@ -1073,11 +1109,15 @@ int b200_ctx_create(uint64_t n, const uint64_t *coeff_modulus, uint64_t count, u
     CU_TRY(cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
     // NTT launch configuration
-    ctx->npass = ntt_schedule(ctx->logn, ctx->pass_L);
-    ctx->ntt_smem = (size_t)ntt_smem_words((int)ctx->n) * sizeof(u64);
+    ctx->ntt_split = ctx->logn >= 15 ? 1 : 0;
+    if (ctx->logn > 15)
+        return fail(B200_E_INVALID, "poly_modulus_degree above 32768 is not supported");
+    const int local_logn = ctx->logn - ctx->ntt_split;
+    ctx->npass = ntt_schedule(local_logn, ctx->pass_L);
+    ctx->ntt_smem = (size_t)ntt_smem_words(1 << local_logn) * sizeof(u64);
     if (ctx->ntt_smem > (size_t)prop.sharedMemPerBlockOptin)
-        return fail(B200_E_INVALID, "poly_modulus_degree too large for the single-CTA NTT (max 16384 in this build)");
-    ctx->ntt_threads = ctx->n >= 16384 ? 512 : (ctx->n >= 1024 ? 256 : 64);
+        return fail(B200_E_INVALID, "poly_modulus_degree too large for the shared-memory NTT");
+    ctx->ntt_threads = local_logn >= 14 ? 512 : (local_logn >= 10 ? 256 : 64);
 #ifndef B200_EMU_HEADER
 #define SET_SMEM(fn)                                                                                                   \
     CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));   \

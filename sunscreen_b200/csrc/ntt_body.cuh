@@ -52,6 +52,8 @@ struct NttJob
     int reduce_input;          // 1: inputs are arbitrary 64-bit words -> Barrett to [0,p) on load
     long long items;           // number of items in this launch
     int slot_major;            // block order (static FP kernel): 1 = all items of slot 0, then slot 1, ...
+    int split;                 // 1: n is too large for one CTA: each CTA transforms one HALF (size n/2) as a sub-transform;
+                               //    the remaining butterfly stage over the whole polynomial runs in ntt_outer_kernel
     int npass;                 // forward pass schedule (host: ntt_schedule); inverse runs it mirrored
     int pass_L[8];
 };
@@ -103,7 +105,8 @@ inline int ntt_schedule(int logn, int *passes)
 
 // ---- forward: Cooley-Tukey group of 2^L elements, L stages -------------------------------------------
 template <int L>
-B200_HD void ntt_fwd_group(u64 *sm, int g, int logs /*log2 sub-stride*/, int M /*groups at first stage*/,
+B200_HD void ntt_fwd_group(u64 *sm, int g, int logs /*log2 sub-stride*/, int M /*groups at first stage (times the
+                           sub-transform multiplier 2+b when the CTA handles half b of a split transform)*/,
                            const u64 *__restrict__ tw, u64 p)
 {
     constexpr int R = 1 << L;
@@ -152,7 +155,7 @@ B200_HD void ntt_fwd_group(u64 *sm, int g, int logs /*log2 sub-stride*/, int M /
 // `last` marks the pass containing the final stage (m = 1), where n^-1 is folded in.
 template <int L>
 B200_HD void ntt_inv_group(u64 *sm, int g, int logs, int logn, const u64 *__restrict__ tw, const NttPrime &P,
-                           bool last)
+                           bool last, int mult = 1)
 {
     constexpr int R = 1 << L;
     const int s = 1 << logs;
@@ -170,7 +173,7 @@ B200_HD void ntt_inv_group(u64 *sm, int g, int logs, int logn, const u64 *__rest
         const int half = 1 << l;
         // global gap G = s*2^l, m = n/(2G) groups at this stage
         const int m = 1 << (logn - 1 - logs - l);
-        const int tw_base = m + (i << (L - l - 1));
+        const int tw_base = m * mult + (i << (L - l - 1));
         const bool fold = last && (l == L - 1);
 #pragma unroll
         for (int grp = 0; grp < (R >> (l + 1)); grp++)
@@ -214,13 +217,14 @@ B200_HD void ntt_inv_group(u64 *sm, int g, int logs, int logn, const u64 *__rest
 template <bool FWD, int L>
 B200_HD void ntt_pass(u64 *sm, int n, int logs, int logn, int M, const NttPrime &P, bool last, int tid, int nthreads)
 {
+    // M carries the sub-transform multiplier in both directions (forward: groups-at-first-stage * mult; inverse: mult)
     const int ngroups = n >> L;
     for (int g = tid; g < ngroups; g += nthreads)
     {
         if (FWD)
             ntt_fwd_group<L>(sm, g, logs, M, P.fwd, P.p);
         else
-            ntt_inv_group<L>(sm, g, logs, logn, P.inv, P, last);
+            ntt_inv_group<L>(sm, g, logs, logn, P.inv, P, last, M);
     }
 }
 
@@ -241,13 +245,17 @@ B200_HD void ntt_pass_dispatch(int L, u64 *sm, int n, int logs, int logn, int M,
 template <bool FWD>
 B200_HD void ntt_block_body(const NttJob &job, long long block, u64 *sm, int tid, int nthreads)
 {
-    const int logn = job.logn;
+    // split transforms: CTA (poly, half) works on n/2 coefficients with twiddle multiplier 2 + half
+    const int half = job.split ? (int)(block & 1) : 0;
+    const long long poly = job.split ? block >> 1 : block;
+    const int logn = job.split ? job.logn - 1 : job.logn;
     const int n = 1 << logn;
-    const long long item = block / job.slots;
-    const int slot = (int)(block - item * job.slots);
+    const int mult = job.split ? 2 + half : 1;
+    const long long item = poly / job.slots;
+    const int slot = (int)(poly - item * job.slots);
     const NttPrime P = job.primes[job.slot_prime[slot]];
-    const u64 *src = job.src + item * job.src_item_stride + job.slot_src[slot];
-    u64 *dst = job.dst + item * job.dst_item_stride + job.slot_dst[slot];
+    const u64 *src = job.src + item * job.src_item_stride + job.slot_src[slot] + (long long)half * n;
+    u64 *dst = job.dst + item * job.dst_item_stride + job.slot_dst[slot] + (long long)half * n;
     const u64 p = P.p;
 
     for (int e = tid; e < n; e += nthreads)
@@ -268,7 +276,7 @@ B200_HD void ntt_block_body(const NttJob &job, long long block, u64 *sm, int tid
             const int L = job.pass_L[pi];
             const int M = 1 << done;
             const int logs = logn - done - L;
-            ntt_pass_dispatch<true>(L, sm, n, logs, logn, M, P, false, tid, nthreads);
+            ntt_pass_dispatch<true>(L, sm, n, logs, logn, M * mult, P, false, tid, nthreads);
             B200_SYNC();
             done += L;
         }
@@ -287,8 +295,8 @@ B200_HD void ntt_block_body(const NttJob &job, long long block, u64 *sm, int tid
         for (int pi = np - 1; pi >= 0; pi--)
         {
             const int L = job.pass_L[pi];
-            const bool last = (pi == 0);
-            ntt_pass_dispatch<false>(L, sm, n, logs, logn, 0, P, last, tid, nthreads);
+            const bool last = (pi == 0) && !job.split; // a sub-transform leaves the final stage (and n^-1) to ntt_outer
+            ntt_pass_dispatch<false>(L, sm, n, logs, logn, mult, P, last, tid, nthreads);
             B200_SYNC();
             logs += L;
         }
@@ -298,5 +306,40 @@ B200_HD void ntt_block_body(const NttJob &job, long long block, u64 *sm, int tid
             v = v >= p ? v - p : v;
             dst[e] = v;
         }
+    }
+}
+
+
+// The butterfly stage a split transform performs over the whole polynomial in global memory:
+//   forward : first stage (m = 1, gap n/2, twiddle fwd[1]), canonical output, src -> dst
+//   inverse : last stage (m = 1) with n^-1 folded in, in place on dst (input = the two inverse sub-transforms, < p)
+template <bool FWD>
+B200_HD void ntt_outer_pair(const NttJob &job, long long poly, int j)
+{
+    const int n = 1 << job.logn;
+    const long long item = poly / job.slots;
+    const int slot = (int)(poly - item * job.slots);
+    const NttPrime P = job.primes[job.slot_prime[slot]];
+    const u64 p = P.p;
+    if (FWD)
+    {
+        const u64 *src = job.src + item * job.src_item_stride + job.slot_src[slot];
+        u64 *dst = job.dst + item * job.dst_item_stride + job.slot_dst[slot];
+        u64 X = src[j], Y = src[j + (n >> 1)];
+        if (job.reduce_input)
+        {
+            X = barrett64(X, p, P.ratio1);
+            Y = barrett64(Y, p, P.ratio1);
+        }
+        const u64 T = shoup_mul(Y, P.fwd[2], P.fwd[3], p);
+        dst[j] = add_mod(X, T, p);
+        dst[j + (n >> 1)] = sub_mod(X, T, p);
+    }
+    else
+    {
+        u64 *dst = job.dst + item * job.dst_item_stride + job.slot_dst[slot];
+        const u64 X = dst[j], Y = dst[j + (n >> 1)];
+        dst[j] = shoup_mul(add_mod(X, Y, p), P.inv_n, P.inv_n_q, p);
+        dst[j + (n >> 1)] = shoup_mul(sub_mod(X, Y, p), P.inv_n_w, P.inv_n_w_q, p);
     }
 }

@@ -55,3 +55,16 @@ def test_encrypted_roundtrip(pair):
     if not pair.ctx.using_batching:
         pytest.skip("needs a batching plain modulus")
     pc.check_encrypted_roundtrip(pair)
+
+
+def test_n32768_two_level_transform(emu_lib, ref):
+    """BASELINE config 5 parameters (n=32768, 15 data residues + special): the two-level NTT and K=15 kernels."""
+    n, moduli, t = PARAMS["n32768"]
+    P = pc.Pair(EmuBackend(emu_lib), n, moduli, t)
+    pc.check_context(P)
+    pc.check_ntt(P, items=1)
+    m3, rm = pc.check_multiply(P, with_sizes=False)
+    pc.check_relin(P, m3, rm)
+    pc.check_galois(P)
+    pc.check_plain(P)
+    pc.check_modswitch(P)

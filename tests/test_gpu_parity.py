@@ -15,7 +15,7 @@ def be():
     return CudaBackend()
 
 
-@pytest.fixture(scope="module", params=["n4096", "n8192", "n8192_54", "n16384"])
+@pytest.fixture(scope="module", params=["n4096", "n8192", "n8192_54", "n16384", "n32768"])
 def pair(request, be, ref):
     n, moduli, t = PARAMS[request.param]
     return pc.Pair(be, n, moduli, t)
@@ -40,7 +40,7 @@ def test_elementwise(pair):
 
 
 def test_multiply_and_relinearize(pair):
-    m3, rm = pc.check_multiply(pair)
+    m3, rm = pc.check_multiply(pair, with_sizes=pair.n <= 16384)
     pc.check_relin(pair, m3, rm)
 
 
@@ -59,7 +59,7 @@ def test_mod_switch(pair):
 
 
 def test_batch_strides(pair):
-    pc.check_batch(pair, batch=5)
+    pc.check_batch(pair, batch=5 if pair.n <= 16384 else 2)
 
 
 def test_encrypted_roundtrip(pair):
