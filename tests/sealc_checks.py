@@ -250,3 +250,71 @@ def keygen_interop(S, n, moduli, t):
         half = n // 2
         expect = np.concatenate([np.roll(vals[:half], -1), np.roll(vals[half:], -1)])
         eq(back, expect, "rotate_rows(1) with our Galois keys")
+
+
+def chi_sq_dag(S, n, moduli, t, evaluations=2):
+    """BASELINE config 4: the optimised chi-squared circuit (examples/chi_sq/src/main.rs:59-88) as the DAG
+    sunscreen_runtime executes it — every Multiply followed by the Relinearize the compiler inserts
+    (sunscreen_backend/src/transforms/insert_relinearizations.rs:17-62) — replayed through both C ABIs on the same
+    fresh encryptions; every output ciphertext word must match, and the outputs decrypt to the plain computation."""
+    R = refseal.RefContext(n, moduli, t)
+    O = S.context(n, moduli, t)
+    kg = R.keygen()
+    sk, pk, rk = R.secret_key(kg), R.public_key(kg), R.relin_keys(kg)
+    enc, dec = R.encryptor(pk), R.decryptor(sk)
+    ork = O.new_ksk(R.ksk_words(rk))
+    rng = np.random.default_rng(12)
+
+    def circuit(E, rlk, n0, n1, n2):
+        mul = lambda a, b: E.relinearize(E.multiply(a, b), rlk)
+        x = E.add(E.add(n0, n0), n1)
+        y = E.add(E.add(n2, n2), n1)
+        a = mul(n0, n2)
+        a = E.add(a, a)
+        a = E.add(a, a)
+        alpha = E.sub(a, mul(n1, n1))
+        alpha = mul(alpha, alpha)
+        b1 = mul(x, x)
+        b1 = E.add(b1, b1)
+        b2 = mul(x, y)
+        b3 = mul(y, y)
+        b3 = E.add(b3, b3)
+        return alpha, b1, b2, b3
+
+    for _ in range(evaluations):
+        vals = [int(v) for v in rng.integers(1, 12, size=3)]
+        rin = [R.encrypt(enc, R.new_pt(np.array([v], dtype=np.uint64))) for v in vals]
+        oin = [O.new_ct(R.ct_words(h)) for h in rin]
+        rout = circuit(R, rk, *rin)
+        oout = circuit(O, ork, *oin)
+        n0, n1, n2 = vals
+        x, y = 2 * n0 + n1, 2 * n2 + n1
+        expect = [(4 * n0 * n2 - n1 * n1) ** 2, 2 * x * x, x * y, 2 * y * y]
+        for name, hr, ho, e in zip(("alpha", "b_1", "b_2", "b_3"), rout, oout, expect):
+            eq(O.ct_words(ho), R.ct_words(hr), f"chi_sq output {name}")
+            got = R.pt_coeffs(R.decrypt(dec, R.new_ct(O.ct_words(ho))))
+            assert int(got[0]) == e % t and got.size == 1, (name, got[:4], e)
+
+
+def rotate_multiply_plain_sweep(S, n, moduli, t, steps=(1, 2, 4, 64)):
+    """BASELINE config 5: rotate_rows by powers of two followed by multiply_plain with a dense plaintext, with
+    Galois keys for exactly those steps, against the reference word for word."""
+    R = refseal.RefContext(n, moduli, t)
+    O = S.context(n, moduli, t)
+    inp = refseal.appendix_b_inputs(n, moduli, t)
+    rng = np.random.default_rng(21)
+    K = len(moduli)
+    keys = {}
+    for s in steps:
+        elt = pow(3, s, 2 * n)
+        key = np.empty((R.k, 2, K, n), dtype=np.uint64)
+        for i in range(K):
+            key[:, :, i, :] = rng.integers(0, moduli[i], size=(R.k, 2, n), dtype=np.uint64)
+        keys[(elt - 1) // 2] = key
+    rg, og = R.new_ksk(keys), O.new_ksk(keys)
+    ra, oa = R.new_ct(inp["a"]), O.new_ct(inp["a"])
+    rp, op = R.new_pt(inp["p"]), O.new_pt(inp["p"])
+    for s in steps:
+        rr, orr = R.rotate_rows(ra, s, rg), O.rotate_rows(oa, s, og)
+        eq(O.ct_words(orr), R.ct_words(rr), f"rotate_rows({s})")
+        eq(O.ct_words(O.multiply_plain(orr, op)), R.ct_words(R.multiply_plain(rr, rp)), f"multiply_plain after rotate_rows({s})")

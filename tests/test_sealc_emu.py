@@ -33,3 +33,7 @@ def test_seeded_encryption_matches_reference(S, ref, name):
 @pytest.mark.parametrize("name", ["n4096", "n8192"])
 def test_keygen_and_encryptor_interoperate_with_reference(S, ref, name):
     sc.keygen_interop(S, *PARAMS[name])
+
+
+def test_chi_sq_dag_small(S, ref):
+    sc.chi_sq_dag(S, *PARAMS["n8192"], evaluations=1)

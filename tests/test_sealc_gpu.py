@@ -63,3 +63,13 @@ def test_seeded_encryption_matches_reference(S, ref, name):
 @pytest.mark.parametrize("name", ["n4096", "n8192", "n16384"])
 def test_keygen_and_encryptor_interoperate_with_reference(S, ref, name):
     sc.keygen_interop(S, *PARAMS[name])
+
+
+def test_config4_chi_sq_dag_n16384(S, ref):
+    """BASELINE config 4 (n=16384, 8 data residues): the chi-squared DAG, word-exact against the reference."""
+    sc.chi_sq_dag(S, *PARAMS["n16384"], evaluations=3)
+
+
+def test_config5_rotate_multiply_plain_sweep_n32768(S, ref):
+    """BASELINE config 5 (n=32768, 15 data residues): rotate_rows + multiply_plain sweep."""
+    sc.rotate_multiply_plain_sweep(S, *PARAMS["n32768"], steps=(1, 2, 4, 64, 1024, 8192))
