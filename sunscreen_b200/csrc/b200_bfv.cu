@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(NT, (LOGN <= 13 ? (NT <= 256 ? 3 : 2) : 1)) nt
     const NttPrime PI_ = job.primes[pidx];
     const u64 *src = job.src + item * job.src_item_stride + job.slot_src[slot];
     u64 *dst = job.dst + item * job.dst_item_stride + job.slot_dst[slot];
-    NttFpStaticPass<LOGN, NT, FWD, 0>::run(job, PF, PI_, src, dst, reinterpret_cast<double *>(ntt_sm), (int)threadIdx.x);
+    NttFpStaticPass<LOGN, NT, FWD, 0>::run(job, PF, PI_, src, dst, reinterpret_cast<double *>(ntt_sm), (int)threadIdx.x, item, slot);
 #endif
 }
 
@@ -777,9 +777,26 @@ static int get_job(b200_ctx *ctx, const std::string &key, const std::vector<int>
     return 0;
 }
 
+struct TensorArgs
+{
+    int mode = 0, sa = 0, sb = 0, rows = 0;
+    const u64 *src = nullptr;
+};
+
+static bool static_fp_ok(b200_ctx *ctx, const JobDesc &jd)
+{
+#ifdef B200_EMU_HEADER
+    (void)ctx;
+    (void)jd;
+    return false;
+#else
+    return jd.all_fp && ctx->logn >= 12 && ctx->logn <= 14 && !std::getenv("B200_NO_STATIC_NTT");
+#endif
+}
+
 template <bool FWD>
 static int launch_ntt(b200_ctx *ctx, const JobDesc &jd, const u64 *src, long long src_stride, u64 *dst, long long dst_stride,
-                      long long items, int reduce_input, cudaStream_t s)
+                      long long items, int reduce_input, cudaStream_t s, const TensorArgs *ta = nullptr)
 {
     if (items == 0 || jd.slots == 0)
         return 0;
@@ -799,6 +816,13 @@ static int launch_ntt(b200_ctx *ctx, const JobDesc &jd, const u64 *src, long lon
     job.items = items;
     static const int slot_major = std::getenv("B200_NTT_ITEM_MAJOR") ? 0 : 1;
     job.slot_major = slot_major;
+    job.tensor_mode = ta ? ta->mode : 0;
+    job.t_sa = ta ? ta->sa : 0;
+    job.t_sb = ta ? ta->sb : 0;
+    job.t_rows = ta ? ta->rows : 0;
+    job.tsrc = ta ? ta->src : nullptr;
+    if (ta && ta->mode && !static_fp_ok(ctx, jd))
+        return fail(B200_E_LOGIC, "internal: fused tensor source needs the static FP64 NTT kernel");
     job.split = ctx->ntt_split;
     job.npass = ctx->npass;
     for (int i = 0; i < 8; i++)
@@ -831,7 +855,7 @@ static int launch_ntt(b200_ctx *ctx, const JobDesc &jd, const u64 *src, long lon
     if (blocks > 0x7fffffffLL)
         return fail(B200_E_INVALID, "batch too large for one NTT launch");
 #ifndef B200_EMU_HEADER
-    if (jd.all_fp && ctx->logn >= 12 && ctx->logn <= 14 && !std::getenv("B200_NO_STATIC_NTT"))
+    if (static_fp_ok(ctx, jd))
     {
         static const int nt13 = std::getenv("B200_NTT_NT") ? atoi(std::getenv("B200_NTT_NT")) : 256;
         void (*sfn)(const NttJob) = ctx->logn == 12   ? ntt_fp_kernel<12, FWD, 256>
@@ -965,13 +989,8 @@ static int multiply_core(b200_ctx *ctx, int level, const u64 *a, int sa, const u
         if ((rc = launch_ntt<true>(ctx, jd, ext, (long long)P * R * n, ext, (long long)P * R * n, batch, 0, s)))
             return rc;
     }
-    // (4) tensor
-    {
-        const long long total = batch * R * n;
-        B200_LAUNCH(tensor_kernel, blocks_for(total, EB), EB, 0, s, L, ext, sa, sb, D, n, total, square ? 1 : 0);
-        ctx->launches++;
-    }
-    // (5) inverse NTTs
+    // (4) tensor + (5) inverse NTTs.  Optionally (FP64 path) the dyadic products are formed inside the inverse
+    // transform's coalesced copy-in (D never materialised in NTT form); by default a separate tensor kernel runs.
     {
         std::vector<int> rows = row_primes(ctx, level, true), prime;
         for (int m = 0; m < Dn; m++)
@@ -979,7 +998,26 @@ static int multiply_core(b200_ctx *ctx, int level, const u64 *a, int sa, const u
         JobDesc jd;
         if ((rc = dense_job(ctx, "muld:" + std::to_string(level) + ":" + std::to_string(Dn), prime, &jd)))
             return rc;
-        if ((rc = launch_ntt<false>(ctx, jd, D, (long long)Dn * R * n, D, (long long)Dn * R * n, batch, 0, s)))
+        // measured on B200 (round 1): the fused variant is SLOWER (10.9 vs 8.9 ms per 1024 ops) — the extra strided
+        // loads sit on the transform's latency-critical copy-in — so it stays opt-in (B200_TENSOR_FUSION=1)
+        static const bool want_fuse = std::getenv("B200_TENSOR_FUSION") != nullptr;
+        const bool fuse = want_fuse && L.fp && static_fp_ok(ctx, jd);
+        TensorArgs ta;
+        if (fuse)
+        {
+            ta.mode = square ? 2 : 1;
+            ta.sa = sa;
+            ta.sb = sb;
+            ta.rows = R;
+            ta.src = ext;
+        }
+        else
+        {
+            const long long total = batch * R * n;
+            B200_LAUNCH(tensor_kernel, blocks_for(total, EB), EB, 0, s, L, ext, sa, sb, D, n, total, square ? 1 : 0);
+            ctx->launches++;
+        }
+        if ((rc = launch_ntt<false>(ctx, jd, D, (long long)Dn * R * n, D, (long long)Dn * R * n, batch, 0, s, fuse ? &ta : nullptr)))
             return rc;
     }
     // (6)-(8) scale

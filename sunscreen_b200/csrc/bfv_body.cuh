@@ -411,14 +411,6 @@ B200_HD double fp_canon(double r, double p) // (-p, p) -> [0, p)
 {
     return r < 0.0 ? B200_DADD(r, p) : r;
 }
-// general product a*b mod p for canonical a, b (no precomputed quotient): result in (-p, p)
-B200_HD double fp_mulmod2(double a, double b, double p, double pinv)
-{
-    const double h = B200_DMUL(a, b);
-    const double l = B200_DFMA(a, b, -h);
-    const double q = B200_DADD(B200_DFMA(h, pinv, B200_MAGIC), -B200_MAGIC);
-    return B200_DADD(B200_DFMA(-q, p, h), l);
-}
 B200_HD u64 fp_to_u64(double r) // exact for 0 <= r < 2^52
 {
 #if defined(__CUDA_ARCH__)

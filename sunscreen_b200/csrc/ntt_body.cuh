@@ -52,6 +52,12 @@ struct NttJob
     int reduce_input;          // 1: inputs are arbitrary 64-bit words -> Barrett to [0,p) on load
     long long items;           // number of items in this launch
     int slot_major;            // block order (static FP kernel): 1 = all items of slot 0, then slot 1, ...
+    // fused tensor source (FP64 static inverse kernel only): instead of reading `src`, slot (m, row) computes
+    // D_m[row] = sum_{r+s=m} A_r[row] * B_s[row] on the fly from the NTT-form operands at `tsrc`
+    // ([item][sa+sb (or sa when squaring)][trows][n]); 0 = off, 1 = product, 2 = square of a size-2 ciphertext
+    int tensor_mode;
+    int t_sa, t_sb, t_rows;
+    const u64 *tsrc;
     int split;                 // 1: n is too large for one CTA: each CTA transforms one HALF (size n/2) as a sub-transform;
                                //    the remaining butterfly stage over the whole polynomial runs in ntt_outer_kernel
     int npass;                 // forward pass schedule (host: ntt_schedule); inverse runs it mirrored

@@ -54,6 +54,14 @@ B200_HD double fp_mulmod(double y, double w, double wp, double p)
     const double q = B200_DADD(B200_DFMA(y, wp, B200_MAGIC), -B200_MAGIC);
     return B200_DADD(B200_DFMA(-q, p, h), l);
 }
+// general product a*b mod p for |a|,|b| < 2^47 (no precomputed quotient): result in (-p, p)
+B200_HD double fp_mulmod2(double a, double b, double p, double pinv)
+{
+    const double h = B200_DMUL(a, b);
+    const double l = B200_DFMA(a, b, -h);
+    const double q = B200_DADD(B200_DFMA(h, pinv, B200_MAGIC), -B200_MAGIC);
+    return B200_DADD(B200_DFMA(-q, p, h), l);
+}
 B200_HD double fp_renorm(double x, double p, double pinv)
 {
     const double q = B200_DADD(B200_DFMA(x, pinv, B200_MAGIC), -B200_MAGIC);
@@ -298,7 +306,7 @@ template <int LOGN, int NT, bool FWD, int STEP /*0..NP-1 in execution order*/>
 struct NttFpStaticPass
 {
     static __device__ __forceinline__ void run(const NttJob &job, const NttPrimeFp &P, const NttPrime &PI_, const u64 *src, u64 *dst,
-                                               double *smd, int tid)
+                                               double *smd, int tid, long long item, int slot)
     {
 #if defined(__CUDA_ARCH__)
         constexpr int N = 1 << LOGN;
@@ -316,18 +324,60 @@ struct NttFpStaticPass
         constexpr bool TW16 = (L == 4 && LOGS == 0);
         constexpr int NGROUPS = N >> L;
         constexpr int ITERS = (NGROUPS + NT - 1) / NT;
-        const bool rn = ((FWD ? P.renorm_fwd : P.renorm_inv) >> STEP) & 1;
+        const bool rn = (((FWD ? P.renorm_fwd : P.renorm_inv) >> STEP) & 1) || (!FWD && STEP == 0 && job.tensor_mode);
         const bool red = EDGE_IN && job.reduce_input != 0;
         if (EDGE_IN && !SG)
         { // coalesced copy-in: u64 -> double
-#pragma unroll
-            for (int it = 0; it < N / NT; it++)
+            if (!FWD && job.tensor_mode)
             {
-                const int e = tid + it * NT;
-                u64 v = src[e];
-                if (red)
-                    v = barrett64(v, PI_.p, PI_.ratio1);
-                smd[ntt_pad(e)] = fp_from_u64(v);
+                // fused BEHZ step (4): this slot is (m, row); operands are canonical NTT-form words
+                const int R = job.t_rows;
+                const int m = slot / R, row = slot - m * R;
+                const int np_ = job.tensor_mode == 2 ? job.t_sa : job.t_sa + job.t_sb;
+                const long long ps = (long long)R * N; // polynomial stride inside an item
+                const u64 *A = job.tsrc + ((long long)item * np_ * R + row) * N;
+                const u64 *B = job.tensor_mode == 2 ? A : A + (long long)job.t_sa * ps;
+#pragma unroll
+                for (int it = 0; it < N / NT; it++)
+                {
+                    const int e = tid + it * NT;
+                    double acc = 0.0;
+                    if (job.tensor_mode == 2)
+                    {
+                        const double a0 = fp_from_u64(A[e]), a1 = fp_from_u64(A[ps + e]);
+                        if (m == 0)
+                            acc = fp_mulmod2(a0, a0, P.p, P.pinv);
+                        else if (m == 1)
+                        {
+                            acc = fp_mulmod2(a0, a1, P.p, P.pinv);
+                            acc = B200_DADD(acc, acc);
+                        }
+                        else
+                            acc = fp_mulmod2(a1, a1, P.p, P.pinv);
+                    }
+                    else
+                    {
+                        for (int r = 0; r < job.t_sa; r++)
+                        {
+                            const int s = m - r;
+                            if (s >= 0 && s < job.t_sb)
+                                acc = B200_DADD(acc, fp_mulmod2(fp_from_u64(A[r * ps + e]), fp_from_u64(B[s * ps + e]), P.p, P.pinv));
+                        }
+                    }
+                    smd[ntt_pad(e)] = acc; // lazy, |acc| < 4p: the first pass renormalises if its bound needs it
+                }
+            }
+            else
+            {
+#pragma unroll
+                for (int it = 0; it < N / NT; it++)
+                {
+                    const int e = tid + it * NT;
+                    u64 v = src[e];
+                    if (red)
+                        v = barrett64(v, PI_.p, PI_.ratio1);
+                    smd[ntt_pad(e)] = fp_from_u64(v);
+                }
             }
             __syncthreads();
         }
@@ -350,7 +400,7 @@ struct NttFpStaticPass
             }
         }
         if (STEP + 1 < NP)
-            NttFpStaticPass<LOGN, NT, FWD, (STEP + 1 < NP ? STEP + 1 : STEP)>::run(job, P, PI_, src, dst, smd, tid);
+            NttFpStaticPass<LOGN, NT, FWD, (STEP + 1 < NP ? STEP + 1 : STEP)>::run(job, P, PI_, src, dst, smd, tid, item, slot);
 #endif
     }
 };
