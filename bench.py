@@ -86,6 +86,26 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def bind_to_gpu_numa(index):
+    """Pin this process to the CPUs of the NUMA node the GPU hangs off, so pinned host buffers are node-local."""
+    try:
+        bdf = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(index)],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if bdf.startswith("00000000:"):
+            bdf = "0000:" + bdf[9:]
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def cpu_reference_rate(threads, iters, warmup=2):
     """Unmodified reference (oracle/_ref/libsealc_ref.so): threads x iters multiply+relinearize_inplace, own pool per thread."""
     import numpy as np
@@ -171,6 +191,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the B200 backend has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_node = None if os.environ.get("B200_BENCH_NO_NUMA") else bind_to_gpu_numa(local)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -299,6 +320,7 @@ def main():
         del slab
         if not args.no_cpu:
             try:
+                os.sched_setaffinity(0, range(os.cpu_count() or 1))
                 cores = os.cpu_count() or 1
                 iters = 32
                 rate, secs = cpu_reference_rate(cores, iters)
@@ -321,7 +343,7 @@ def main():
                        "l2": "inputs (1 GiB per GPU) exceed the 126 MB L2; no explicit flush"},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "ops/s", "h2d_bytes_per_step": 2 * B * ct_bytes, "d2h_bytes_per_step": B * ct_bytes,
-                    "steps": e2e_steps, "matches_device_path": same},
+                    "steps": e2e_steps, "matches_device_path": same, "host_numa_node": numa_node},
             "roofline": roof, "cpu_baseline": cpu,
         }
         print(json.dumps(line))

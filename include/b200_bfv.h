@@ -89,6 +89,9 @@ int b200_stream_synchronize(b200_ctx *ctx, void *stream);
 int b200_ntt_forward(b200_ctx *ctx, int level, uint64_t *data, uint64_t items, void *stream);
 int b200_ntt_inverse(b200_ctx *ctx, int level, uint64_t *data, uint64_t items, void *stream);
 
+/* negacyclic NTT modulo the plain modulus t over [items][n] (BatchEncoder encode = inverse, decode = forward) */
+int b200_plain_ntt(b200_ctx *ctx, uint64_t *data, uint64_t items, int inverse, void *stream);
+
 /* ---- ciphertext arithmetic, batched over `batch` independent items (device pointers) ---- */
 int b200_add(b200_ctx *ctx, int level, const uint64_t *a, const uint64_t *b, uint64_t *out, int size, uint64_t batch,
              void *stream);

@@ -176,6 +176,15 @@ SEAL_C_FUNC Encryptor_Destroy(void *thisptr);
 SEAL_C_FUNC Encryptor_Encrypt(void *thisptr, void *plaintext, void *destination, void *pool_handle);
 SEAL_C_FUNC Encryptor_EncryptSymmetric(void *thisptr, void *plaintext, bool save_seed, void *destination, void *pool_handle);
 
+/* ---- BatchEncoder (S/c/batchencoder.h): slot permutation on the host, negacyclic NTT mod t on the GPU ---- */
+SEAL_C_FUNC BatchEncoder_Create(void *context, void **batch_encoder);
+SEAL_C_FUNC BatchEncoder_Destroy(void *thisptr);
+SEAL_C_FUNC BatchEncoder_Encode1(void *thisptr, uint64_t count, uint64_t *values, void *destination);
+SEAL_C_FUNC BatchEncoder_Encode2(void *thisptr, uint64_t count, int64_t *values, void *destination);
+SEAL_C_FUNC BatchEncoder_Decode1(void *thisptr, void *plain, uint64_t *count, uint64_t *destination, void *pool);
+SEAL_C_FUNC BatchEncoder_Decode2(void *thisptr, void *plain, uint64_t *count, int64_t *destination, void *pool);
+SEAL_C_FUNC BatchEncoder_GetSlotCount(void *thisptr, uint64_t *slot_count);
+
 /* ---- extensions (not in the reference) ---- */
 /* deterministic pk-encryption from a 64-byte seed: the same random stream (and therefore the same ciphertext words)
    as the reference's Encryptor_EncryptReturnComponentsSetSeed (S/c/encryptor.cpp:185-240) */

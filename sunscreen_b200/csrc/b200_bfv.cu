@@ -426,6 +426,8 @@ struct b200_ctx
     NttPrime *d_ntt_primes = nullptr;
     NttPrimeFp *d_fp_primes = nullptr;
     bool fp_enabled = false;
+    std::vector<bool> prime_fp;  // per device prime: takes the FP64 path
+    int plain_prime_idx = -1;    // index of the plain modulus in the device prime tables (-1: no batching)
     PrimeDev *d_primes = nullptr;       // [all primes] key primes first
     std::vector<LevelDev> levels;       // device pointers inside
     std::vector<const u64 *> d_inv_qlast; // per level
@@ -496,12 +498,22 @@ static int build_device(b200_ctx *ctx)
 {
     BfvHostContext &H = *ctx->host;
     const size_t n = H.n;
-    // twiddle tables + per-prime descriptors
-    std::vector<NttPrime> np(H.primes.size());
-    std::vector<PrimeDev> pd(H.primes.size());
-    for (size_t i = 0; i < H.primes.size(); i++)
+    // twiddle tables + per-prime descriptors; the plain modulus (when it supports batching) is appended as an
+    // extra NTT prime for BatchEncoder (S/batchencoder.cpp:50-149)
+    std::vector<b200::NttPrimeHost *> allp;
+    for (auto &P : H.primes)
+        allp.push_back(&P);
+    ctx->plain_prime_idx = -1;
+    if (H.using_batching)
     {
-        auto &P = H.primes[i];
+        ctx->plain_prime_idx = (int)allp.size();
+        allp.push_back(&H.plain_ntt);
+    }
+    std::vector<NttPrime> np(allp.size());
+    std::vector<PrimeDev> pd(allp.size());
+    for (size_t i = 0; i < allp.size(); i++)
+    {
+        auto &P = *allp[i];
         u64 *dfwd = nullptr, *dinv = nullptr;
         UP(P.fwd, &dfwd);
         UP(P.inv, &dinv);
@@ -522,11 +534,12 @@ static int build_device(b200_ctx *ctx)
         // below 2^51; a forward stage adds < p to the bound, an inverse stage doubles it.
         const bool no_fp = std::getenv("B200_NO_FP64_NTT") != nullptr || ctx->ntt_split;
         ctx->fp_enabled = !no_fp;
-        std::vector<NttPrimeFp> fp(H.primes.size());
+        std::vector<NttPrimeFp> fp(allp.size());
         const double LIMIT = 2251799813685248.0; // 2^51
-        for (size_t i = 0; i < H.primes.size(); i++)
+        ctx->prime_fp.assign(allp.size(), false);
+        for (size_t i = 0; i < allp.size(); i++)
         {
-            auto &P = H.primes[i];
+            auto &P = *allp[i];
             memset(&fp[i], 0, sizeof(NttPrimeFp));
             if (!P.fp || no_fp)
                 continue;
@@ -543,6 +556,7 @@ static int build_device(b200_ctx *ctx)
             fp[i].fwd = dfwd;
             fp[i].inv = dinv;
             fp[i].enabled = 1;
+            ctx->prime_fp[i] = true;
             if (ctx->logn >= 4)
             { // transposed tables for the sub-stride-1 radix-16 pass (lanes read consecutive entries)
                 const int n16 = (int)(n >> 4), lg = ctx->logn;
@@ -768,7 +782,7 @@ static int get_job(b200_ctx *ctx, const std::string &key, const std::vector<int>
     j.slots = (int)prime.size();
     j.all_fp = ctx->fp_enabled;
     for (int pi : prime)
-        j.all_fp = j.all_fp && ctx->host->primes[pi].fp;
+        j.all_fp = j.all_fp && ctx->prime_fp[pi];
     UP(prime, &j.d_prime);
     UP(src, &j.d_src);
     UP(dst, &j.d_dst);
@@ -1362,6 +1376,25 @@ int b200_ntt_forward(b200_ctx *ctx, int level, uint64_t *data, uint64_t items, v
 int b200_ntt_inverse(b200_ctx *ctx, int level, uint64_t *data, uint64_t items, void *stream)
 {
     return ntt_slab(ctx, level, (u64 *)data, items, stream, false);
+}
+
+// negacyclic NTT modulo the PLAIN modulus t over [items][n] (BatchEncoder's transform, S/batchencoder.cpp:129,149)
+int b200_plain_ntt(b200_ctx *ctx, uint64_t *data, uint64_t items, int inverse, void *stream)
+{
+    if (!ctx)
+        return fail(B200_E_NULL, "null context");
+    if (!data)
+        return fail(B200_E_NULL, "null data");
+    if (ctx->plain_prime_idx < 0)
+        return fail(B200_E_INVALID, "encryption parameters are not valid for batching");
+    JobDesc jd;
+    int rc = dense_job(ctx, "plain", std::vector<int>(1, ctx->plain_prime_idx), &jd);
+    if (rc)
+        return rc;
+    const long long stride = (long long)ctx->n;
+    if (inverse)
+        return launch_ntt<false>(ctx, jd, (u64 *)data, stride, (u64 *)data, stride, (long long)items, 0, (cudaStream_t)stream);
+    return launch_ntt<true>(ctx, jd, (u64 *)data, stride, (u64 *)data, stride, (long long)items, 0, (cudaStream_t)stream);
 }
 
 // ---- add / sub / negate ----

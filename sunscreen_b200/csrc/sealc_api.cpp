@@ -291,6 +291,12 @@ struct KSwitchKeys_
 
 struct Evaluator_ { Context_ *ctx; };
 
+struct BatchEncoder_
+{
+    Context_ *ctx;
+    std::vector<size_t> index_map; // populate_matrix_reps_index_map (S/batchencoder.cpp:62-80)
+};
+
 struct Decryptor_
 {
     Context_ *ctx;
@@ -2502,6 +2508,140 @@ long Encryptor_EncryptSymmetric(void *p, void *plaintext, bool /*save_seed*/, vo
         u64 *out = dst.prepare_output(c, c->ids[lv], 2, k);
         dev_check(b200_add_plain(c->dev, lv, d0.p, 2, dpl.p, 1, out, 1, nullptr));
         dev_check(b200_stream_synchronize(c->dev, nullptr));
+    });
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// BatchEncoder (S/c/batchencoder.cpp -> S/batchencoder.cpp): slot permutation on the host, NTT mod t on the GPU
+// ---------------------------------------------------------------------------------------------------------
+long BatchEncoder_Create(void *context, void **out)
+{
+    NULLRET(context);
+    NULLRET(out);
+    auto *c = (Context_ *)context;
+    if (!c->parameters_set || !c->using_batching)
+        return E_INVALIDARG_; // "encryption parameters are not valid for batching"
+    auto *b = new BatchEncoder_();
+    b->ctx = c;
+    const size_t n = c->parms.n, row = n >> 1, m = n << 1;
+    int logn = 0;
+    while (((size_t)1 << logn) < n)
+        logn++;
+    b->index_map.resize(n);
+    u64 pos = 1;
+    for (size_t i = 0; i < row; i++)
+    {
+        b->index_map[i] = (size_t)b200::reverse_bits((pos - 1) >> 1, logn);
+        b->index_map[row | i] = (size_t)b200::reverse_bits((m - pos - 1) >> 1, logn);
+        pos = (pos * 3) & (m - 1);
+    }
+    *out = b;
+    return S_OK_;
+}
+long BatchEncoder_Destroy(void *p)
+{
+    NULLRET(p);
+    delete (BatchEncoder_ *)p;
+    return S_OK_;
+}
+long BatchEncoder_GetSlotCount(void *p, uint64_t *count)
+{
+    NULLRET(p);
+    NULLRET(count);
+    *count = ((BatchEncoder_ *)p)->ctx->parms.n;
+    return S_OK_;
+}
+static void batch_encode(BatchEncoder_ *b, const std::vector<u64> &vals, Plaintext_ &dst)
+{
+    Context_ *c = b->ctx;
+    const size_t n = c->parms.n;
+    if (vals.size() > n)
+        throw InvalidArg("values_matrix size is too large");
+    std::vector<u64> slots(n, 0);
+    for (size_t i = 0; i < vals.size(); i++)
+    {
+        if (vals[i] >= c->parms.plain)
+            throw InvalidArg("input value is larger than plain_modulus");
+        slots[b->index_map[i]] = vals[i];
+    }
+    std::lock_guard<std::mutex> lk(c->mu);
+    DevBuf d(c, slots);
+    dev_check(b200_plain_ntt(c->dev, d.p, 1, 1, nullptr));
+    dst.coeffs = d.download();
+    dst.parms_id = kZeroId;
+    dst.scale = 1.0;
+}
+long BatchEncoder_Encode1(void *p, uint64_t count, uint64_t *values, void *destination)
+{
+    NULLRET(p);
+    NULLRET(destination);
+    if (count)
+        NULLRET(values);
+    return guard([&] { batch_encode((BatchEncoder_ *)p, std::vector<u64>(values, values + count), *(Plaintext_ *)destination); });
+}
+long BatchEncoder_Encode2(void *p, uint64_t count, int64_t *values, void *destination)
+{
+    NULLRET(p);
+    NULLRET(destination);
+    if (count)
+        NULLRET(values);
+    auto *b = (BatchEncoder_ *)p;
+    return guard([&] {
+        const u64 t = b->ctx->parms.plain;
+        const u64 half = t >> 1; // plain_modulus_div_two (S/batchencoder.cpp:184-200)
+        std::vector<u64> v(count);
+        for (uint64_t i = 0; i < count; i++)
+        {
+            const int64_t x = values[i];
+            if ((x < 0 ? (u64)(-x) : (u64)x) > half)
+                throw InvalidArg("input value is larger than plain_modulus");
+            v[i] = x < 0 ? t + (u64)x : (u64)x;
+        }
+        batch_encode(b, v, *(Plaintext_ *)destination);
+    });
+}
+static std::vector<u64> batch_decode(BatchEncoder_ *b, const Plaintext_ &pl)
+{
+    Context_ *c = b->ctx;
+    const size_t n = c->parms.n;
+    if (pl.parms_id != kZeroId)
+        throw InvalidArg("plain cannot be in NTT form");
+    std::vector<u64> v = padded_plain(c, pl);
+    std::vector<u64> out(n);
+    std::lock_guard<std::mutex> lk(c->mu);
+    DevBuf d(c, v);
+    dev_check(b200_plain_ntt(c->dev, d.p, 1, 0, nullptr));
+    std::vector<u64> f = d.download();
+    for (size_t i = 0; i < n; i++)
+        out[i] = f[b->index_map[i]];
+    return out;
+}
+long BatchEncoder_Decode1(void *p, void *plain, uint64_t *count, uint64_t *destination, void *)
+{
+    NULLRET(p);
+    NULLRET(plain);
+    NULLRET(count);
+    NULLRET(destination);
+    auto *b = (BatchEncoder_ *)p;
+    return guard([&] {
+        std::vector<u64> out = batch_decode(b, *(Plaintext_ *)plain);
+        std::copy(out.begin(), out.end(), destination);
+        *count = out.size();
+    });
+}
+long BatchEncoder_Decode2(void *p, void *plain, uint64_t *count, int64_t *destination, void *)
+{
+    NULLRET(p);
+    NULLRET(plain);
+    NULLRET(count);
+    NULLRET(destination);
+    auto *b = (BatchEncoder_ *)p;
+    return guard([&] {
+        std::vector<u64> out = batch_decode(b, *(Plaintext_ *)plain);
+        const u64 t = b->ctx->parms.plain, half = t >> 1;
+        for (size_t i = 0; i < out.size(); i++)
+            destination[i] = out[i] > half ? (int64_t)out[i] - (int64_t)t : (int64_t)out[i];
+        *count = out.size();
     });
 }
 

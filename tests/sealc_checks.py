@@ -318,3 +318,42 @@ def rotate_multiply_plain_sweep(S, n, moduli, t, steps=(1, 2, 4, 64)):
         rr, orr = R.rotate_rows(ra, s, rg), O.rotate_rows(oa, s, og)
         eq(O.ct_words(orr), R.ct_words(rr), f"rotate_rows({s})")
         eq(O.ct_words(O.multiply_plain(orr, op)), R.ct_words(R.multiply_plain(rr, rp)), f"multiply_plain after rotate_rows({s})")
+
+
+def batch_encoder_parity(S, n, moduli, t):
+    """BatchEncoder_Encode/Decode (slot permutation + negacyclic NTT mod t) against the reference."""
+    R = refseal.RefContext(n, moduli, t)
+    O = S.context(n, moduli, t)
+    rbe = R.batch_encoder()
+    obe = vp()
+    O.S.call("BatchEncoder_Create", O.ctx, C.byref(obe))
+    cnt = u64()
+    O.S.call("BatchEncoder_GetSlotCount", obe, C.byref(cnt))
+    assert cnt.value == n
+    rng = np.random.default_rng(33)
+    for size in (n, 7, 0):
+        vals = rng.integers(0, t, size=size, dtype=np.uint64)
+        rp = R.batch_encode(rbe, vals)
+        op = vp()
+        O.S.call("Plaintext_Create1", None, C.byref(op))
+        O.S.call("BatchEncoder_Encode1", obe, u64(size), vals.ctypes.data_as(C.POINTER(u64)), op)
+        eq(O.pt_coeffs(op), R.pt_coeffs(rp), f"BatchEncoder_Encode1 ({size} values)")
+        out = np.zeros(n, dtype=np.uint64)
+        c2 = u64(n)
+        O.S.call("BatchEncoder_Decode1", obe, op, C.byref(c2), out.ctypes.data_as(C.POINTER(u64)), None)
+        exp = np.zeros(n, dtype=np.uint64)
+        exp[:size] = vals
+        eq(out, exp, "BatchEncoder_Decode1 round trip")
+    # signed variant
+    sv = rng.integers(-(t // 2), t // 2, size=n, dtype=np.int64)
+    op = vp()
+    O.S.call("Plaintext_Create1", None, C.byref(op))
+    O.S.call("BatchEncoder_Encode2", obe, u64(n), sv.ctypes.data_as(C.POINTER(C.c_int64)), op)
+    rp = vp()
+    R.ref.call("Plaintext_Create1", None, C.byref(rp))
+    R.ref.call("BatchEncoder_Encode2", rbe, u64(n), sv.ctypes.data_as(C.POINTER(C.c_int64)), rp)
+    eq(O.pt_coeffs(op), R.pt_coeffs(rp), "BatchEncoder_Encode2")
+    so = np.zeros(n, dtype=np.int64)
+    c2 = u64(n)
+    O.S.call("BatchEncoder_Decode2", obe, op, C.byref(c2), so.ctypes.data_as(C.POINTER(C.c_int64)), None)
+    assert np.array_equal(so, sv)

@@ -37,3 +37,8 @@ def test_keygen_and_encryptor_interoperate_with_reference(S, ref, name):
 
 def test_chi_sq_dag_small(S, ref):
     sc.chi_sq_dag(S, *PARAMS["n8192"], evaluations=1)
+
+
+@pytest.mark.parametrize("name", ["n8192"])
+def test_batch_encoder(S, ref, name):
+    sc.batch_encoder_parity(S, *PARAMS[name])

@@ -73,3 +73,8 @@ def test_config4_chi_sq_dag_n16384(S, ref):
 def test_config5_rotate_multiply_plain_sweep_n32768(S, ref):
     """BASELINE config 5 (n=32768, 15 data residues): rotate_rows + multiply_plain sweep."""
     sc.rotate_multiply_plain_sweep(S, *PARAMS["n32768"], steps=(1, 2, 4, 64, 1024, 8192))
+
+
+@pytest.mark.parametrize("name", ["n8192", "n16384", "n32768"])
+def test_batch_encoder(S, ref, name):
+    sc.batch_encoder_parity(S, *PARAMS[name])
