@@ -48,6 +48,7 @@ SEAL_C_FUNC Modulus_Value(void *thisptr, uint64_t *value);
 SEAL_C_FUNC Modulus_BitCount(void *thisptr, int *bit_count);
 SEAL_C_FUNC CoeffModulus_MaxBitCount(uint64_t poly_modulus_degree, int sec_level, int *bit_count);
 SEAL_C_FUNC CoeffModulus_BFVDefault(uint64_t poly_modulus_degree, int sec_level, uint64_t *length, void **coeffs);
+SEAL_C_FUNC CoeffModulus_Create1(uint64_t poly_modulus_degree, uint64_t length, int *bit_sizes, void **coeffs);
 
 /* ---- EncryptionParameters (S/c/encryptionparameters.h) ---- */
 SEAL_C_FUNC EncParams_Create1(uint8_t scheme, void **enc_params);

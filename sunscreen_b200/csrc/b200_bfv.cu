@@ -86,6 +86,21 @@ __global__ void __launch_bounds__(NT, (LOGN <= 13 ? (NT <= 256 ? 3 : 2) : 1)) nt
     const NttPrime PI_ = job.primes[pidx];
     const u64 *src = job.src + item * job.src_item_stride + job.slot_src[slot];
     u64 *dst = job.dst + item * job.dst_item_stride + job.slot_dst[slot];
+    if (job.prefetch_dist > 0 && !job.tensor_mode)
+    {
+        // pull the polynomial that the CTA one wave later will transform into L2 (its pass-1 loads then hit L2)
+        const long long nb = block + job.prefetch_dist;
+        if (nb < (long long)gridDim.x)
+        {
+            const int nslot = job.slot_major ? (int)(nb / job.items) : (int)(nb % job.slots);
+            const long long nitem = job.slot_major ? nb - (long long)nslot * job.items : nb / job.slots;
+            const char *np_ = reinterpret_cast<const char *>(job.src + nitem * job.src_item_stride + job.slot_src[nslot]);
+            constexpr int LINES = (8 << LOGN) / 128;
+#pragma unroll
+            for (int l = (int)threadIdx.x; l < LINES; l += NT)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(np_ + (size_t)l * 128));
+        }
+    }
     NttFpStaticPass<LOGN, NT, FWD, 0>::run(job, PF, PI_, src, dst, reinterpret_cast<double *>(ntt_sm), (int)threadIdx.x, item, slot);
 #endif
 }
@@ -828,6 +843,8 @@ static int launch_ntt(b200_ctx *ctx, const JobDesc &jd, const u64 *src, long lon
     job.fprimes = ctx->d_fp_primes;
     job.reduce_input = reduce_input;
     job.items = items;
+    static const int pf = std::getenv("B200_NTT_PREFETCH") ? atoi(std::getenv("B200_NTT_PREFETCH")) : 0;
+    job.prefetch_dist = pf;
     static const int slot_major = std::getenv("B200_NTT_ITEM_MAJOR") ? 0 : 1;
     job.slot_major = slot_major;
     job.tensor_mode = ta ? ta->mode : 0;

@@ -880,6 +880,45 @@ long CoeffModulus_BFVDefault(uint64_t n, int sec, uint64_t *length, void **coeff
     return S_OK_;
 }
 
+long CoeffModulus_Create1(uint64_t n, uint64_t length, int *bit_sizes, void **coeffs)
+{
+    NULLRET(bit_sizes);
+    NULLRET(coeffs);
+    // CoeffModulus::Create (S/modulus.cpp:143-184): per distinct bit size the largest primes == 1 mod 2n, handed out
+    // from the back of each list in the order the sizes were requested
+    return guard([&] {
+        if (n < 2 || n > 131072 || (n & (n - 1)))
+            throw InvalidArg("poly_modulus_degree is invalid");
+        if (length > 64)
+            throw InvalidArg("bit_sizes is invalid");
+        std::vector<std::pair<int, std::vector<b200::u64>>> tables;
+        for (uint64_t i = 0; i < length; i++)
+        {
+            if (bit_sizes[i] > 60 || bit_sizes[i] < 2)
+                throw InvalidArg("bit_sizes is invalid");
+            bool found = false;
+            for (auto &t : tables)
+                found = found || t.first == bit_sizes[i];
+            if (!found)
+            {
+                size_t cnt = 0;
+                for (uint64_t j = 0; j < length; j++)
+                    cnt += bit_sizes[j] == bit_sizes[i];
+                tables.emplace_back(bit_sizes[i], b200::get_primes(2 * n, bit_sizes[i], cnt));
+            }
+        }
+        for (uint64_t i = 0; i < length; i++)
+            for (auto &t : tables)
+                if (t.first == bit_sizes[i])
+                {
+                    auto *m = new Modulus_();
+                    m->value = t.second.back();
+                    t.second.pop_back();
+                    coeffs[i] = m;
+                }
+    });
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // EncryptionParameters
 // ---------------------------------------------------------------------------------------------------------

@@ -1,0 +1,14 @@
+"""The seal_fhe crate's unit tests (restated in tests/seal_fhe_crate_tests.py) on the CPU emulation build."""
+import seal_fhe_crate_tests as crate
+from sunscreen_b200 import seal_fhe
+
+
+def test_bfv_evaluator_crate_tests(emu_lib):
+    seal_fhe.use_library(emu_lib.lib)
+    done = crate.all_tests()
+    assert len(done) == 11
+
+
+def test_lane_overflow_assumption(emu_lib):
+    seal_fhe.use_library(emu_lib.lib)
+    crate.lane_overflow_assumption()
