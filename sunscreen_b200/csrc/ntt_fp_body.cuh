@@ -19,6 +19,7 @@
 // renormalised (x -= rint(x/p)*p, 3 DP ops).
 #pragma once
 #include "ntt_body.cuh"
+#include <type_traits>
 
 #if defined(__CUDA_ARCH__)
 #define B200_DMUL(a, b) __dmul_rn((a), (b))
@@ -159,7 +160,19 @@ B200_HD void fp_stage(double (&x)[1 << L], const double *__restrict__ tw, int g,
     }
 }
 
-template <int L, bool FWD, bool SRC_GLOBAL, bool DST_GLOBAL, bool TW16 = false>
+// padded shared-memory index of element j of a group: base + j*2^logs.  For sub-strides that are multiples of 16 the
+// padding of j*2^logs is a constant, and for the sub-stride-1 radix-16 group (base = 16 g) it is g — so only one
+// padded base per group is computed at run time and every element offset is a compile-time constant after inlining.
+B200_HD int fp_elem_index(int pbase, int base, int j, int logs)
+{
+    if (logs >= 4)
+        return pbase + j * ((1 << logs) + (1 << (logs - 4)));
+    if (logs == 0)
+        return pbase + j + (((base & 15) + j) >> 4);
+    return ntt_pad(base + (j << logs));
+}
+
+template <int L, bool FWD, bool SRC_GLOBAL, bool DST_GLOBAL, bool TW16 = false, bool RENORM = true, bool REDUCE = true>
 B200_HD void ntt_fp_group(double *sm, const u64 *__restrict__ gsrc, u64 *__restrict__ gdst, int g, int logs, int logn, int M,
                           const NttPrimeFp &P, bool renorm, bool last_inv, bool reduce_input, u64 pint, u64 ratio1)
 {
@@ -168,6 +181,7 @@ B200_HD void ntt_fp_group(double *sm, const u64 *__restrict__ gsrc, u64 *__restr
     const int i = g >> logs;
     const int o = g & (s - 1);
     const int base = (i << (logs + L)) + o;
+    const int pbase = ntt_pad(base);
     const double p = P.p;
     double x[R];
 #pragma unroll
@@ -176,13 +190,13 @@ B200_HD void ntt_fp_group(double *sm, const u64 *__restrict__ gsrc, u64 *__restr
         if (SRC_GLOBAL)
         {
             u64 v = gsrc[base + (j << logs)];
-            if (reduce_input)
+            if (REDUCE && reduce_input)
                 v = barrett64(v, pint, ratio1);
             x[j] = fp_from_u64(v);
         }
         else
-            x[j] = sm[ntt_pad(base + (j << logs))];
-        if (renorm)
+            x[j] = sm[fp_elem_index(pbase, base, j, logs)];
+        if (RENORM && renorm)
             x[j] = fp_renorm(x[j], p, P.pinv);
     }
     const double *__restrict__ tw = TW16 ? (FWD ? P.fwd16 : P.inv16) : (FWD ? P.fwd : P.inv);
@@ -200,7 +214,7 @@ B200_HD void ntt_fp_group(double *sm, const u64 *__restrict__ gsrc, u64 *__restr
         if (DST_GLOBAL)
             gdst[base + (j << logs)] = fp_to_canonical(x[j], p, P.pinv);
         else
-            sm[ntt_pad(base + (j << logs))] = x[j];
+            sm[fp_elem_index(pbase, base, j, logs)] = x[j];
     }
 }
 
@@ -326,6 +340,8 @@ struct NttFpStaticPass
         constexpr int ITERS = (NGROUPS + NT - 1) / NT;
         const bool rn = (((FWD ? P.renorm_fwd : P.renorm_inv) >> STEP) & 1) || (!FWD && STEP == 0 && job.tensor_mode);
         const bool red = EDGE_IN && job.reduce_input != 0;
+        const int ptid = ntt_pad(tid);              // NT is a multiple of 16: pad(tid + it*NT) = pad(tid) + it*(NT + NT/16)
+        constexpr int PNT = NT + (NT >> 4);
         if (EDGE_IN && !SG)
         { // coalesced copy-in: u64 -> double
             if (!FWD && job.tensor_mode)
@@ -364,40 +380,55 @@ struct NttFpStaticPass
                                 acc = B200_DADD(acc, fp_mulmod2(fp_from_u64(A[r * ps + e]), fp_from_u64(B[s * ps + e]), P.p, P.pinv));
                         }
                     }
-                    smd[ntt_pad(e)] = acc; // lazy, |acc| < 4p: the first pass renormalises if its bound needs it
+                    smd[ptid + it * PNT] = acc; // lazy, |acc| < 4p: the first pass renormalises if its bound needs it
                 }
+            }
+            else if (red)
+            {
+#pragma unroll
+                for (int it = 0; it < N / NT; it++)
+                    smd[ptid + it * PNT] = fp_from_u64(barrett64(src[tid + it * NT], PI_.p, PI_.ratio1));
             }
             else
             {
 #pragma unroll
                 for (int it = 0; it < N / NT; it++)
-                {
-                    const int e = tid + it * NT;
-                    u64 v = src[e];
-                    if (red)
-                        v = barrett64(v, PI_.p, PI_.ratio1);
-                    smd[ntt_pad(e)] = fp_from_u64(v);
-                }
+                    smd[ptid + it * PNT] = fp_from_u64(src[tid + it * NT]);
             }
             __syncthreads();
         }
+        // renormalisation / input reduction are block-uniform run-time flags: branch ONCE to a compile-time variant
+        // (as predicated code they cost 12 FP64 ops and ~10 IMADs per element whether needed or not)
+        auto groups = [&](auto RN, auto RD) {
 #pragma unroll
-        for (int it = 0; it < ITERS; it++)
+            for (int it = 0; it < ITERS; it++)
+            {
+                const int g = tid + it * NT;
+                if (NGROUPS % NT == 0 || g < NGROUPS)
+                    ntt_fp_group<L, FWD, SG, DG, TW16, decltype(RN)::value, decltype(RD)::value>(
+                        smd, src, dst, g, LOGS, LOGN, M, P, true, !FWD && EDGE_OUT, true, PI_.p, PI_.ratio1);
+            }
+        };
+        if (rn)
         {
-            const int g = tid + it * NT;
-            if (NGROUPS % NT == 0 || g < NGROUPS)
-                ntt_fp_group<L, FWD, SG, DG, TW16>(smd, src, dst, g, LOGS, LOGN, M, P, rn, !FWD && EDGE_OUT, SG && red, PI_.p,
-                                                   PI_.ratio1);
+            if (SG && red)
+                groups(std::true_type{}, std::true_type{});
+            else
+                groups(std::true_type{}, std::false_type{});
+        }
+        else
+        {
+            if (SG && red)
+                groups(std::false_type{}, std::true_type{});
+            else
+                groups(std::false_type{}, std::false_type{});
         }
         __syncthreads();
         if (EDGE_OUT && !DG)
         { // coalesced copy-out: lazy double -> canonical u64
 #pragma unroll
             for (int it = 0; it < N / NT; it++)
-            {
-                const int e = tid + it * NT;
-                dst[e] = fp_to_canonical(smd[ntt_pad(e)], P.p, P.pinv);
-            }
+                dst[tid + it * NT] = fp_to_canonical(smd[ptid + it * PNT], P.p, P.pinv);
         }
         if (STEP + 1 < NP)
             NttFpStaticPass<LOGN, NT, FWD, (STEP + 1 < NP ? STEP + 1 : STEP)>::run(job, P, PI_, src, dst, smd, tid, item, slot);
