@@ -142,6 +142,9 @@ int b200_ntt_roundtrip_host(b200_ctx *ctx, int level, const uint64_t *in_host, u
 
 /* number of kernel launches issued by this library since the context was created (bench.py: gpu_launches) */
 uint64_t b200_launch_count(const b200_ctx *ctx);
+/* developer aid: with B200_TRACE=1 in the environment every kernel launch is bracketed by CUDA events;
+   this prints the per-kernel totals to stderr and clears the log (no-op otherwise) */
+void b200_trace_dump(void);
 
 #ifdef __cplusplus
 }

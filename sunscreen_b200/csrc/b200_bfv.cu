@@ -20,7 +20,42 @@
 #include B200_EMU_HEADER
 #else
 #include <cuda_runtime.h>
-#define B200_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#include <map>
+#include <string>
+#include <vector>
+// Developer trace (B200_TRACE=1): CUDA events around every launch, summed per kernel name and printed by
+// b200_trace_dump().  Off by default: the launch macro then costs one predictable branch.
+struct B200TraceRec
+{
+    const char *name;
+    cudaEvent_t e0, e1;
+};
+static int g_trace_on = -1;
+static std::vector<B200TraceRec> g_trace;
+static const char *g_trace_name = nullptr; // optional label for the next launch (function-pointer launches)
+static inline bool trace_on()
+{
+    if (g_trace_on < 0)
+        g_trace_on = getenv("B200_TRACE") ? 1 : 0;
+    return g_trace_on == 1;
+}
+#define B200_LAUNCH(kernel, grid, block, smem, stream, ...)                                                            \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        if (trace_on())                                                                                                \
+        {                                                                                                              \
+            B200TraceRec r_{ g_trace_name ? g_trace_name : #kernel, nullptr, nullptr };                                \
+            g_trace_name = nullptr;                                                                                    \
+            cudaEventCreate(&r_.e0);                                                                                   \
+            cudaEventCreate(&r_.e1);                                                                                   \
+            cudaEventRecord(r_.e0, stream);                                                                            \
+            kernel<<<grid, block, smem, stream>>>(__VA_ARGS__);                                                        \
+            cudaEventRecord(r_.e1, stream);                                                                            \
+            g_trace.push_back(r_);                                                                                     \
+        }                                                                                                              \
+        else                                                                                                           \
+            kernel<<<grid, block, smem, stream>>>(__VA_ARGS__);                                                        \
+    } while (0)
 #endif
 #include <map>
 #include <memory>
@@ -217,6 +252,147 @@ __global__ void ksmac_kernel(const PrimeDev *primes, const NttPrimeFp *fprimes, 
     }
     ksmac_coeff<K>(P, ops, n, kp, 2LL * key_rows * n, (long long)key_rows * n, o0, o1, c);
 }
+
+#ifndef B200_EMU_HEADER
+// ---- FP64 element-wise kernels, two adjacent coefficients per thread (128-bit global accesses) ----
+__device__ __forceinline__ ulonglong2 ldg2(const u64 *p) { return __ldg(reinterpret_cast<const ulonglong2 *>(p)); }
+__device__ __forceinline__ void stg2(u64 *p, u64 a, u64 b) { *reinterpret_cast<ulonglong2 *>(p) = make_ulonglong2(a, b); }
+
+template <int K>
+__global__ void lift_kernel_v2(const LevelDev L, const u64 *a, int sa, const u64 *b, int sb, u64 *ext, long long n, long long total)
+{
+    const long long idx = GLOBAL_IDX();
+    if (idx >= total)
+        return;
+    const int P = sa + sb;
+    const long long hn = n >> 1;
+    const long long c = (idx % hn) * 2;
+    const long long t = idx / hn;
+    const int p = (int)(t % P);
+    const long long item = t / P;
+    const int R = K + L.nBsk;
+    const u64 *src = p < sa ? a + (item * sa + p) * K * n : b + (item * sb + (p - sa)) * K * n;
+    u64 *dst = ext + ((item * P + p) * R + K) * n;
+    u64 xs[2][K], zs[2][K + 2];
+#pragma unroll
+    for (int i = 0; i < K; i++)
+    {
+        const ulonglong2 v = ldg2(src + i * n + c);
+        xs[0][i] = v.x;
+        xs[1][i] = v.y;
+    }
+    lift_coeff_fp<K>(L, xs[0], zs[0], 1, 0);
+    lift_coeff_fp<K>(L, xs[1], zs[1], 1, 0);
+#pragma unroll
+    for (int j = 0; j < K + 2; j++)
+        if (j < L.nBsk)
+            stg2(dst + j * n + c, zs[0][j], zs[1][j]);
+}
+
+__global__ void tensor_kernel_v2(const LevelDev L, const u64 *ext, u64 *D, long long n, long long total, int square)
+{
+    // size-2 x size-2 (or square of size 2) only: D0, D1, D2
+    const long long idx = GLOBAL_IDX();
+    if (idx >= total)
+        return;
+    const int R = L.k + L.nBsk;
+    const long long hn = n >> 1;
+    const long long c = (idx % hn) * 2;
+    const long long t = idx / hn;
+    const int r = (int)(t % R);
+    const long long item = t / R;
+    const double *pd = r < L.k ? &L.dq[2 * r] : &L.dbsk[2 * (r - L.k)];
+    const double p = __ldg(pd), pinv = __ldg(pd + 1);
+    const int Pn = square ? 2 : 4;
+    const u64 *A = ext + ((item * Pn) * R + r) * n + c;
+    u64 *Dp = D + ((item * 3) * R + r) * n + c;
+    const long long ps = (long long)R * n;
+    const ulonglong2 a0 = ldg2(A), a1 = ldg2(A + ps);
+    u64 in[2][4], out[2][3];
+    in[0][0] = a0.x; in[1][0] = a0.y; in[0][1] = a1.x; in[1][1] = a1.y;
+    if (!square)
+    {
+        const ulonglong2 b0 = ldg2(A + 2 * ps), b1 = ldg2(A + 3 * ps);
+        in[0][2] = b0.x; in[1][2] = b0.y; in[0][3] = b1.x; in[1][3] = b1.y;
+    }
+#pragma unroll
+    for (int u = 0; u < 2; u++)
+    {
+        if (square)
+            square_coeff_fp(p, pinv, in[u], 1, out[u], 1, 0);
+        else
+            tensor_coeff_fp(p, pinv, in[u], 1, 2, in[u] + 2, 1, 2, out[u], 1, 0);
+    }
+#pragma unroll
+    for (int m = 0; m < 3; m++)
+        stg2(Dp + m * ps, out[0][m], out[1][m]);
+}
+
+template <int K>
+__global__ void scale_kernel_v2(const LevelDev L, const u64 *D, int Dn, u64 *dst0, int split, u64 *dst1, long long n, long long total)
+{
+    const long long idx = GLOBAL_IDX();
+    if (idx >= total)
+        return;
+    const int R = K + L.nBsk;
+    const long long hn = n >> 1;
+    const long long c = (idx % hn) * 2;
+    const long long t = idx / hn;
+    const int m = (int)(t % Dn);
+    const long long item = t / Dn;
+    const u64 *src = D + ((item * Dn + m) * R) * n + c;
+    u64 *dst = (m < split ? dst0 + ((item * split + m) * K) * n : dst1 + ((item * (Dn - split) + (m - split)) * K) * n) + c;
+    u64 in[2][2 * K + 2], out[2][K];
+#pragma unroll
+    for (int i = 0; i < 2 * K + 2; i++)
+        if (i < R)
+        {
+            const ulonglong2 v = ldg2(src + i * n);
+            in[0][i] = v.x;
+            in[1][i] = v.y;
+        }
+    scale_coeff_fp<K>(L, in[0], out[0], 1, 0);
+    scale_coeff_fp<K>(L, in[1], out[1], 1, 0);
+#pragma unroll
+    for (int i = 0; i < K; i++)
+        stg2(dst + i * n, out[0][i], out[1][i]);
+}
+
+template <int K>
+__global__ void ksmac_kernel_v2(const NttPrimeFp *fprimes, int special_idx, int key_rows, const u64 *ks1, const u64 *key, u64 *ks2,
+                                long long n, long long total)
+{
+    const long long idx = GLOBAL_IDX();
+    if (idx >= total)
+        return;
+    const long long hn = n >> 1;
+    const long long c = (idx % hn) * 2;
+    const long long t = idx / hn;
+    const int I = (int)(t % (K + 1));
+    const long long item = t / (K + 1);
+    const int prime_idx = I < K ? I : special_idx;
+    const int key_res = I < K ? I : key_rows - 1;
+    const double p = __ldg(&fprimes[prime_idx].p), pinv = __ldg(&fprimes[prime_idx].pinv);
+    const u64 *ops = ks1 + ((item * (K + 1) + I) * K) * n + c;
+    const u64 *kp = key + (long long)key_res * n + c;
+    double acc[2][2] = { { 0.0, 0.0 }, { 0.0, 0.0 } };
+#pragma unroll
+    for (int J = 0; J < K; J++)
+    {
+        const ulonglong2 x = ldg2(ops + J * n);
+        const ulonglong2 k0 = ldg2(kp + J * 2LL * key_rows * n), k1 = ldg2(kp + J * 2LL * key_rows * n + (long long)key_rows * n);
+        const double x0 = fp_from_u64(x.x), x1 = fp_from_u64(x.y);
+        acc[0][0] = B200_DADD(acc[0][0], fp_mulmod2(x0, fp_from_u64(k0.x), p, pinv));
+        acc[0][1] = B200_DADD(acc[0][1], fp_mulmod2(x0, fp_from_u64(k1.x), p, pinv));
+        acc[1][0] = B200_DADD(acc[1][0], fp_mulmod2(x1, fp_from_u64(k0.y), p, pinv));
+        acc[1][1] = B200_DADD(acc[1][1], fp_mulmod2(x1, fp_from_u64(k1.y), p, pinv));
+    }
+    u64 *o0 = ks2 + ((item * 2 + 0) * (K + 1) + I) * n + c;
+    u64 *o1 = ks2 + ((item * 2 + 1) * (K + 1) + I) * n + c;
+    stg2(o0, fp_to_canonical(acc[0][0], p, pinv), fp_to_canonical(acc[1][0], p, pinv));
+    stg2(o1, fp_to_canonical(acc[0][1], p, pinv), fp_to_canonical(acc[1][1], p, pinv));
+}
+#endif
 
 template <int K>
 __global__ void ksmoddown_kernel(const PrimeDev *primes, int special_idx, const u64 *inv_qsp, const u64 *ks2,
@@ -459,6 +635,7 @@ struct b200_ctx
     cudaStream_t s_side[NSIDE] = { nullptr, nullptr, nullptr, nullptr };
     cudaEvent_t ev_fork = nullptr, ev_join[NSIDE] = { nullptr, nullptr, nullptr, nullptr };
     int mr_split = 1;
+    int ew_v2 = 1; // FP64 element-wise kernels: two adjacent coefficients per thread with 128-bit accesses
     // staging ring of the *_host entry points (allocated on first use, reused afterwards)
     static const int NBUF = 3;
     u64 *hp_a[NBUF] = { nullptr, nullptr, nullptr }, *hp_b[NBUF] = { nullptr, nullptr, nullptr }, *hp_o[NBUF] = { nullptr, nullptr, nullptr };
@@ -575,7 +752,7 @@ static int build_device(b200_ctx *ctx)
             if (ctx->logn >= 4)
             { // transposed tables for the sub-stride-1 radix-16 pass (lanes read consecutive entries)
                 const int n16 = (int)(n >> 4), lg = ctx->logn;
-                std::vector<double> f16((size_t)15 * n16 * 2), i16((size_t)15 * n16 * 2);
+                std::vector<double> f16((size_t)15 * n16), i16((size_t)15 * n16);
                 for (int g = 0; g < n16; g++)
                     for (int l = 0; l < 4; l++)
                     {
@@ -583,15 +760,13 @@ static int build_device(b200_ctx *ctx)
                         { // forward: M = n/16 groups at the first stage of the pass
                             const size_t idx = ((size_t)n16 << l) + ((size_t)g << l) + grp;
                             const size_t slot = (size_t)((1 << l) - 1 + grp) * n16 + g;
-                            f16[2 * slot] = P.dfwd[2 * idx];
-                            f16[2 * slot + 1] = P.dfwd[2 * idx + 1];
+                            f16[slot] = P.dfwd[idx];
                         }
                         for (int grp = 0; grp < (8 >> l); grp++)
                         { // inverse: stage l has m = n/2 >> l groups
                             const size_t idx = ((size_t)1 << (lg - 1 - l)) + ((size_t)g << (3 - l)) + grp;
                             const size_t slot = (size_t)(16 - (16 >> l) + grp) * n16 + g;
-                            i16[2 * slot] = P.dinv[2 * idx];
-                            i16[2 * slot + 1] = P.dinv[2 * idx + 1];
+                            i16[slot] = P.dinv[idx];
                         }
                     }
                 double *d16 = nullptr;
@@ -893,6 +1068,14 @@ static int launch_ntt(b200_ctx *ctx, const JobDesc &jd, const u64 *src, long lon
                                     : ctx->logn == 13 ? (nt13 == 256 ? ntt_fp_kernel<13, FWD, 256> : ntt_fp_kernel<13, FWD, 512>)
                                                       : ntt_fp_kernel<14, FWD, 1024>;
         const int nt = ctx->logn == 12 ? 256 : ctx->logn == 13 ? (nt13 == 256 ? 256 : 512) : 1024;
+        if (trace_on())
+        {
+            static char labels[2][128][40];
+            const int sl = jd.slots < 128 ? jd.slots : 127;
+            snprintf(labels[FWD ? 1 : 0][sl], sizeof(labels[0][0]), "ntt_fp_kernel<%s> rows/item=%d%s", FWD ? "fwd" : "inv", jd.slots,
+                     job.tensor_mode ? " +tensor" : "");
+            g_trace_name = labels[FWD ? 1 : 0][sl];
+        }
         B200_LAUNCH(sfn, (unsigned)blocks, nt, ctx->ntt_smem, s, job);
         ctx->launches++;
         CU_TRY(cudaGetLastError());
@@ -978,9 +1161,20 @@ static int multiply_core(b200_ctx *ctx, int level, const u64 *a, int sa, const u
         return rc;
     // (1)-(2) lift to Bsk
     {
-        const long long total = batch * P * n;
-        DISPATCH_K(k, B200_LAUNCH(lift_kernel<KK>, blocks_for(total, EB), EB, 0, s, L, a, sa, square ? a : b, square ? 0 : sb, ext, n,
-                                                                           total));
+#ifndef B200_EMU_HEADER
+        if (L.fp && ctx->ew_v2)
+        {
+            const long long total = batch * P * (n >> 1);
+            DISPATCH_K(k, B200_LAUNCH(lift_kernel_v2<KK>, blocks_for(total, EB), EB, 0, s, L, a, sa, square ? a : b, square ? 0 : sb,
+                                      ext, n, total));
+        }
+        else
+#endif
+        {
+            const long long total = batch * P * n;
+            DISPATCH_K(k, B200_LAUNCH(lift_kernel<KK>, blocks_for(total, EB), EB, 0, s, L, a, sa, square ? a : b, square ? 0 : sb, ext,
+                                      n, total));
+        }
         ctx->launches++;
     }
     // (3) forward NTTs: q rows straight from the inputs, Bsk rows in place
@@ -1044,8 +1238,18 @@ static int multiply_core(b200_ctx *ctx, int level, const u64 *a, int sa, const u
         }
         else
         {
-            const long long total = batch * R * n;
-            B200_LAUNCH(tensor_kernel, blocks_for(total, EB), EB, 0, s, L, ext, sa, sb, D, n, total, square ? 1 : 0);
+#ifndef B200_EMU_HEADER
+            if (L.fp && ctx->ew_v2 && (square || (sa == 2 && sb == 2)))
+            {
+                const long long total = batch * R * (n >> 1);
+                B200_LAUNCH(tensor_kernel_v2, blocks_for(total, EB), EB, 0, s, L, ext, D, n, total, square ? 1 : 0);
+            }
+            else
+#endif
+            {
+                const long long total = batch * R * n;
+                B200_LAUNCH(tensor_kernel, blocks_for(total, EB), EB, 0, s, L, ext, sa, sb, D, n, total, square ? 1 : 0);
+            }
             ctx->launches++;
         }
         if ((rc = launch_ntt<false>(ctx, jd, D, (long long)Dn * R * n, D, (long long)Dn * R * n, batch, 0, s, fuse ? &ta : nullptr)))
@@ -1053,8 +1257,18 @@ static int multiply_core(b200_ctx *ctx, int level, const u64 *a, int sa, const u
     }
     // (6)-(8) scale
     {
-        const long long total = batch * Dn * n;
-        DISPATCH_K(k, B200_LAUNCH(scale_kernel<KK>, blocks_for(total, EB), EB, 0, s, L, D, Dn, dst0, split, dst1, n, total));
+#ifndef B200_EMU_HEADER
+        if (L.fp && ctx->ew_v2)
+        {
+            const long long total = batch * Dn * (n >> 1);
+            DISPATCH_K(k, B200_LAUNCH(scale_kernel_v2<KK>, blocks_for(total, EB), EB, 0, s, L, D, Dn, dst0, split, dst1, n, total));
+        }
+        else
+#endif
+        {
+            const long long total = batch * Dn * n;
+            DISPATCH_K(k, B200_LAUNCH(scale_kernel<KK>, blocks_for(total, EB), EB, 0, s, L, D, Dn, dst0, split, dst1, n, total));
+        }
         ctx->launches++;
     }
     CU_TRY(cudaGetLastError());
@@ -1098,9 +1312,20 @@ static int keyswitch_core(b200_ctx *ctx, int level, const u64 *d, long long d_st
             return rc;
     }
     {
-        const long long total = batch * (k + 1) * n;
-        DISPATCH_K(k, B200_LAUNCH(ksmac_kernel<KK>, blocks_for(total, EB), EB, 0, s, ctx->d_primes, ctx->d_fp_primes, (int)(L.fp != 0), special, Kkey, ks1, key, ks2, n,
-                                                                            total));
+#ifndef B200_EMU_HEADER
+        if (L.fp && ctx->ew_v2)
+        {
+            const long long total = batch * (k + 1) * (n >> 1);
+            DISPATCH_K(k, B200_LAUNCH(ksmac_kernel_v2<KK>, blocks_for(total, EB), EB, 0, s, ctx->d_fp_primes, special, Kkey, ks1, key,
+                                      ks2, n, total));
+        }
+        else
+#endif
+        {
+            const long long total = batch * (k + 1) * n;
+            DISPATCH_K(k, B200_LAUNCH(ksmac_kernel<KK>, blocks_for(total, EB), EB, 0, s, ctx->d_primes, ctx->d_fp_primes,
+                                      (int)(L.fp != 0), special, Kkey, ks1, key, ks2, n, total));
+        }
         ctx->launches++;
     }
     {
@@ -1222,6 +1447,8 @@ int b200_ctx_create(uint64_t n, const uint64_t *coeff_modulus, uint64_t count, u
         CU_TRY(cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming));
     }
     CU_TRY(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    if (getenv("B200_EW_V1"))
+        ctx->ew_v2 = 0;
     if (const char *sp = getenv("B200_MR_SPLIT"))
         ctx->mr_split = std::max(1, std::min((int)b200_ctx::NSIDE, atoi(sp)));
     CU_TRY(cudaDeviceSynchronize());
@@ -1366,6 +1593,33 @@ int b200_stream_synchronize(b200_ctx *ctx, void *stream)
         return fail(B200_E_NULL, "null argument");
     CU_TRY(cudaStreamSynchronize((cudaStream_t)stream));
     return 0;
+}
+
+void b200_trace_dump(void)
+{
+#ifndef B200_EMU_HEADER
+    cudaDeviceSynchronize();
+    std::map<std::string, std::pair<double, int>> acc;
+    std::vector<std::string> order;
+    double total = 0;
+    for (auto &r : g_trace)
+    {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, r.e0, r.e1);
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+        if (!acc.count(r.name))
+            order.push_back(r.name);
+        acc[r.name].first += ms;
+        acc[r.name].second++;
+        total += ms;
+    }
+    for (auto &nm : order)
+        fprintf(stderr, "[b200 trace] %-44s launches %5d  total %9.3f ms  avg %8.4f ms  %5.1f%%\n", nm.c_str(), acc[nm].second,
+                acc[nm].first, acc[nm].first / acc[nm].second, 100.0 * acc[nm].first / total);
+    fprintf(stderr, "[b200 trace] total %.3f ms\n", total);
+    g_trace.clear();
+#endif
 }
 
 uint64_t b200_launch_count(const b200_ctx *ctx) { return ctx ? ctx->launches.load() : 0; }

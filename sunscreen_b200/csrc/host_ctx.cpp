@@ -387,14 +387,12 @@ static NttPrimeHost make_ntt_prime(u64 p, int logn, bool allow_fp = true)
     if (P.fp)
     {
         const double pd = (double)p;
-        P.dfwd.resize(2 * n);
-        P.dinv.resize(2 * n);
+        P.dfwd.resize(n);
+        P.dinv.resize(n);
         for (size_t i = 0; i < n; i++)
         {
-            P.dfwd[2 * i] = (double)pw[i];
-            P.dfwd[2 * i + 1] = (double)pw[i] / pd;
-            P.dinv[2 * i] = (double)ipw[i];
-            P.dinv[2 * i + 1] = (double)ipw[i] / pd;
+            P.dfwd[i] = (double)pw[i];
+            P.dinv[i] = (double)ipw[i];
         }
         P.inv_n_d[0] = (double)P.inv_n.w;
         P.inv_n_d[1] = (double)P.inv_n.w / pd;

@@ -66,7 +66,7 @@ struct NttPrimeHost
     std::vector<u64> fwd, inv;
     // FP64 fast path (primes < 2^FP_PRIME_BITS): the same twiddles as exact integer-valued doubles {w, w/p}
     bool fp = false;
-    std::vector<double> dfwd, dinv; // [2n]
+    std::vector<double> dfwd, dinv; // [n] twiddles as doubles (FP64 transform)
     double inv_n_d[2] = { 0, 0 }, inv_n_w_d[2] = { 0, 0 };
     unsigned renorm_inv_mask = 0;   // bit i: renormalise the inputs of inverse pass i (see ntt_fp_body.cuh)
     unsigned renorm_fwd_mask = 0;

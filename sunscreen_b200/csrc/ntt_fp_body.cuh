@@ -4,8 +4,9 @@
 // lanes/clk/SM (measured, tools/ubench.cu), while DFMA/DMUL/DADD issue at 64 lanes/clk/SM.  A modular
 // multiplication by a precomputed twiddle can be done EXACTLY in 6 double-precision operations:
 //     h = y*w (rounded)            l = fma(y, w, -h)        (h + l == y*w exactly)
-//     q = rint(y * (w/p))          (magic-number rounding: fma(y, wp, 1.5*2^52) - 1.5*2^52)
-//     r = fma(-q, p, h) + l        (== y*w - q*p exactly: an integer of magnitude < p)
+//     q = rint(h * (1/p))          (magic-number rounding: fma(h, pinv, 1.5*2^52) - 1.5*2^52)
+//     r = fma(-q, p, h) + l        (== y*w - q*p exactly: an integer of magnitude <= p(1/2 + |y|/2^52) < p)
+// (the twiddle tables therefore hold w only: one 8-byte load per butterfly group instead of a {w, w/p} pair)
 // All values are integer-valued doubles in a signed lazy range; every operation above is exact as long as
 // |y| < 2^51 and p < 2^47, so the transform computes the same residues as the integer path — the outputs are
 // reduced to the canonical [0,p) before they leave the kernel and are bit-identical to the reference's
@@ -39,10 +40,10 @@
 struct NttPrimeFp
 {
     double p, pinv;
-    double inv_n[2], inv_n_w[2]; // {w, w/p}
-    const double *fwd;           // [2n] {w, w/p}
+    double inv_n[2], inv_n_w[2]; // {w, w/p} (only [0] is used by the transform)
+    const double *fwd;           // [n] w, bit-reversed order
     const double *inv;
-    const double *fwd16;         // transposed twiddles of the sub-stride-1 radix-16 pass: [15][n/16] {w, w/p}
+    const double *fwd16;         // transposed twiddles of the sub-stride-1 radix-16 pass: [15][n/16]
     const double *inv16;
     unsigned renorm_fwd, renorm_inv; // bit i: renormalise inputs of pass i (pass order of the respective transform)
     int enabled;
@@ -88,40 +89,71 @@ B200_HD double fp_from_u64(u64 v) // exact for v < 2^52
 #endif
 }
 
-B200_HD void fp_load_tw(const double *__restrict__ tw, int idx, double &w, double &wp)
+B200_HD double fp_load_tw(const double *__restrict__ tw, int idx)
 {
 #if defined(__CUDA_ARCH__)
-    const double2 t2 = __ldg(reinterpret_cast<const double2 *>(tw) + idx);
-    w = t2.x;
-    wp = t2.y;
+    return __ldg(tw + idx);
 #else
-    w = tw[2 * idx];
-    wp = tw[2 * idx + 1];
+    return tw[idx];
 #endif
 }
 
-// one butterfly stage `l` of a radix-2^L group (compile-time stage index so everything stays in registers)
-template <int L, int l, bool FWD, bool TW16>
-B200_HD void fp_stage(double (&x)[1 << L], const double *__restrict__ tw, int g, int i, int logs, int logn, int M, int n16,
-                      const NttPrimeFp &P, bool last_inv)
+// All R-1 twiddles of a radix-2^L group, loaded up front so that their (L2) latency is paid once per group and
+// overlaps the data loads.  Slot order: forward stage l, sub-group grp -> (2^l - 1) + grp;
+// inverse stage l, sub-group grp -> R - (R >> l) + grp  (the TW16 tables use the same slot order).
+template <int L, bool FWD, bool TW16>
+B200_HD void fp_load_group_tw(double (&tws)[(1 << L) - 1], const double *__restrict__ tw, int g, int i, int logs, int logn, int M,
+                              int n16, const NttPrimeFp &P, bool last_inv)
 {
     constexpr int R = 1 << L;
-    const double p = P.p;
+#pragma unroll
+    for (int l = 0; l < L; l++)
+    {
+        if (FWD)
+        {
+            const int tw_base = (M << l) + (i << l);
+#pragma unroll
+            for (int grp = 0; grp < (1 << l); grp++)
+            {
+                const int slot = (1 << l) - 1 + grp;
+                tws[slot] = fp_load_tw(tw, TW16 ? slot * n16 + g : tw_base + grp);
+            }
+        }
+        else
+        {
+            const int m = 1 << (logn - 1 - logs - l);
+            const int tw_base = m + (i << (L - l - 1));
+#pragma unroll
+            for (int grp = 0; grp < (R >> (l + 1)); grp++)
+            {
+                const int slot = R - (R >> l) + grp;
+                if (last_inv && l == L - 1)
+                    tws[slot] = P.inv_n_w[0]; // final stage of the whole inverse: twiddle pre-multiplied by n^-1
+                else
+                    tws[slot] = fp_load_tw(tw, TW16 ? slot * n16 + g : tw_base + grp);
+            }
+        }
+    }
+}
+
+// one butterfly stage `l` of a radix-2^L group (compile-time stage index so everything stays in registers)
+template <int L, int l, bool FWD>
+B200_HD void fp_stage(double (&x)[1 << L], const double (&tws)[(1 << L) - 1], const NttPrimeFp &P, bool last_inv)
+{
+    constexpr int R = 1 << L;
+    const double p = P.p, pinv = P.pinv;
     if (FWD)
     {
         constexpr int half = 1 << (L - 1 - l);
-        const int tw_base = (M << l) + (i << l);
 #pragma unroll
         for (int grp = 0; grp < (1 << l); grp++)
         {
-            const int idx = TW16 ? (((1 << l) - 1 + grp) * n16 + g) : (tw_base + grp);
-            double w, wp;
-            fp_load_tw(tw, idx, w, wp);
+            const double w = tws[(1 << l) - 1 + grp];
 #pragma unroll
             for (int jj = 0; jj < half; jj++)
             {
                 const int j = grp * 2 * half + jj;
-                const double T = fp_mulmod(x[j + half], w, wp, p);
+                const double T = fp_mulmod2(x[j + half], w, p, pinv);
                 const double X = x[j];
                 x[j] = B200_DADD(X, T);
                 x[j + half] = B200_DADD(X, -T);
@@ -131,30 +163,19 @@ B200_HD void fp_stage(double (&x)[1 << L], const double *__restrict__ tw, int g,
     else
     {
         constexpr int half = 1 << l;
-        const int m = 1 << (logn - 1 - logs - l);
-        const int tw_base = m + (i << (L - l - 1));
         const bool fold = last_inv && (l == L - 1);
 #pragma unroll
         for (int grp = 0; grp < (R >> (l + 1)); grp++)
         {
-            // TW16 slots (L == 4): l=0 -> 0..7, l=1 -> 8..11, l=2 -> 12..13, l=3 -> 14
-            const int idx = TW16 ? ((16 - (16 >> l) + grp) * n16 + g) : (tw_base + grp);
-            double w, wp;
-            if (fold)
-            {
-                w = P.inv_n_w[0];
-                wp = P.inv_n_w[1];
-            }
-            else
-                fp_load_tw(tw, idx, w, wp);
+            const double w = tws[R - (R >> l) + grp];
 #pragma unroll
             for (int jj = 0; jj < half; jj++)
             {
                 const int j = grp * 2 * half + jj;
                 const double X = x[j], Y = x[j + half];
                 const double U = B200_DADD(X, Y);
-                x[j + half] = fp_mulmod(B200_DADD(X, -Y), w, wp, p);
-                x[j] = fold ? fp_mulmod(U, P.inv_n[0], P.inv_n[1], p) : U;
+                x[j + half] = fp_mulmod2(B200_DADD(X, -Y), w, p, pinv);
+                x[j] = fold ? fp_mulmod2(U, P.inv_n[0], p, pinv) : U;
             }
         }
     }
@@ -183,6 +204,10 @@ B200_HD void ntt_fp_group(double *sm, const u64 *__restrict__ gsrc, u64 *__restr
     const int base = (i << (logs + L)) + o;
     const int pbase = ntt_pad(base);
     const double p = P.p;
+    const double *__restrict__ tw = TW16 ? (FWD ? P.fwd16 : P.inv16) : (FWD ? P.fwd : P.inv);
+    const int n16 = 1 << (logn - 4); // groups of the radix-16 pass (TW16 layout: [slot][group])
+    double tws[R - 1];
+    fp_load_group_tw<L, FWD, TW16>(tws, tw, g, i, logs, logn, M, n16, P, last_inv);
     double x[R];
 #pragma unroll
     for (int j = 0; j < R; j++)
@@ -199,15 +224,13 @@ B200_HD void ntt_fp_group(double *sm, const u64 *__restrict__ gsrc, u64 *__restr
         if (RENORM && renorm)
             x[j] = fp_renorm(x[j], p, P.pinv);
     }
-    const double *__restrict__ tw = TW16 ? (FWD ? P.fwd16 : P.inv16) : (FWD ? P.fwd : P.inv);
-    const int n16 = 1 << (logn - 4); // groups of the radix-16 pass (TW16 layout: [slot][group])
-    fp_stage<L, 0, FWD, TW16>(x, tw, g, i, logs, logn, M, n16, P, last_inv);
+    fp_stage<L, 0, FWD>(x, tws, P, last_inv);
     if constexpr (L > 1)
-        fp_stage<L, 1, FWD, TW16>(x, tw, g, i, logs, logn, M, n16, P, last_inv);
+        fp_stage<L, 1, FWD>(x, tws, P, last_inv);
     if constexpr (L > 2)
-        fp_stage<L, 2, FWD, TW16>(x, tw, g, i, logs, logn, M, n16, P, last_inv);
+        fp_stage<L, 2, FWD>(x, tws, P, last_inv);
     if constexpr (L > 3)
-        fp_stage<L, 3, FWD, TW16>(x, tw, g, i, logs, logn, M, n16, P, last_inv);
+        fp_stage<L, 3, FWD>(x, tws, P, last_inv);
 #pragma unroll
     for (int j = 0; j < R; j++)
     {

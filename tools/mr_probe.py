@@ -25,3 +25,5 @@ for _ in range(5):
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 5
 print(f"split={os.environ.get('B200_MR_SPLIT','1')} batch={B}: {ms:.3f} ms/step {B/ms*1e3:.0f} ops/s  checksum {int(out.sum().item()) & 0xffffffff:08x}")
+if os.environ.get("B200_TRACE"):
+    ctx.L.lib.b200_trace_dump()  # per-kernel totals over the 3 warm-up + 5 timed steps
