@@ -779,12 +779,13 @@ static int build_device(b200_ctx *ctx)
             for (int pi = 0; pi < ctx->npass; pi++)
             {
                 const int L = ctx->pass_L[pi];
-                if (B + L * p >= LIMIT)
+                // a butterfly output is X +- T with |T| <= p(5/8 + |y|/2^52) <= 1.125 p for |y| < 2^51 (ntt_fp_body.cuh)
+                if (B + L * 1.125 * p >= LIMIT)
                 {
                     fp[i].renorm_fwd |= 1u << pi;
-                    B = 0.51 * p;
+                    B = 0.76 * p;
                 }
-                B += L * p;
+                B += L * 1.125 * p;
             }
             B = p;
             int step = 0;
@@ -794,7 +795,7 @@ static int build_device(b200_ctx *ctx)
                 if (B * (double)(1 << L) >= LIMIT)
                 {
                     fp[i].renorm_inv |= 1u << step;
-                    B = 0.51 * p;
+                    B = 0.76 * p;
                 }
                 B *= (double)(1 << L);
                 if (B >= LIMIT)

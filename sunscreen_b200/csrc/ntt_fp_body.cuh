@@ -4,8 +4,8 @@
 // lanes/clk/SM (measured, tools/ubench.cu), while DFMA/DMUL/DADD issue at 64 lanes/clk/SM.  A modular
 // multiplication by a precomputed twiddle can be done EXACTLY in 6 double-precision operations:
 //     h = y*w (rounded)            l = fma(y, w, -h)        (h + l == y*w exactly)
-//     q = rint(h * (1/p))          (magic-number rounding: fma(h, pinv, 1.5*2^52) - 1.5*2^52)
-//     r = fma(-q, p, h) + l        (== y*w - q*p exactly: an integer of magnitude <= p(1/2 + |y|/2^52) < p)
+//     q = rint(h * (1/p))          (DMUL + FRND.F64; the rounding runs on the XU pipe, not the FP64 pipe)
+//     r = fma(-q, p, h) + l        (== y*w - q*p exactly: an integer of magnitude <= p(5/8 + |y|/2^52) <= 1.125 p)
 // (the twiddle tables therefore hold w only: one 8-byte load per butterfly group instead of a {w, w/p} pair)
 // All values are integer-valued doubles in a signed lazy range; every operation above is exact as long as
 // |y| < 2^51 and p < 2^47, so the transform computes the same residues as the integer path — the outputs are
@@ -15,7 +15,7 @@
 // Schedule: identical pass structure to ntt_body.cuh (radix-8/16 groups, padded shared memory), except that
 // the FIRST pass reads its group straight from global memory (u64 -> double) and the LAST pass writes its
 // group straight to global memory (double -> canonical u64), saving two shared-memory round trips.
-// Magnitude bookkeeping (host, b200_bfv.cu:fp_renorm_masks): a forward butterfly adds < p to the bound, an
+// Magnitude bookkeeping (host, b200_bfv.cu build_device): a forward butterfly adds <= 1.125 p to the bound, an
 // inverse butterfly doubles it on the sum path; whenever a pass would exceed 2^50 its inputs are first
 // renormalised (x -= rint(x/p)*p, 3 DP ops).
 #pragma once
@@ -26,12 +26,22 @@
 #define B200_DMUL(a, b) __dmul_rn((a), (b))
 #define B200_DADD(a, b) __dadd_rn((a), (b))
 #define B200_DFMA(a, b, c) __fma_rn((a), (b), (c))
+// round to nearest integer: FRND.F64 issues on the XU pipe (measured 14.6 lanes/clk/SM, tools/ubench.cu), i.e. it
+// takes the rounding OFF the FP64 pipe that bounds these kernels (the magic-number add/sub costs two FP64 slots)
+__device__ __forceinline__ double b200_rint(double x)
+{
+    double r;
+    asm("cvt.rni.f64.f64 %0, %1;" : "=d"(r) : "d"(x));
+    return r;
+}
+#define B200_RINT(x) b200_rint(x)
 #else
 #include <cmath>
 // host (tests/emu): built with -ffp-contract=off so these stay separate IEEE operations
 #define B200_DMUL(a, b) ((a) * (b))
 #define B200_DADD(a, b) ((a) + (b))
 #define B200_DFMA(a, b, c) std::fma((a), (b), (c))
+#define B200_RINT(x) std::nearbyint(x)
 #endif
 
 #define B200_MAGIC 6755399441055744.0   /* 1.5 * 2^52 */
@@ -53,6 +63,8 @@ B200_HD double fp_mulmod(double y, double w, double wp, double p)
 {
     const double h = B200_DMUL(y, w);
     const double l = B200_DFMA(y, w, -h);
+    // magic-number rounding (two FP64 slots): the element-wise BEHZ kernels that use this form issue almost nothing
+    // but modular products, and routing all their roundings through the 16-lane XU pipe was measured slower
     const double q = B200_DADD(B200_DFMA(y, wp, B200_MAGIC), -B200_MAGIC);
     return B200_DADD(B200_DFMA(-q, p, h), l);
 }
@@ -61,7 +73,7 @@ B200_HD double fp_mulmod2(double a, double b, double p, double pinv)
 {
     const double h = B200_DMUL(a, b);
     const double l = B200_DFMA(a, b, -h);
-    const double q = B200_DADD(B200_DFMA(h, pinv, B200_MAGIC), -B200_MAGIC);
+    const double q = B200_RINT(B200_DMUL(h, pinv));
     return B200_DADD(B200_DFMA(-q, p, h), l);
 }
 B200_HD double fp_renorm(double x, double p, double pinv)
@@ -69,10 +81,17 @@ B200_HD double fp_renorm(double x, double p, double pinv)
     const double q = B200_DADD(B200_DFMA(x, pinv, B200_MAGIC), -B200_MAGIC);
     return B200_DFMA(-q, p, x);
 }
+// same with the rounding on the XU pipe (used inside the transform, where FP64 issue slots are the bound)
+B200_HD double fp_renorm_x(double x, double p, double pinv)
+{
+    const double q = B200_RINT(B200_DMUL(x, pinv));
+    return B200_DFMA(-q, p, x);
+}
 // any lazy value -> canonical [0,p) as u64
+template <bool XU = false>
 B200_HD u64 fp_to_canonical(double x, double p, double pinv)
 {
-    double r = fp_renorm(x, p, pinv); // |r| <= p/2 + 1
+    double r = XU ? fp_renorm_x(x, p, pinv) : fp_renorm(x, p, pinv); // |r| <= 0.76 p
     r = r < 0.0 ? B200_DADD(r, p) : r;
 #if defined(__CUDA_ARCH__)
     return (u64)__double_as_longlong(r + B200_TWO52) & 0x000FFFFFFFFFFFFFULL; // exact: 0 <= r < 2^47
@@ -222,7 +241,7 @@ B200_HD void ntt_fp_group(double *sm, const u64 *__restrict__ gsrc, u64 *__restr
         else
             x[j] = sm[fp_elem_index(pbase, base, j, logs)];
         if (RENORM && renorm)
-            x[j] = fp_renorm(x[j], p, P.pinv);
+            x[j] = fp_renorm_x(x[j], p, P.pinv);
     }
     fp_stage<L, 0, FWD>(x, tws, P, last_inv);
     if constexpr (L > 1)
@@ -235,7 +254,7 @@ B200_HD void ntt_fp_group(double *sm, const u64 *__restrict__ gsrc, u64 *__restr
     for (int j = 0; j < R; j++)
     {
         if (DST_GLOBAL)
-            gdst[base + (j << logs)] = fp_to_canonical(x[j], p, P.pinv);
+            gdst[base + (j << logs)] = fp_to_canonical<true>(x[j], p, P.pinv);
         else
             sm[fp_elem_index(pbase, base, j, logs)] = x[j];
     }
@@ -451,7 +470,7 @@ struct NttFpStaticPass
         { // coalesced copy-out: lazy double -> canonical u64
 #pragma unroll
             for (int it = 0; it < N / NT; it++)
-                dst[tid + it * NT] = fp_to_canonical(smd[ptid + it * PNT], P.p, P.pinv);
+                dst[tid + it * NT] = fp_to_canonical<true>(smd[ptid + it * PNT], P.p, P.pinv);
         }
         if (STEP + 1 < NP)
             NttFpStaticPass<LOGN, NT, FWD, (STEP + 1 < NP ? STEP + 1 : STEP)>::run(job, P, PI_, src, dst, smd, tid, item, slot);

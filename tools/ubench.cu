@@ -165,6 +165,8 @@ __global__ void k_fp(double *out, double a0, double b0)
                 acc[i] = acc[i] * a;
             else if (MODE == 2)
                 acc[i] = acc[i] + a;
+            else if (MODE == 3)
+                asm volatile("cvt.rni.f64.f64 %0, %0;" : "+d"(acc[i]));
         }
     }
     double s = 0;
@@ -186,6 +188,17 @@ __device__ __forceinline__ void bf_fp(double &X, double &Y, double w, double wp,
     Y = X - r;
     X = X + r;
 }
+// variant: q = rint(h * pinv) with the rounding done by FRND (cvt.rni.f64.f64) instead of the magic add/sub
+__device__ __forceinline__ void bf_fp_rnd(double &X, double &Y, double w, double pinv, double p)
+{
+    double h = Y * w;
+    double l = fma(Y, w, -h);
+    double q = h * pinv;
+    asm("cvt.rni.f64.f64 %0, %0;" : "+d"(q));
+    double r = fma(-q, p, h) + l;
+    Y = X - r;
+    X = X + r;
+}
 template <int MODE>
 __global__ void k_bf_fp(double *out, const double *tw, double p)
 {
@@ -203,7 +216,12 @@ __global__ void k_bf_fp(double *out, const double *tw, double p)
 #pragma unroll
             for (int j = 0; j < 8; j++)
                 if (!(j & half))
-                    bf_fp(x[j], x[j + half], w, wp, p);
+                {
+                    if (MODE == 2)
+                        bf_fp_rnd(x[j], x[j + half], w, 1.0 / p, p);
+                    else
+                        bf_fp(x[j], x[j + half], w, wp, p);
+                }
             w = w * 0.999 + 1.0;
             wp = w / p;
         }
@@ -341,7 +359,7 @@ int main()
                bfs / ms / 1e3 / 53248.0);                                                                              \
     }
     RUNB(0) RUNB(1) RUNB(2)
-    const char *fn[] = { "DFMA", "DMUL", "DADD" };
+    const char *fn[] = { "DFMA", "DMUL", "DADD", "FRND.F64" };
 #define RUNF(M)                                                                                                        \
     {                                                                                                                  \
         float ms = timeit([&] { k_fp<M><<<blocks, threads>>>((double *)out, 1.0000001, 0.5); });                       \
@@ -349,9 +367,9 @@ int main()
         printf("%-14s %8.3f ms  %8.2f Tlane-instr/s (%.1f lanes/clk/SM @1.9GHz)\n", fn[M], ms, ops / ms / 1e9,       \
                ops / ms / 1e3 / 1.9e9 / sms * 1e3);                                                                    \
     }
-    RUNF(0) RUNF(1) RUNF(2)
+    RUNF(0) RUNF(1) RUNF(2) RUNF(3)
     cudaMemset(out, 0, (size_t)blocks * threads * 8 * sizeof(u64));
-    const char *bfn[] = { "bf fp64 (no renorm)", "bf fp64 (+renorm/3)" };
+    const char *bfn[] = { "bf fp64 (no renorm)", "bf fp64 (+renorm/3)", "bf fp64 (FRND quotient)" };
 #define RUNBF(M)                                                                                                       \
     {                                                                                                                  \
         float ms = timeit([&] { k_bf_fp<M><<<blocks, threads>>>((double *)out, (const double *)tw, 8796092858369.0); }); \
@@ -359,7 +377,7 @@ int main()
         printf("%-20s %8.3f ms  %8.2f G butterflies/s -> %.2f M NTT(8192)/s\n", bfn[M], ms, bfs / ms / 1e6,          \
                bfs / ms / 1e3 / 53248.0);                                                                              \
     }
-    RUNBF(0) RUNBF(1)
+    RUNBF(0) RUNBF(1) RUNBF(2)
     {
         float ms = timeit([&] { k_bf_mixed<<<blocks, threads>>>(out, tw, 0x7fffffd8001ULL); });
         double bfs = (double)blocks * threads * (ITERS / 8) * 12;
