@@ -11,11 +11,11 @@
  * SEALContext, enqueue under a mutex), matching the reference's thread-safety contract for the rayon DAG
  * executor (sunscreen_runtime/src/run.rs:415-469).
  *
- * Covered in this round: parameter objects, SEALContext, Ciphertext/Plaintext/PublicKey/SecretKey/KSwitchKeys data
- * objects, the whole BFV Evaluator surface seal_fhe uses, Decryptor (decrypt + invariant noise budget), KeyGenerator
- * and Encryptor (sampling on the host with the reference's PRNG stream, arithmetic on the GPU).
- * BatchEncoder / Save-Load / PolynomialArray / the ReturnComponents encryption variants are "next" rows
- * (SURVEY.md §8(f)).
+ * Covered: all 121 functions seal_fhe references (grep `bindgen::` in seal_fhe/src) — parameter objects,
+ * SEALContext, Ciphertext/Plaintext/PublicKey/SecretKey/KSwitchKeys data objects and their wire format
+ * (SaveSize/Save/Load, S/serialization.h), the whole BFV Evaluator surface, Decryptor (decrypt, invariant noise and
+ * noise budget), KeyGenerator and Encryptor incl. the fork's ReturnComponents variants (sampling on the host with the
+ * reference's PRNG stream, arithmetic on the GPU), BatchEncoder, PolynomialArray.
  * B200_* names are extensions (bulk word access, batching) that the reference does not have.
  */
 #ifndef B200_SEALC_H
@@ -94,12 +94,15 @@ SEAL_C_FUNC Ciphertext_IsTransparent(void *thisptr, bool *result);
 /* ---- Plaintext (S/c/plaintext.h) ---- */
 SEAL_C_FUNC Plaintext_Create1(void *memoryPoolHandle, void **plaintext);
 SEAL_C_FUNC Plaintext_Create2(uint64_t coeffCount, void *memoryPoolHandle, void **plaintext);
+SEAL_C_FUNC Plaintext_Create4(uint8_t *hex_poly, void *memoryPoolHandle, void **plaintext);
 SEAL_C_FUNC Plaintext_Create5(void *copy, void **plaintext);
 SEAL_C_FUNC Plaintext_Destroy(void *thisptr);
 SEAL_C_FUNC Plaintext_CoeffCount(void *thisptr, uint64_t *coeff_count);
 SEAL_C_FUNC Plaintext_CoeffAt(void *thisptr, uint64_t index, uint64_t *coeff);
 SEAL_C_FUNC Plaintext_SetCoeffAt(void *thisptr, uint64_t index, uint64_t value);
 SEAL_C_FUNC Plaintext_Resize(void *thisptr, uint64_t coeff_count);
+SEAL_C_FUNC Plaintext_GetParmsId(void *thisptr, uint64_t *parms_id);
+SEAL_C_FUNC Plaintext_SetParmsId(void *thisptr, uint64_t *parms_id);
 SEAL_C_FUNC Plaintext_IsNTTForm(void *thisptr, bool *is_ntt_form);
 SEAL_C_FUNC Plaintext_IsZero(void *thisptr, bool *is_zero);
 
@@ -145,6 +148,7 @@ SEAL_C_FUNC Evaluator_MultiplyPlain(void *thisptr, void *encrypted, void *plain,
 SEAL_C_FUNC Evaluator_Square(void *thisptr, void *encrypted, void *destination, void *pool);
 SEAL_C_FUNC Evaluator_Relinearize(void *thisptr, void *encrypted, void *relinKeys, void *destination, void *pool);
 SEAL_C_FUNC Evaluator_ModSwitchToNext1(void *thisptr, void *encrypted, void *destination, void *pool);
+SEAL_C_FUNC Evaluator_ModSwitchToNext2(void *thisptr, void *plain, void *destination);
 SEAL_C_FUNC Evaluator_Exponentiate(void *thisptr, void *encrypted, uint64_t exponent, void *relin_keys, void *destination,
                                    void *pool);
 SEAL_C_FUNC Evaluator_ApplyGalois(void *thisptr, void *encrypted, uint32_t galois_elt, void *galois_keys, void *destination,
@@ -158,6 +162,7 @@ SEAL_C_FUNC Decryptor_Create(void *context, void *secret_key, void **decryptor);
 SEAL_C_FUNC Decryptor_Destroy(void *thisptr);
 SEAL_C_FUNC Decryptor_Decrypt(void *thisptr, void *encrypted, void *destination);
 SEAL_C_FUNC Decryptor_InvariantNoiseBudget(void *thisptr, void *encrypted, int *invariant_noise_budget);
+SEAL_C_FUNC Decryptor_InvariantNoise(void *thisptr, void *encrypted, double *invariant_noise);
 
 /* ---- KeyGenerator (S/c/keygenerator.h) : host-side sampling (the reference's Blake2xb stream), GPU arithmetic ---- */
 SEAL_C_FUNC KeyGenerator_Create1(void *context, void **key_generator);
@@ -176,6 +181,19 @@ SEAL_C_FUNC Encryptor_Create(void *context, void *public_key, void *secret_key, 
 SEAL_C_FUNC Encryptor_Destroy(void *thisptr);
 SEAL_C_FUNC Encryptor_Encrypt(void *thisptr, void *plaintext, void *destination, void *pool_handle);
 SEAL_C_FUNC Encryptor_EncryptSymmetric(void *thisptr, void *plaintext, bool save_seed, void *destination, void *pool_handle);
+/* the Sunscreen fork's entry points that also return u, e (PolynomialArray handles) and the rounding remainder
+   (S/c/encryptor.h:24-40, S/c/encryptor.cpp:136-240,300-372) */
+SEAL_C_FUNC Encryptor_EncryptReturnComponents(void *thisptr, void *plaintext, bool disable_special_modulus, void *destination,
+                                              void *u_destination, void *e_destination, void *remainder_destination,
+                                              void *pool_handle);
+SEAL_C_FUNC Encryptor_EncryptReturnComponentsSetSeed(void *thisptr, void *plaintext, bool disable_special_modulus,
+                                                     void *destination, void *u_destination, void *e_destination,
+                                                     void *remainder_destination, void *seed, void *pool_handle);
+SEAL_C_FUNC Encryptor_EncryptSymmetricReturnComponents(void *thisptr, void *plaintext, void *destination, void *e_destination,
+                                                       void *remainder_destination, void *pool_handle);
+SEAL_C_FUNC Encryptor_EncryptSymmetricReturnComponentsSetSeed(void *thisptr, void *plaintext, void *destination,
+                                                              void *e_destination, void *remainder_destination, void *seed,
+                                                              void *pool_handle);
 
 /* ---- BatchEncoder (S/c/batchencoder.h): slot permutation on the host, negacyclic NTT mod t on the GPU ---- */
 SEAL_C_FUNC BatchEncoder_Create(void *context, void **batch_encoder);
@@ -185,6 +203,50 @@ SEAL_C_FUNC BatchEncoder_Encode2(void *thisptr, uint64_t count, int64_t *values,
 SEAL_C_FUNC BatchEncoder_Decode1(void *thisptr, void *plain, uint64_t *count, uint64_t *destination, void *pool);
 SEAL_C_FUNC BatchEncoder_Decode2(void *thisptr, void *plain, uint64_t *count, int64_t *destination, void *pool);
 SEAL_C_FUNC BatchEncoder_GetSlotCount(void *thisptr, uint64_t *slot_count);
+
+/* ---- wire format (S/c/ciphertext.h:80-86, plaintext.h:82-88, kswitchkeys.h:40-46, publickey.h:30-36,
+        secretkey.h:30-36 -> S/serialization.h): compr_mode 0 none, 1 zlib, 2 zstd ---- */
+#define B200_COR_E_IO_HR 0x80131620L
+SEAL_C_FUNC Ciphertext_SaveSize(void *thisptr, uint8_t compr_mode, int64_t *result);
+SEAL_C_FUNC Ciphertext_Save(void *thisptr, uint8_t *outptr, uint64_t size, uint8_t compr_mode, int64_t *out_bytes);
+SEAL_C_FUNC Ciphertext_UnsafeLoad(void *thisptr, void *context, uint8_t *inptr, uint64_t size, int64_t *in_bytes);
+SEAL_C_FUNC Ciphertext_Load(void *thisptr, void *context, uint8_t *inptr, uint64_t size, int64_t *in_bytes);
+SEAL_C_FUNC Plaintext_SaveSize(void *thisptr, uint8_t compr_mode, int64_t *result);
+SEAL_C_FUNC Plaintext_Save(void *thisptr, uint8_t *outptr, uint64_t size, uint8_t compr_mode, int64_t *out_bytes);
+SEAL_C_FUNC Plaintext_UnsafeLoad(void *thisptr, void *context, uint8_t *inptr, uint64_t size, int64_t *in_bytes);
+SEAL_C_FUNC Plaintext_Load(void *thisptr, void *context, uint8_t *inptr, uint64_t size, int64_t *in_bytes);
+SEAL_C_FUNC PublicKey_SaveSize(void *thisptr, uint8_t compr_mode, int64_t *result);
+SEAL_C_FUNC PublicKey_Save(void *thisptr, uint8_t *outptr, uint64_t size, uint8_t compr_mode, int64_t *out_bytes);
+SEAL_C_FUNC PublicKey_UnsafeLoad(void *thisptr, void *context, uint8_t *inptr, uint64_t size, int64_t *in_bytes);
+SEAL_C_FUNC PublicKey_Load(void *thisptr, void *context, uint8_t *inptr, uint64_t size, int64_t *in_bytes);
+SEAL_C_FUNC SecretKey_SaveSize(void *thisptr, uint8_t compr_mode, int64_t *result);
+SEAL_C_FUNC SecretKey_Save(void *thisptr, uint8_t *outptr, uint64_t size, uint8_t compr_mode, int64_t *out_bytes);
+SEAL_C_FUNC SecretKey_UnsafeLoad(void *thisptr, void *context, uint8_t *inptr, uint64_t size, int64_t *in_bytes);
+SEAL_C_FUNC SecretKey_Load(void *thisptr, void *context, uint8_t *inptr, uint64_t size, int64_t *in_bytes);
+SEAL_C_FUNC KSwitchKeys_SaveSize(void *thisptr, uint8_t compr_mode, int64_t *result);
+SEAL_C_FUNC KSwitchKeys_Save(void *thisptr, uint8_t *outptr, uint64_t size, uint8_t compr_mode, int64_t *out_bytes);
+SEAL_C_FUNC KSwitchKeys_UnsafeLoad(void *thisptr, void *context, uint8_t *inptr, uint64_t size, int64_t *in_bytes);
+SEAL_C_FUNC KSwitchKeys_Load(void *thisptr, void *context, uint8_t *inptr, uint64_t size, int64_t *in_bytes);
+
+/* ---- PolynomialArray (S/c/polyarray.h, added by the Sunscreen fork) ---- */
+SEAL_C_FUNC PolynomialArray_Create(void *memoryPoolHandle, void **poly_array);
+SEAL_C_FUNC PolynomialArray_CreateFromCiphertext(void *memoryPoolHandle, void *context, void *ciphertext, void **poly_array);
+SEAL_C_FUNC PolynomialArray_CreateFromPublicKey(void *memoryPoolHandle, void *context, void *public_key, void **poly_array);
+SEAL_C_FUNC PolynomialArray_CreateFromSecretKey(void *memoryPoolHandle, void *context, void *secret_key, void **poly_array);
+SEAL_C_FUNC PolynomialArray_Copy(void *copy, void **poly_array);
+SEAL_C_FUNC PolynomialArray_Destroy(void *thisptr);
+SEAL_C_FUNC PolynomialArray_IsReserved(void *thisptr, bool *is_reserved);
+SEAL_C_FUNC PolynomialArray_IsRns(void *thisptr, bool *is_rns);
+SEAL_C_FUNC PolynomialArray_IsMultiprecision(void *thisptr, bool *is_multiprecision);
+SEAL_C_FUNC PolynomialArray_ToRns(void *thisptr);
+SEAL_C_FUNC PolynomialArray_ToMultiprecision(void *thisptr);
+SEAL_C_FUNC PolynomialArray_GetPolynomial(void *thisptr, uint64_t poly_index, uint64_t *data);
+SEAL_C_FUNC PolynomialArray_ExportSize(void *thisptr, uint64_t *size);
+SEAL_C_FUNC PolynomialArray_PerformExport(void *thisptr, uint64_t *data);
+SEAL_C_FUNC PolynomialArray_PolySize(void *thisptr, uint64_t *size);
+SEAL_C_FUNC PolynomialArray_PolyModulusDegree(void *thisptr, uint64_t *size);
+SEAL_C_FUNC PolynomialArray_CoeffModulusSize(void *thisptr, uint64_t *size);
+SEAL_C_FUNC PolynomialArray_Drop(void *thisptr, void **poly_array);
 
 /* ---- extensions (not in the reference) ---- */
 /* deterministic pk-encryption from a 64-byte seed: the same random stream (and therefore the same ciphertext words)

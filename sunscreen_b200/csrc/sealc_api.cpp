@@ -24,454 +24,11 @@
 
 namespace
 {
-typedef uint64_t u64;
-typedef std::array<u64, 4> ParmsId;
-const ParmsId kZeroId = { { 0, 0, 0, 0 } };
-
-const long S_OK_ = 0L;
-const long E_POINTER_ = (long)0x80004003L;
-const long E_INVALIDARG_ = (long)0x80070057L;
-const long E_OUTOFMEMORY_ = (long)0x8007000EL;
-const long E_UNEXPECTED_ = (long)0x8000FFFFL;
-const long COR_E_INVALIDOPERATION_ = (long)0x80131509L;
-const long ERROR_INVALID_INDEX_ = (long)0x80070585L;
-
-struct InvalidArg : std::runtime_error { using std::runtime_error::runtime_error; };
-struct LogicErr : std::runtime_error { using std::runtime_error::runtime_error; };
-
-struct Modulus_ { u64 value = 0; };
-
-struct EncParams_
+} // namespace
+#include "sealc_types.h"
+namespace
 {
-    uint8_t scheme = 1; // bfv
-    u64 n = 0;
-    std::vector<u64> coeff;
-    u64 plain = 0;
-};
-
-// BFV default coefficient moduli for 128-bit security (values of S/util/globals.cpp:23-71) and the HE-standard
-// total bit bounds (S/util/hestdparms.h).
-const u64 kDefault1024[] = { 0x7e00001 };
-const u64 kDefault2048[] = { 0x3fffffff000001 };
-const u64 kDefault4096[] = { 0xffffee001, 0xffffc4001, 0x1ffffe0001 };
-const u64 kDefault8192[] = { 0x7fffffd8001, 0x7fffffc8001, 0xfffffffc001, 0xffffff6c001, 0xfffffebc001 };
-const u64 kDefault16384[] = { 0xfffffffd8001, 0xfffffffa0001, 0xfffffff00001, 0x1fffffff68001, 0x1fffffff50001,
-                              0x1ffffffee8001, 0x1ffffffea0001, 0x1ffffffe88001, 0x1ffffffe48001 };
-const u64 kDefault32768[] = { 0x7fffffffe90001, 0x7fffffffbf0001, 0x7fffffffbd0001, 0x7fffffffba0001, 0x7fffffffaa0001,
-                              0x7fffffffa50001, 0x7fffffff9f0001, 0x7fffffff7e0001, 0x7fffffff770001, 0x7fffffff380001,
-                              0x7fffffff330001, 0x7fffffff2d0001, 0x7fffffff170001, 0x7fffffff150001, 0x7ffffffef00001,
-                              0xfffffffff70001 };
-int max_bits_tc128(u64 n)
-{
-    switch (n)
-    {
-    case 1024: return 27;
-    case 2048: return 54;
-    case 4096: return 109;
-    case 8192: return 218;
-    case 16384: return 438;
-    case 32768: return 881;
-    default: return 0;
-    }
-}
-int max_bits(u64 n, int sec)
-{
-    if (sec == 128)
-        return max_bits_tc128(n);
-    if (sec == 192)
-    {
-        switch (n) { case 1024: return 19; case 2048: return 37; case 4096: return 75; case 8192: return 152;
-                     case 16384: return 305; case 32768: return 611; default: return 0; }
-    }
-    if (sec == 256)
-    {
-        switch (n) { case 1024: return 14; case 2048: return 29; case 4096: return 58; case 8192: return 118;
-                     case 16384: return 237; case 32768: return 476; default: return 0; }
-    }
-    return 0;
-}
-
-struct Context_
-{
-    EncParams_ parms;
-    bool parameters_set = false;
-    bool using_keyswitching = false;
-    bool using_batching = false;
-    b200_ctx *dev = nullptr;
-    int levels = 0, first_level = 0;
-    std::vector<ParmsId> ids; // per level
-    std::vector<int> level_k;
-    std::mutex mu;            // serialises enqueue on the context's stream (the legacy default stream)
-    bool check_transparent = true;
-    ~Context_()
-    {
-        if (dev)
-            b200_ctx_destroy(dev);
-    }
-    int level_of(const ParmsId &id) const
-    {
-        for (int i = 0; i < (int)ids.size(); i++)
-            if (ids[i] == id)
-                return i;
-        return -1;
-    }
-};
-
-void dev_check(int rc)
-{
-    if (rc == 0)
-        return;
-    if (rc == B200_E_INVALID)
-        throw InvalidArg(b200_last_error());
-    if (rc == B200_E_LOGIC)
-        throw LogicErr(b200_last_error());
-    if (rc == B200_E_NOMEM)
-        throw std::bad_alloc();
-    throw std::runtime_error(b200_last_error());
-}
-
-// Ciphertext: device-resident words with a lazily materialised host mirror.
-struct Ciphertext_
-{
-    ParmsId parms_id = kZeroId;
-    bool is_ntt_form = false;
-    u64 size = 0, n = 0, k = 0;
-    double scale = 1.0;
-    u64 correction_factor = 1;
-    Context_ *ctx = nullptr; // owner of the device buffer (set once data exists)
-    mutable std::vector<u64> host;
-    mutable bool host_valid = true;
-    u64 *dev = nullptr;
-    size_t dev_words = 0;
-    bool dev_valid = false;
-
-    size_t words() const { return (size_t)(size * n * k); }
-    ~Ciphertext_() { release_dev(); }
-    void release_dev()
-    {
-        if (dev && ctx && ctx->dev)
-            b200_free(ctx->dev, dev);
-        dev = nullptr;
-        dev_words = 0;
-        dev_valid = false;
-    }
-    void ensure_dev_capacity(Context_ *c)
-    {
-        if (ctx != c || dev_words < words() || !dev)
-        {
-            release_dev();
-            ctx = c;
-            void *p = nullptr;
-            dev_check(b200_malloc(c->dev, std::max<size_t>(words(), 1) * sizeof(u64), &p));
-            dev = (u64 *)p;
-            dev_words = words();
-        }
-    }
-    // make the device copy current (upload the host mirror if that is the valid one)
-    const u64 *dev_ptr(Context_ *c)
-    {
-        if (!dev_valid || ctx != c)
-        {
-            if (!host_valid)
-                sync_host();
-            ensure_dev_capacity(c);
-            if (words())
-                dev_check(b200_memcpy_h2d(c->dev, dev, host.data(), words() * sizeof(u64), nullptr));
-            dev_check(b200_stream_synchronize(c->dev, nullptr));
-            dev_valid = true;
-        }
-        return dev;
-    }
-    void sync_host() const
-    {
-        if (host_valid)
-            return;
-        host.resize(words());
-        if (words() && dev && ctx)
-        {
-            dev_check(b200_memcpy_d2h(ctx->dev, host.data(), dev, words() * sizeof(u64), nullptr));
-            dev_check(b200_stream_synchronize(ctx->dev, nullptr));
-        }
-        host_valid = true;
-    }
-    // prepare as an output of shape (size, k) for context c; contents undefined, device copy becomes the valid one
-    u64 *prepare_output(Context_ *c, const ParmsId &id, u64 new_size, u64 new_k)
-    {
-        parms_id = id;
-        size = new_size;
-        k = new_k;
-        n = c->parms.n;
-        is_ntt_form = false;
-        scale = 1.0;
-        correction_factor = 1;
-        ensure_dev_capacity(c);
-        dev_valid = true;
-        host_valid = false;
-        return dev;
-    }
-    void assign(const Ciphertext_ &o)
-    {
-        if (this == &o)
-            return;
-        o.sync_host();
-        release_dev();
-        parms_id = o.parms_id;
-        is_ntt_form = o.is_ntt_form;
-        size = o.size;
-        n = o.n;
-        k = o.k;
-        scale = o.scale;
-        correction_factor = o.correction_factor;
-        ctx = o.ctx;
-        host = o.host;
-        host_valid = true;
-    }
-};
-
-struct Plaintext_
-{
-    ParmsId parms_id = kZeroId;
-    std::vector<u64> coeffs;
-    double scale = 1.0;
-};
-
-struct PublicKey_ { Ciphertext_ data; };
-struct SecretKey_ { Plaintext_ data; };
-
-struct KSwitchKeys_
-{
-    ParmsId parms_id = kZeroId;
-    std::vector<std::vector<PublicKey_ *>> keys; // owned
-    // device cache of flattened key lists
-    struct Flat { u64 *dev = nullptr; Context_ *ctx = nullptr; };
-    std::vector<Flat> flat;
-    ~KSwitchKeys_() { clear(); }
-    void clear()
-    {
-        for (auto &l : keys)
-            for (auto *p : l)
-                delete p;
-        keys.clear();
-        drop_flat();
-    }
-    void drop_flat()
-    {
-        for (auto &f : flat)
-            if (f.dev && f.ctx && f.ctx->dev)
-                b200_free(f.ctx->dev, f.dev);
-        flat.clear();
-    }
-    const u64 *flat_dev(Context_ *c, size_t index, int decomp)
-    {
-        if (flat.size() <= index)
-            flat.resize(index + 1);
-        Flat &f = flat[index];
-        if (f.dev && f.ctx == c)
-            return f.dev;
-        const size_t K = c->parms.coeff.size(), n = c->parms.n;
-        const size_t per = 2 * K * n;
-        std::vector<u64> buf(per * decomp);
-        for (int j = 0; j < decomp; j++)
-        {
-            Ciphertext_ &ct = keys[index][j]->data;
-            ct.sync_host();
-            if (ct.words() != per)
-                throw InvalidArg("kswitch_keys is not valid for encryption parameters");
-            std::memcpy(buf.data() + per * j, ct.host.data(), per * sizeof(u64));
-        }
-        void *p = nullptr;
-        dev_check(b200_malloc(c->dev, buf.size() * sizeof(u64), &p));
-        dev_check(b200_memcpy_h2d(c->dev, p, buf.data(), buf.size() * sizeof(u64), nullptr));
-        dev_check(b200_stream_synchronize(c->dev, nullptr));
-        f.dev = (u64 *)p;
-        f.ctx = c;
-        return f.dev;
-    }
-};
-
-struct Evaluator_ { Context_ *ctx; };
-
-struct BatchEncoder_
-{
-    Context_ *ctx;
-    std::vector<size_t> index_map; // populate_matrix_reps_index_map (S/batchencoder.cpp:62-80)
-};
-
-struct Decryptor_
-{
-    Context_ *ctx;
-    std::vector<u64> sk; // key level NTT form [K][n]
-    // device cache: powers s^1..s^m packed per (level, terms)
-    struct Pow { int level, terms; u64 *dev; };
-    std::vector<Pow> cache;
-    ~Decryptor_()
-    {
-        for (auto &p : cache)
-            if (p.dev)
-                b200_free(ctx->dev, p.dev);
-    }
-    const u64 *powers(int level, int terms)
-    {
-        for (auto &p : cache)
-            if (p.level == level && p.terms == terms)
-                return p.dev;
-        const size_t n = ctx->parms.n;
-        const int k = ctx->level_k[level];
-        std::vector<u64> buf((size_t)terms * k * n);
-        for (int r = 0; r < k; r++)
-        {
-            const u64 q = ctx->parms.coeff[r];
-            const u64 *s1 = sk.data() + (size_t)r * n;
-            for (size_t c = 0; c < n; c++)
-            {
-                u64 cur = s1[c];
-                for (int j = 0; j < terms; j++)
-                {
-                    buf[((size_t)j * k + r) * n + c] = cur;
-                    cur = (u64)((unsigned __int128)cur * s1[c] % q);
-                }
-            }
-        }
-        void *p = nullptr;
-        dev_check(b200_malloc(ctx->dev, buf.size() * sizeof(u64), &p));
-        dev_check(b200_memcpy_h2d(ctx->dev, p, buf.data(), buf.size() * sizeof(u64), nullptr));
-        dev_check(b200_stream_synchronize(ctx->dev, nullptr));
-        cache.push_back({ level, terms, (u64 *)p });
-        return (u64 *)p;
-    }
-};
-
-// ---- small device helpers for key generation / encryption (all arithmetic on the GPU through layer 1) ----
-struct DevBuf
-{
-    Context_ *c;
-    u64 *p = nullptr;
-    size_t words;
-    DevBuf(Context_ *ctx, size_t w) : c(ctx), words(w)
-    {
-        void *q = nullptr;
-        dev_check(b200_malloc(c->dev, std::max<size_t>(w, 1) * 8, &q));
-        p = (u64 *)q;
-    }
-    DevBuf(Context_ *ctx, const std::vector<u64> &h) : DevBuf(ctx, h.size()) { upload(h); }
-    ~DevBuf()
-    {
-        b200_stream_synchronize(c->dev, nullptr);
-        b200_free(c->dev, p);
-    }
-    void upload(const std::vector<u64> &h) { dev_check(b200_memcpy_h2d(c->dev, p, h.data(), h.size() * 8, nullptr)); }
-    std::vector<u64> download()
-    {
-        std::vector<u64> h(words);
-        dev_check(b200_memcpy_d2h(c->dev, h.data(), p, words * 8, nullptr));
-        dev_check(b200_stream_synchronize(c->dev, nullptr));
-        return h;
-    }
-    DevBuf(const DevBuf &) = delete;
-};
-
-// encrypt_zero_symmetric at the key level, NTT form, no seed saving (S/util/rlwe.cpp:312-459): returns [2][K][n]
-// c1 <- uniform (a fresh PRNG seeded from the bootstrap PRNG), c0 = -(s*c1 + e)
-std::vector<u64> encrypt_zero_symmetric_key_level(Context_ *c, const std::vector<u64> &sk, b200::Blake2xbPrng &bootstrap)
-{
-    const size_t n = c->parms.n, K = c->parms.coeff.size();
-    b200::PrngSeed pub;
-    bootstrap.generate(sizeof(pub), pub.data());
-    b200::Blake2xbPrng ct_prng(pub);
-    std::vector<u64> c1(K * n), noise(K * n);
-    b200::sample_poly_uniform(ct_prng, n, c->parms.coeff, c1.data());
-    b200::sample_poly_normal(bootstrap, n, c->parms.coeff, noise.data());
-    DevBuf d1(c, c1), de(c, noise), ds(c, sk), d0(c, K * n);
-    dev_check(b200_dyadic_product(c->dev, 0, ds.p, 1, d1.p, 1, d0.p, 1, nullptr)); // s (*) c1
-    dev_check(b200_ntt_forward(c->dev, 0, de.p, 1, nullptr));                      // NTT(e)
-    dev_check(b200_add(c->dev, 0, d0.p, de.p, d0.p, 1, 1, nullptr));
-    dev_check(b200_negate(c->dev, 0, d0.p, d0.p, 1, 1, nullptr));
-    std::vector<u64> out = d0.download();
-    out.insert(out.end(), c1.begin(), c1.end());
-    return out;
-}
-
-struct KeyGenerator_
-{
-    Context_ *ctx;
-    std::vector<u64> sk; // key level, NTT form [K][n]
-    // generate_one_kswitch_key (S/keygenerator.cpp:303-337): new_key = [K][n] NTT form
-    void one_kswitch_key(const std::vector<u64> &new_key, std::vector<PublicKey_ *> &dest)
-    {
-        Context_ *c = ctx;
-        const size_t n = c->parms.n, K = c->parms.coeff.size();
-        const int decomp = c->level_k[c->first_level];
-        const u64 qsp = c->parms.coeff.back();
-        b200::Blake2xbPrng bootstrap(b200::random_seed());
-        for (int J = 0; J < decomp; J++)
-        {
-            std::vector<u64> w = encrypt_zero_symmetric_key_level(c, sk, bootstrap);
-            const u64 qj = c->parms.coeff[J];
-            const u64 factor = qsp % qj;
-            for (size_t i = 0; i < n; i++)
-            { // c0[J] += factor * new_key[J]  (S/keygenerator.cpp:330-334)
-                u64 t = (u64)((unsigned __int128)new_key[(size_t)J * n + i] * factor % qj);
-                u64 &d = w[(size_t)J * n + i];
-                d = (u64)(((unsigned __int128)d + t) % qj);
-            }
-            auto *pk = new PublicKey_();
-            pk->data.parms_id = c->ids[0];
-            pk->data.size = 2;
-            pk->data.k = K;
-            pk->data.n = n;
-            pk->data.is_ntt_form = true;
-            pk->data.host = std::move(w);
-            pk->data.host_valid = true;
-            dest.push_back(pk);
-        }
-    }
-};
-
-struct Encryptor_
-{
-    Context_ *ctx;
-    bool has_pk = false, has_sk = false;
-    std::vector<u64> pk; // [2][K][n] NTT form, key level
-    std::vector<u64> sk; // [K][n]
-};
-
-template <class F>
-long guard(F f)
-{
-    try
-    {
-        f();
-        return S_OK_;
-    }
-    catch (const InvalidArg &)
-    {
-        return E_INVALIDARG_;
-    }
-    catch (const std::invalid_argument &)
-    {
-        return E_INVALIDARG_;
-    }
-    catch (const LogicErr &)
-    {
-        return COR_E_INVALIDOPERATION_;
-    }
-    catch (const std::logic_error &)
-    {
-        return COR_E_INVALIDOPERATION_;
-    }
-    catch (const std::bad_alloc &)
-    {
-        return E_OUTOFMEMORY_;
-    }
-    catch (...)
-    {
-        return E_UNEXPECTED_;
-    }
-}
-
-#define NULLRET(p)                                                                                                     \
-    if (!(p))                                                                                                          \
-    return E_POINTER_
+using namespace b200c;
 
 // is_metadata_valid_for (S/valcheck.cpp:67-112): known data-level parms_id, matching shape
 int data_level(Context_ *c, const Ciphertext_ &ct, const char *what)
@@ -1033,7 +590,7 @@ long EncParams_SetPlainModulus2(void *p, uint64_t v)
 // ---------------------------------------------------------------------------------------------------------
 // SEALContext
 // ---------------------------------------------------------------------------------------------------------
-long SEALContext_Create(void *parms, bool /*expand_mod_chain*/, int sec_level, void **out)
+long SEALContext_Create(void *parms, bool expand_mod_chain, int sec_level, void **out)
 {
     NULLRET(parms);
     NULLRET(out);
@@ -1094,6 +651,12 @@ long SEALContext_Create(void *parms, bool /*expand_mod_chain*/, int sec_level, v
                 std::copy_n(li.parms_id, 4, id.begin());
                 c->ids.push_back(id);
                 c->level_k.push_back(li.k);
+            }
+            if (!expand_mod_chain && c->levels > c->first_level + 1)
+            { // only the key level and the first data level exist (S/context.cpp:478-497)
+                c->levels = c->first_level + 1;
+                c->ids.resize(c->levels);
+                c->level_k.resize(c->levels);
             }
         }
     }
@@ -1368,6 +931,91 @@ long Plaintext_Create2(uint64_t count, void *, void **out)
     *out = p;
     return S_OK_;
 }
+// Plaintext(const std::string &hex_poly) (S/plaintext.cpp:88-203): "7FFx^3 + 1x^1 + 3" — hexadecimal coefficients,
+// strictly decreasing decimal powers, terms separated by " + ", the constant term without "x^0"
+long Plaintext_Create4(uint8_t *hex_poly, void *, void **out)
+{
+    NULLRET(out);
+    NULLRET(hex_poly);
+    const char *s = (const char *)hex_poly;
+    const size_t len = std::strlen(s);
+    auto is_hex = [](char ch) { return (ch >= '0' && ch <= '9') || (ch >= 'A' && ch <= 'F') || (ch >= 'a' && ch <= 'f'); };
+    auto hex_val = [](char ch) -> u64 { return ch <= '9' ? (u64)(ch - '0') : (u64)((ch | 0x20) - 'a' + 10); };
+    struct Term
+    {
+        u64 coeff;
+        long power;
+    };
+    std::vector<Term> terms;
+    size_t pos = 0;
+    long last_power = 0x7fffffffL;
+    long count = 0;
+    int max_bits = 0;
+    while (pos < len)
+    {
+        size_t cl = 0;
+        while (is_hex(s[pos + cl]))
+            cl++;
+        if (!cl)
+            return E_INVALIDARG_; // "unable to parse hex_poly"
+        // significant bits of the coefficient (leading zeros do not count)
+        size_t lead = 0;
+        while (lead < cl && s[pos + lead] == '0')
+            lead++;
+        int bits = 0;
+        if (lead < cl)
+        {
+            const u64 top = hex_val(s[pos + lead]);
+            bits = (int)(4 * (cl - lead - 1)) + (64 - __builtin_clzll(top));
+        }
+        max_bits = std::max(max_bits, bits);
+        u64 v = 0;
+        if (bits <= 64)
+            for (size_t i = lead; i < cl; i++)
+                v = (v << 4) | hex_val(s[pos + i]);
+        pos += cl;
+        long power = 0;
+        if (s[pos] != '\0')
+        {
+            if (s[pos] != 'x' || s[pos + 1] != '^')
+                return E_INVALIDARG_;
+            pos += 2;
+            while (s[pos] >= '0' && s[pos] <= '9')
+            {
+                power = power * 10 + (s[pos] - '0');
+                if (power > 0x7fffffffL)
+                    return E_INVALIDARG_;
+                pos++;
+            }
+        }
+        if (power >= last_power)
+            return E_INVALIDARG_;
+        if (terms.empty())
+            count = power + 1;
+        last_power = power;
+        terms.push_back({ v, power });
+        if (s[pos] != '\0')
+        {
+            if (s[pos] != ' ' || s[pos + 1] != '+' || s[pos + 2] != ' ')
+                return E_INVALIDARG_;
+            pos += 3;
+        }
+    }
+    auto *pl = new Plaintext_();
+    if (count && max_bits)
+    {
+        if (max_bits > 64)
+        {
+            delete pl;
+            return E_INVALIDARG_; // "hex_poly has too large coefficients"
+        }
+        pl->coeffs.assign((size_t)count, 0);
+        for (auto &t : terms)
+            pl->coeffs[(size_t)t.power] = t.coeff;
+    }
+    *out = pl;
+    return S_OK_;
+}
 long Plaintext_Create5(void *copy, void **out)
 {
     NULLRET(copy);
@@ -1414,6 +1062,20 @@ long Plaintext_Resize(void *p, uint64_t c)
     if (pl->parms_id != kZeroId)
         return COR_E_INVALIDOPERATION_; // "cannot resize an NTT transformed Plaintext"
     pl->coeffs.resize(c, 0);
+    return S_OK_;
+}
+long Plaintext_GetParmsId(void *p, uint64_t *parms_id)
+{
+    NULLRET(p);
+    NULLRET(parms_id);
+    std::copy_n(((Plaintext_ *)p)->parms_id.begin(), 4, parms_id);
+    return S_OK_;
+}
+long Plaintext_SetParmsId(void *p, uint64_t *parms_id)
+{
+    NULLRET(p);
+    NULLRET(parms_id);
+    std::copy_n(parms_id, 4, ((Plaintext_ *)p)->parms_id.begin());
     return S_OK_;
 }
 long Plaintext_IsNTTForm(void *p, bool *b)
@@ -1889,6 +1551,42 @@ long Evaluator_ModSwitchToNext1(void *p, void *a, void *dst, void *)
         transparent_guard(c, lv + 1, d);
     });
 }
+// Evaluator::mod_switch_to_next(const Plaintext &, Plaintext &) (S/evaluator.h:380-407, evaluator.cpp:1307-1340):
+// only NTT-form plaintexts can be switched; the last residue polynomial is dropped
+long Evaluator_ModSwitchToNext2(void *p, void *plain, void *dst)
+{
+    NULLRET(p);
+    NULLRET(plain);
+    NULLRET(dst);
+    auto *c = ((Evaluator_ *)p)->ctx;
+    auto &src = *(Plaintext_ *)plain;
+    return guard([&] {
+        Plaintext_ t(src);
+        const size_t n = c->parms.n;
+        // is_valid_for(plain) (S/valcheck.cpp:20-65,246-294)
+        if (t.parms_id == kZeroId)
+        {
+            if (t.coeffs.size() > n)
+                throw InvalidArg("plain is not valid for encryption parameters");
+            for (u64 x : t.coeffs)
+                if (x >= c->parms.plain)
+                    throw InvalidArg("plain is not valid for encryption parameters");
+            throw InvalidArg("plain is not in NTT form");
+        }
+        const int lv = c->level_of(t.parms_id);
+        if (lv < c->first_level || t.coeffs.size() != (size_t)c->level_k[lv] * n)
+            throw InvalidArg("plain is not valid for encryption parameters");
+        for (int r = 0; r < c->level_k[lv]; r++)
+            for (size_t i = 0; i < n; i++)
+                if (t.coeffs[(size_t)r * n + i] >= c->parms.coeff[r])
+                    throw InvalidArg("plain is not valid for encryption parameters");
+        if (lv + 1 >= c->levels)
+            throw InvalidArg("end of modulus switching chain reached");
+        t.coeffs.resize((size_t)c->level_k[lv + 1] * n);
+        t.parms_id = c->ids[lv + 1];
+        *(Plaintext_ *)dst = std::move(t);
+    });
+}
 long Evaluator_AddPlain(void *p, void *a, void *pl, void *dst)
 {
     NULLRET(p);
@@ -2072,15 +1770,12 @@ long Decryptor_Decrypt(void *p, void *enc, void *dst)
         pl.scale = 1.0;
     });
 }
-long Decryptor_InvariantNoiseBudget(void *p, void *enc, int *budget)
+// Decryptor::invariant_noise_internal (S/decryptor.cpp:424-485): infinity norm of the centred t * (ct . sk) mod Q as
+// a multi-precision integer (little-endian words); also returns the level's residue count and bit length of Q
+static void noise_norm(Decryptor_ *d, Ciphertext_ &ct, std::vector<u64> &norm_out, int &k_out, int &q_bits_out)
 {
-    NULLRET(p);
-    NULLRET(enc);
-    NULLRET(budget);
-    auto *d = (Decryptor_ *)p;
     auto *c = d->ctx;
-    auto &ct = *(Ciphertext_ *)enc;
-    return guard([&] {
+    {
         // Decryptor::invariant_noise_budget (S/decryptor.cpp:424-527): norm of t * (ct . sk) mod Q, centred
         std::lock_guard<std::mutex> lk(c->mu);
         int lv = data_level(c, ct, "encrypted is not valid for encryption parameters");
@@ -2182,6 +1877,20 @@ long Decryptor_InvariantNoiseBudget(void *p, void *enc, int *budget)
             if (ge(acc, norm))
                 norm = acc;
         }
+        norm_out = norm;
+        k_out = k;
+        q_bits_out = Q.bit_length();
+    }
+}
+long Decryptor_InvariantNoiseBudget(void *p, void *enc, int *budget)
+{
+    NULLRET(p);
+    NULLRET(enc);
+    NULLRET(budget);
+    return guard([&] {
+        std::vector<u64> norm;
+        int k = 0, qbits = 0;
+        noise_norm((Decryptor_ *)p, *(Ciphertext_ *)enc, norm, k, qbits);
         int nb = 0;
         for (size_t i = norm.size(); i-- > 0;)
             if (norm[i])
@@ -2189,7 +1898,28 @@ long Decryptor_InvariantNoiseBudget(void *p, void *enc, int *budget)
                 nb = (int)(64 * i + 64 - __builtin_clzll(norm[i]));
                 break;
             }
-        *budget = std::max(0, Q.bit_length() - nb - 1);
+        *budget = std::max(0, qbits - nb - 1);
+    });
+}
+// Decryptor::invariant_noise (S/decryptor.cpp:487-510, added by the Sunscreen fork): the same norm as a double,
+// divided by Q; the floating-point operations are issued in the reference's order so that the result is identical
+long Decryptor_InvariantNoise(void *p, void *enc, double *invariant_noise)
+{
+    NULLRET(p);
+    NULLRET(enc);
+    NULLRET(invariant_noise);
+    auto *d = (Decryptor_ *)p;
+    return guard([&] {
+        std::vector<u64> norm;
+        int k = 0, qbits = 0;
+        noise_norm(d, *(Ciphertext_ *)enc, norm, k, qbits);
+        double v = 0.0;
+        for (int i = 0; i < k; i++)
+            v += (double)((size_t)i < norm.size() ? norm[i] : 0) * std::exp2((double)(64 * i));
+        double total = 1.0;
+        for (int i = 0; i < k; i++)
+            total *= (double)d->ctx->parms.coeff[i];
+        *invariant_noise = v / total;
     });
 }
 
@@ -2448,27 +2178,68 @@ long Encryptor_Destroy(void *p)
     return S_OK_;
 }
 
+// Components of an encryption as the reference exports them (S/util/rlwe.cpp:243-288,403-407; S/util/scalingvariant.cpp:96-119)
+struct EncComponents
+{
+    PolynomialArray_ *u = nullptr, *e = nullptr;
+    Plaintext_ *remainder = nullptr;
+};
+
+// round(Q m / t) correction term of every plaintext coefficient: fix = floor(((Q mod t) m + floor((t+1)/2)) / t)
+static void export_remainder(Context_ *c, const Plaintext_ &plain, Plaintext_ &dst)
+{
+    b200_level_info li;
+    dev_check(b200_ctx_level_info(c->dev, c->first_level, &li));
+    const u64 t = c->parms.plain, half = (t + 1) >> 1;
+    Plaintext_ r;
+    r.coeffs.resize(plain.coeffs.size());
+    for (size_t i = 0; i < plain.coeffs.size(); i++)
+        r.coeffs[i] = (u64)(((unsigned __int128)plain.coeffs[i] * li.q_mod_t + half) / t);
+    dst = std::move(r);
+}
+
 // pk encryption of `plain` with the given PRNG: encrypt_zero_asymmetric at the key level, divide-and-round by the
-// special prime, then add round(q m / t) (S/util/rlwe.cpp:193-310, S/encryptor.cpp:160-208,300-312)
-static void encrypt_asymmetric(Encryptor_ *e, const Plaintext_ &plain, b200::Blake2xbPrng &prng, Ciphertext_ &dst)
+// special prime, then add round(q m / t) (S/util/rlwe.cpp:193-310, S/encryptor.cpp:160-208,300-312).  With
+// `disable_special_modulus` the zero encryption is made directly at the first data level from the first k residues
+// of the public key and no modulus switch follows (S/encryptor.cpp:160-163,210-224).
+static void encrypt_asymmetric(Encryptor_ *e, const Plaintext_ &plain, b200::Blake2xbPrng &prng, Ciphertext_ &dst,
+                               bool disable_special_modulus = false, EncComponents *comp = nullptr)
 {
     Context_ *c = e->ctx;
     if (!e->has_pk)
         throw LogicErr("public key is not set");
     std::vector<u64> pv = padded_plain(c, plain);
     const size_t n = c->parms.n, K = c->parms.coeff.size();
-    const bool drop = c->first_level == 1; // a key level above the data level exists
-    std::vector<u64> u(K * n), e0(K * n), e1(K * n);
-    b200::sample_poly_ternary(prng, n, c->parms.coeff, u.data());
-    b200::sample_poly_normal(prng, n, c->parms.coeff, e0.data());
-    b200::sample_poly_normal(prng, n, c->parms.coeff, e1.data());
-    std::vector<u64> ee(e0);
-    ee.insert(ee.end(), e1.begin(), e1.end());
-    DevBuf du(c, u), dpk(c, e->pk), de(c, ee), dct(c, 2 * K * n), dpl(c, pv);
-    dev_check(b200_ntt_forward(c->dev, 0, du.p, 1, nullptr));
-    dev_check(b200_dyadic_product(c->dev, 0, dpk.p, 2, du.p, 1, dct.p, 1, nullptr)); // pk_j (*) NTT(u)
-    dev_check(b200_ntt_inverse(c->dev, 0, dct.p, 2, nullptr));                       // two polys = two slab items
-    dev_check(b200_add(c->dev, 0, dct.p, de.p, dct.p, 2, 1, nullptr));               // + e_j
+    const bool drop = c->first_level == 1 && !disable_special_modulus; // encrypt at the key level, then switch down
+    const int enc_lv = drop ? 0 : c->first_level;
+    const size_t ke = (size_t)c->level_k[enc_lv];
+    const std::vector<u64> mods(c->parms.coeff.begin(), c->parms.coeff.begin() + ke);
+    std::vector<u64> u(ke * n), ee(2 * ke * n);
+    b200::sample_poly_ternary(prng, n, mods, u.data());
+    b200::sample_poly_normal(prng, n, mods, ee.data());
+    b200::sample_poly_normal(prng, n, mods, ee.data() + ke * n);
+    if (comp)
+    {
+        if (comp->u)
+        {
+            comp->u->reserve(1, n, mods);
+            comp->u->insert(0, u.data());
+        }
+        if (comp->e)
+        {
+            comp->e->reserve(2, n, mods);
+            comp->e->insert(0, ee.data());
+            comp->e->insert(1, ee.data() + ke * n);
+        }
+    }
+    std::vector<u64> pk(2 * ke * n); // first ke residues of both public-key polynomials
+    for (int j = 0; j < 2; j++)
+        std::copy_n(e->pk.begin() + (size_t)j * K * n, ke * n, pk.begin() + (size_t)j * ke * n);
+    DevBuf du(c, u), dpk(c, pk), de(c, ee), dct(c, 2 * ke * n), dpl(c, pv);
+    dev_check(b200_ntt_forward(c->dev, enc_lv, du.p, 1, nullptr));
+    dev_check(b200_dyadic_product(c->dev, enc_lv, dpk.p, 2, du.p, 1, dct.p, 1, nullptr)); // pk_j (*) NTT(u)
+    dev_check(b200_ntt_inverse(c->dev, enc_lv, dct.p, 2, nullptr));                       // two polys = two slab items
+    dev_check(b200_add(c->dev, enc_lv, dct.p, de.p, dct.p, 2, 1, nullptr));               // + e_j
     const int lv = c->first_level;
     u64 *out = dst.prepare_output(c, c->ids[lv], 2, c->level_k[lv]);
     if (drop)
@@ -2480,6 +2251,114 @@ static void encrypt_asymmetric(Encryptor_ *e, const Plaintext_ &plain, b200::Bla
     else
         dev_check(b200_add_plain(c->dev, lv, dct.p, 2, dpl.p, 1, out, 1, nullptr));
     dev_check(b200_stream_synchronize(c->dev, nullptr));
+    if (comp && comp->remainder)
+        export_remainder(c, plain, *comp->remainder);
+}
+
+// sk encryption: encrypt_zero_symmetric at the first data level, coefficient form (S/util/rlwe.cpp:312-459), then
+// add round(q m / t).  `bootstrap` supplies the public seed of the uniform polynomial and the noise.
+static void encrypt_symmetric(Encryptor_ *e, const Plaintext_ &plain, b200::Blake2xbPrng &bootstrap, Ciphertext_ &dst,
+                              EncComponents *comp = nullptr)
+{
+    Context_ *c = e->ctx;
+    if (!e->has_sk)
+        throw LogicErr("secret key is not set");
+    std::vector<u64> pv = padded_plain(c, plain);
+    const int lv = c->first_level;
+    const size_t n = c->parms.n;
+    const int k = c->level_k[lv];
+    std::vector<u64> mods(c->parms.coeff.begin(), c->parms.coeff.begin() + k);
+    b200::PrngSeed pub;
+    bootstrap.generate(sizeof(pub), pub.data());
+    b200::Blake2xbPrng ct_prng(pub);
+    std::vector<u64> c1((size_t)k * n), noise((size_t)k * n);
+    b200::sample_poly_uniform(ct_prng, n, mods, c1.data());
+    b200::sample_poly_normal(bootstrap, n, mods, noise.data());
+    if (comp && comp->e)
+    {
+        comp->e->reserve(1, n, mods);
+        comp->e->insert(0, noise.data());
+    }
+    std::vector<u64> skl(e->sk.begin(), e->sk.begin() + (size_t)k * n);
+    DevBuf d1(c, c1), de(c, noise), ds(c, skl), d0(c, (size_t)2 * k * n), dpl(c, pv);
+    // c0 = -(INTT(s (*) c1) + e); c1 is sampled in the NTT domain and converted back at the end
+    dev_check(b200_dyadic_product(c->dev, lv, ds.p, 1, d1.p, 1, d0.p, 1, nullptr));
+    dev_check(b200_ntt_inverse(c->dev, lv, d0.p, 1, nullptr));
+    dev_check(b200_add(c->dev, lv, d0.p, de.p, d0.p, 1, 1, nullptr));
+    dev_check(b200_negate(c->dev, lv, d0.p, d0.p, 1, 1, nullptr));
+    dev_check(b200_ntt_inverse(c->dev, lv, d1.p, 1, nullptr));
+    dev_check(b200_memcpy_d2d(c->dev, d0.p + (size_t)k * n, d1.p, (size_t)k * n * 8, nullptr));
+    u64 *out = dst.prepare_output(c, c->ids[lv], 2, k);
+    dev_check(b200_add_plain(c->dev, lv, d0.p, 2, dpl.p, 1, out, 1, nullptr));
+    dev_check(b200_stream_synchronize(c->dev, nullptr));
+    if (comp && comp->remainder)
+        export_remainder(c, plain, *comp->remainder);
+}
+
+// Encryptor_Encrypt{,Symmetric}ReturnComponents{,SetSeed} (S/c/encryptor.cpp:136-240,300-372): the fork's entry points
+// that also hand back u, e and the rounding remainder; `seed8` == nullptr draws a fresh seed
+static long encrypt_components(void *p, void *plaintext, bool asymmetric, bool disable_special_modulus, void *destination,
+                               void *u_dst, void *e_dst, void *r_dst, const uint64_t *seed8)
+{
+    auto *e = (Encryptor_ *)p;
+    return guard([&] {
+        std::lock_guard<std::mutex> lk(e->ctx->mu);
+        b200::PrngSeed sd = seed8 ? b200::PrngSeed{} : b200::random_seed();
+        if (seed8)
+            std::copy_n(seed8, 8, sd.begin());
+        b200::Blake2xbPrng prng(sd);
+        EncComponents comp{ (PolynomialArray_ *)u_dst, (PolynomialArray_ *)e_dst, (Plaintext_ *)r_dst };
+        // the component arrays must be fresh: reserve() refuses a second use, like the reference's
+        if ((comp.u && comp.u->reserved) || (comp.e && comp.e->reserved))
+            throw LogicErr("PolynomialArray can only be reserved once.");
+        if (asymmetric)
+            encrypt_asymmetric(e, *(Plaintext_ *)plaintext, prng, *(Ciphertext_ *)destination, disable_special_modulus, &comp);
+        else
+            encrypt_symmetric(e, *(Plaintext_ *)plaintext, prng, *(Ciphertext_ *)destination, &comp);
+    });
+}
+long Encryptor_EncryptReturnComponents(void *p, void *plaintext, bool disable_special_modulus, void *destination, void *u_dst,
+                                       void *e_dst, void *r_dst, void *)
+{
+    NULLRET(p);
+    NULLRET(plaintext);
+    NULLRET(destination);
+    NULLRET(u_dst);
+    NULLRET(e_dst);
+    NULLRET(r_dst);
+    return encrypt_components(p, plaintext, true, disable_special_modulus, destination, u_dst, e_dst, r_dst, nullptr);
+}
+long Encryptor_EncryptReturnComponentsSetSeed(void *p, void *plaintext, bool disable_special_modulus, void *destination,
+                                              void *u_dst, void *e_dst, void *r_dst, void *seed, void *)
+{
+    NULLRET(p);
+    NULLRET(plaintext);
+    NULLRET(destination);
+    NULLRET(u_dst);
+    NULLRET(e_dst);
+    NULLRET(r_dst);
+    NULLRET(seed);
+    return encrypt_components(p, plaintext, true, disable_special_modulus, destination, u_dst, e_dst, r_dst, (const uint64_t *)seed);
+}
+long Encryptor_EncryptSymmetricReturnComponents(void *p, void *plaintext, void *destination, void *e_dst, void *r_dst, void *)
+{
+    NULLRET(p);
+    NULLRET(plaintext);
+    NULLRET(destination);
+    NULLRET(e_dst);
+    NULLRET(r_dst);
+    return encrypt_components(p, plaintext, false, false, destination, nullptr, e_dst, r_dst, nullptr);
+}
+long Encryptor_EncryptSymmetricReturnComponentsSetSeed(void *p, void *plaintext, void *destination, void *e_dst, void *r_dst,
+                                                       void *seed, void *)
+{
+    NULLRET(p);
+    NULLRET(plaintext);
+    NULLRET(destination);
+    NULLRET(e_dst);
+    NULLRET(r_dst);
+    NULLRET(seed);
+    return encrypt_components(p, plaintext, false, false, destination, nullptr, e_dst, r_dst, (const uint64_t *)seed);
 }
 
 long Encryptor_Encrypt(void *p, void *plaintext, void *destination, void *)
@@ -2512,41 +2391,16 @@ long B200_Encryptor_EncryptSetSeed(void *p, void *plaintext, const uint64_t *see
 }
 long Encryptor_EncryptSymmetric(void *p, void *plaintext, bool /*save_seed*/, void *destination, void *)
 {
+    // save_seed only changes how the result is later serialised (S/util/rlwe.cpp:441-457); the ciphertext handed
+    // back here is always the expanded one, which every consumer accepts
     NULLRET(p);
     NULLRET(plaintext);
     NULLRET(destination);
     auto *e = (Encryptor_ *)p;
-    auto *c = e->ctx;
     return guard([&] {
-        std::lock_guard<std::mutex> lk(c->mu);
-        if (!e->has_sk)
-            throw LogicErr("secret key is not set");
-        std::vector<u64> pv = padded_plain(c, *(Plaintext_ *)plaintext);
-        // encrypt_zero_symmetric at the first data level, coefficient form (S/util/rlwe.cpp:312-459)
-        const int lv = c->first_level;
-        const size_t n = c->parms.n;
-        const int k = c->level_k[lv];
-        std::vector<u64> mods(c->parms.coeff.begin(), c->parms.coeff.begin() + k);
+        std::lock_guard<std::mutex> lk(e->ctx->mu);
         b200::Blake2xbPrng bootstrap(b200::random_seed());
-        b200::PrngSeed pub;
-        bootstrap.generate(sizeof(pub), pub.data());
-        b200::Blake2xbPrng ct_prng(pub);
-        std::vector<u64> c1((size_t)k * n), noise((size_t)k * n);
-        b200::sample_poly_uniform(ct_prng, n, mods, c1.data());
-        b200::sample_poly_normal(bootstrap, n, mods, noise.data());
-        std::vector<u64> skl(e->sk.begin(), e->sk.begin() + (size_t)k * n);
-        DevBuf d1(c, c1), de(c, noise), ds(c, skl), d0(c, (size_t)2 * k * n), dpl(c, pv);
-        // c0 = -(INTT(s (*) c1) + e); c1 is sampled in the NTT domain and converted back at the end
-        dev_check(b200_dyadic_product(c->dev, lv, ds.p, 1, d1.p, 1, d0.p, 1, nullptr));
-        dev_check(b200_ntt_inverse(c->dev, lv, d0.p, 1, nullptr));
-        dev_check(b200_add(c->dev, lv, d0.p, de.p, d0.p, 1, 1, nullptr));
-        dev_check(b200_negate(c->dev, lv, d0.p, d0.p, 1, 1, nullptr));
-        dev_check(b200_ntt_inverse(c->dev, lv, d1.p, 1, nullptr));
-        dev_check(b200_memcpy_d2d(c->dev, d0.p + (size_t)k * n, d1.p, (size_t)k * n * 8, nullptr));
-        auto &dst = *(Ciphertext_ *)destination;
-        u64 *out = dst.prepare_output(c, c->ids[lv], 2, k);
-        dev_check(b200_add_plain(c->dev, lv, d0.p, 2, dpl.p, 1, out, 1, nullptr));
-        dev_check(b200_stream_synchronize(c->dev, nullptr));
+        encrypt_symmetric(e, *(Plaintext_ *)plaintext, bootstrap, *(Ciphertext_ *)destination);
     });
 }
 

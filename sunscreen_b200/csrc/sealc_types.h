@@ -1,0 +1,503 @@
+// sealc_types.h — handle types behind the SEAL-named C ABI (include/b200_sealc.h), shared by sealc_api.cpp
+// (contexts, evaluator, keys, encryptor, decryptor, encoder), sealc_wire.cpp (Save/Load wire format) and
+// sealc_polyarray.cpp (PolynomialArray).  Each struct mirrors the state the reference's C++ object carries
+// (S/ciphertext.h:337-715, S/plaintext.h, S/kswitchkeys.h:340, S/publickey.h, S/secretkey.h, S/context.h).
+#pragma once
+#include "../../include/b200_bfv.h"
+#include "host_ctx.h"
+#include "sampling.h"
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <vector>
+
+namespace b200c
+{
+typedef uint64_t u64;
+typedef std::array<u64, 4> ParmsId;
+static const ParmsId kZeroId = { { 0, 0, 0, 0 } };
+
+static const long S_OK_ = 0L;
+static const long E_POINTER_ = (long)0x80004003L;
+static const long E_INVALIDARG_ = (long)0x80070057L;
+static const long E_OUTOFMEMORY_ = (long)0x8007000EL;
+static const long E_UNEXPECTED_ = (long)0x8000FFFFL;
+static const long COR_E_INVALIDOPERATION_ = (long)0x80131509L;
+static const long ERROR_INVALID_INDEX_ = (long)0x80070585L;
+
+struct InvalidArg : std::runtime_error { using std::runtime_error::runtime_error; };
+struct LogicErr : std::runtime_error { using std::runtime_error::runtime_error; };
+
+struct Modulus_ { u64 value = 0; };
+
+struct EncParams_
+{
+    uint8_t scheme = 1; // bfv
+    u64 n = 0;
+    std::vector<u64> coeff;
+    u64 plain = 0;
+};
+
+// BFV default coefficient moduli for 128-bit security (values of S/util/globals.cpp:23-71) and the HE-standard
+// total bit bounds (S/util/hestdparms.h).
+static const u64 kDefault1024[] = { 0x7e00001 };
+static const u64 kDefault2048[] = { 0x3fffffff000001 };
+static const u64 kDefault4096[] = { 0xffffee001, 0xffffc4001, 0x1ffffe0001 };
+static const u64 kDefault8192[] = { 0x7fffffd8001, 0x7fffffc8001, 0xfffffffc001, 0xffffff6c001, 0xfffffebc001 };
+static const u64 kDefault16384[] = { 0xfffffffd8001, 0xfffffffa0001, 0xfffffff00001, 0x1fffffff68001, 0x1fffffff50001,
+                              0x1ffffffee8001, 0x1ffffffea0001, 0x1ffffffe88001, 0x1ffffffe48001 };
+static const u64 kDefault32768[] = { 0x7fffffffe90001, 0x7fffffffbf0001, 0x7fffffffbd0001, 0x7fffffffba0001, 0x7fffffffaa0001,
+                              0x7fffffffa50001, 0x7fffffff9f0001, 0x7fffffff7e0001, 0x7fffffff770001, 0x7fffffff380001,
+                              0x7fffffff330001, 0x7fffffff2d0001, 0x7fffffff170001, 0x7fffffff150001, 0x7ffffffef00001,
+                              0xfffffffff70001 };
+inline int max_bits_tc128(u64 n)
+{
+    switch (n)
+    {
+    case 1024: return 27;
+    case 2048: return 54;
+    case 4096: return 109;
+    case 8192: return 218;
+    case 16384: return 438;
+    case 32768: return 881;
+    default: return 0;
+    }
+}
+inline int max_bits(u64 n, int sec)
+{
+    if (sec == 128)
+        return max_bits_tc128(n);
+    if (sec == 192)
+    {
+        switch (n) { case 1024: return 19; case 2048: return 37; case 4096: return 75; case 8192: return 152;
+                     case 16384: return 305; case 32768: return 611; default: return 0; }
+    }
+    if (sec == 256)
+    {
+        switch (n) { case 1024: return 14; case 2048: return 29; case 4096: return 58; case 8192: return 118;
+                     case 16384: return 237; case 32768: return 476; default: return 0; }
+    }
+    return 0;
+}
+
+struct Context_
+{
+    EncParams_ parms;
+    bool parameters_set = false;
+    bool using_keyswitching = false;
+    bool using_batching = false;
+    b200_ctx *dev = nullptr;
+    int levels = 0, first_level = 0;
+    std::vector<ParmsId> ids; // per level
+    std::vector<int> level_k;
+    std::mutex mu;            // serialises enqueue on the context's stream (the legacy default stream)
+    bool check_transparent = true;
+    ~Context_()
+    {
+        if (dev)
+            b200_ctx_destroy(dev);
+    }
+    int level_of(const ParmsId &id) const
+    {
+        for (int i = 0; i < (int)ids.size(); i++)
+            if (ids[i] == id)
+                return i;
+        return -1;
+    }
+};
+
+inline void dev_check(int rc)
+{
+    if (rc == 0)
+        return;
+    if (rc == B200_E_INVALID)
+        throw InvalidArg(b200_last_error());
+    if (rc == B200_E_LOGIC)
+        throw LogicErr(b200_last_error());
+    if (rc == B200_E_NOMEM)
+        throw std::bad_alloc();
+    throw std::runtime_error(b200_last_error());
+}
+
+// Ciphertext: device-resident words with a lazily materialised host mirror.
+struct Ciphertext_
+{
+    ParmsId parms_id = kZeroId;
+    bool is_ntt_form = false;
+    u64 size = 0, n = 0, k = 0;
+    double scale = 1.0;
+    u64 correction_factor = 1;
+    Context_ *ctx = nullptr; // owner of the device buffer (set once data exists)
+    mutable std::vector<u64> host;
+    mutable bool host_valid = true;
+    u64 *dev = nullptr;
+    size_t dev_words = 0;
+    bool dev_valid = false;
+
+    size_t words() const { return (size_t)(size * n * k); }
+    ~Ciphertext_() { release_dev(); }
+    void release_dev()
+    {
+        if (dev && ctx && ctx->dev)
+            b200_free(ctx->dev, dev);
+        dev = nullptr;
+        dev_words = 0;
+        dev_valid = false;
+    }
+    void ensure_dev_capacity(Context_ *c)
+    {
+        if (ctx != c || dev_words < words() || !dev)
+        {
+            release_dev();
+            ctx = c;
+            void *p = nullptr;
+            dev_check(b200_malloc(c->dev, std::max<size_t>(words(), 1) * sizeof(u64), &p));
+            dev = (u64 *)p;
+            dev_words = words();
+        }
+    }
+    // make the device copy current (upload the host mirror if that is the valid one)
+    const u64 *dev_ptr(Context_ *c)
+    {
+        if (!dev_valid || ctx != c)
+        {
+            if (!host_valid)
+                sync_host();
+            ensure_dev_capacity(c);
+            if (words())
+                dev_check(b200_memcpy_h2d(c->dev, dev, host.data(), words() * sizeof(u64), nullptr));
+            dev_check(b200_stream_synchronize(c->dev, nullptr));
+            dev_valid = true;
+        }
+        return dev;
+    }
+    void sync_host() const
+    {
+        if (host_valid)
+            return;
+        host.resize(words());
+        if (words() && dev && ctx)
+        {
+            dev_check(b200_memcpy_d2h(ctx->dev, host.data(), dev, words() * sizeof(u64), nullptr));
+            dev_check(b200_stream_synchronize(ctx->dev, nullptr));
+        }
+        host_valid = true;
+    }
+    // prepare as an output of shape (size, k) for context c; contents undefined, device copy becomes the valid one
+    u64 *prepare_output(Context_ *c, const ParmsId &id, u64 new_size, u64 new_k)
+    {
+        parms_id = id;
+        size = new_size;
+        k = new_k;
+        n = c->parms.n;
+        is_ntt_form = false;
+        scale = 1.0;
+        correction_factor = 1;
+        ensure_dev_capacity(c);
+        dev_valid = true;
+        host_valid = false;
+        return dev;
+    }
+    void assign(const Ciphertext_ &o)
+    {
+        if (this == &o)
+            return;
+        o.sync_host();
+        release_dev();
+        parms_id = o.parms_id;
+        is_ntt_form = o.is_ntt_form;
+        size = o.size;
+        n = o.n;
+        k = o.k;
+        scale = o.scale;
+        correction_factor = o.correction_factor;
+        ctx = o.ctx;
+        host = o.host;
+        host_valid = true;
+    }
+};
+
+struct Plaintext_
+{
+    ParmsId parms_id = kZeroId;
+    std::vector<u64> coeffs;
+    double scale = 1.0;
+};
+
+struct PublicKey_ { Ciphertext_ data; };
+struct SecretKey_ { Plaintext_ data; };
+
+struct KSwitchKeys_
+{
+    ParmsId parms_id = kZeroId;
+    std::vector<std::vector<PublicKey_ *>> keys; // owned
+    // device cache of flattened key lists
+    struct Flat { u64 *dev = nullptr; Context_ *ctx = nullptr; };
+    std::vector<Flat> flat;
+    ~KSwitchKeys_() { clear(); }
+    void clear()
+    {
+        for (auto &l : keys)
+            for (auto *p : l)
+                delete p;
+        keys.clear();
+        drop_flat();
+    }
+    void drop_flat()
+    {
+        for (auto &f : flat)
+            if (f.dev && f.ctx && f.ctx->dev)
+                b200_free(f.ctx->dev, f.dev);
+        flat.clear();
+    }
+    const u64 *flat_dev(Context_ *c, size_t index, int decomp)
+    {
+        if (flat.size() <= index)
+            flat.resize(index + 1);
+        Flat &f = flat[index];
+        if (f.dev && f.ctx == c)
+            return f.dev;
+        const size_t K = c->parms.coeff.size(), n = c->parms.n;
+        const size_t per = 2 * K * n;
+        std::vector<u64> buf(per * decomp);
+        for (int j = 0; j < decomp; j++)
+        {
+            Ciphertext_ &ct = keys[index][j]->data;
+            ct.sync_host();
+            if (ct.words() != per)
+                throw InvalidArg("kswitch_keys is not valid for encryption parameters");
+            std::memcpy(buf.data() + per * j, ct.host.data(), per * sizeof(u64));
+        }
+        void *p = nullptr;
+        dev_check(b200_malloc(c->dev, buf.size() * sizeof(u64), &p));
+        dev_check(b200_memcpy_h2d(c->dev, p, buf.data(), buf.size() * sizeof(u64), nullptr));
+        dev_check(b200_stream_synchronize(c->dev, nullptr));
+        f.dev = (u64 *)p;
+        f.ctx = c;
+        return f.dev;
+    }
+};
+
+
+// PolynomialArray (S/polyarray.h:20-282): a stack of polynomials in RNS ([poly][residue][coeff]) or, after
+// to_multiprecision, coefficient-major multi-precision form ([poly][coeff][word]).
+struct PolynomialArray_
+{
+    std::vector<u64> moduli;
+    size_t poly_size = 0, coeff_size = 0;
+    std::vector<u64> data;
+    std::vector<bool> filled;
+    bool reserved = false, is_rns = true;
+    size_t poly_len() const { return coeff_size * moduli.size(); }
+    void reserve(size_t polys, size_t coeffs, const std::vector<u64> &base)
+    {
+        if (reserved)
+            throw LogicErr("PolynomialArray can only be reserved once.");
+        moduli = base;
+        poly_size = polys;
+        coeff_size = coeffs;
+        data.assign(polys * poly_len(), 0);
+        filled.assign(polys, false);
+        reserved = true;
+    }
+    void insert(size_t index, const u64 *src)
+    {
+        if (index >= poly_size)
+            throw LogicErr("Polynomial index greater than number of polynomials stored");
+        if (filled[index])
+            throw LogicErr("Attempted to overwrite a polynomial in PolynomialArray.");
+        std::memcpy(data.data() + index * poly_len(), src, poly_len() * sizeof(u64));
+        filled[index] = true;
+    }
+};
+
+struct Evaluator_ { Context_ *ctx; };
+
+struct BatchEncoder_
+{
+    Context_ *ctx;
+    std::vector<size_t> index_map; // populate_matrix_reps_index_map (S/batchencoder.cpp:62-80)
+};
+
+struct Decryptor_
+{
+    Context_ *ctx;
+    std::vector<u64> sk; // key level NTT form [K][n]
+    // device cache: powers s^1..s^m packed per (level, terms)
+    struct Pow { int level, terms; u64 *dev; };
+    std::vector<Pow> cache;
+    ~Decryptor_()
+    {
+        for (auto &p : cache)
+            if (p.dev)
+                b200_free(ctx->dev, p.dev);
+    }
+    const u64 *powers(int level, int terms)
+    {
+        for (auto &p : cache)
+            if (p.level == level && p.terms == terms)
+                return p.dev;
+        const size_t n = ctx->parms.n;
+        const int k = ctx->level_k[level];
+        std::vector<u64> buf((size_t)terms * k * n);
+        for (int r = 0; r < k; r++)
+        {
+            const u64 q = ctx->parms.coeff[r];
+            const u64 *s1 = sk.data() + (size_t)r * n;
+            for (size_t c = 0; c < n; c++)
+            {
+                u64 cur = s1[c];
+                for (int j = 0; j < terms; j++)
+                {
+                    buf[((size_t)j * k + r) * n + c] = cur;
+                    cur = (u64)((unsigned __int128)cur * s1[c] % q);
+                }
+            }
+        }
+        void *p = nullptr;
+        dev_check(b200_malloc(ctx->dev, buf.size() * sizeof(u64), &p));
+        dev_check(b200_memcpy_h2d(ctx->dev, p, buf.data(), buf.size() * sizeof(u64), nullptr));
+        dev_check(b200_stream_synchronize(ctx->dev, nullptr));
+        cache.push_back({ level, terms, (u64 *)p });
+        return (u64 *)p;
+    }
+};
+
+// ---- small device helpers for key generation / encryption (all arithmetic on the GPU through layer 1) ----
+struct DevBuf
+{
+    Context_ *c;
+    u64 *p = nullptr;
+    size_t words;
+    DevBuf(Context_ *ctx, size_t w) : c(ctx), words(w)
+    {
+        void *q = nullptr;
+        dev_check(b200_malloc(c->dev, std::max<size_t>(w, 1) * 8, &q));
+        p = (u64 *)q;
+    }
+    DevBuf(Context_ *ctx, const std::vector<u64> &h) : DevBuf(ctx, h.size()) { upload(h); }
+    ~DevBuf()
+    {
+        b200_stream_synchronize(c->dev, nullptr);
+        b200_free(c->dev, p);
+    }
+    void upload(const std::vector<u64> &h) { dev_check(b200_memcpy_h2d(c->dev, p, h.data(), h.size() * 8, nullptr)); }
+    std::vector<u64> download()
+    {
+        std::vector<u64> h(words);
+        dev_check(b200_memcpy_d2h(c->dev, h.data(), p, words * 8, nullptr));
+        dev_check(b200_stream_synchronize(c->dev, nullptr));
+        return h;
+    }
+    DevBuf(const DevBuf &) = delete;
+};
+
+// encrypt_zero_symmetric at the key level, NTT form, no seed saving (S/util/rlwe.cpp:312-459): returns [2][K][n]
+// c1 <- uniform (a fresh PRNG seeded from the bootstrap PRNG), c0 = -(s*c1 + e)
+inline std::vector<u64> encrypt_zero_symmetric_key_level(Context_ *c, const std::vector<u64> &sk, b200::Blake2xbPrng &bootstrap)
+{
+    const size_t n = c->parms.n, K = c->parms.coeff.size();
+    b200::PrngSeed pub;
+    bootstrap.generate(sizeof(pub), pub.data());
+    b200::Blake2xbPrng ct_prng(pub);
+    std::vector<u64> c1(K * n), noise(K * n);
+    b200::sample_poly_uniform(ct_prng, n, c->parms.coeff, c1.data());
+    b200::sample_poly_normal(bootstrap, n, c->parms.coeff, noise.data());
+    DevBuf d1(c, c1), de(c, noise), ds(c, sk), d0(c, K * n);
+    dev_check(b200_dyadic_product(c->dev, 0, ds.p, 1, d1.p, 1, d0.p, 1, nullptr)); // s (*) c1
+    dev_check(b200_ntt_forward(c->dev, 0, de.p, 1, nullptr));                      // NTT(e)
+    dev_check(b200_add(c->dev, 0, d0.p, de.p, d0.p, 1, 1, nullptr));
+    dev_check(b200_negate(c->dev, 0, d0.p, d0.p, 1, 1, nullptr));
+    std::vector<u64> out = d0.download();
+    out.insert(out.end(), c1.begin(), c1.end());
+    return out;
+}
+
+struct KeyGenerator_
+{
+    Context_ *ctx;
+    std::vector<u64> sk; // key level, NTT form [K][n]
+    // generate_one_kswitch_key (S/keygenerator.cpp:303-337): new_key = [K][n] NTT form
+    void one_kswitch_key(const std::vector<u64> &new_key, std::vector<PublicKey_ *> &dest)
+    {
+        Context_ *c = ctx;
+        const size_t n = c->parms.n, K = c->parms.coeff.size();
+        const int decomp = c->level_k[c->first_level];
+        const u64 qsp = c->parms.coeff.back();
+        b200::Blake2xbPrng bootstrap(b200::random_seed());
+        for (int J = 0; J < decomp; J++)
+        {
+            std::vector<u64> w = encrypt_zero_symmetric_key_level(c, sk, bootstrap);
+            const u64 qj = c->parms.coeff[J];
+            const u64 factor = qsp % qj;
+            for (size_t i = 0; i < n; i++)
+            { // c0[J] += factor * new_key[J]  (S/keygenerator.cpp:330-334)
+                u64 t = (u64)((unsigned __int128)new_key[(size_t)J * n + i] * factor % qj);
+                u64 &d = w[(size_t)J * n + i];
+                d = (u64)(((unsigned __int128)d + t) % qj);
+            }
+            auto *pk = new PublicKey_();
+            pk->data.parms_id = c->ids[0];
+            pk->data.size = 2;
+            pk->data.k = K;
+            pk->data.n = n;
+            pk->data.is_ntt_form = true;
+            pk->data.host = std::move(w);
+            pk->data.host_valid = true;
+            dest.push_back(pk);
+        }
+    }
+};
+
+struct Encryptor_
+{
+    Context_ *ctx;
+    bool has_pk = false, has_sk = false;
+    std::vector<u64> pk; // [2][K][n] NTT form, key level
+    std::vector<u64> sk; // [K][n]
+};
+
+template <class F>
+long guard(F f)
+{
+    try
+    {
+        f();
+        return S_OK_;
+    }
+    catch (const InvalidArg &)
+    {
+        return E_INVALIDARG_;
+    }
+    catch (const std::invalid_argument &)
+    {
+        return E_INVALIDARG_;
+    }
+    catch (const LogicErr &)
+    {
+        return COR_E_INVALIDOPERATION_;
+    }
+    catch (const std::logic_error &)
+    {
+        return COR_E_INVALIDOPERATION_;
+    }
+    catch (const std::bad_alloc &)
+    {
+        return E_OUTOFMEMORY_;
+    }
+    catch (...)
+    {
+        return E_UNEXPECTED_;
+    }
+}
+
+#define NULLRET(p)                                                                                                     \
+    if (!(p))                                                                                                          \
+    return E_POINTER_
+
+} // namespace b200c

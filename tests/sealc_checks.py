@@ -357,3 +357,407 @@ def batch_encoder_parity(S, n, moduli, t):
     c2 = u64(n)
     O.S.call("BatchEncoder_Decode2", obe, op, C.byref(c2), so.ctypes.data_as(C.POINTER(C.c_int64)), None)
     assert np.array_equal(so, sv)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# wire format, PolynomialArray, component-returning encryption, small leftovers of the seal_fhe surface
+# ------------------------------------------------------------------------------------------------------------
+COMPR_NONE, COMPR_ZLIB, COMPR_ZSTD = 0, 1, 2
+E_INVALIDARG, COR_E_INVALIDOPERATION, COR_E_IO = 0x80070057, 0x80131509, 0x80131620
+_CREATE = {"Ciphertext": ("Ciphertext_Create1", True), "Plaintext": ("Plaintext_Create1", True),
+           "PublicKey": ("PublicKey_Create1", False), "SecretKey": ("SecretKey_Create1", False),
+           "KSwitchKeys": ("KSwitchKeys_Create1", False)}
+
+
+class _Lib:
+    """Uniform view of `call` / `rc` over the reference (RefLib) and our Sealc driver."""
+
+    def __init__(self, call, rc, ctx):
+        self.call, self.rc, self.ctx = call, rc, ctx
+
+    def new(self, kind):
+        name, pool = _CREATE[kind]
+        h = vp()
+        self.call(name, None, C.byref(h)) if pool else self.call(name, C.byref(h))
+        return h
+
+    def save_size(self, kind, h, mode):
+        r = C.c_int64()
+        self.call(kind + "_SaveSize", h, C.c_uint8(mode), C.byref(r))
+        return r.value
+
+    def save(self, kind, h, mode):
+        cap = self.save_size(kind, h, mode)
+        buf = (C.c_uint8 * cap)()
+        n = C.c_int64()
+        self.call(kind + "_Save", h, buf, u64(cap), C.c_uint8(mode), C.byref(n))
+        assert 16 <= n.value <= cap
+        return bytes(buf[: n.value])
+
+    def load_rc(self, kind, h, data, unsafe=False):
+        n = C.c_int64()
+        buf = (C.c_uint8 * max(len(data), 1)).from_buffer_copy(data if data else b"\0")
+        rc = self.rc(kind + ("_UnsafeLoad" if unsafe else "_Load"), h, self.ctx, buf, u64(len(data)), C.byref(n))
+        return rc, n.value
+
+    def load(self, kind, data, unsafe=False):
+        h = self.new(kind)
+        rc, n = self.load_rc(kind, h, data, unsafe)
+        assert rc == 0, f"{kind}_Load -> 0x{rc:08x}"
+        assert n == len(data)
+        return h
+
+
+def _libs(R, O):
+    return _Lib(R.ref.call, R.ref.call_rc, R.ctx), _Lib(O.S.call, O.S.rc, O.ctx)
+
+
+def wire_format(S, n, moduli, t):
+    """Save / SaveSize / Load of every data object: byte-identical to the reference with compr_mode none, and
+    interchangeable with it in both directions with zlib and Zstandard; the same HRESULTs on malformed input."""
+    R = refseal.RefContext(n, moduli, t)
+    O = S.context(n, moduli, t)
+    RL, OL = _libs(R, O)
+    kg = R.keygen()
+    sk, pk, rlk = R.secret_key(kg), R.public_key(kg), R.relin_keys(kg)
+    glk = R.galois_keys_steps(kg, [1]) if t % (2 * n) == 1 else None
+    enc = R.encryptor(pk, sk)
+    rng = np.random.default_rng(11)
+    msg = rng.integers(0, t, size=n // 2 + 3, dtype=np.uint64)
+    pt = R.new_pt(msg)
+    ct = R.encrypt(enc, pt)
+    ct3 = R.multiply(ct, ct)
+    empty_ct = R.new_ct()
+    objs = [("Ciphertext", ct), ("Ciphertext", ct3), ("Plaintext", pt), ("Plaintext", R.new_pt(np.zeros(0, dtype=np.uint64))), ("PublicKey", pk),
+            ("SecretKey", sk), ("KSwitchKeys", rlk)]
+    if glk is not None:
+        objs.append(("KSwitchKeys", glk))
+    for kind, h in objs:
+        raw = RL.save(kind, h, COMPR_NONE)
+        assert RL.save_size(kind, h, COMPR_NONE) == len(raw)
+        ours = OL.load(kind, raw)
+        assert OL.save_size(kind, ours, COMPR_NONE) == len(raw)
+        assert OL.save(kind, ours, COMPR_NONE) == raw, f"{kind}: Save(none) differs from the reference"
+        for mode in (COMPR_ZLIB, COMPR_ZSTD):
+            assert OL.save_size(kind, ours, mode) == RL.save_size(kind, h, mode)
+            # reference -> ours
+            z_ref = RL.save(kind, h, mode)
+            assert OL.save(kind, OL.load(kind, z_ref), COMPR_NONE) == raw, f"{kind}: cannot read the reference's mode {mode}"
+            # ours -> reference
+            z_our = OL.save(kind, ours, mode)
+            assert len(z_our) < len(raw) or len(raw) < 256
+            assert RL.save(kind, RL.load(kind, z_our), COMPR_NONE) == raw, f"{kind}: reference cannot read our mode {mode}"
+    # seeded symmetric ciphertext (S/util/rlwe.cpp:441-457 -> S/ciphertext.cpp:118-151,204-224): half-size on the wire,
+    # expanded from the stored PRNG seed when loaded
+    sct = R.new_ct()
+    R.ref.call("Encryptor_EncryptSymmetric", enc, pt, C.c_bool(True), sct, None)
+    sraw = RL.save("Ciphertext", sct, COMPR_NONE)
+    full = RL.save("Ciphertext", ct, COMPR_NONE)
+    assert len(sraw) < 0.6 * len(full)
+    ref_expanded = RL.save("Ciphertext", RL.load("Ciphertext", sraw), COMPR_NONE)
+    assert len(ref_expanded) == len(full)
+    assert OL.save("Ciphertext", OL.load("Ciphertext", sraw), COMPR_NONE) == ref_expanded, "seed expansion differs"
+    # ---- HRESULTs on bad input, side by side ----
+    raw_ct = RL.save("Ciphertext", ct, COMPR_NONE)
+    raw_pk = RL.save("PublicKey", pk, COMPR_NONE)
+    bad_magic = b"\x00\x00" + raw_ct[2:]
+    bad_version = raw_ct[:3] + b"\x09" + raw_ct[4:]
+    bad_mode = raw_ct[:5] + b"\x07" + raw_ct[6:]
+    big = bytearray(raw_ct)
+    off = len(raw_ct) - 8  # last coefficient of the last residue polynomial
+    big[off:off + 8] = (2**63).to_bytes(8, "little")
+    wrong_size = bytearray(raw_ct)
+    wrong_size[16 + 33:16 + 41] = (9).to_bytes(8, "little")  # the size_ member
+    raw_empty = RL.save("Ciphertext", empty_ct, COMPR_NONE)
+    assert OL.save("Ciphertext", OL.new("Ciphertext"), COMPR_NONE) == raw_empty, "empty ciphertext serialises differently"
+    cases = [("empty ciphertext", "Ciphertext", raw_empty, False), ("empty ciphertext, unsafe", "Ciphertext", raw_empty, True),
+             ("truncated", "Ciphertext", raw_ct[:-5], False), ("too short", "Ciphertext", raw_ct[:10], False),
+             ("bad magic", "Ciphertext", bad_magic, False), ("bad version", "Ciphertext", bad_version, False),
+             ("bad compr mode", "Ciphertext", bad_mode, False), ("coefficient out of range", "Ciphertext", bytes(big), False),
+             ("coefficient out of range, unsafe", "Ciphertext", bytes(big), True), ("size member 9", "Ciphertext", bytes(wrong_size), False),
+             ("key-level ct via Ciphertext_Load", "Ciphertext", raw_pk, False),
+             ("key-level ct via Ciphertext_UnsafeLoad", "Ciphertext", raw_pk, True),
+             ("ct bytes via Plaintext_Load", "Plaintext", raw_ct, False), ("ct bytes via KSwitchKeys_Load", "KSwitchKeys", raw_ct, False),
+             ("zstd garbage", "Ciphertext", raw_ct[:5] + b"\x02" + raw_ct[6:], False),
+             ("zlib garbage", "Ciphertext", raw_ct[:5] + b"\x01" + raw_ct[6:], False)]
+    for label, kind, data, unsafe in cases:
+        r_rc, _ = RL.load_rc(kind, RL.new(kind), data, unsafe)
+        o_rc, _ = OL.load_rc(kind, OL.new(kind), data, unsafe)
+        assert o_rc == r_rc, f"{label}: ours 0x{o_rc:08x}, reference 0x{r_rc:08x}"
+    for L in (RL, OL):
+        r = C.c_int64()
+        assert L.rc("Ciphertext_SaveSize", L.load("Ciphertext", raw_ct), C.c_uint8(9), C.byref(r)) == E_INVALIDARG
+        buf = (C.c_uint8 * len(raw_ct))()
+        h = L.load("Ciphertext", raw_ct)
+        assert L.rc("Ciphertext_Save", h, buf, u64(len(raw_ct)), C.c_uint8(9), C.byref(r)) == E_INVALIDARG
+        assert L.rc("Ciphertext_Save", h, buf, u64(8), C.c_uint8(0), C.byref(r)) == E_INVALIDARG
+        assert L.rc("Ciphertext_Save", h, buf, u64(len(raw_ct) - 1), C.c_uint8(0), C.byref(r)) == COR_E_IO
+
+
+def _pa_export(L, h):
+    vals = {}
+    for name in ("ExportSize", "PolySize", "PolyModulusDegree", "CoeffModulusSize"):
+        v = u64()
+        L.call("PolynomialArray_" + name, h, C.byref(v))
+        vals[name] = v.value
+    for name in ("IsReserved", "IsRns", "IsMultiprecision"):
+        b = C.c_bool()
+        L.call("PolynomialArray_" + name, h, C.byref(b))
+        vals[name] = b.value
+    out = np.zeros(vals["ExportSize"], dtype=np.uint64)
+    if out.size:
+        L.call("PolynomialArray_PerformExport", h, out.ctypes.data_as(C.POINTER(u64)))
+    return vals, out
+
+
+def _pa_same(RL, OL, rh, oh, what):
+    rv, rw = _pa_export(RL, rh)
+    ov, ow = _pa_export(OL, oh)
+    assert ov == rv, f"{what}: {ov} vs {rv}"
+    eq(ow, rw, what)
+
+
+def polynomial_array_parity(S, n, moduli, t):
+    """PolynomialArray_* (the fork's container for proof inputs): construction from ciphertext / public key / secret key,
+    RNS <-> multi-precision conversion, Drop and Copy give the reference's words."""
+    R = refseal.RefContext(n, moduli, t)
+    O = S.context(n, moduli, t)
+    RL, OL = _libs(R, O)
+    kg = R.keygen()
+    sk, pk = R.secret_key(kg), R.public_key(kg)
+    ct = R.encrypt(R.encryptor(pk), R.new_pt(np.arange(1, 40, dtype=np.uint64) % t))
+    blobs = {"Ciphertext": RL.save("Ciphertext", ct, 0), "PublicKey": RL.save("PublicKey", pk, 0), "SecretKey": RL.save("SecretKey", sk, 0)}
+    for kind, raw in blobs.items():
+        oh_src = OL.load(kind, raw)
+        rh_src = {"Ciphertext": ct, "PublicKey": pk, "SecretKey": sk}[kind]
+        rh, oh = vp(), vp()
+        RL.call("PolynomialArray_CreateFrom" + kind, None, R.ctx, rh_src, C.byref(rh))
+        OL.call("PolynomialArray_CreateFrom" + kind, None, O.ctx, oh_src, C.byref(oh))
+        _pa_same(RL, OL, rh, oh, f"PolynomialArray from {kind}")
+        rc_, oc_ = vp(), vp()
+        RL.call("PolynomialArray_Copy", rh, C.byref(rc_))
+        OL.call("PolynomialArray_Copy", oh, C.byref(oc_))
+        _pa_same(RL, OL, rc_, oc_, f"Copy of {kind} array")
+        if kind != "SecretKey":
+            rd, od = vp(), vp()
+            RL.call("PolynomialArray_Drop", rh, C.byref(rd))
+            OL.call("PolynomialArray_Drop", oh, C.byref(od))
+            _pa_same(RL, OL, rd, od, f"Drop of {kind} array")
+        RL.call("PolynomialArray_ToMultiprecision", rh)
+        OL.call("PolynomialArray_ToMultiprecision", oh)
+        _pa_same(RL, OL, rh, oh, f"{kind} array in multi-precision form")
+        RL.call("PolynomialArray_ToRns", rh)
+        OL.call("PolynomialArray_ToRns", oh)
+        _pa_same(RL, OL, rh, oh, f"{kind} array back in RNS form")
+        RL.call("PolynomialArray_Destroy", rh)
+        OL.call("PolynomialArray_Destroy", oh)
+    # an unreserved array
+    rh, oh = vp(), vp()
+    RL.call("PolynomialArray_Create", None, C.byref(rh))
+    OL.call("PolynomialArray_Create", None, C.byref(oh))
+    _pa_same(RL, OL, rh, oh, "fresh PolynomialArray")
+
+
+def encryption_components_parity(S, n, moduli, t):
+    """Encryptor_Encrypt{,Symmetric}ReturnComponentsSetSeed: ciphertext, u, e and the rounding remainder all equal the
+    reference's for the same seed, with and without the special modulus."""
+    R = refseal.RefContext(n, moduli, t)
+    O = S.context(n, moduli, t)
+    RL, OL = _libs(R, O)
+    kg = R.keygen()
+    sk, pk = R.secret_key(kg), R.public_key(kg)
+    renc = R.encryptor(pk, sk)
+    opk, osk = OL.load("PublicKey", RL.save("PublicKey", pk, 0)), OL.load("SecretKey", RL.save("SecretKey", sk, 0))
+    oenc = vp()
+    O.S.call("Encryptor_Create", O.ctx, opk, osk, C.byref(oenc))
+    rng = np.random.default_rng(21)
+    for trial in range(3):
+        msg = rng.integers(0, t, size=(5, n, n // 3)[trial], dtype=np.uint64)
+        seed = (u64 * 8)(*[int(x) for x in rng.integers(0, 2**63, size=8)])
+        for disable in (False, True):
+            outs = []
+            for L, encryptor, new_pt in ((RL, renc, R.new_pt), (OL, oenc, O.new_pt)):
+                ct, u, e, rem = L.new("Ciphertext"), vp(), vp(), L.new("Plaintext")
+                L.call("PolynomialArray_Create", None, C.byref(u))
+                L.call("PolynomialArray_Create", None, C.byref(e))
+                L.call("Encryptor_EncryptReturnComponentsSetSeed", encryptor, new_pt(msg), C.c_bool(disable), ct, u, e, rem, seed, None)
+                outs.append((L.save("Ciphertext", ct, 0), _pa_export(L, u), _pa_export(L, e), L.save("Plaintext", rem, 0)))
+            (rct, ru, re_, rrem), (oct_, ou, oe, orem) = outs
+            assert oct_ == rct, f"asymmetric ciphertext differs (disable_special_modulus={disable})"
+            assert ou[0] == ru[0] and oe[0] == re_[0]
+            eq(ou[1], ru[1], "u component")
+            eq(oe[1], re_[1], "e component")
+            assert orem == rrem, "remainder differs"
+        # Symmetric variant.  The reference does NOT forward the seed on this path (S/encryptor.cpp:225-236 calls
+        # encrypt_zero_symmetric without it, S/util/rlwe.h:128-143), so its output is random even with SetSeed; ours
+        # honours the seed.  Checked: the reference really is non-deterministic here, ours is deterministic, the
+        # remainder matches, the exported noise is a clipped Gaussian sample with consistent residues, and the
+        # reference decrypts our ciphertext.
+        def sym(L, encryptor, new_pt):
+            ct, e, rem = L.new("Ciphertext"), vp(), L.new("Plaintext")
+            L.call("PolynomialArray_Create", None, C.byref(e))
+            L.call("Encryptor_EncryptSymmetricReturnComponentsSetSeed", encryptor, new_pt(msg), ct, e, rem, seed, None)
+            return L.save("Ciphertext", ct, 0), _pa_export(L, e), L.save("Plaintext", rem, 0)
+        r1, r2 = sym(RL, renc, R.new_pt), sym(RL, renc, R.new_pt)
+        o1, o2 = sym(OL, oenc, O.new_pt), sym(OL, oenc, O.new_pt)
+        assert r1[0] != r2[0], "the reference's symmetric SetSeed path became deterministic: compare words instead"
+        assert o1[0] == o2[0] and np.array_equal(o1[1][1], o2[1][1])
+        assert o1[2] == r1[2], "remainder differs"
+        assert o1[1][0] == r1[1][0], "shape of the exported noise differs"
+        k = R.k
+        ev = o1[1][1].reshape(k, n)
+        signed = [np.where(ev[i] > moduli[i] // 2, ev[i].astype(np.int64) - np.int64(moduli[i]), ev[i].astype(np.int64)) for i in range(k)]
+        assert all(np.array_equal(signed[0], s) for s in signed) and np.abs(signed[0]).max() <= 19 and np.abs(signed[0]).max() >= 3
+        back = R.pt_coeffs(R.decrypt(R.decryptor(sk), RL.load("Ciphertext", o1[0])))
+        eq(back, msg[: np.flatnonzero(msg)[-1] + 1], "reference decrypts our seeded symmetric encryption")
+    # unseeded variants run and decrypt
+    dec = R.decryptor(sk)
+    for name, args in (("Encryptor_EncryptReturnComponents", lambda ct, u, e, rem: (C.c_bool(False), ct, u, e, rem, None)),
+                       ("Encryptor_EncryptSymmetricReturnComponents", lambda ct, u, e, rem: (ct, e, rem, None))):
+        ct, u, e, rem = OL.new("Ciphertext"), vp(), vp(), OL.new("Plaintext")
+        OL.call("PolynomialArray_Create", None, C.byref(u))
+        OL.call("PolynomialArray_Create", None, C.byref(e))
+        msg = rng.integers(1, t, size=17, dtype=np.uint64)
+        OL.call(name, oenc, O.new_pt(msg), *args(ct, u, e, rem))
+        back = R.pt_coeffs(R.decrypt(dec, RL.load("Ciphertext", OL.save("Ciphertext", ct, 0))))
+        eq(back, msg, name)
+
+
+def leftovers_parity(S, n, moduli, t):
+    """Plaintext_Create4 (hex polynomial strings), Evaluator_ModSwitchToNext2 (NTT-form plaintexts) and
+    Decryptor_InvariantNoise (double), each against the reference: values and HRESULTs."""
+    R = refseal.RefContext(n, moduli, t)
+    O = S.context(n, moduli, t)
+    RL, OL = _libs(R, O)
+    for s in ("", "0", "1", "7FFx^3 + 1x^1 + 3", "1x^4095", "ABCDEFabcdef0123x^2", "1x^2 + 2x^2", "1x^1 + 2x^2", "3 + 1x^1", "x^2",
+              "1x^", "1 x^2", "1x^2+3", "00000000000000000001x^1", "10000000000000000x^1", "FFFFFFFFFFFFFFFFx^1 + 0", "1x^3 + ",
+              "Gx^1", "2x^1 + 0x^0"):
+        rh, oh = vp(), vp()
+        r_rc = RL.rc("Plaintext_Create4", s.encode(), None, C.byref(rh))
+        o_rc = OL.rc("Plaintext_Create4", s.encode(), None, C.byref(oh))
+        assert o_rc == r_rc, f"Plaintext_Create4({s!r}): ours 0x{o_rc:08x}, reference 0x{r_rc:08x}"
+        if r_rc == 0:
+            eq(O.pt_coeffs(oh), R.pt_coeffs(rh), f"Plaintext_Create4({s!r})")
+    # an NTT-form plaintext at the first data level: k*n residues + parms_id
+    k = R.k
+    rng = np.random.default_rng(2)
+    words = np.concatenate([rng.integers(0, moduli[i], size=n, dtype=np.uint64) for i in range(k)])
+    outs = []
+    for L, first_id, make in ((RL, R.first_parms_id, R.new_pt), (OL, O.first_id, O.new_pt)):
+        p = make(words)
+        L.call("Plaintext_SetParmsId", p, first_id)
+        d = L.new("Plaintext")
+        ev = R.ev if L is RL else O.ev
+        rc = L.rc("Evaluator_ModSwitchToNext2", ev, p, d)
+        plain = make(np.array([1, 2, 3], dtype=np.uint64))
+        rc_plain = L.rc("Evaluator_ModSwitchToNext2", ev, plain, L.new("Plaintext"))
+        bad = make(words + np.uint64(2**62))
+        L.call("Plaintext_SetParmsId", bad, first_id)
+        rc_bad = L.rc("Evaluator_ModSwitchToNext2", ev, bad, L.new("Plaintext"))
+        outs.append((rc, rc_plain, rc_bad, L.save("Plaintext", d, 0) if rc == 0 else None))
+    assert outs[0] == outs[1], f"ModSwitchToNext2: reference {outs[0][:3]}, ours {outs[1][:3]}"
+    # invariant noise as a double
+    kg = R.keygen()
+    sk, pk, rlk = R.secret_key(kg), R.public_key(kg), R.relin_keys(kg)
+    ct = R.encrypt(R.encryptor(pk), R.new_pt(np.array([3, 1, 4, 1, 5], dtype=np.uint64)))
+    prod = R.relinearize(R.multiply(ct, ct), rlk)
+    osk = OL.load("SecretKey", RL.save("SecretKey", sk, 0))
+    rdec, odec = R.decryptor(sk), vp()
+    O.S.call("Decryptor_Create", O.ctx, osk, C.byref(odec))
+    for h in (ct, prod):
+        oh = OL.load("Ciphertext", RL.save("Ciphertext", h, 0))
+        a, b = C.c_double(), C.c_double()
+        RL.call("Decryptor_InvariantNoise", rdec, h, C.byref(a))
+        OL.call("Decryptor_InvariantNoise", odec, oh, C.byref(b))
+        assert a.value == b.value and 0.0 < a.value < 0.5, (a.value, b.value)
+
+
+def _siphash13(data):
+    """Rust's DefaultHasher (SipHash-1-3, zero keys) over `data`."""
+    M = (1 << 64) - 1
+    rotl = lambda x, b: ((x << b) | (x >> (64 - b))) & M
+    v = [0x736f6d6570736575, 0x646f72616e646f6d, 0x6c7967656e657261, 0x7465646279746573]
+
+    def rnd():
+        v[0] = (v[0] + v[1]) & M; v[1] = rotl(v[1], 13) ^ v[0]; v[0] = rotl(v[0], 32)
+        v[2] = (v[2] + v[3]) & M; v[3] = rotl(v[3], 16) ^ v[2]
+        v[0] = (v[0] + v[3]) & M; v[3] = rotl(v[3], 21) ^ v[0]
+        v[2] = (v[2] + v[1]) & M; v[1] = rotl(v[1], 17) ^ v[2]; v[2] = rotl(v[2], 32)
+
+    nbytes = len(data)
+    for m in np.frombuffer(data[: nbytes - nbytes % 8], dtype="<u8").tolist():
+        v[3] ^= m; rnd(); v[0] ^= m
+    b = (nbytes & 0xff) << 56
+    for i, ch in enumerate(data[nbytes - nbytes % 8:]):
+        b |= ch << (8 * i)
+    v[3] ^= b; rnd(); v[0] ^= b
+    v[2] ^= 0xff; rnd(); rnd(); rnd()
+    return v[0] ^ v[1] ^ v[2] ^ v[3]
+
+
+def seal_fhe_golden_fixture(S, golden_dir):
+    """seal_fhe's own deterministic-encryption test (seal_fhe/src/encryptor_decryptor.rs:886-932) replayed through the FFI:
+    the fixture keys (tests/data/{public,secret}_key.bin, Zstandard) load, encrypt_deterministic(seed 0) of 0..8191 gives
+    the reference's ciphertext word for word — and the reference's serialisation of it hashes to the crate's golden value."""
+    import os
+    n, bits = 8192, [50, 30, 30, 50, 50]
+    Rl = refseal.RefLib.get()
+    ctxs = []
+    for call in (Rl.call, S.call):
+        arr = (vp * len(bits))()
+        call("CoeffModulus_Create1", u64(n), u64(len(bits)), (C.c_int * len(bits))(*bits), arr)
+        mods = []
+        for h in arr:
+            v = u64()
+            call("Modulus_Value", vp(h), C.byref(v))
+            mods.append(v.value)
+        pm = (vp * 1)()
+        call("CoeffModulus_Create1", u64(n), u64(1), (C.c_int * 1)(20), pm)
+        tv = u64()
+        call("Modulus_Value", vp(pm[0]), C.byref(tv))
+        parms, ctx = vp(), vp()
+        call("EncParams_Create1", C.c_uint8(1), C.byref(parms))
+        call("EncParams_SetPolyModulusDegree", parms, u64(n))
+        call("EncParams_SetCoeffModulus", parms, u64(len(bits)), arr)
+        call("EncParams_SetPlainModulus2", parms, tv)
+        call("SEALContext_Create", parms, C.c_bool(False), C.c_int(128), C.byref(ctx))
+        ctxs.append((mods, tv.value, ctx))
+    assert ctxs[0][:2] == ctxs[1][:2], "CoeffModulus_Create1 / PlainModulus::batching primes differ"
+    assert ctxs[0][1] == 1032193
+    RL, OL = _Lib(Rl.call, Rl.call_rc, ctxs[0][2]), _Lib(S.call, S.rc, ctxs[1][2])
+    pkb = open(os.path.join(golden_dir, "public_key.bin"), "rb").read()
+    skb = open(os.path.join(golden_dir, "secret_key.bin"), "rb").read()
+    results = []
+    for L in (RL, OL):
+        last = (u64 * 4)()
+        first = (u64 * 4)()
+        L.call("SEALContext_LastParmsId", L.ctx, last)
+        L.call("SEALContext_FirstParmsId", L.ctx, first)
+        assert list(last) == list(first), "expand_mod_chain = false: the chain ends at the first data level"
+        pk, sk = L.load("PublicKey", pkb), L.load("SecretKey", skb)
+        be, enc, dec = vp(), vp(), vp()
+        L.call("BatchEncoder_Create", L.ctx, C.byref(be))
+        L.call("Encryptor_Create", L.ctx, pk, sk, C.byref(enc))
+        L.call("Decryptor_Create", L.ctx, sk, C.byref(dec))
+        vals = (u64 * n)(*range(n))
+        pt = L.new("Plaintext")
+        L.call("BatchEncoder_Encode1", be, u64(n), vals, pt)
+        ct, u, e, rem = L.new("Ciphertext"), vp(), vp(), L.new("Plaintext")
+        L.call("PolynomialArray_Create", None, C.byref(u))
+        L.call("PolynomialArray_Create", None, C.byref(e))
+        L.call("Encryptor_EncryptReturnComponentsSetSeed", enc, pt, C.c_bool(False), ct, u, e, rem, (u64 * 8)(), None)
+        out = L.new("Plaintext")
+        L.call("Decryptor_Decrypt", dec, ct, out)
+        cnt = u64(n)
+        back = (u64 * n)()
+        L.call("BatchEncoder_Decode1", be, out, C.byref(cnt), back, None)
+        assert list(back) == list(range(n))
+        results.append((L.save("PublicKey", pk, 0), L.save("SecretKey", sk, 0), L.save("Ciphertext", ct, 0), ct))
+    assert results[0][0] == results[1][0] and results[0][1] == results[1][1], "fixture keys decode differently"
+    assert results[0][2] == results[1][2], "deterministic encryption differs from the reference"
+    # the crate's golden value pins the REFERENCE build (its vendored zstd 1.4.5 included); our Zstandard bytes come from
+    # the system library, so for our side the check is that the reference reads them back to the same ciphertext
+    zref = RL.save("Ciphertext", results[0][3], COMPR_ZSTD)
+    assert _siphash13(len(zref).to_bytes(8, "little") + zref) == 9942548233613012008
+    zour = OL.save("Ciphertext", results[1][3], COMPR_ZSTD)
+    assert RL.save("Ciphertext", RL.load("Ciphertext", zour), 0) == results[0][2]

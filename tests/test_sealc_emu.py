@@ -42,3 +42,26 @@ def test_chi_sq_dag_small(S, ref):
 @pytest.mark.parametrize("name", ["n8192"])
 def test_batch_encoder(S, ref, name):
     sc.batch_encoder_parity(S, *PARAMS[name])
+
+
+@pytest.mark.parametrize("name", ["n4096", "n8192"])
+def test_wire_format(S, ref, name):
+    sc.wire_format(S, *PARAMS[name])
+
+
+def test_polynomial_array(S, ref):
+    sc.polynomial_array_parity(S, *PARAMS["n4096"])
+
+
+@pytest.mark.parametrize("name", ["n4096", "n8192"])
+def test_encryption_components(S, ref, name):
+    sc.encryption_components_parity(S, *PARAMS[name])
+
+
+def test_leftover_entry_points(S, ref):
+    sc.leftovers_parity(S, *PARAMS["n4096"])
+
+
+def test_seal_fhe_golden_fixture(S, ref):
+    import os
+    sc.seal_fhe_golden_fixture(S, os.path.join(os.path.dirname(__file__), "golden", "seal_fhe_data"))
