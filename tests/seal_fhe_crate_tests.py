@@ -7,11 +7,11 @@ import random
 from sunscreen_b200 import seal_fhe as s
 
 
-def run_bfv_test(test):
+def run_bfv_test(test, expand_mod_chain=False):
     params = (s.BfvEncryptionParametersBuilder().set_poly_modulus_degree(8192)
               .set_coefficient_modulus(s.CoefficientModulus.create(8192, [50, 30, 30, 50, 50]))
               .set_plain_modulus(s.PlainModulus.batching(8192, 20)).build())
-    ctx = s.Context(params, False, s.SecurityLevel.TC128)
+    ctx = s.Context(params, expand_mod_chain, s.SecurityLevel.TC128)
     gen = s.KeyGenerator(ctx)
     encoder = s.BFVEncoder(ctx)
     public_key, secret_key = gen.create_public_key(), gen.secret_key()
@@ -111,13 +111,25 @@ def all_tests():
         assert c.coeff_modulus_size() == 3
         assert enc_.decode_signed(dec.decrypt(c)) == a
 
+    def cannot_mod_switch_without_chain(dec, enc_, encr, ev, _):
+        # Context::new(.., expand_mod_chain = false, ..): the chain ends at the first data level (S/context.cpp:478-497)
+        try:
+            ev.mod_switch_to_next(encr.encrypt(enc_.encode_signed(make_vec(enc_, rng))))
+        except s.Error as e:
+            assert "InvalidArgument" in str(e)
+        else:
+            raise AssertionError("mod_switch_to_next must fail at the end of the chain")
+
     def symmetric_encryption_roundtrip(dec, enc_, encr, ev, _):
         a = make_vec(enc_, rng)
         assert enc_.decode_signed(dec.decrypt(encr.encrypt_symmetric(enc_.encode_signed(a)))) == a
 
     for fn in (can_negate, can_negate_inplace, can_add_sub, can_add_many, can_multiply_and_relinearize, can_square,
-               can_multiply_many_and_exponentiate, can_plain_ops, can_rotate, can_mod_switch, symmetric_encryption_roundtrip):
+               can_multiply_many_and_exponentiate, can_plain_ops, can_rotate, cannot_mod_switch_without_chain,
+               symmetric_encryption_roundtrip):
         t(fn)
+    run_bfv_test(can_mod_switch, expand_mod_chain=True)
+    done.append("can_mod_switch")
     return done
 
 

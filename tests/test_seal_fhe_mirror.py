@@ -6,7 +6,7 @@ from sunscreen_b200 import seal_fhe
 def test_bfv_evaluator_crate_tests(emu_lib):
     seal_fhe.use_library(emu_lib.lib)
     done = crate.all_tests()
-    assert len(done) == 11
+    assert len(done) == 12
 
 
 def test_lane_overflow_assumption(emu_lib):
