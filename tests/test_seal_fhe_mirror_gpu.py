@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 def test_bfv_evaluator_crate_tests():
     from sunscreen_b200.lib import B200Lib
     seal_fhe.use_library(B200Lib.default().lib)
-    assert len(crate.all_tests()) == 11
+    assert len(crate.all_tests()) == 12
 
 
 def test_lane_overflow_assumption():
