@@ -75,6 +75,37 @@ class _Handle:
             pass
 
 
+class CompressionType:
+    """seal_fhe/src/lib.rs:39-45 (serialization::CompressionType)."""
+    NONE, ZLIB, ZSTD = 0, 1, 2
+
+
+class _Serializable:
+    """ToBytes / FromBytes of seal_fhe (plaintext_ciphertext.rs:88-160,452-500; key_generator.rs:200-700): the crate
+    always asks for Zstandard; `compression` is exposed here because byte-exact comparisons need NONE."""
+    _prefix = None
+    _create = None  # (function name, takes a pool argument)
+
+    def as_bytes(self, compression=CompressionType.ZSTD):
+        n = C.c_int64()
+        _call(self._prefix + "_SaveSize", self.handle, C.c_uint8(compression), C.byref(n))
+        buf = (C.c_uint8 * n.value)()
+        out = C.c_int64()
+        _call(self._prefix + "_Save", self.handle, buf, u64(n.value), C.c_uint8(compression), C.byref(out))
+        return bytes(buf[: out.value])
+
+    @classmethod
+    def from_bytes(cls, ctx, data):
+        name, pool = cls._create
+        h = vp()
+        _call(name, None, C.byref(h)) if pool else _call(name, C.byref(h))
+        obj = cls(h)
+        buf = (C.c_uint8 * max(len(data), 1)).from_buffer_copy(data if data else b"\0")
+        n = C.c_int64()
+        _call(cls._prefix + "_Load", h, ctx.handle, buf, u64(len(data)), C.byref(n))
+        return obj
+
+
 class Modulus(_Handle):
     _destroy = "Modulus_Destroy"
 
@@ -199,8 +230,16 @@ class Context(_Handle):
         return list(a)
 
 
-class Plaintext(_Handle):
+class Plaintext(_Handle, _Serializable):
     _destroy = "Plaintext_Destroy"
+    _prefix, _create = "Plaintext", ("Plaintext_Create1", True)
+
+    @classmethod
+    def from_hex_string(cls, hex_str):
+        """Plaintext::from_hex_string (plaintext_ciphertext.rs): "7FFx^3 + 1x^1 + 3"."""
+        h = vp()
+        _call("Plaintext_Create4", hex_str.encode(), None, C.byref(h))
+        return cls(h)
 
     def __init__(self, handle=None):
         if handle is None:
@@ -225,8 +264,9 @@ class Plaintext(_Handle):
         return n.value
 
 
-class Ciphertext(_Handle):
+class Ciphertext(_Handle, _Serializable):
     _destroy = "Ciphertext_Destroy"
+    _prefix, _create = "Ciphertext", ("Ciphertext_Create1", True)
 
     def __init__(self, handle=None):
         if handle is None:
@@ -260,20 +300,85 @@ class Ciphertext(_Handle):
         return Ciphertext(h)
 
 
-class PublicKey(_Handle):
+class PublicKey(_Handle, _Serializable):
     _destroy = "PublicKey_Destroy"
+    _prefix, _create = "PublicKey", ("PublicKey_Create1", False)
 
 
-class SecretKey(_Handle):
+class SecretKey(_Handle, _Serializable):
     _destroy = "SecretKey_Destroy"
+    _prefix, _create = "SecretKey", ("SecretKey_Create1", False)
 
 
-class RelinearizationKeys(_Handle):
+class RelinearizationKeys(_Handle, _Serializable):
     _destroy = "KSwitchKeys_Destroy"
+    _prefix, _create = "KSwitchKeys", ("KSwitchKeys_Create1", False)
 
 
-class GaloisKeys(_Handle):
+class GaloisKeys(_Handle, _Serializable):
     _destroy = "KSwitchKeys_Destroy"
+    _prefix, _create = "KSwitchKeys", ("KSwitchKeys_Create1", False)
+
+
+class PolynomialArray(_Handle):
+    """seal_fhe/src/poly_array.rs: the (u, e, key) polynomial container handed to the proof code."""
+    _destroy = "PolynomialArray_Destroy"
+
+    def __init__(self, handle=None):
+        if handle is None:
+            handle = vp()
+            _call("PolynomialArray_Create", None, C.byref(handle))
+        super().__init__(handle)
+
+    @classmethod
+    def _from(cls, fn, ctx, obj):
+        h = vp()
+        _call(fn, None, ctx.handle, obj.handle, C.byref(h))
+        return cls(h)
+
+    new_from_ciphertext = classmethod(lambda cls, ctx, ct: cls._from("PolynomialArray_CreateFromCiphertext", ctx, ct))
+    new_from_public_key = classmethod(lambda cls, ctx, pk: cls._from("PolynomialArray_CreateFromPublicKey", ctx, pk))
+    new_from_secret_key = classmethod(lambda cls, ctx, sk: cls._from("PolynomialArray_CreateFromSecretKey", ctx, sk))
+
+    def _u64(self, name):
+        v = u64()
+        _call("PolynomialArray_" + name, self.handle, C.byref(v))
+        return v.value
+
+    def _bool(self, name):
+        b = C.c_bool()
+        _call("PolynomialArray_" + name, self.handle, C.byref(b))
+        return b.value
+
+    num_polynomials = lambda self: self._u64("PolySize")
+    poly_modulus_degree = lambda self: self._u64("PolyModulusDegree")
+    coeff_modulus_size = lambda self: self._u64("CoeffModulusSize")
+    is_reserved = lambda self: self._bool("IsReserved")
+    is_rns = lambda self: self._bool("IsRns")
+    is_multiprecision = lambda self: not self._bool("IsRns")
+
+    def to_rns(self):
+        _call("PolynomialArray_ToRns", self.handle)
+
+    def to_multiprecision(self):
+        _call("PolynomialArray_ToMultiprecision", self.handle)
+
+    def as_u64_slice(self):
+        n = self._u64("ExportSize")
+        buf = (u64 * max(n, 1))()
+        if n:
+            _call("PolynomialArray_PerformExport", self.handle, buf)
+        return list(buf[:n])
+
+    def drop(self):
+        h = vp()
+        _call("PolynomialArray_Drop", self.handle, C.byref(h))
+        return PolynomialArray(h)
+
+    def clone(self):
+        h = vp()
+        _call("PolynomialArray_Copy", self.handle, C.byref(h))
+        return PolynomialArray(h)
 
 
 class KeyGenerator(_Handle):
@@ -333,6 +438,30 @@ class Encryptor(_Handle):
         _call("Encryptor_EncryptSymmetric", self.handle, plaintext.handle, C.c_bool(False), c.handle, None)
         return c
 
+    def encrypt_return_components(self, plaintext, disable_special_modulus=False, seed=None):
+        """encrypt_return_components{,_deterministic} (encryptor_decryptor.rs:250-420): (ciphertext, u, e, remainder)."""
+        c, u_, e_, r = Ciphertext(), PolynomialArray(), PolynomialArray(), Plaintext()
+        if seed is None:
+            _call("Encryptor_EncryptReturnComponents", self.handle, plaintext.handle, C.c_bool(disable_special_modulus), c.handle,
+                  u_.handle, e_.handle, r.handle, None)
+        else:
+            _call("Encryptor_EncryptReturnComponentsSetSeed", self.handle, plaintext.handle, C.c_bool(disable_special_modulus),
+                  c.handle, u_.handle, e_.handle, r.handle, (u64 * 8)(*seed), None)
+        return c, u_, e_, r
+
+    def encrypt_deterministic(self, plaintext, seed):
+        """encryptor_decryptor.rs:319-345 (feature "deterministic"): INSECURE, for tests and demonstrations only."""
+        return self.encrypt_return_components(plaintext, False, seed)[0]
+
+    def encrypt_symmetric_return_components(self, plaintext, seed=None):
+        c, e_, r = Ciphertext(), PolynomialArray(), Plaintext()
+        if seed is None:
+            _call("Encryptor_EncryptSymmetricReturnComponents", self.handle, plaintext.handle, c.handle, e_.handle, r.handle, None)
+        else:
+            _call("Encryptor_EncryptSymmetricReturnComponentsSetSeed", self.handle, plaintext.handle, c.handle, e_.handle,
+                  r.handle, (u64 * 8)(*seed), None)
+        return c, e_, r
+
 
 class Decryptor(_Handle):
     _destroy = "Decryptor_Destroy"
@@ -351,6 +480,11 @@ class Decryptor(_Handle):
         b = C.c_int()
         _call("Decryptor_InvariantNoiseBudget", self.handle, ciphertext.handle, C.byref(b))
         return b.value
+
+    def invariant_noise(self, ciphertext):
+        d = C.c_double()
+        _call("Decryptor_InvariantNoise", self.handle, ciphertext.handle, C.byref(d))
+        return d.value
 
 
 class BFVEncoder(_Handle):

@@ -133,6 +133,84 @@ def all_tests():
     return done
 
 
+def serialization_and_components_tests():
+    """plaintext_ciphertext.rs / key_generator.rs / encryptor_decryptor.rs / poly_array.rs unit tests, restated:
+    can_{save,load}_* round trips through as_bytes / from_bytes, encrypt_deterministic is repeatable and decrypts,
+    the exported components have the crate's shapes."""
+    rng = random.Random(11)
+    done = []
+
+    def roundtrips(dec, enc_, encr, ev, gen):
+        ctx = gen.ctx
+        a = make_vec(enc_, rng)
+        pt = enc_.encode_signed(a)
+        ct = encr.encrypt(pt)
+        for mode in (s.CompressionType.ZSTD, s.CompressionType.ZLIB, s.CompressionType.NONE):
+            pt2 = s.Plaintext.from_bytes(ctx, pt.as_bytes(mode))
+            assert enc_.decode_signed(pt2) == a
+            ct2 = s.Ciphertext.from_bytes(ctx, ct.as_bytes(mode))
+            assert ct2.as_bytes(s.CompressionType.NONE) == ct.as_bytes(s.CompressionType.NONE)
+            assert enc_.decode_signed(dec.decrypt(ct2)) == a
+        sk2 = s.SecretKey.from_bytes(ctx, gen.secret_key().as_bytes())
+        assert enc_.decode_signed(s.Decryptor(ctx, sk2).decrypt(ct)) == a
+        pk2 = s.PublicKey.from_bytes(ctx, gen.create_public_key().as_bytes())
+        assert enc_.decode_signed(dec.decrypt(s.Encryptor.with_public_key(ctx, pk2).encrypt(pt))) == a
+        rk2 = s.RelinearizationKeys.from_bytes(ctx, gen.create_relinearization_keys().as_bytes())
+        small = make_small_vec(enc_, rng)
+        cs = encr.encrypt(enc_.encode_signed(small))
+        assert enc_.decode_signed(dec.decrypt(ev.relinearize(ev.multiply(cs, cs), rk2))) == [x * x for x in small]
+        gk2 = s.GaloisKeys.from_bytes(ctx, gen.create_galois_keys().as_bytes())
+        half = len(a) // 2
+        assert enc_.decode_signed(dec.decrypt(ev.rotate_columns(ct, gk2))) == a[half:] + a[:half]
+        try:
+            s.Ciphertext.from_bytes(ctx, ct.as_bytes()[:-3])
+        except s.Error:
+            pass
+        else:
+            raise AssertionError("a truncated ciphertext must not load")
+
+    def deterministic(dec, enc_, encr, ev, gen):
+        a = make_vec(enc_, rng)
+        pt = enc_.encode_signed(a)
+        seed = [rng.getrandbits(63) for _ in range(8)]
+        c1, c2 = encr.encrypt_deterministic(pt, seed), encr.encrypt_deterministic(pt, seed)
+        assert c1.as_bytes(s.CompressionType.NONE) == c2.as_bytes(s.CompressionType.NONE)
+        assert encr.encrypt(pt).as_bytes(s.CompressionType.NONE) != c1.as_bytes(s.CompressionType.NONE)
+        assert enc_.decode_signed(dec.decrypt(c1)) == a
+        ct, u, e, r = encr.encrypt_return_components(pt, False, seed)
+        assert ct.as_bytes(s.CompressionType.NONE) == c1.as_bytes(s.CompressionType.NONE)
+        assert (u.num_polynomials(), e.num_polynomials()) == (1, 2) and u.coeff_modulus_size() == 5 and r.len() == pt.len()
+        assert u.poly_modulus_degree() == 8192 and set(u.as_u64_slice()[:8192]) <= {0, 1, gen.ctx.params.get_coefficient_modulus()[0].value() - 1}
+        assert dec.invariant_noise_budget(ct) > 0 and 0.0 < dec.invariant_noise(ct) < 2.0 ** -20
+
+    def polynomial_arrays(dec, enc_, encr, ev, gen):
+        ctx = gen.ctx
+        ct = encr.encrypt(enc_.encode_signed(make_vec(enc_, rng)))
+        pa = s.PolynomialArray.new_from_ciphertext(ctx, ct)
+        assert (pa.num_polynomials(), pa.coeff_modulus_size(), pa.poly_modulus_degree()) == (2, 4, 8192) and pa.is_rns()
+        words = pa.as_u64_slice()
+        assert words[:8] == [ct.get_data(i) for i in range(8)]
+        pa.to_multiprecision()
+        assert pa.is_multiprecision()
+        pa.to_rns()
+        assert pa.as_u64_slice() == words
+        pk = s.PolynomialArray.new_from_public_key(ctx, gen.create_public_key())
+        assert (pk.num_polynomials(), pk.coeff_modulus_size()) == (2, 4)
+        assert pk.drop().coeff_modulus_size() == 3 and pk.clone().as_u64_slice() == pk.as_u64_slice()
+        sk = s.PolynomialArray.new_from_secret_key(ctx, gen.secret_key())
+        assert sk.num_polynomials() == 1 and set(sk.as_u64_slice()[:8192]) <= {0, 1, gen.ctx.params.get_coefficient_modulus()[0].value() - 1}
+        assert not s.PolynomialArray().is_reserved()
+
+    def hex_strings(dec, enc_, encr, ev, gen):
+        p = s.Plaintext.from_hex_string("1234x^2 + 4321")
+        assert (p.len(), p.get_coefficient(0), p.get_coefficient(1), p.get_coefficient(2)) == (3, 0x4321, 0, 0x1234)
+
+    for fn in (roundtrips, deterministic, polynomial_arrays, hex_strings):
+        run_bfv_test(fn)
+        done.append(fn.__name__)
+    return done
+
+
 def lane_overflow_assumption():
     """seal_fhe/tests/assumptions.rs:5-34: lanes wrap modulo the plain modulus (default parameters, n=8192, t=114689?)
     restated: with t = PlainModulus::batching(8192, 17), 300*400 wraps to 120000 mod t in every lane."""

@@ -12,3 +12,8 @@ def test_bfv_evaluator_crate_tests(emu_lib):
 def test_lane_overflow_assumption(emu_lib):
     seal_fhe.use_library(emu_lib.lib)
     crate.lane_overflow_assumption()
+
+
+def test_serialization_components_polyarray_crate_tests(emu_lib):
+    seal_fhe.use_library(emu_lib.lib)
+    assert len(crate.serialization_and_components_tests()) == 4

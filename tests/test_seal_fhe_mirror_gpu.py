@@ -17,3 +17,9 @@ def test_lane_overflow_assumption():
     from sunscreen_b200.lib import B200Lib
     seal_fhe.use_library(B200Lib.default().lib)
     crate.lane_overflow_assumption()
+
+
+def test_serialization_components_polyarray_crate_tests():
+    from sunscreen_b200.lib import B200Lib
+    seal_fhe.use_library(B200Lib.default().lib)
+    assert len(crate.serialization_and_components_tests()) == 4
