@@ -167,10 +167,7 @@ __global__ void lift_kernel(const LevelDev L, const u64 *a, int sa, const u64 *b
     const int R = K + L.nBsk;
     const u64 *src = p < sa ? a + (item * sa + p) * K * n : b + (item * sb + (p - sa)) * K * n;
     u64 *dst = ext + ((item * P + p) * R + K) * n;
-    if (L.fp)
-        lift_coeff_fp<K>(L, src, dst, n, c);
-    else
-        lift_coeff<K>(L, src, dst, n, c);
+    lift_coeff<K>(L, src, dst, n, c); // integer path; the FP64 path is lift_kernel_v2
 }
 
 // rows: residue rows r in [0,R): r<K -> q[r], else bsk[r-K]
@@ -220,10 +217,7 @@ __global__ void scale_kernel(const LevelDev L, const u64 *D, int Dn, u64 *dst0, 
     const long long item = t / Dn;
     const u64 *src = D + ((item * Dn + m) * R) * n;
     u64 *dst = m < split ? dst0 + ((item * split + m) * K) * n : dst1 + ((item * (Dn - split) + (m - split)) * K) * n;
-    if (L.fp)
-        scale_coeff_fp<K>(L, src, dst, n, c);
-    else
-        scale_coeff<K>(L, src, dst, n, c);
+    scale_coeff<K>(L, src, dst, n, c); // integer path; the FP64 path is scale_kernel_v2
 }
 
 template <int K>
@@ -253,13 +247,26 @@ __global__ void ksmac_kernel(const PrimeDev *primes, const NttPrimeFp *fprimes, 
     ksmac_coeff<K>(P, ops, n, kp, 2LL * key_rows * n, (long long)key_rows * n, o0, o1, c);
 }
 
-#ifndef B200_EMU_HEADER
 // ---- FP64 element-wise kernels, two adjacent coefficients per thread (128-bit global accesses) ----
-__device__ __forceinline__ ulonglong2 ldg2(const u64 *p) { return __ldg(reinterpret_cast<const ulonglong2 *>(p)); }
+#ifdef B200_EMU_HEADER
+struct b200_u64x2
+{
+    u64 x, y;
+};
+static inline b200_u64x2 ldg2(const u64 *p) { return b200_u64x2{ p[0], p[1] }; }
+static inline void stg2(u64 *p, u64 a, u64 b)
+{
+    p[0] = a;
+    p[1] = b;
+}
+#else
+typedef ulonglong2 b200_u64x2;
+__device__ __forceinline__ ulonglong2 ldg2(const u64 *p) { return __ldg(reinterpret_cast<const b200_u64x2 *>(p)); }
 __device__ __forceinline__ void stg2(u64 *p, u64 a, u64 b) { *reinterpret_cast<ulonglong2 *>(p) = make_ulonglong2(a, b); }
+#endif
 
 template <int K>
-__global__ void lift_kernel_v2(const LevelDev L, const u64 *a, int sa, const u64 *b, int sb, u64 *ext, long long n, long long total)
+__global__ void lift_kernel_v2(const LiftFpC<K> L, const u64 *a, int sa, const u64 *b, int sb, u64 *ext, long long n, long long total)
 {
     const long long idx = GLOBAL_IDX();
     if (idx >= total)
@@ -277,7 +284,7 @@ __global__ void lift_kernel_v2(const LevelDev L, const u64 *a, int sa, const u64
 #pragma unroll
     for (int i = 0; i < K; i++)
     {
-        const ulonglong2 v = ldg2(src + i * n + c);
+        const b200_u64x2 v = ldg2(src + i * n + c);
         xs[0][i] = v.x;
         xs[1][i] = v.y;
     }
@@ -307,12 +314,12 @@ __global__ void tensor_kernel_v2(const LevelDev L, const u64 *ext, u64 *D, long 
     const u64 *A = ext + ((item * Pn) * R + r) * n + c;
     u64 *Dp = D + ((item * 3) * R + r) * n + c;
     const long long ps = (long long)R * n;
-    const ulonglong2 a0 = ldg2(A), a1 = ldg2(A + ps);
+    const b200_u64x2 a0 = ldg2(A), a1 = ldg2(A + ps);
     u64 in[2][4], out[2][3];
     in[0][0] = a0.x; in[1][0] = a0.y; in[0][1] = a1.x; in[1][1] = a1.y;
     if (!square)
     {
-        const ulonglong2 b0 = ldg2(A + 2 * ps), b1 = ldg2(A + 3 * ps);
+        const b200_u64x2 b0 = ldg2(A + 2 * ps), b1 = ldg2(A + 3 * ps);
         in[0][2] = b0.x; in[1][2] = b0.y; in[0][3] = b1.x; in[1][3] = b1.y;
     }
 #pragma unroll
@@ -329,7 +336,7 @@ __global__ void tensor_kernel_v2(const LevelDev L, const u64 *ext, u64 *D, long 
 }
 
 template <int K>
-__global__ void scale_kernel_v2(const LevelDev L, const u64 *D, int Dn, u64 *dst0, int split, u64 *dst1, long long n, long long total)
+__global__ void scale_kernel_v2(const ScaleFpC<K> L, const u64 *D, int Dn, u64 *dst0, int split, u64 *dst1, long long n, long long total)
 {
     const long long idx = GLOBAL_IDX();
     if (idx >= total)
@@ -347,7 +354,7 @@ __global__ void scale_kernel_v2(const LevelDev L, const u64 *D, int Dn, u64 *dst
     for (int i = 0; i < 2 * K + 2; i++)
         if (i < R)
         {
-            const ulonglong2 v = ldg2(src + i * n);
+            const b200_u64x2 v = ldg2(src + i * n);
             in[0][i] = v.x;
             in[1][i] = v.y;
         }
@@ -379,8 +386,8 @@ __global__ void ksmac_kernel_v2(const NttPrimeFp *fprimes, int special_idx, int 
 #pragma unroll
     for (int J = 0; J < K; J++)
     {
-        const ulonglong2 x = ldg2(ops + J * n);
-        const ulonglong2 k0 = ldg2(kp + J * 2LL * key_rows * n), k1 = ldg2(kp + J * 2LL * key_rows * n + (long long)key_rows * n);
+        const b200_u64x2 x = ldg2(ops + J * n);
+        const b200_u64x2 k0 = ldg2(kp + J * 2LL * key_rows * n), k1 = ldg2(kp + J * 2LL * key_rows * n + (long long)key_rows * n);
         const double x0 = fp_from_u64(x.x), x1 = fp_from_u64(x.y);
         acc[0][0] = B200_DADD(acc[0][0], fp_mulmod2(x0, fp_from_u64(k0.x), p, pinv));
         acc[0][1] = B200_DADD(acc[0][1], fp_mulmod2(x0, fp_from_u64(k1.x), p, pinv));
@@ -392,7 +399,6 @@ __global__ void ksmac_kernel_v2(const NttPrimeFp *fprimes, int special_idx, int 
     stg2(o0, fp_to_canonical(acc[0][0], p, pinv), fp_to_canonical(acc[1][0], p, pinv));
     stg2(o1, fp_to_canonical(acc[0][1], p, pinv), fp_to_canonical(acc[1][1], p, pinv));
 }
-#endif
 
 template <int K>
 __global__ void ksmoddown_kernel(const PrimeDev *primes, int special_idx, const u64 *inv_qsp, const u64 *ks2,
@@ -606,8 +612,20 @@ struct JobDesc
     long long *d_dst = nullptr;
 };
 
+// host copies of the FP64 BEHZ constants of one level ({w, w/p} pairs), from which the kernel-parameter structs are filled
+struct LevelFpHost
+{
+    std::vector<double> dq, dbsk, lift_c, lift_mat, lift_qm, scale_c, scale_tq, scale_mat, sk_c, sk_mat_q, sk_mat_msk, prod_b_q,
+        negprod_b_q;
+    std::vector<u64> lift_mt;
+    u64 neg_inv_q_mod_mt = 0;
+    double inv_b_msk[2] = { 0, 0 };
+    int k = 0, nB = 0, nBsk = 0;
+};
+
 struct b200_ctx
 {
+    std::vector<LevelFpHost> fp_levels; // indexed like `levels`; empty tables when the level is not on the FP64 path
     std::unique_ptr<BfvHostContext> host;
     int device = 0;
     int sm_count = 0;
@@ -635,7 +653,6 @@ struct b200_ctx
     cudaStream_t s_side[NSIDE] = { nullptr, nullptr, nullptr, nullptr };
     cudaEvent_t ev_fork = nullptr, ev_join[NSIDE] = { nullptr, nullptr, nullptr, nullptr };
     int mr_split = 1;
-    int ew_v2 = 1; // FP64 element-wise kernels: two adjacent coefficients per thread with 128-bit accesses
     // staging ring of the *_host entry points (allocated on first use, reused afterwards)
     static const int NBUF = 3;
     u64 *hp_a[NBUF] = { nullptr, nullptr, nullptr }, *hp_b[NBUF] = { nullptr, nullptr, nullptr }, *hp_o[NBUF] = { nullptr, nullptr, nullptr };
@@ -848,6 +865,7 @@ static int build_device(b200_ctx *ctx)
         UPF(plain_inc, Lh.plain_upper_half_inc);
         L.q_mod_t = Lh.q_mod_t;
         L.plain_thr = Lh.plain_upper_half_threshold;
+        LevelFpHost fp_level;
         {
             bool lfp = ctx->fp_enabled && H.aux_bits == b200::FP_PRIME_BITS;
             for (int idx : Lh.q_idx)
@@ -900,23 +918,32 @@ static int build_device(b200_ctx *ctx)
                 const int k = Lh.k, nB = Lh.nB;
                 UPD(dq, primes_d(qv));
                 UPD(dbsk, primes_d(bv));
-                UPD(dlift_c, pairs(shoup_w(Lh.lift_c), qv, 1));
-                UPD(dlift_mat, pairs(Lh.lift_mat, bv, k));
-                UPD(dlift_qm, pairs(Lh.lift_qm, bv, 1));
-                UPD(dscale_c, pairs(shoup_w(Lh.scale_c), qv, 1));
-                UPD(dscale_tq, pairs(Lh.scale_tq, bv, 1));
-                UPD(dscale_mat, pairs(Lh.scale_mat, bv, k));
-                UPD(dsk_c, pairs(shoup_w(Lh.sk_c), bv, 1));
-                UPD(dsk_mat_q, pairs(Lh.sk_mat_q, qv, nB));
+                LevelFpHost F;
+                F.k = k;
+                F.nB = nB;
+                F.nBsk = Lh.nBsk;
+                F.dq = primes_d(qv);
+                F.dbsk = primes_d(bv);
+                F.lift_c = pairs(shoup_w(Lh.lift_c), qv, 1);
+                F.lift_mat = pairs(Lh.lift_mat, bv, k);
+                F.lift_qm = pairs(Lh.lift_qm, bv, 1);
+                F.lift_mt = Lh.lift_mt;
+                F.neg_inv_q_mod_mt = Lh.neg_inv_q_mod_mt;
+                F.scale_c = pairs(shoup_w(Lh.scale_c), qv, 1);
+                F.scale_tq = pairs(Lh.scale_tq, bv, 1);
+                F.scale_mat = pairs(Lh.scale_mat, bv, k);
+                F.sk_c = pairs(shoup_w(Lh.sk_c), bv, 1);
+                F.sk_mat_q = pairs(Lh.sk_mat_q, qv, nB);
                 std::vector<u64> msk_t(1, bv[nB]);
-                UPD(dsk_mat_msk, pairs(Lh.sk_mat_msk, msk_t, nB > 0 ? nB : 1));
-                UPD(dsk_prod_b_q, pairs(Lh.sk_prod_b_q, qv, 1));
+                F.sk_mat_msk = pairs(Lh.sk_mat_msk, msk_t, nB > 0 ? nB : 1);
+                F.prod_b_q = pairs(Lh.sk_prod_b_q, qv, 1);
                 std::vector<u64> negpb;
                 for (int i = 0; i < k; i++)
                     negpb.push_back((qv[i] - Lh.sk_prod_b_q[i]) % qv[i]);
-                UPD(dsk_negprod_b_q, pairs(negpb, qv, 1));
-                L.dsk_inv_b_msk[0] = (double)Lh.sk_inv_b_msk;
-                L.dsk_inv_b_msk[1] = (double)Lh.sk_inv_b_msk / (double)bv[nB];
+                F.negprod_b_q = pairs(negpb, qv, 1);
+                F.inv_b_msk[0] = (double)Lh.sk_inv_b_msk;
+                F.inv_b_msk[1] = (double)Lh.sk_inv_b_msk / (double)bv[nB];
+                fp_level = F;
 #undef UPD
             }
         }
@@ -926,6 +953,7 @@ static int build_device(b200_ctx *ctx)
         L.inv_gamma_mod_t = Lh.inv_gamma_mod_t;
 #undef UPF
         ctx->levels.push_back(L);
+        ctx->fp_levels.push_back(fp_level);
     }
     ctx->d_inv_qsp = ctx->levels[0].inv_qlast;
     (void)n;
@@ -1114,6 +1142,51 @@ static int launch_ntt(b200_ctx *ctx, const JobDesc &jd, const u64 *src, long lon
     default: return fail(B200_E_INVALID, "unsupported residue count (max 16 data residues)");                          \
     }
 
+template <int K>
+static LiftFpC<K> make_lift_fpc(const b200_ctx *ctx, int level)
+{
+    const LevelFpHost &H = ctx->fp_levels[level];
+    LiftFpC<K> C;
+    memset(&C, 0, sizeof(C));
+    C.nBsk = H.nBsk;
+    C.neg_inv_q_mod_mt = H.neg_inv_q_mod_mt;
+    for (int i = 0; i < K; i++)
+        C.mt[i] = H.lift_mt[i];
+    std::copy(H.dq.begin(), H.dq.end(), C.dq);
+    std::copy(H.dbsk.begin(), H.dbsk.end(), C.dbsk);
+    std::copy(H.lift_c.begin(), H.lift_c.end(), C.c);
+    std::copy(H.lift_mat.begin(), H.lift_mat.end(), C.mat); // rows of K pairs, as in the struct
+    std::copy(H.lift_qm.begin(), H.lift_qm.end(), C.qm);
+    return C;
+}
+template <int K>
+static ScaleFpC<K> make_scale_fpc(const b200_ctx *ctx, int level)
+{
+    const LevelFpHost &H = ctx->fp_levels[level];
+    ScaleFpC<K> C;
+    memset(&C, 0, sizeof(C));
+    C.nB = H.nB;
+    C.nBsk = H.nBsk;
+    std::copy(H.dq.begin(), H.dq.end(), C.dq);
+    std::copy(H.dbsk.begin(), H.dbsk.end(), C.dbsk);
+    std::copy(H.scale_c.begin(), H.scale_c.end(), C.c);
+    std::copy(H.scale_tq.begin(), H.scale_tq.end(), C.tq);
+    std::copy(H.scale_mat.begin(), H.scale_mat.end(), C.mat);
+    std::copy(H.sk_c.begin(), H.sk_c.end(), C.sk_c);
+    for (int i = 0; i < K; i++) // host rows have nB columns, the struct K+1
+        for (int b = 0; b < H.nB; b++)
+        {
+            C.sk_mat_q[2 * (i * (K + 1) + b)] = H.sk_mat_q[2 * (i * H.nB + b)];
+            C.sk_mat_q[2 * (i * (K + 1) + b) + 1] = H.sk_mat_q[2 * (i * H.nB + b) + 1];
+        }
+    std::copy(H.sk_mat_msk.begin(), H.sk_mat_msk.end(), C.sk_mat_msk);
+    std::copy(H.prod_b_q.begin(), H.prod_b_q.end(), C.prod_b_q);
+    std::copy(H.negprod_b_q.begin(), H.negprod_b_q.end(), C.negprod_b_q);
+    C.inv_b_msk[0] = H.inv_b_msk[0];
+    C.inv_b_msk[1] = H.inv_b_msk[1];
+    return C;
+}
+
 static const int EB = 256; // element-wise block size
 
 static int check_level(b200_ctx *ctx, int level)
@@ -1162,15 +1235,13 @@ static int multiply_core(b200_ctx *ctx, int level, const u64 *a, int sa, const u
         return rc;
     // (1)-(2) lift to Bsk
     {
-#ifndef B200_EMU_HEADER
-        if (L.fp && ctx->ew_v2)
+        if (L.fp)
         {
             const long long total = batch * P * (n >> 1);
-            DISPATCH_K(k, B200_LAUNCH(lift_kernel_v2<KK>, blocks_for(total, EB), EB, 0, s, L, a, sa, square ? a : b, square ? 0 : sb,
-                                      ext, n, total));
+            DISPATCH_K(k, B200_LAUNCH(lift_kernel_v2<KK>, blocks_for(total, EB), EB, 0, s, make_lift_fpc<KK>(ctx, level), a, sa,
+                                      square ? a : b, square ? 0 : sb, ext, n, total));
         }
         else
-#endif
         {
             const long long total = batch * P * n;
             DISPATCH_K(k, B200_LAUNCH(lift_kernel<KK>, blocks_for(total, EB), EB, 0, s, L, a, sa, square ? a : b, square ? 0 : sb, ext,
@@ -1239,14 +1310,12 @@ static int multiply_core(b200_ctx *ctx, int level, const u64 *a, int sa, const u
         }
         else
         {
-#ifndef B200_EMU_HEADER
-            if (L.fp && ctx->ew_v2 && (square || (sa == 2 && sb == 2)))
+            if (L.fp && (square || (sa == 2 && sb == 2)))
             {
                 const long long total = batch * R * (n >> 1);
                 B200_LAUNCH(tensor_kernel_v2, blocks_for(total, EB), EB, 0, s, L, ext, D, n, total, square ? 1 : 0);
             }
             else
-#endif
             {
                 const long long total = batch * R * n;
                 B200_LAUNCH(tensor_kernel, blocks_for(total, EB), EB, 0, s, L, ext, sa, sb, D, n, total, square ? 1 : 0);
@@ -1258,14 +1327,13 @@ static int multiply_core(b200_ctx *ctx, int level, const u64 *a, int sa, const u
     }
     // (6)-(8) scale
     {
-#ifndef B200_EMU_HEADER
-        if (L.fp && ctx->ew_v2)
+        if (L.fp)
         {
             const long long total = batch * Dn * (n >> 1);
-            DISPATCH_K(k, B200_LAUNCH(scale_kernel_v2<KK>, blocks_for(total, EB), EB, 0, s, L, D, Dn, dst0, split, dst1, n, total));
+            DISPATCH_K(k, B200_LAUNCH(scale_kernel_v2<KK>, blocks_for(total, EB), EB, 0, s, make_scale_fpc<KK>(ctx, level), D, Dn,
+                                      dst0, split, dst1, n, total));
         }
         else
-#endif
         {
             const long long total = batch * Dn * n;
             DISPATCH_K(k, B200_LAUNCH(scale_kernel<KK>, blocks_for(total, EB), EB, 0, s, L, D, Dn, dst0, split, dst1, n, total));
@@ -1313,15 +1381,13 @@ static int keyswitch_core(b200_ctx *ctx, int level, const u64 *d, long long d_st
             return rc;
     }
     {
-#ifndef B200_EMU_HEADER
-        if (L.fp && ctx->ew_v2)
+        if (L.fp)
         {
             const long long total = batch * (k + 1) * (n >> 1);
             DISPATCH_K(k, B200_LAUNCH(ksmac_kernel_v2<KK>, blocks_for(total, EB), EB, 0, s, ctx->d_fp_primes, special, Kkey, ks1, key,
                                       ks2, n, total));
         }
         else
-#endif
         {
             const long long total = batch * (k + 1) * n;
             DISPATCH_K(k, B200_LAUNCH(ksmac_kernel<KK>, blocks_for(total, EB), EB, 0, s, ctx->d_primes, ctx->d_fp_primes,
@@ -1448,8 +1514,6 @@ int b200_ctx_create(uint64_t n, const uint64_t *coeff_modulus, uint64_t count, u
         CU_TRY(cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming));
     }
     CU_TRY(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
-    if (getenv("B200_EW_V1"))
-        ctx->ew_v2 = 0;
     if (const char *sp = getenv("B200_MR_SPLIT"))
         ctx->mr_split = std::max(1, std::min((int)b200_ctx::NSIDE, atoi(sp)));
     CU_TRY(cudaDeviceSynchronize());

@@ -60,9 +60,7 @@ struct LevelDev
     int fp;
     const double *dq;        // [2k]     {q_i, 1/q_i}
     const double *dbsk;      // [2nBsk]  {p_j, 1/p_j}
-    const double *dlift_c, *dlift_mat, *dlift_qm;
-    const double *dscale_c, *dscale_tq, *dscale_mat, *dsk_c, *dsk_mat_q, *dsk_mat_msk, *dsk_prod_b_q, *dsk_negprod_b_q;
-    double dsk_inv_b_msk[2];
+    // (the BEHZ base-conversion constants of the FP64 path travel as kernel PARAMETERS: LiftFpC / ScaleFpC below)
     // decrypt
     const u64 *dec_c;      // [2k]
     const u64 *dec_mat_t;  // [k]
@@ -421,17 +419,48 @@ B200_HD u64 fp_to_u64(double r) // exact for 0 <= r < 2^52
 }
 B200_HD double ldd(const double *p) { return B200_LDG(p); }
 
+// BEHZ constants of the FP64 path, passed BY VALUE as a kernel parameter: they live in the constant bank, so each
+// use is a constant operand of the DFMA/DMUL itself (or one uniform load) instead of a global load through L1 —
+// with ~70 (lift) / ~140 (scale) constants per coefficient the pointer-based version kept L1TEX at 62 % busy and the
+// FP64 pipe at 47-53 % (profiles/r1_ncu_elementwise.txt).  Entries are {w, w/p_target} pairs, primes {p, 1/p}.
 template <int K>
-B200_HD void lift_coeff_fp(const LevelDev &L, const u64 *__restrict__ src, u64 *__restrict__ dst, long long n, long long c)
+struct LiftFpC
+{
+    int nBsk;
+    u64 neg_inv_q_mod_mt;
+    u64 mt[K];                      // (Q/q_i) mod m~
+    double dq[2 * K];               // {q_i, 1/q_i}
+    double dbsk[2 * (K + 2)];       // {p_j, 1/p_j}
+    double c[2 * K];                // m~ (Q/q_i)^-1 mod q_i
+    double mat[2 * (K + 2) * K];    // (Q/q_i) m~^-1 mod p_j   (row j, column i)
+    double qm[2 * (K + 2)];         // Q m~^-1 mod p_j
+};
+template <int K>
+struct ScaleFpC
+{
+    int nB, nBsk;
+    double dq[2 * K], dbsk[2 * (K + 2)];
+    double c[2 * K];                     // t (Q/q_i)^-1 mod q_i
+    double tq[2 * (K + 2)];              // t Q^-1 mod p_j
+    double mat[2 * (K + 2) * K];         // -(Q/q_i) Q^-1 mod p_j
+    double sk_c[2 * (K + 1)];            // (B/b)^-1 mod b
+    double sk_mat_q[2 * K * (K + 1)];    // (B/b) mod q_i   (row i, column b)
+    double sk_mat_msk[2 * (K + 1)];      // (B/b) mod m_sk
+    double prod_b_q[2 * K], negprod_b_q[2 * K];
+    double inv_b_msk[2];
+};
+
+template <int K>
+B200_HD void lift_coeff_fp(const LiftFpC<K> &L, const u64 *__restrict__ src, u64 *__restrict__ dst, long long n, long long c)
 {
     double y[K];
     u64 ymt = 0;
 #pragma unroll
     for (int i = 0; i < K; i++)
     {
-        const double q = ldd(&L.dq[2 * i]);
-        y[i] = fp_canon(fp_mulmod(fp_from_u64(src[i * n + c]), ldd(&L.dlift_c[2 * i]), ldd(&L.dlift_c[2 * i + 1]), q), q);
-        ymt += fp_to_u64(y[i]) * B200_LDG(&L.lift_mt[i]);
+        const double q = L.dq[2 * i];
+        y[i] = fp_canon(fp_mulmod(fp_from_u64(src[i * n + c]), L.c[2 * i], L.c[2 * i + 1], q), q);
+        ymt += fp_to_u64(y[i]) * L.mt[i];
     }
     const u64 r = ((ymt & 0xffffffffULL) * L.neg_inv_q_mod_mt) & 0xffffffffULL;
     // centred representative of r (exact small integer)
@@ -441,11 +470,11 @@ B200_HD void lift_coeff_fp(const LevelDev &L, const u64 *__restrict__ src, u64 *
     {
         if (j < L.nBsk)
         {
-            const double p = ldd(&L.dbsk[2 * j]), pinv = ldd(&L.dbsk[2 * j + 1]);
-            double acc = fp_mulmod(rc, ldd(&L.dlift_qm[2 * j]), ldd(&L.dlift_qm[2 * j + 1]), p);
+            const double p = L.dbsk[2 * j], pinv = L.dbsk[2 * j + 1];
+            double acc = fp_mulmod(rc, L.qm[2 * j], L.qm[2 * j + 1], p);
 #pragma unroll
             for (int i = 0; i < K; i++)
-                acc = B200_DADD(acc, fp_mulmod(y[i], ldd(&L.dlift_mat[2 * (j * K + i)]), ldd(&L.dlift_mat[2 * (j * K + i) + 1]), p));
+                acc = B200_DADD(acc, fp_mulmod(y[i], L.mat[2 * (j * K + i)], L.mat[2 * (j * K + i) + 1], p));
             dst[j * n + c] = fp_to_canonical(acc, p, pinv);
         }
     }
@@ -491,14 +520,14 @@ B200_HD void square_coeff_fp(double p, double pinv, const u64 *__restrict__ A, l
 }
 
 template <int K>
-B200_HD void scale_coeff_fp(const LevelDev &L, const u64 *__restrict__ src, u64 *__restrict__ dst, long long n, long long c)
+B200_HD void scale_coeff_fp(const ScaleFpC<K> &L, const u64 *__restrict__ src, u64 *__restrict__ dst, long long n, long long c)
 {
     double y[K];
 #pragma unroll
     for (int i = 0; i < K; i++)
     {
-        const double q = ldd(&L.dq[2 * i]);
-        y[i] = fp_canon(fp_mulmod(fp_from_u64(src[i * n + c]), ldd(&L.dscale_c[2 * i]), ldd(&L.dscale_c[2 * i + 1]), q), q);
+        const double q = L.dq[2 * i];
+        y[i] = fp_canon(fp_mulmod(fp_from_u64(src[i * n + c]), L.c[2 * i], L.c[2 * i + 1], q), q);
     }
     double yb[K + 1];
     double w_sk = 0.0;
@@ -507,39 +536,48 @@ B200_HD void scale_coeff_fp(const LevelDev &L, const u64 *__restrict__ src, u64 
     {
         if (j < L.nBsk)
         {
-            const double p = ldd(&L.dbsk[2 * j]), pinv = ldd(&L.dbsk[2 * j + 1]);
-            double acc = fp_mulmod(fp_from_u64(src[(K + j) * n + c]), ldd(&L.dscale_tq[2 * j]), ldd(&L.dscale_tq[2 * j + 1]), p);
+            const double p = L.dbsk[2 * j], pinv = L.dbsk[2 * j + 1];
+            double acc = fp_mulmod(fp_from_u64(src[(K + j) * n + c]), L.tq[2 * j], L.tq[2 * j + 1], p);
 #pragma unroll
             for (int i = 0; i < K; i++)
-                acc = B200_DADD(acc, fp_mulmod(y[i], ldd(&L.dscale_mat[2 * (j * K + i)]), ldd(&L.dscale_mat[2 * (j * K + i) + 1]), p));
+                acc = B200_DADD(acc, fp_mulmod(y[i], L.mat[2 * (j * K + i)], L.mat[2 * (j * K + i) + 1], p));
             // canonical w_j
             double w = fp_renorm(acc, p, pinv);
             w = fp_canon(w, p);
             if (j < L.nB)
-                yb[j < K + 1 ? j : 0] = fp_canon(fp_mulmod(w, ldd(&L.dsk_c[2 * j]), ldd(&L.dsk_c[2 * j + 1]), p), p);
+                yb[j < K + 1 ? j : 0] = fp_canon(fp_mulmod(w, L.sk_c[2 * (j < K + 1 ? j : 0)], L.sk_c[2 * (j < K + 1 ? j : 0) + 1], p), p);
             else
                 w_sk = w;
         }
     }
-    const double ms = ldd(&L.dbsk[2 * L.nB]), msinv = ldd(&L.dbsk[2 * L.nB + 1]);
-    double alpha = fp_mulmod(-w_sk, L.dsk_inv_b_msk[0], L.dsk_inv_b_msk[1], ms);
+    const int im = L.nB < K + 2 ? L.nB : K + 1; // index of m_sk in Bsk
+    double ms = 0.0, msinv = 0.0;
+#pragma unroll
+    for (int j = 0; j < K + 2; j++) // constant-bank arrays want compile-time indices
+        if (j == im)
+        {
+            ms = L.dbsk[2 * j];
+            msinv = L.dbsk[2 * j + 1];
+        }
+    double alpha = fp_mulmod(-w_sk, L.inv_b_msk[0], L.inv_b_msk[1], ms);
 #pragma unroll
     for (int b = 0; b < K + 1; b++)
         if (b < L.nB)
-            alpha = B200_DADD(alpha, fp_mulmod(yb[b], ldd(&L.dsk_mat_msk[2 * b]), ldd(&L.dsk_mat_msk[2 * b + 1]), ms));
+            alpha = B200_DADD(alpha, fp_mulmod(yb[b], L.sk_mat_msk[2 * b], L.sk_mat_msk[2 * b + 1], ms));
     alpha = fp_canon(fp_renorm(alpha, ms, msinv), ms);
     const bool neg = alpha > B200_DMUL(ms, 0.5); // m_sk odd: alpha > floor(m_sk/2)  <=>  alpha > m_sk/2
     const double mag = neg ? B200_DADD(ms, -alpha) : alpha;
 #pragma unroll
     for (int i = 0; i < K; i++)
     {
-        const double q = ldd(&L.dq[2 * i]), qinv = ldd(&L.dq[2 * i + 1]);
-        const double *pb = neg ? &L.dsk_prod_b_q[2 * i] : &L.dsk_negprod_b_q[2 * i];
-        double acc = fp_mulmod(mag, ldd(pb), ldd(pb + 1), q);
+        const double q = L.dq[2 * i], qinv = L.dq[2 * i + 1];
+        const double pw = neg ? L.prod_b_q[2 * i] : L.negprod_b_q[2 * i];
+        const double pwp = neg ? L.prod_b_q[2 * i + 1] : L.negprod_b_q[2 * i + 1];
+        double acc = fp_mulmod(mag, pw, pwp, q);
 #pragma unroll
         for (int b = 0; b < K + 1; b++)
             if (b < L.nB)
-                acc = B200_DADD(acc, fp_mulmod(yb[b], ldd(&L.dsk_mat_q[2 * (i * L.nB + b)]), ldd(&L.dsk_mat_q[2 * (i * L.nB + b) + 1]), q));
+                acc = B200_DADD(acc, fp_mulmod(yb[b], L.sk_mat_q[2 * (i * (K + 1) + b)], L.sk_mat_q[2 * (i * (K + 1) + b) + 1], q));
         dst[i * n + c] = fp_to_canonical(acc, q, qinv);
     }
 }
