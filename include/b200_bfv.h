@@ -145,6 +145,9 @@ uint64_t b200_launch_count(const b200_ctx *ctx);
 /* developer aid: with B200_TRACE=1 in the environment every kernel launch is bracketed by CUDA events;
    this prints the per-kernel totals to stderr and clears the log (no-op otherwise) */
 void b200_trace_dump(void);
+/* developer aid: per-CTA phase timestamps of the next NTT launches ({smid, t_start, t_pass..., t_end} x 8 u64 per CTA,
+   globaltimer ns) into a caller-provided device buffer; NULL detaches */
+void b200_ntt_timeline(b200_ctx *ctx, unsigned long long *device_buffer);
 
 #ifdef __cplusplus
 }

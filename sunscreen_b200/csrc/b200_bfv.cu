@@ -121,6 +121,15 @@ __global__ void __launch_bounds__(NT, (LOGN <= 13 ? (NT <= 256 ? 3 : 2) : 1)) nt
     const NttPrime PI_ = job.primes[pidx];
     const u64 *src = job.src + item * job.src_item_stride + job.slot_src[slot];
     u64 *dst = job.dst + item * job.dst_item_stride + job.slot_dst[slot];
+    if (job.timeline && threadIdx.x == 0)
+    {
+        unsigned long long t;
+        unsigned smid;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        job.timeline[block * 8] = smid;
+        job.timeline[block * 8 + 1] = t;
+    }
     if (job.prefetch_dist > 0 && !job.tensor_mode)
     {
         // pull the polynomial that the CTA one wave later will transform into L2 (its pass-1 loads then hit L2)
@@ -137,6 +146,12 @@ __global__ void __launch_bounds__(NT, (LOGN <= 13 ? (NT <= 256 ? 3 : 2) : 1)) nt
         }
     }
     NttFpStaticPass<LOGN, NT, FWD, 0>::run(job, PF, PI_, src, dst, reinterpret_cast<double *>(ntt_sm), (int)threadIdx.x, item, slot);
+    if (job.timeline && threadIdx.x == 0)
+    {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        job.timeline[block * 8 + 7] = t;
+    }
 #endif
 }
 
@@ -625,6 +640,7 @@ struct LevelFpHost
 
 struct b200_ctx
 {
+    unsigned long long *ntt_timeline = nullptr; // developer aid, see b200_ntt_timeline()
     std::vector<LevelFpHost> fp_levels; // indexed like `levels`; empty tables when the level is not on the FP64 path
     std::unique_ptr<BfvHostContext> host;
     int device = 0;
@@ -1049,6 +1065,7 @@ static int launch_ntt(b200_ctx *ctx, const JobDesc &jd, const u64 *src, long lon
     job.items = items;
     static const int pf = std::getenv("B200_NTT_PREFETCH") ? atoi(std::getenv("B200_NTT_PREFETCH")) : 0;
     job.prefetch_dist = pf;
+    job.timeline = ctx->ntt_timeline;
     static const int slot_major = std::getenv("B200_NTT_ITEM_MAJOR") ? 0 : 1;
     job.slot_major = slot_major;
     job.tensor_mode = ta ? ta->mode : 0;
@@ -1658,6 +1675,14 @@ int b200_stream_synchronize(b200_ctx *ctx, void *stream)
         return fail(B200_E_NULL, "null argument");
     CU_TRY(cudaStreamSynchronize((cudaStream_t)stream));
     return 0;
+}
+
+// developer aid: attach a device buffer of 8 u64 per CTA that the NEXT static NTT launches fill with
+// {smid, t_start, t_after_each_pass (<=5), t_end} (globaltimer ns); pass nullptr to detach
+void b200_ntt_timeline(b200_ctx *ctx, unsigned long long *device_buffer)
+{
+    if (ctx)
+        ctx->ntt_timeline = device_buffer;
 }
 
 void b200_trace_dump(void)

@@ -52,6 +52,7 @@ struct NttJob
     int reduce_input;          // 1: inputs are arbitrary 64-bit words -> Barrett to [0,p) on load
     long long items;           // number of items in this launch
     int prefetch_dist;         // >0: each CTA prefetches (L2) the input of CTA blockIdx + prefetch_dist
+    unsigned long long *timeline; // developer aid (B200_NTT_TIMELINE): per CTA {smid, t_start, t_after_pass_1..4, t_end} in ns
     int slot_major;            // block order (static FP kernel): 1 = all items of slot 0, then slot 1, ...
     // fused tensor source (FP64 static inverse kernel only): instead of reading `src`, slot (m, row) computes
     // D_m[row] = sum_{r+s=m} A_r[row] * B_s[row] on the fly from the NTT-form operands at `tsrc`

@@ -212,9 +212,11 @@ B200_HD int fp_elem_index(int pbase, int base, int j, int logs)
     return ntt_pad(base + (j << logs));
 }
 
-template <int L, bool FWD, bool SRC_GLOBAL, bool DST_GLOBAL, bool TW16 = false, bool RENORM = true, bool REDUCE = true>
+template <int L, bool FWD, bool SRC_GLOBAL, bool DST_GLOBAL, bool TW16 = false, bool RENORM = true, bool REDUCE = true, bool PRELOADED = false,
+          bool RAW_IN = false /* shared memory holds the raw input words (landed by cp.async): convert on read */>
 B200_HD void ntt_fp_group(double *sm, const u64 *__restrict__ gsrc, u64 *__restrict__ gdst, int g, int logs, int logn, int M,
-                          const NttPrimeFp &P, bool renorm, bool last_inv, bool reduce_input, u64 pint, u64 ratio1)
+                          const NttPrimeFp &P, bool renorm, bool last_inv, bool reduce_input, u64 pint, u64 ratio1,
+                          const u64 *pre = nullptr /* PRELOADED: the group's 2^L raw input words, already in registers */)
 {
     constexpr int R = 1 << L;
     const int s = 1 << logs;
@@ -233,10 +235,19 @@ B200_HD void ntt_fp_group(double *sm, const u64 *__restrict__ gsrc, u64 *__restr
     {
         if (SRC_GLOBAL)
         {
-            u64 v = gsrc[base + (j << logs)];
+            u64 v = PRELOADED ? pre[j] : gsrc[base + (j << logs)];
             if (REDUCE && reduce_input)
                 v = barrett64(v, pint, ratio1);
             x[j] = fp_from_u64(v);
+        }
+        else if (RAW_IN)
+        {
+#if defined(__CUDA_ARCH__)
+            u64 v = (u64)__double_as_longlong(sm[fp_elem_index(pbase, base, j, logs)]);
+            if (REDUCE && reduce_input)
+                v = barrett64(v, pint, ratio1);
+            x[j] = fp_from_u64(v);
+#endif
         }
         else
             x[j] = sm[fp_elem_index(pbase, base, j, logs)];
@@ -376,7 +387,14 @@ struct NttFpStaticPass
         // sub-stride-1 pass would make every lane touch its own 128-byte line (32 L1 wavefronts per request), so
         // its global side is staged through shared memory with coalesced copies instead.
         constexpr bool EDGE_IN = STEP == 0, EDGE_OUT = STEP == NP - 1;
-        constexpr bool SG = EDGE_IN && LOGS >= 5, DG = EDGE_OUT && LOGS >= 5;
+#ifndef B200_NTT_DIRECT_IN
+#define B200_NTT_DIRECT_IN 1
+#endif
+        // Direct global I/O only where consecutive lanes touch consecutive words (large sub-stride).  Staging the forward
+        // input through cp.async instead (B200_NTT_DIRECT_IN=0) measures the same within noise (0.72 vs 0.71 ms for
+        // 16384 polynomials): the per-CTA timeline (tools/ntt_timeline.py) shows the copy-in itself takes only 2.6 us of
+        // a CTA's 18.4 us; the kernel is co-limited by the FP64 pipe (52 %) and the shared-memory pipe (55-58 %).
+        constexpr bool SG = EDGE_IN && LOGS >= 5 && B200_NTT_DIRECT_IN, DG = EDGE_OUT && LOGS >= 5;
         constexpr bool TW16 = (L == 4 && LOGS == 0);
         constexpr int NGROUPS = N >> L;
         constexpr int ITERS = (NGROUPS + NT - 1) / NT;
@@ -425,47 +443,106 @@ struct NttFpStaticPass
                     smd[ptid + it * PNT] = acc; // lazy, |acc| < 4p: the first pass renormalises if its bound needs it
                 }
             }
-            else if (red)
-            {
-#pragma unroll
-                for (int it = 0; it < N / NT; it++)
-                    smd[ptid + it * PNT] = fp_from_u64(barrett64(src[tid + it * NT], PI_.p, PI_.ratio1));
-            }
             else
             {
+                // asynchronous copy (LDGSTS): no registers are held, so all N/NT requests of a thread are in flight at
+                // once; the words land raw and the first pass converts them when it reads (RAW_IN)
+                const unsigned sbase = (unsigned)__cvta_generic_to_shared(smd + ptid);
 #pragma unroll
                 for (int it = 0; it < N / NT; it++)
-                    smd[ptid + it * PNT] = fp_from_u64(src[tid + it * NT]);
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sbase + (unsigned)(it * PNT * 8)), "l"(src + tid + it * NT)
+                                 : "memory");
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
             }
             __syncthreads();
+            if (job.timeline && tid == 0)
+            {
+                unsigned long long t;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                job.timeline[(unsigned long long)blockIdx.x * 8 + 6] = t; // copy-in complete
+            }
         }
+        constexpr bool RAW = EDGE_IN && !SG; // (the tensor-fused copy-in writes doubles: handled by the run-time flag below)
         // renormalisation / input reduction are block-uniform run-time flags: branch ONCE to a compile-time variant
         // (as predicated code they cost 12 FP64 ops and ~10 IMADs per element whether needed or not)
         auto groups = [&](auto RN, auto RD) {
-#pragma unroll
-            for (int it = 0; it < ITERS; it++)
+            if constexpr (SG && NGROUPS % NT == 0 && ITERS > 1)
             {
-                const int g = tid + it * NT;
-                if (NGROUPS % NT == 0 || g < NGROUPS)
-                    ntt_fp_group<L, FWD, SG, DG, TW16, decltype(RN)::value, decltype(RD)::value>(
-                        smd, src, dst, g, LOGS, LOGN, M, P, true, !FWD && EDGE_OUT, true, PI_.p, PI_.ratio1);
+                // direct first pass, software-pipelined: the raw words of group it+1 are requested before group `it` is
+                // transformed, so one DRAM latency is exposed per polynomial instead of one per group
+                constexpr int R = 1 << L;
+                u64 cur[R], nxt[R];
+                {
+                    const int g = tid, i0 = g >> LOGS, o0 = g & ((1 << LOGS) - 1);
+                    const int b0 = (i0 << (LOGS + L)) + o0;
+#pragma unroll
+                    for (int j = 0; j < R; j++)
+                        cur[j] = src[b0 + (j << LOGS)];
+                }
+#pragma unroll
+                for (int it = 0; it < ITERS; it++)
+                {
+                    const int g = tid + it * NT;
+                    if (it + 1 < ITERS)
+                    {
+                        const int gn = g + NT, in_ = gn >> LOGS, on = gn & ((1 << LOGS) - 1);
+                        const int bn = (in_ << (LOGS + L)) + on;
+#pragma unroll
+                        for (int j = 0; j < R; j++)
+                            nxt[j] = src[bn + (j << LOGS)];
+                    }
+                    ntt_fp_group<L, FWD, SG, DG, TW16, decltype(RN)::value, decltype(RD)::value, true>(
+                        smd, src, dst, g, LOGS, LOGN, M, P, true, !FWD && EDGE_OUT, true, PI_.p, PI_.ratio1, cur);
+#pragma unroll
+                    for (int j = 0; j < R; j++)
+                        cur[j] = nxt[j];
+                }
+            }
+            else
+            {
+                auto run = [&](auto RAWF) {
+#pragma unroll
+                    for (int it = 0; it < ITERS; it++)
+                    {
+                        const int g = tid + it * NT;
+                        if (NGROUPS % NT == 0 || g < NGROUPS)
+                            ntt_fp_group<L, FWD, SG, DG, TW16, decltype(RN)::value, decltype(RD)::value, false, decltype(RAWF)::value>(
+                                smd, src, dst, g, LOGS, LOGN, M, P, true, !FWD && EDGE_OUT, true, PI_.p, PI_.ratio1);
+                    }
+                };
+                if constexpr (RAW)
+                {
+                    if (!FWD && job.tensor_mode)
+                        run(std::false_type{});
+                    else
+                        run(std::true_type{});
+                }
+                else
+                    run(std::false_type{});
             }
         };
         if (rn)
         {
-            if (SG && red)
+            if ((SG || RAW) && red)
                 groups(std::true_type{}, std::true_type{});
             else
                 groups(std::true_type{}, std::false_type{});
         }
         else
         {
-            if (SG && red)
+            if ((SG || RAW) && red)
                 groups(std::false_type{}, std::true_type{});
             else
                 groups(std::false_type{}, std::false_type{});
         }
         __syncthreads();
+        if (job.timeline && tid == 0)
+        {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            job.timeline[(unsigned long long)blockIdx.x * 8 + 2 + STEP] = t;
+        }
         if (EDGE_OUT && !DG)
         { // coalesced copy-out: lazy double -> canonical u64
 #pragma unroll
