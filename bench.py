@@ -275,6 +275,7 @@ def main():
         e2e_s = float(ts.item())
     e2e_value = world * B * e2e_steps / e2e_s
     same = bool(torch.equal(oh.to(dev), out))
+    pack_num = 6 if (max(MODULI[:k]) < 2 ** 48 and os.environ.get("B200_HOST_PACK", "0") not in ("", "0")) else 8
 
     # ---- roofline of the dominant kernel: batched forward NTT, 4096 polys x 4 residues (1 GiB slab > L2) ----
     roof = None
@@ -342,7 +343,12 @@ def main():
                        "parallelism": f"batch sharded over {world} GPU(s), no data-path collective",
                        "l2": "inputs (1 GiB per GPU) exceed the 126 MB L2; no explicit flush"},
             "clocks": clocks, "gpu_launches": int(launches),
-            "e2e": {"value": e2e_value, "unit": "ops/s", "h2d_bytes_per_step": 2 * B * ct_bytes, "d2h_bytes_per_step": B * ct_bytes,
+            "e2e": {"value": e2e_value, "unit": "ops/s",
+                    # bytes that actually cross PCIe per step (with B200_HOST_PACK=1 the library narrows each residue word
+                    # to 6 bytes on the host and widens it again on the device; off by default: measured slower)
+                    "h2d_bytes_per_step": 2 * B * ct_bytes * pack_num // 8, "d2h_bytes_per_step": B * ct_bytes * pack_num // 8,
+                    "host_buffer_bytes_in_per_step": 2 * B * ct_bytes, "host_buffer_bytes_out_per_step": B * ct_bytes,
+                    "transfer": "6-byte packed residues" if pack_num == 6 else "8-byte words",
                     "steps": e2e_steps, "matches_device_path": same, "host_numa_node": numa_node},
             "roofline": roof, "cpu_baseline": cpu,
         }

@@ -57,10 +57,14 @@ static inline bool trace_on()
             kernel<<<grid, block, smem, stream>>>(__VA_ARGS__);                                                        \
     } while (0)
 #endif
+#include <condition_variable>
+#include <functional>
 #include <map>
 #include <memory>
 #include <mutex>
+#include <sched.h>
 #include <string>
+#include <thread>
 #include <vector>
 
 using b200::BfvHostContext;
@@ -675,6 +679,11 @@ struct b200_ctx
     cudaEvent_t hp_in[NBUF], hp_comp[NBUF], hp_out[NBUF];
     size_t hp_words = 0;
     std::mutex hp_mu;
+    // packed (6 bytes per word) PCIe staging of the host-buffer entry points: pinned host buffers and device landing zones
+    uint8_t *hst_a[NBUF] = { nullptr, nullptr, nullptr }, *hst_b[NBUF] = { nullptr, nullptr, nullptr }, *hst_o[NBUF] = { nullptr, nullptr, nullptr };
+    u64 *dpk_a[NBUF] = { nullptr, nullptr, nullptr }, *dpk_b[NBUF] = { nullptr, nullptr, nullptr }, *dpk_o[NBUF] = { nullptr, nullptr, nullptr };
+    size_t pk_words = 0;
+    struct HostPool *pool = nullptr;
     int ntt_threads = 256;
     size_t ntt_smem = 0;
     int ntt_split = 0; // 1: n > 16384 -> two-level transform (ntt_outer_kernel + half-size sub-transforms)
@@ -1547,6 +1556,18 @@ void b200_ctx_destroy(b200_ctx *ctx)
     for (void *p : ctx->allocations)
         cudaFree(p);
     for (int i = 0; i < b200_ctx::NBUF; i++)
+        if (ctx->hst_a[i])
+        {
+            cudaFreeHost(ctx->hst_a[i]);
+            cudaFreeHost(ctx->hst_b[i]);
+            cudaFreeHost(ctx->hst_o[i]);
+            cudaFree(ctx->dpk_a[i]);
+            cudaFree(ctx->dpk_b[i]);
+            cudaFree(ctx->dpk_o[i]);
+        }
+    delete ctx->pool;
+    ctx->pool = nullptr;
+    for (int i = 0; i < b200_ctx::NBUF; i++)
         if (ctx->hp_a[i])
         {
             cudaFree(ctx->hp_a[i]);
@@ -2230,6 +2251,280 @@ static int host_ring(b200_ctx *ctx, size_t words_per_slot)
     return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Packed PCIe transfers for the host-buffer entry points (OPT-IN, see level_packs).  A canonical residue of a level
+// whose primes are all below 2^48 carries at most 6 significant bytes, and the end-to-end rate of
+// multiply+relinearize is set by PCIe (1 MiB in + 0.5 MiB out per op against ~7 us of GPU time), so the words can
+// cross the link as 6 bytes each: host threads pack into pinned staging while the previous chunk is in flight, the
+// GPU expands after landing (and packs the result before it leaves).  Bit-exact: every word is checked to fit
+// before it is narrowed.
+// ---------------------------------------------------------------------------------------------------------
+static const u64 PACK_MASK = 0x0000FFFFFFFFFFFFULL;
+
+// 4 words <- 3 u64 (24 bytes)
+__global__ void unpack48_kernel(const u64 *packed, u64 *out, long long groups)
+{
+    const long long g = GLOBAL_IDX();
+    if (g >= groups)
+        return;
+    const u64 a = packed[3 * g], b = packed[3 * g + 1], c = packed[3 * g + 2];
+    out[4 * g] = a & PACK_MASK;
+    out[4 * g + 1] = ((a >> 48) | (b << 16)) & PACK_MASK;
+    out[4 * g + 2] = ((b >> 32) | (c << 32)) & PACK_MASK;
+    out[4 * g + 3] = c >> 16;
+}
+__global__ void pack48_kernel(const u64 *in, u64 *packed, long long groups)
+{
+    const long long g = GLOBAL_IDX();
+    if (g >= groups)
+        return;
+    const u64 w0 = in[4 * g], w1 = in[4 * g + 1], w2 = in[4 * g + 2], w3 = in[4 * g + 3];
+    packed[3 * g] = w0 | (w1 << 48);
+    packed[3 * g + 1] = (w1 >> 16) | (w2 << 32);
+    packed[3 * g + 2] = (w2 >> 32) | (w3 << 16);
+}
+
+// minimal fork-join pool (the packing loops are pure streaming work; 8-16 threads saturate what PCIe can take)
+struct HostPool
+{
+    std::vector<std::thread> th;
+    std::mutex mu;
+    std::condition_variable cv_work, cv_done;
+    std::function<void(int, int)> task;
+    long long generation = 0;
+    int pending = 0;
+    bool stop = false;
+    int nth = 1;
+    explicit HostPool(int n) : nth(n < 1 ? 1 : n)
+    {
+        for (int i = 1; i < nth; i++)
+            th.emplace_back([this, i] { loop(i); });
+    }
+    ~HostPool()
+    {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            stop = true;
+        }
+        cv_work.notify_all();
+        for (auto &t : th)
+            t.join();
+    }
+    void loop(int id)
+    {
+        long long seen = 0;
+        for (;;)
+        {
+            std::function<void(int, int)> fn;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv_work.wait(lk, [&] { return stop || generation != seen; });
+                if (stop)
+                    return;
+                seen = generation;
+                fn = task;
+            }
+            fn(id, nth);
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                if (--pending == 0)
+                    cv_done.notify_one();
+            }
+        }
+    }
+    void run(const std::function<void(int, int)> &fn)
+    {
+        if (nth == 1)
+        {
+            fn(0, 1);
+            return;
+        }
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            task = fn;
+            pending = nth - 1;
+            generation++;
+        }
+        cv_work.notify_all();
+        fn(0, nth);
+        std::unique_lock<std::mutex> lk(mu);
+        cv_done.wait(lk, [&] { return pending == 0; });
+    }
+};
+
+static HostPool *host_pool(b200_ctx *ctx)
+{
+    if (!ctx->pool)
+    {
+        int n = 0;
+        if (const char *e = getenv("B200_HOST_THREADS"))
+            n = atoi(e);
+        if (n <= 0)
+        {
+            cpu_set_t set;
+            CPU_ZERO(&set);
+            int avail = sched_getaffinity(0, sizeof(set), &set) == 0 ? CPU_COUNT(&set) : (int)std::thread::hardware_concurrency();
+            n = std::max(1, std::min(16, avail / 2));
+        }
+        ctx->pool = new HostPool(n);
+    }
+    return ctx->pool;
+}
+
+// src[words] -> dst[6*words (+2 slack)]; returns the OR of all words (to verify that they fit 48 bits)
+static u64 cpu_pack48(HostPool *pool, const u64 *src, uint8_t *dst, size_t words)
+{
+    std::vector<u64> ors((size_t)pool->nth, 0);
+    pool->run([&](int id, int nth) {
+        const size_t lo = words * (size_t)id / (size_t)nth, hi = words * (size_t)(id + 1) / (size_t)nth;
+        if (lo >= hi)
+            return;
+        u64 m = 0;
+        uint8_t *d = dst + 6 * lo;
+        for (size_t i = lo; i + 1 < hi; i++, d += 6)
+        {
+            const u64 w = src[i];
+            m |= w;
+            std::memcpy(d, &w, 8); // the two spill bytes are overwritten by the next word of this range
+        }
+        const u64 w = src[hi - 1];
+        m |= w;
+        std::memcpy(d, &w, 6);
+        ors[(size_t)id] = m;
+    });
+    u64 m = 0;
+    for (u64 x : ors)
+        m |= x;
+    return m;
+}
+static void cpu_unpack48(HostPool *pool, const uint8_t *src, u64 *dst, size_t words)
+{
+    pool->run([&](int id, int nth) {
+        const size_t lo = words * (size_t)id / (size_t)nth, hi = words * (size_t)(id + 1) / (size_t)nth;
+        const uint8_t *s = src + 6 * lo;
+        for (size_t i = lo; i < hi; i++, s += 6)
+        {
+            u64 w;
+            std::memcpy(&w, s, 8); // staging buffers carry 8 bytes of slack
+            dst[i] = w & PACK_MASK;
+        }
+    });
+}
+
+static bool level_packs(const b200_ctx *ctx, int level)
+{
+    // Opt-in (B200_HOST_PACK=1).  Measured on the pool's hosts (profiles/r1_e2e_packing.txt): narrowing on the CPU costs
+    // more host memory traffic (~5 GiB per 1024 ops instead of 1.5) than PCIe saves — 31 k ops/s with 16 packing
+    // threads against 46.5 k ops/s for plain pinned DMA — so the default is the plain pipeline.
+    const char *e = getenv("B200_HOST_PACK");
+    if (!e || atoi(e) == 0 || (ctx->n & 3))
+        return false;
+    const auto &Lh = ctx->host->levels[level];
+    for (int idx : Lh.q_idx)
+        if (ctx->host->primes[idx].mod.p >> 48)
+            return false;
+    return true;
+}
+
+static int pack_ring(b200_ctx *ctx, size_t words_per_slot)
+{
+    if (ctx->pk_words >= words_per_slot)
+        return 0;
+    const size_t bytes = words_per_slot * 6 + 16;
+    for (int i = 0; i < b200_ctx::NBUF; i++)
+    {
+        if (ctx->hst_a[i])
+        {
+            cudaFreeHost(ctx->hst_a[i]);
+            cudaFreeHost(ctx->hst_b[i]);
+            cudaFreeHost(ctx->hst_o[i]);
+            cudaFree(ctx->dpk_a[i]);
+            cudaFree(ctx->dpk_b[i]);
+            cudaFree(ctx->dpk_o[i]);
+        }
+        CU_TRY(cudaMallocHost((void **)&ctx->hst_a[i], bytes));
+        CU_TRY(cudaMallocHost((void **)&ctx->hst_b[i], bytes));
+        CU_TRY(cudaMallocHost((void **)&ctx->hst_o[i], bytes));
+        CU_TRY(cudaMalloc((void **)&ctx->dpk_a[i], bytes));
+        CU_TRY(cudaMalloc((void **)&ctx->dpk_b[i], bytes));
+        CU_TRY(cudaMalloc((void **)&ctx->dpk_o[i], bytes));
+    }
+    ctx->pk_words = words_per_slot;
+    return 0;
+}
+
+// multiply+relinearize over host buffers with packed transfers (see above); same contract as the plain pipeline
+static int multiply_relin_host_packed(b200_ctx *ctx, int level, const u64 *a_host, const u64 *b_host, const u64 *relin_key_dev,
+                                      u64 *out_host, uint64_t batch, long long chunk, size_t ct_words)
+{
+    int rc = 0;
+    if ((rc = host_ring(ctx, (size_t)chunk * ct_words)) || (rc = pack_ring(ctx, (size_t)chunk * ct_words)))
+        return rc;
+    HostPool *pool = host_pool(ctx);
+    const int NBUF = b200_ctx::NBUF, LAG = NBUF - 1;
+    std::vector<uint64_t> offs;
+    for (uint64_t off = 0; off < batch; off += (uint64_t)chunk)
+        offs.push_back(off);
+    const int iters = (int)offs.size();
+    auto drain = [&](int j) { // bring the result of iteration j home
+        const int sl = j % NBUF;
+        const size_t words = (size_t)std::min<uint64_t>((uint64_t)chunk, batch - offs[j]) * ct_words;
+        cudaEventSynchronize(ctx->hp_out[sl]);
+        cpu_unpack48(pool, ctx->hst_o[sl], out_host + offs[j] * ct_words, words);
+    };
+    u64 ormask = 0;
+    for (int it = 0; it < iters && rc == 0; it++)
+    {
+        const int sl = it % NBUF;
+        const uint64_t off = offs[it];
+        const long long cnt = (long long)std::min<uint64_t>((uint64_t)chunk, batch - off);
+        const size_t words = (size_t)cnt * ct_words, pbytes = words * 6, groups = words / 4;
+        if (it >= NBUF)
+            cudaEventSynchronize(ctx->hp_in[sl]); // the staging buffers of this slot have left the host
+        ormask |= cpu_pack48(pool, a_host + off * ct_words, ctx->hst_a[sl], words);
+        ormask |= cpu_pack48(pool, b_host + off * ct_words, ctx->hst_b[sl], words);
+        if (ormask >> 48)
+        {
+            rc = fail(B200_E_INVALID, "ciphertext word does not fit the residue width of this level");
+            break;
+        }
+        if (it >= NBUF)
+            cudaStreamWaitEvent(ctx->s_h2d, ctx->hp_out[sl], 0); // device slot free once its previous output left
+        cudaMemcpyAsync(ctx->dpk_a[sl], ctx->hst_a[sl], pbytes, cudaMemcpyHostToDevice, ctx->s_h2d);
+        cudaMemcpyAsync(ctx->dpk_b[sl], ctx->hst_b[sl], pbytes, cudaMemcpyHostToDevice, ctx->s_h2d);
+        cudaEventRecord(ctx->hp_in[sl], ctx->s_h2d);
+        cudaStreamWaitEvent(ctx->s_comp, ctx->hp_in[sl], 0);
+        B200_LAUNCH(unpack48_kernel, blocks_for((long long)groups, 256), 256, 0, ctx->s_comp, (const u64 *)ctx->dpk_a[sl], ctx->hp_a[sl],
+                    (long long)groups);
+        B200_LAUNCH(unpack48_kernel, blocks_for((long long)groups, 256), 256, 0, ctx->s_comp, (const u64 *)ctx->dpk_b[sl], ctx->hp_b[sl],
+                    (long long)groups);
+        ctx->launches += 2;
+        rc = b200_multiply_relin(ctx, level, (const uint64_t *)ctx->hp_a[sl], (const uint64_t *)ctx->hp_b[sl],
+                                 (const uint64_t *)relin_key_dev, (uint64_t *)ctx->hp_o[sl], (uint64_t)cnt, ctx->s_comp);
+        B200_LAUNCH(pack48_kernel, blocks_for((long long)groups, 256), 256, 0, ctx->s_comp, (const u64 *)ctx->hp_o[sl], ctx->dpk_o[sl],
+                    (long long)groups);
+        ctx->launches++;
+        cudaEventRecord(ctx->hp_comp[sl], ctx->s_comp);
+        cudaStreamWaitEvent(ctx->s_d2h, ctx->hp_comp[sl], 0);
+        cudaMemcpyAsync(ctx->hst_o[sl], ctx->dpk_o[sl], pbytes, cudaMemcpyDeviceToHost, ctx->s_d2h);
+        cudaEventRecord(ctx->hp_out[sl], ctx->s_d2h);
+        if (it >= LAG)
+            drain(it - LAG);
+    }
+    cudaError_t e1 = cudaStreamSynchronize(ctx->s_h2d);
+    cudaError_t e2 = cudaStreamSynchronize(ctx->s_comp);
+    cudaError_t e3 = cudaStreamSynchronize(ctx->s_d2h);
+    if (rc)
+        return rc;
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
+        return fail(B200_E_CUDA, std::string("host pipeline: ") +
+                                     cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
+    for (int j = std::max(0, iters - LAG); j < iters; j++)
+        drain(j);
+    return 0;
+}
+
 int b200_multiply_relin_host(b200_ctx *ctx, int level, const uint64_t *a_host, const uint64_t *b_host,
                              const uint64_t *relin_key_dev, uint64_t *out_host, uint64_t batch)
 {
@@ -2251,6 +2546,9 @@ int b200_multiply_relin_host(b200_ctx *ctx, int level, const uint64_t *a_host, c
         chunk = 1;
     if ((uint64_t)chunk > batch)
         chunk = (long long)batch;
+    if (level_packs(ctx, level))
+        return multiply_relin_host_packed(ctx, level, (const u64 *)a_host, (const u64 *)b_host, (const u64 *)relin_key_dev,
+                                          (u64 *)out_host, batch, chunk, ct_words);
     if ((rc = host_ring(ctx, (size_t)chunk * ct_words)))
         return rc;
     const int NBUF = b200_ctx::NBUF;

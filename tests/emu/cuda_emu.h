@@ -53,6 +53,7 @@ inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, int) { return 
 inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, int) { *e = nullptr; return 0; }
 inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return 0; }
 inline cudaError_t cudaEventDestroy(cudaEvent_t) { return 0; }
+inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
 inline unsigned long long __ldg(const unsigned long long *p) { return *p; }
 inline double __ldg(const double *p) { return *p; }
 inline int __syncthreads_or(int v) { return v; }

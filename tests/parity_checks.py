@@ -243,3 +243,43 @@ def check_encrypted_roundtrip(P, seed=3):
     expect = (v1.astype(object) * v2.astype(object)) % P.t
     assert np.array_equal(vals.astype(object), expect)
     return dict(dec=dec, sk=sk, ct=got, expect_plain=R.pt_coeffs(R.decrypt(dec, back)))
+
+
+def check_host_pipeline(P, batch=5, seed=17):
+    """b200_multiply_relin_host (host buffers in, host buffers out; chunked, overlapped, packed 6-byte transfers when the
+    level's primes fit 48 bits) returns the same words as the device-resident entry point, also when the ring of staging
+    slots wraps (chunk of 1 item, 5 items, 3 slots); a word that does not fit the residue width is rejected."""
+    import os
+    rng = np.random.default_rng(seed)
+    A = rand_ct(rng, P.moduli, P.k, P.n, batch=batch)
+    B = rand_ct(rng, P.moduli, P.k, P.n, batch=batch)
+    key = rand_ksk(rng, P.moduli, P.k, P.n)
+    dK = P.dev(key)
+    o2 = P.out(batch, 2, P.k, P.n)
+    P.ctx.multiply_relin(P.dev(A), P.dev(B), dK, o2, batch)
+    want = P.host(o2)
+    old = os.environ.get("B200_HOST_CHUNK")
+    old_pack = os.environ.get("B200_HOST_PACK")
+    try:
+        for pack in ("0", "1"):
+            os.environ["B200_HOST_PACK"] = pack
+            for chunk in ("1", "2", "64"):
+                os.environ["B200_HOST_CHUNK"] = chunk
+                oh = np.zeros((batch, 2, P.k, P.n), dtype=np.uint64)
+                P.ctx.multiply_relin_host(A, B, dK, oh, batch)
+                eq(oh, want, f"multiply_relin_host, chunk {chunk}, pack {pack}")
+        if max(P.moduli[: P.k]) < 2**48:
+            bad = A.copy()
+            bad[batch - 1, 1, P.k - 1, P.n - 1] = np.uint64(2**48)
+            try:
+                P.ctx.multiply_relin_host(bad, B, dK, np.zeros_like(want), batch)
+            except Exception as e:  # B200Error(B200_E_INVALID)
+                assert "residue width" in str(e) or "-1" in str(e), e
+            else:
+                raise AssertionError("an out-of-range ciphertext word must be rejected by the packed pipeline")
+    finally:
+        for name, val in (("B200_HOST_CHUNK", old), ("B200_HOST_PACK", old_pack)):
+            if val is None:
+                os.environ.pop(name, None)
+            else:
+                os.environ[name] = val

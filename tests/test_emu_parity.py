@@ -51,6 +51,12 @@ def test_batch_strides(pair):
     pc.check_batch(pair)
 
 
+def test_host_buffer_pipeline(pair):
+    if pair.n > 4096:
+        pytest.skip("host pipeline test runs on the smallest set only (emulation speed)")
+    pc.check_host_pipeline(pair)
+
+
 def test_encrypted_roundtrip(pair):
     if not pair.ctx.using_batching:
         pytest.skip("needs a batching plain modulus")

@@ -58,6 +58,12 @@ def test_mod_switch(pair):
     pc.check_modswitch(pair)
 
 
+def test_host_buffer_pipeline(pair):
+    if pair.n > 16384:
+        pytest.skip("covered at n <= 16384")
+    pc.check_host_pipeline(pair, batch=7)
+
+
 def test_batch_strides(pair):
     pc.check_batch(pair, batch=5 if pair.n <= 16384 else 2)
 
