@@ -319,7 +319,7 @@ def main():
                 "inverse_achieved": alg_bytes / (inv_ms / 1000.0) / 1e9,
                 "mul_relin_algorithmic_gbs": (8 * n * k * 6) * value / world / 1e9}
         del slab
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:  # the CPU baseline is an N=1 leg (the reference arm covers every N)
             try:
                 os.sched_setaffinity(0, range(os.cpu_count() or 1))
                 cores = os.cpu_count() or 1
