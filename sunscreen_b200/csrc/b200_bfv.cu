@@ -769,7 +769,6 @@ static int build_device(b200_ctx *ctx)
         const bool no_fp = std::getenv("B200_NO_FP64_NTT") != nullptr || ctx->ntt_split;
         ctx->fp_enabled = !no_fp;
         std::vector<NttPrimeFp> fp(allp.size());
-        const double LIMIT = 2251799813685248.0; // 2^51
         ctx->prime_fp.assign(allp.size(), false);
         for (size_t i = 0; i < allp.size(); i++)
         {
@@ -817,31 +816,59 @@ static int build_device(b200_ctx *ctx)
                 UP(i16, &d16);
                 fp[i].inv16 = d16;
             }
-            double B = p;
+            // Magnitude bookkeeping.  Every stored value must stay an exactly representable integer (|x| <= 2^53), and a
+            // modular product y*w - rint(fl(fl(y*w) * fl(1/p))) * p of an input |y| <= 2^53 has magnitude at most
+            // p * (1/2 + 3 * 2^-53 * |y|)  (three roundings of relative size 2^-53 in the quotient, one rint), computed
+            // exactly (ntt_fp_body.cuh).  Forward butterfly: X +- T.  Inverse butterfly: X + Y and (X - Y) * w.
+            const double LIMIT = 9007199254740992.0; // 2^53
+            auto prod_bound = [&](double y) { return p * (0.5 + 3.0 * y / LIMIT) + 1.0; };
+            const double RENORMED = 0.76 * p;       // |x - rint(x/p) p| after fp_renorm / fp_renorm_x
+            auto fwd_pass = [&](double b, int L, bool &ok) {
+                for (int s = 0; s < L; s++)
+                {
+                    b += prod_bound(b);
+                    ok = ok && b <= LIMIT;
+                }
+                return b;
+            };
+            auto inv_pass = [&](double b, int L, bool &ok) {
+                for (int s = 0; s < L; s++)
+                {
+                    ok = ok && 2.0 * b <= LIMIT;
+                    b = std::max(2.0 * b, prod_bound(2.0 * b));
+                }
+                return b;
+            };
+            double B = p; // canonical (or Barrett-reduced) input
             for (int pi = 0; pi < ctx->npass; pi++)
             {
-                const int L = ctx->pass_L[pi];
-                // a butterfly output is X +- T with |T| <= p(5/8 + |y|/2^52) <= 1.125 p for |y| < 2^51 (ntt_fp_body.cuh)
-                if (B + L * 1.125 * p >= LIMIT)
+                bool ok = true;
+                double nb = fwd_pass(B, ctx->pass_L[pi], ok);
+                if (!ok)
                 {
                     fp[i].renorm_fwd |= 1u << pi;
-                    B = 0.76 * p;
+                    ok = true;
+                    nb = fwd_pass(RENORMED, ctx->pass_L[pi], ok);
+                    if (!ok)
+                        return fail(B200_E_LOGIC, "internal: FP64 NTT bound analysis failed (forward)");
                 }
-                B += L * 1.125 * p;
+                B = nb;
             }
             B = p;
             int step = 0;
             for (int pi = ctx->npass - 1; pi >= 0; pi--, step++)
             {
-                const int L = ctx->pass_L[pi];
-                if (B * (double)(1 << L) >= LIMIT)
+                bool ok = true;
+                double nb = inv_pass(B, ctx->pass_L[pi], ok);
+                if (!ok)
                 {
                     fp[i].renorm_inv |= 1u << step;
-                    B = 0.76 * p;
+                    ok = true;
+                    nb = inv_pass(RENORMED, ctx->pass_L[pi], ok);
+                    if (!ok)
+                        return fail(B200_E_LOGIC, "internal: FP64 NTT bound analysis failed (inverse)");
                 }
-                B *= (double)(1 << L);
-                if (B >= LIMIT)
-                    return fail(B200_E_LOGIC, "internal: FP64 NTT bound analysis failed");
+                B = nb;
             }
         }
         UP(fp, &ctx->d_fp_primes);
@@ -892,7 +919,7 @@ static int build_device(b200_ctx *ctx)
         L.plain_thr = Lh.plain_upper_half_threshold;
         LevelFpHost fp_level;
         {
-            bool lfp = ctx->fp_enabled && H.aux_bits == b200::FP_PRIME_BITS;
+            bool lfp = ctx->fp_enabled && H.aux_bits <= b200::FP_PRIME_BITS;
             for (int idx : Lh.q_idx)
                 lfp = lfp && H.primes[idx].fp;
             for (int idx : Lh.bsk_idx)

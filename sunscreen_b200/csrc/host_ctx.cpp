@@ -448,13 +448,18 @@ BfvHostContext::BfvHostContext(size_t poly_modulus_degree, const std::vector<u64
     // (t * n * K * Q * (1+rho)^2 < prod(B) * m_sk, the reference's own condition, rns.cpp:617-624): every
     // approximation error in the BEHZ chain (the q-overflows of the two fast base conversions) is a function of
     // the base-q residues alone, and the Shenoy-Kumaresan step is exact.  So when every user prime fits the FP64
-    // NTT path we pick 47-bit auxiliary primes instead, so that the Bsk transforms take the same fast path;
+    // NTT path we pick 47..49-bit auxiliary primes instead (as wide as the widest user prime, at least 47), so that the
+    // Bsk transforms take the same fast path;
     // gamma (decryption only, never transformed) stays the reference's.
     aux0 = K;
     bool all_fp = std::getenv("B200_FORCE_AUX61") == nullptr;
     for (int i = 0; i < K; i++)
         all_fp = all_fp && primes[i].fp;
-    aux_bits = all_fp ? FP_PRIME_BITS : 61;
+    int user_bits = 0;
+    for (int i = 0; i < K; i++)
+        user_bits = std::max(user_bits, primes[i].mod.bits);
+    aux_bits = all_fp ? std::max(FP_AUX_BITS_MIN, user_bits) : 61;
+    const int aux_centibits = aux_bits * 100 - 10; // every prime found just below 2^aux_bits carries more than this
     const std::vector<u64> ref_aux = get_primes(2 * (u64)n, 61, 2);
     // enough 47-bit primes for the largest level: bits(prod(B) * m_sk) >= 33 + bits(t) + bits(Q)
     size_t aux_count = (size_t)K + 3;
@@ -463,9 +468,20 @@ BfvHostContext::BfvHostContext(size_t poly_modulus_degree, const std::vector<u64
         BigUInt Qall(1);
         for (int i = 0; i < K; i++)
             Qall.mul(coeff_modulus[i]);
-        aux_count = (size_t)((33 + t_mod.bits + Qall.bit_length()) * 100 / 4690 + 3);
+        aux_count = (size_t)((33 + t_mod.bits + Qall.bit_length()) * 100 / aux_centibits + 3);
     }
-    std::vector<u64> aux = get_primes(2 * (u64)n, aux_bits, aux_count);
+    std::vector<u64> aux;
+    { // descending from 2^aux_bits, skipping anything the user's chain (or t) already uses
+        std::vector<u64> cand = get_primes(2 * (u64)n, aux_bits, aux_count + (size_t)K + 1);
+        for (u64 v : cand)
+        {
+            bool used = v == plain_modulus;
+            for (int i = 0; i < K; i++)
+                used = used || v == coeff_modulus[i];
+            if (!used && aux.size() < aux_count)
+                aux.push_back(v);
+        }
+    }
     aux[1] = ref_aux[1]; // gamma: the reference's second 61-bit prime
     for (size_t i = 0; i < aux.size(); i++)
         primes.push_back(make_ntt_prime(aux[i], logn));
@@ -497,9 +513,9 @@ BfvHostContext::BfvHostContext(size_t poly_modulus_degree, const std::vector<u64
                 L.nB++;
         }
         else
-        { // same inequality, solved for 47-bit primes (each contributes > 46.9 bits)
+        { // same inequality, solved for aux_bits-bit primes (each contributes > aux_bits - 0.1 bits)
             int need = 33 + t_mod.bits + L.total_bits;
-            int cnt = (need * 100 + 4689) / 4690;
+            int cnt = (need * 100 + aux_centibits - 1) / aux_centibits;
             L.nB = std::max(1, cnt - 1);
         }
         L.nBsk = L.nB + 1;

@@ -74,7 +74,12 @@ struct NttPrimeHost
 
 // Largest prime size (bits) the FP64 NTT path accepts; also the size of the auxiliary BEHZ primes we pick
 // when every user prime qualifies.
-static const int FP_PRIME_BITS = 47;
+// Primes up to this many bits take the FP64 path.  Every value the FP64 kernels hold is an integer of magnitude <= 2^53
+// (exactly representable); the host-side bound bookkeeping (b200_bfv.cu: build_device) places a renormalisation before
+// any NTT pass whose butterflies could exceed that.  49 bits is the largest width for which a radix-16 inverse pass
+// (x16 growth on the sum path) still fits after a renormalisation: 16 * 0.76 * 2^49 < 2^53.
+static const int FP_PRIME_BITS = 49;
+static const int FP_AUX_BITS_MIN = 47; // auxiliary BEHZ primes are at least this wide (fewer of them are needed)
 
 // One level of the modulus chain (mirrors ContextData + RNSTool for that level).
 // Index conventions: q_idx / bsk_idx / gamma_idx index into BfvHostContext::primes.
@@ -127,7 +132,7 @@ struct BfvHostContext
     std::vector<NttPrimeHost> primes; // key primes [0,K), then aux primes: m_sk, gamma, B...
     int K = 0;                        // key-level prime count
     int aux0 = 0;                     // index of m_sk; gamma = aux0+1; B_i = aux0+2+i
-    int aux_bits = 61;                // 61 = the reference's aux base; 47 = FP64-friendly base (same results)
+    int aux_bits = 61;                // 61 = the reference's aux base; 47..49 = FP64-friendly base (same results)
     std::vector<LevelHost> levels;    // levels[0] = key level, levels[1] = first data level, ...
     bool using_keyswitching = false;  // K > 1
     bool using_batching = false;      // t prime and t == 1 mod 2n

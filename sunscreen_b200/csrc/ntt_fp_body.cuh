@@ -5,19 +5,20 @@
 // multiplication by a precomputed twiddle can be done EXACTLY in 6 double-precision operations:
 //     h = y*w (rounded)            l = fma(y, w, -h)        (h + l == y*w exactly)
 //     q = rint(h * (1/p))          (DMUL + FRND.F64; the rounding runs on the XU pipe, not the FP64 pipe)
-//     r = fma(-q, p, h) + l        (== y*w - q*p exactly: an integer of magnitude <= p(5/8 + |y|/2^52) <= 1.125 p)
+//     r = fma(-q, p, h) + l        (== y*w - q*p exactly: an integer of magnitude <= p(1/2 + 3|y|/2^53))
 // (the twiddle tables therefore hold w only: one 8-byte load per butterfly group instead of a {w, w/p} pair)
-// All values are integer-valued doubles in a signed lazy range; every operation above is exact as long as
-// |y| < 2^51 and p < 2^47, so the transform computes the same residues as the integer path — the outputs are
+// All values are integer-valued doubles in a signed lazy range; every operation above is exact as long as every
+// value stays an integer of magnitude <= 2^53 (p up to 49 bits: host_ctx.h FP_PRIME_BITS), so the transform computes
+// the same residues as the integer path — the outputs are
 // reduced to the canonical [0,p) before they leave the kernel and are bit-identical to the reference's
 // ntt_negacyclic_harvey / inverse_ntt_negacyclic_harvey (S/util/ntt.cpp:393-474).
 //
 // Schedule: identical pass structure to ntt_body.cuh (radix-8/16 groups, padded shared memory), except that
 // the FIRST pass reads its group straight from global memory (u64 -> double) and the LAST pass writes its
 // group straight to global memory (double -> canonical u64), saving two shared-memory round trips.
-// Magnitude bookkeeping (host, b200_bfv.cu build_device): a forward butterfly adds <= 1.125 p to the bound, an
-// inverse butterfly doubles it on the sum path; whenever a pass would exceed 2^50 its inputs are first
-// renormalised (x -= rint(x/p)*p, 3 DP ops).
+// Magnitude bookkeeping (host, b200_bfv.cu build_device): a forward butterfly adds the product bound above to the
+// magnitude, an inverse butterfly doubles it on the sum path; whenever a pass could exceed 2^53 its inputs are first
+// renormalised (x -= rint(x/p)*p, 2 FP64 ops + FRND).
 #pragma once
 #include "ntt_body.cuh"
 #include <type_traits>

@@ -62,10 +62,14 @@ def check_context(P):
         # the reference's own auxiliary base (61-bit primes)
         assert li["bsk"] == ri["bsk_primes"] and (li["nB"], li["nBsk"]) == (ri["B"], ri["Bsk"])
     else:
-        # FP64-friendly auxiliary base: 47-bit NTT primes with at least the reference's dynamic range condition
+        # FP64-friendly auxiliary base: 47..49-bit NTT primes (as wide as the widest user prime), distinct from the user's
+        # primes, with at least the reference's dynamic range condition
         # 32 + bits(t) + bits(Q) < bits(prod(B) * m_sk)   (S/util/rns.cpp:617-624); results are base-independent.
         import math
-        assert all(p < (1 << 47) and p % (2 * P.n) == 1 for p in li["bsk"]) and len(set(li["bsk"])) == len(li["bsk"])
+        width = max(47, max(int(m).bit_length() for m in P.moduli))
+        assert width <= 49
+        assert all(p < (1 << width) and p % (2 * P.n) == 1 for p in li["bsk"]) and len(set(li["bsk"])) == len(li["bsk"])
+        assert not set(li["bsk"]) & set(int(m) for m in P.moduli)
         Q = math.prod(li["q"])
         assert math.prod(li["bsk"]).bit_length() > 32 + P.t.bit_length() + Q.bit_length()
     pi = P.ref.plain_info()
@@ -75,11 +79,20 @@ def check_context(P):
         assert P.ref.ref.ntt_root(q, P.n) == r
 
 
-def check_ntt(P, items=3, seed=1):
+def check_ntt(P, items=6, seed=1):
     rng = np.random.default_rng(seed)
     x = rand_ct(rng, P.moduli, P.k, P.n, size=1, batch=items)[:, 0]
     x[0, :, :8] = 0
     x[0, 0, 0] = 1  # delta -> all-ones spectrum
+    # magnitude extremes for the lazy (signed FP64 / Harvey) representations: every coefficient q-1, alternating 0 / q-1,
+    # and a +-1 pattern (q-1 = -1) that makes the butterflies add up coherently
+    qm1 = np.array([m - 1 for m in P.moduli[: P.k]], dtype=np.uint64)[:, None]
+    if items >= 6:
+        x[3] = np.broadcast_to(qm1, (P.k, P.n))
+        x[4] = 0
+        x[4, :, ::2] = qm1
+        x[5] = 1
+        x[5, :, 1::3] = qm1
     d = P.dev(x)
     P.ctx.ntt_forward(d, items)
     got = P.host(d)

@@ -8,7 +8,7 @@ from backends import EmuBackend
 from params import PARAMS
 
 
-@pytest.fixture(scope="module", params=["n4096", "n8192", "n8192_54"])
+@pytest.fixture(scope="module", params=["n4096", "n8192", "n8192_54", "n8192_49"])
 def pair(request, emu_lib, ref):
     n, moduli, t = PARAMS[request.param]
     return pc.Pair(EmuBackend(emu_lib), n, moduli, t)

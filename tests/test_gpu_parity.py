@@ -15,7 +15,7 @@ def be():
     return CudaBackend()
 
 
-@pytest.fixture(scope="module", params=["n4096", "n8192", "n8192_54", "n16384", "n32768"])
+@pytest.fixture(scope="module", params=["n4096", "n8192", "n8192_54", "n8192_49", "n16384", "n32768"])
 def pair(request, be, ref):
     n, moduli, t = PARAMS[request.param]
     return pc.Pair(be, n, moduli, t)

@@ -4,6 +4,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from sunscreen_b200.lib import B200Context
 from bench import MODULI, PLAIN, N_POLY
+if os.environ.get("B200_PROBE"):  # e.g. n8192_54, n16384, n32768 (tests/params.py)
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+    from params import PARAMS
+    N_POLY, MODULI, PLAIN = PARAMS[os.environ["B200_PROBE"]]
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 ctx = B200Context(N_POLY, MODULI, PLAIN)
 k = ctx.k(); n = N_POLY
