@@ -206,6 +206,11 @@ __global__ void tensor_kernel(const LevelDev L, const u64 *ext, int sa, int sb, 
     const int Dn = square ? 3 : sa + sb - 1;
     const u64 *A = ext + ((item * Pn) * R + r) * n;
     u64 *Dp = D + ((item * Dn) * R + r) * n;
+    if (!square && (sa > 4 || sb > 4))
+    {
+        tensor_coeff_general(P, A, R * n, sa, A + (long long)sa * R * n, R * n, sb, Dp, R * n, c);
+        return;
+    }
     if (L.fp)
     {
         const double *pd = r < L.k ? &L.dq[2 * r] : &L.dbsk[2 * (r - L.k)];
@@ -1851,8 +1856,8 @@ int b200_multiply(b200_ctx *ctx, int level, const uint64_t *a, int sa, const uin
         return rc;
     if (!a || !b || !out)
         return fail(B200_E_NULL, "null ciphertext pointer");
-    if (sa < 1 || sb < 1 || sa > 4 || sb > 4)
-        return fail(B200_E_INVALID, "ciphertext sizes must be in [1,4] (destination size <= 7)");
+    if (sa < 1 || sb < 1 || sa + sb - 1 > 16)
+        return fail(B200_E_INVALID, "ciphertext sizes must be >= 1 with a destination size of at most 16");
     if (batch == 0)
         return 0;
     CU_TRY(cudaSetDevice(ctx->device));

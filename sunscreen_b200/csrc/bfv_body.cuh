@@ -151,6 +151,23 @@ B200_HD void tensor_coeff(const PrimeDev &P, const u64 *__restrict__ A, long lon
     }
 }
 
+// operands of more than 4 polynomials (the reference allows any sizes with sa + sb - 1 <= 16, S/evaluator.cpp:395-567):
+// plain loops over global memory — a rare shape, kept simple; works for every prime width
+B200_HD void tensor_coeff_general(const PrimeDev &P, const u64 *__restrict__ A, long long a_poly_stride, int sa,
+                                  const u64 *__restrict__ B, long long b_poly_stride, int sb, u64 *__restrict__ D,
+                                  long long d_poly_stride, long long c)
+{
+    for (int m = 0; m < sa + sb - 1; m++)
+    {
+        u64 lo = 0, hi = 0;
+        const int r0 = m - (sb - 1) > 0 ? m - (sb - 1) : 0;
+        const int r1 = m < sa - 1 ? m : sa - 1;
+        for (int r = r0; r <= r1; r++)
+            mac128(A[r * a_poly_stride + c], B[(m - r) * b_poly_stride + c], lo, hi);
+        D[m * d_poly_stride + c] = barrett128(lo, hi, P.p, P.r0, P.r1);
+    }
+}
+
 // square of a size-2 ciphertext: D0 = A0^2, D1 = 2 A0 A1, D2 = A1^2  (S/evaluator.cpp:933-948)
 B200_HD void square_coeff(const PrimeDev &P, const u64 *__restrict__ A, long long a_poly_stride, u64 *__restrict__ D,
                           long long d_poly_stride, long long c)

@@ -34,7 +34,7 @@ using namespace b200c;
 int data_level(Context_ *c, const Ciphertext_ &ct, const char *what)
 {
     int lv = c->level_of(ct.parms_id);
-    if (lv < 0 || (lv == 0 && c->first_level == 1) || ct.n != c->parms.n || (int)ct.k != c->level_k[lv] || ct.size < 2 || ct.size > 6)
+    if (lv < 0 || (lv == 0 && c->first_level == 1) || ct.n != c->parms.n || (int)ct.k != c->level_k[lv] || ct.size < 2 || ct.size > 16)
         throw InvalidArg(what);
     return lv;
 }
@@ -146,8 +146,8 @@ void op_multiply(Context_ *c, Ciphertext_ &a, Ciphertext_ &b, Ciphertext_ &dst, 
     }
     const u64 sb = square ? a.size : (&a == &b ? a.size : b.size);
     const u64 ds = square ? 3 : a.size + sb - 1;
-    if (a.size > 4 || sb > 4)
-        throw LogicErr("invalid parameters");
+    if (ds > 16)
+        throw InvalidArg("invalid size"); // Ciphertext::resize_internal, SEAL_CIPHERTEXT_SIZE_MAX (S/ciphertext.cpp:100-106)
     with_output(c, dst, { &a, &b }, a.parms_id, ds, k, [&](u64 *out) {
         if (square)
             dev_check(b200_square(c->dev, lv, pa, out, 1, nullptr));

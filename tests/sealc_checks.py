@@ -761,3 +761,156 @@ def seal_fhe_golden_fixture(S, golden_dir):
     assert _siphash13(len(zref).to_bytes(8, "little") + zref) == 9942548233613012008
     zour = OL.save("Ciphertext", results[1][3], COMPR_ZSTD)
     assert RL.save("Ciphertext", RL.load("Ciphertext", zour), 0) == results[0][2]
+
+
+def single_prime_context(S, n, moduli, t):
+    """Chains of ONE prime (BFVDefault for n = 1024 / 2048): no key level above the data level, no key switching
+    (S/context.cpp:478-497: using_keyswitching() is false).  Encryption, addition, ciphertext x ciphertext multiplication
+    (size 3, cannot be relinearized), plain operations and decryption of the size-3 result agree with the reference; asking
+    for relinearization keys fails the same way."""
+    assert len(moduli) == 1
+    R = refseal.RefContext(n, moduli, t)
+    O = S.context(n, moduli, t)
+    assert O.parameters_set
+    assert list(O.first_id) == list(R.first_parms_id) == list(O.key_id) == list(R.key_parms_id)
+    RL, OL = _libs(R, O)
+    for L in (RL, OL):
+        b = C.c_bool(True)
+        L.call("SEALContext_UsingKeyswitching", L.ctx, C.byref(b))
+        assert b.value is False
+    kg = R.keygen()
+    sk, pk = R.secret_key(kg), R.public_key(kg)
+    okg, orl = vp(), vp()
+    O.S.call("KeyGenerator_Create1", O.ctx, C.byref(okg))
+    rrl = vp()
+    r_rc = RL.rc("KeyGenerator_CreateRelinKeys", kg, C.c_bool(False), C.byref(rrl))
+    o_rc = OL.rc("KeyGenerator_CreateRelinKeys", okg, C.c_bool(False), C.byref(orl))
+    assert r_rc == o_rc != 0, (hex(r_rc), hex(o_rc))
+    enc, dec = R.encryptor(pk, sk), R.decryptor(sk)
+    rng = np.random.default_rng(5)
+    m1 = rng.integers(0, t, size=n, dtype=np.uint64)
+    m2 = rng.integers(0, min(t, 4), size=5, dtype=np.uint64)
+    m2[-1] = 1
+    c1, c2 = R.encrypt(enc, R.new_pt(m1)), R.encrypt(enc, R.new_pt(m2))
+    o1, o2 = OL.load("Ciphertext", RL.save("Ciphertext", c1, 0)), OL.load("Ciphertext", RL.save("Ciphertext", c2, 0))
+
+    def same(rh, oh, what):
+        eq(np.frombuffer(OL.save("Ciphertext", oh, 0), dtype=np.uint8), np.frombuffer(RL.save("Ciphertext", rh, 0), dtype=np.uint8), what)
+
+    same(R.add(c1, c2), O.add(o1, o2), "add (single prime)")
+    same(R.sub(c1, c2), O.sub(o1, o2), "sub (single prime)")
+    rm, om = R.multiply(c1, c2), O.multiply(o1, o2)
+    same(rm, om, "multiply (single prime, size 3)")
+    same(R.square(c2), O.square(o2), "square (single prime)")
+    pt = rng.integers(1, t, size=7, dtype=np.uint64)
+    same(R.multiply_plain(c1, R.new_pt(pt)), O.multiply_plain(o1, O.new_pt(pt)), "multiply_plain (single prime)")
+    same(R.add_plain(c1, R.new_pt(pt)), O.add_plain(o1, O.new_pt(pt)), "add_plain (single prime)")
+    # decrypt the size-3 product with OUR decryptor and the reference's
+    osk = OL.load("SecretKey", RL.save("SecretKey", sk, 0))
+    odec = vp()
+    O.S.call("Decryptor_Create", O.ctx, osk, C.byref(odec))
+    out = OL.new("Plaintext")
+    O.S.call("Decryptor_Decrypt", odec, om, out)
+    eq(O.pt_coeffs(out), R.pt_coeffs(R.decrypt(dec, rm)), "decrypt size-3 (single prime)")
+    nb_r, nb_o = C.c_int(), C.c_int()
+    RL.call("Decryptor_InvariantNoiseBudget", dec, rm, C.byref(nb_r))
+    OL.call("Decryptor_InvariantNoiseBudget", odec, om, C.byref(nb_o))
+    assert nb_r.value == nb_o.value
+    # our own keys / encryptions on such a context decrypt on the reference
+    opk, oenc, osk2 = vp(), vp(), vp()
+    O.S.call("KeyGenerator_SecretKey", okg, C.byref(osk2))
+    O.S.call("KeyGenerator_CreatePublicKey", okg, C.c_bool(False), C.byref(opk))
+    O.S.call("Encryptor_Create", O.ctx, opk, osk2, C.byref(oenc))
+    oc = OL.new("Ciphertext")
+    O.S.call("Encryptor_Encrypt", oenc, O.new_pt(m2), oc, None)
+    rsk = RL.load("SecretKey", OL.save("SecretKey", osk2, 0))
+    rdec2 = R.decryptor(rsk)
+    eq(R.pt_coeffs(R.decrypt(rdec2, RL.load("Ciphertext", OL.save("Ciphertext", oc, 0)))), m2, "reference decrypts our encryption (single prime)")
+
+
+def deep_chain_parity(S, n, moduli, t):
+    """The rest of the modulus-switching chain and the larger ciphertext sizes: at EVERY data level (down to one
+    residue) multiply / square / relinearize / rotate / plain operations / decrypt agree word for word with the reference;
+    products of size-3 operands (sizes 4 and 5), their sums, and the HRESULTs of what cannot be done with them
+    (relinearize without s^3 keys, rotate a size-3 ciphertext, switch below the last level)."""
+    R = refseal.RefContext(n, moduli, t)
+    O = S.context(n, moduli, t)
+    RL, OL = _libs(R, O)
+    kg = R.keygen()
+    sk, pk, rlk = R.secret_key(kg), R.public_key(kg), R.relin_keys(kg)
+    batching = t % (2 * n) == 1
+    glk = R.galois_keys_steps(kg, [1, 4, -1]) if batching else None
+    enc, dec = R.encryptor(pk, sk), R.decryptor(sk)
+    orlk = OL.load("KSwitchKeys", RL.save("KSwitchKeys", rlk, 0))
+    oglk = OL.load("KSwitchKeys", RL.save("KSwitchKeys", glk, 0)) if batching else None
+    osk = OL.load("SecretKey", RL.save("SecretKey", sk, 0))
+    odec = vp()
+    O.S.call("Decryptor_Create", O.ctx, osk, C.byref(odec))
+    rng = np.random.default_rng(31)
+    to_ours = lambda h: OL.load("Ciphertext", RL.save("Ciphertext", h, 0))
+
+    def same(rh, oh, what):
+        a, b = OL.save("Ciphertext", oh, 0), RL.save("Ciphertext", rh, 0)
+        assert a == b, f"{what}: serialised ciphertexts differ"
+
+    def rc_pair(name, r_args, o_args):
+        r, o = RL.rc(name, *r_args), OL.rc(name, *o_args)
+        assert r == o, f"{name}: reference 0x{r:08x}, ours 0x{o:08x}"
+        return r
+
+    ra = R.encrypt(enc, R.new_pt(rng.integers(0, t, size=n, dtype=np.uint64)))
+    rb = R.encrypt(enc, R.new_pt(rng.integers(0, t, size=n // 2, dtype=np.uint64)))
+    oa, ob = to_ours(ra), to_ours(rb)
+    pl = rng.integers(1, t, size=n, dtype=np.uint64)
+    level = 0
+    while True:
+        tag = f"level +{level}"
+        rm, om = R.multiply(ra, rb), O.multiply(oa, ob)
+        same(rm, om, f"multiply, {tag}")
+        same(R.square(ra), O.square(oa), f"square, {tag}")
+        rr, orr = R.relinearize(rm, rlk), O.relinearize(om, orlk)
+        same(rr, orr, f"relinearize, {tag}")
+        same(R.multiply_plain(ra, R.new_pt(pl)), O.multiply_plain(oa, O.new_pt(pl)), f"multiply_plain, {tag}")
+        same(R.add_plain(rb, R.new_pt(pl)), O.add_plain(ob, O.new_pt(pl)), f"add_plain, {tag}")
+        same(R.sub_plain(rb, R.new_pt(pl)), O.sub_plain(ob, O.new_pt(pl)), f"sub_plain, {tag}")
+        if batching:
+            same(R.rotate_rows(ra, 1, glk), O.rotate_rows(oa, 1, oglk), f"rotate_rows(1), {tag}")
+            same(R.rotate_rows(ra, 3, glk), O.rotate_rows(oa, 3, oglk), f"rotate_rows(3) via its NAF 4 - 1, {tag}")
+        out = OL.new("Plaintext")
+        O.S.call("Decryptor_Decrypt", odec, orr, out)
+        eq(O.pt_coeffs(out), R.pt_coeffs(R.decrypt(dec, rr)), f"decrypt, {tag}")
+        assert O.noise_budget(odec, orr) == R.noise_budget(dec, rr)
+        if level == 0:
+            # sizes 4 and 5
+            r4, o4 = R.multiply(rm, rb), O.multiply(om, ob)
+            same(r4, o4, "multiply (3,2) -> 4")
+            r5, o5 = R.multiply(rm, rm), O.multiply(om, om)
+            same(r5, o5, "multiply (3,3) -> 5")
+            same(R.square(rm), O.square(om), "square of a size-3 ciphertext (falls back to multiply)")
+            same(R.add(r5, r4), O.add(o5, o4), "add (5,4)")
+            same(R.sub(r4, r5), O.sub(o4, o5), "sub (4,5)")
+            same(R.negate(r5), O.negate(o5), "negate size 5")
+            out = OL.new("Plaintext")
+            O.S.call("Decryptor_Decrypt", odec, o4, out)
+            eq(O.pt_coeffs(out), R.pt_coeffs(R.decrypt(dec, r4)), "decrypt size 4")
+            assert rc_pair("Evaluator_Relinearize", (R.ev, r4, rlk, RL.new("Ciphertext"), None), (O.ev, o4, orlk, OL.new("Ciphertext"), None)) != 0
+            if batching:
+                assert rc_pair("Evaluator_RotateRows", (R.ev, rm, C.c_int(1), glk, RL.new("Ciphertext"), None),
+                               (O.ev, om, C.c_int(1), oglk, OL.new("Ciphertext"), None)) != 0
+            # the reference multiplies anything up to a destination of SEAL_CIPHERTEXT_SIZE_MAX = 16 polynomials (the noise
+            # budget is long gone; the words are still a deterministic function of the inputs)
+            r9, o9 = R.multiply(r5, r5), O.multiply(o5, o5)
+            same(r9, o9, "multiply (5,5) -> 9")
+            assert rc_pair("Evaluator_Multiply", (R.ev, r9, r9, RL.new("Ciphertext"), None), (O.ev, o9, o9, OL.new("Ciphertext"), None)) != 0
+        # next level (operands of different levels must be rejected alike)
+        rn, on = RL.new("Ciphertext"), OL.new("Ciphertext")
+        rc = rc_pair("Evaluator_ModSwitchToNext1", (R.ev, ra, rn, None), (O.ev, oa, on, None))
+        if rc != 0:
+            break
+        same(rn, on, f"mod_switch_to_next, {tag}")
+        assert rc_pair("Evaluator_Add", (R.ev, ra, rn, RL.new("Ciphertext")), (O.ev, oa, on, OL.new("Ciphertext"))) != 0
+        rbn, obn = RL.new("Ciphertext"), OL.new("Ciphertext")
+        rc_pair("Evaluator_ModSwitchToNext1", (R.ev, rb, rbn, None), (O.ev, ob, obn, None))
+        ra, oa, rb, ob = rn, on, rbn, obn
+        level += 1
+    assert level == len(moduli) - 2, "the chain should end at a single residue"

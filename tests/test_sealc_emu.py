@@ -65,3 +65,13 @@ def test_leftover_entry_points(S, ref):
 def test_seal_fhe_golden_fixture(S, ref):
     import os
     sc.seal_fhe_golden_fixture(S, os.path.join(os.path.dirname(__file__), "golden", "seal_fhe_data"))
+
+
+@pytest.mark.parametrize("n,moduli,t", [(1024, [0x7e00001], 1 << 8), (2048, [0x3fffffff000001], 65537)])
+def test_single_prime_chain(S, ref, n, moduli, t):
+    sc.single_prime_context(S, n, moduli, t)
+
+
+@pytest.mark.parametrize("name", ["n4096", "n8192"])
+def test_whole_chain_and_large_sizes(S, ref, name):
+    sc.deep_chain_parity(S, *PARAMS[name])
