@@ -297,7 +297,11 @@ void op_rotate(Context_ *c, Ciphertext_ &a, int steps, KSwitchKeys_ &keys, Ciphe
     dst.assign(cur);
 }
 
-std::vector<u64> padded_plain(Context_ *c, const Plaintext_ &p)
+// Plaintext operand padded to n coefficients.  `check_values` mirrors WHICH reference entry points look at the
+// coefficients: Encryptor::encrypt and BatchEncoder::decode call is_valid_for (metadata + every coefficient < t,
+// S/valcheck.cpp:246-294), the Evaluator's plain operations only is_metadata_valid_for + is_buffer_valid
+// (S/evaluator.cpp:1645-1660,1858-1870) and then compute with whatever 64-bit words they are given.
+std::vector<u64> padded_plain(Context_ *c, const Plaintext_ &p, bool check_values = true)
 {
     if (p.parms_id != kZeroId)
         throw InvalidArg("plain is not valid for encryption parameters");
@@ -306,7 +310,7 @@ std::vector<u64> padded_plain(Context_ *c, const Plaintext_ &p)
     std::vector<u64> v(c->parms.n, 0);
     for (size_t i = 0; i < p.coeffs.size(); i++)
     {
-        if (p.coeffs[i] >= c->parms.plain)
+        if (check_values && p.coeffs[i] >= c->parms.plain)
             throw InvalidArg("plain is not valid for encryption parameters");
         v[i] = p.coeffs[i];
     }
@@ -319,7 +323,7 @@ void op_plain(Context_ *c, Ciphertext_ &a, const Plaintext_ &p, Ciphertext_ &dst
     int lv = data_level(c, a, "encrypted is not valid for encryption parameters");
     if (a.is_ntt_form)
         throw InvalidArg("BFV encrypted cannot be in NTT form");
-    std::vector<u64> pv = padded_plain(c, p);
+    std::vector<u64> pv = padded_plain(c, p, false);
     if (which == 2)
     {
         bool zero = true;
@@ -2139,6 +2143,8 @@ long Encryptor_Create(void *context, void *public_key, void *secret_key, void **
     NULLRET(context);
     NULLRET(out);
     auto *c = (Context_ *)context;
+    if (!public_key && !secret_key)
+        return E_POINTER_; // S/c/encryptor.cpp:46-49
     if (!c->parameters_set)
         return E_INVALIDARG_;
     auto *e = new Encryptor_();
@@ -2451,12 +2457,9 @@ static void batch_encode(BatchEncoder_ *b, const std::vector<u64> &vals, Plainte
     if (vals.size() > n)
         throw InvalidArg("values_matrix size is too large");
     std::vector<u64> slots(n, 0);
-    for (size_t i = 0; i < vals.size(); i++)
-    {
-        if (vals[i] >= c->parms.plain)
-            throw InvalidArg("input value is larger than plain_modulus");
-        slots[b->index_map[i]] = vals[i];
-    }
+    for (size_t i = 0; i < vals.size(); i++) // the reference range-checks the values only in SEAL_DEBUG builds
+        slots[b->index_map[i]] = vals[i] % c->parms.plain; // (S/batchencoder.cpp:118-128); its transform works mod t
+
     std::lock_guard<std::mutex> lk(c->mu);
     DevBuf d(c, slots);
     dev_check(b200_plain_ntt(c->dev, d.p, 1, 1, nullptr));
@@ -2481,13 +2484,10 @@ long BatchEncoder_Encode2(void *p, uint64_t count, int64_t *values, void *destin
     auto *b = (BatchEncoder_ *)p;
     return guard([&] {
         const u64 t = b->ctx->parms.plain;
-        const u64 half = t >> 1; // plain_modulus_div_two (S/batchencoder.cpp:184-200)
         std::vector<u64> v(count);
         for (uint64_t i = 0; i < count; i++)
         {
-            const int64_t x = values[i];
-            if ((x < 0 ? (u64)(-x) : (u64)x) > half)
-                throw InvalidArg("input value is larger than plain_modulus");
+            const int64_t x = values[i]; // range check only in SEAL_DEBUG builds (S/batchencoder.cpp:163-175)
             v[i] = x < 0 ? t + (u64)x : (u64)x;
         }
         batch_encode(b, v, *(Plaintext_ *)destination);

@@ -914,3 +914,116 @@ def deep_chain_parity(S, n, moduli, t):
         ra, oa, rb, ob = rn, on, rbn, obn
         level += 1
     assert level == len(moduli) - 2, "the chain should end at a single residue"
+
+
+def misuse_hresults(S, n, moduli, t):
+    """A sweep of calls the Rust wrappers can make with bad arguments: both libraries must answer every one of them with
+    the same HRESULT (and leave the same values where there are any)."""
+    R = refseal.RefContext(n, moduli, t)
+    O = S.context(n, moduli, t)
+    RL, OL = _libs(R, O)
+    kg = R.keygen()
+    sk, pk, rlk = R.secret_key(kg), R.public_key(kg), R.relin_keys(kg)
+    enc = R.encryptor(pk, sk)
+    msg = np.arange(1, 9, dtype=np.uint64)
+    rct = R.encrypt(enc, R.new_pt(msg))
+    blob = {"ct": RL.save("Ciphertext", rct, 0), "pk": RL.save("PublicKey", pk, 0), "sk": RL.save("SecretKey", sk, 0),
+            "rlk": RL.save("KSwitchKeys", rlk, 0)}
+    mismatches = []
+
+    def both(label, fn):
+        """fn(L, objs) -> (hresult or tuple); compared across the two libraries"""
+        res = []
+        for L, ev in ((RL, R.ev), (OL, O.ev)):
+            objs = {"ct": L.load("Ciphertext", blob["ct"]), "pk": L.load("PublicKey", blob["pk"]), "sk": L.load("SecretKey", blob["sk"]),
+                    "rlk": L.load("KSwitchKeys", blob["rlk"]), "ev": ev, "dst": L.new("Ciphertext"), "pt": L.new("Plaintext")}
+            try:
+                res.append(fn(L, objs))
+            except Exception as e:  # a helper raised: record its text so that both sides must raise alike
+                res.append(("raised", type(e).__name__, str(e)[-40:]))
+        if res[0] != res[1]:
+            mismatches.append(f"{label}: reference {res[0]}, ours {res[1]}")
+
+    def new_pt(L, coeffs):
+        h = L.new("Plaintext")
+        L.call("Plaintext_Resize", h, u64(len(coeffs)))
+        for i, v in enumerate(coeffs):
+            L.call("Plaintext_SetCoeffAt", h, u64(i), u64(int(v)))
+        return h
+
+    # plaintext operands that are not valid for the parameters
+    both("AddPlain, coefficient >= t", lambda L, o: L.rc("Evaluator_AddPlain", o["ev"], o["ct"], new_pt(L, [t]), o["dst"]))
+    both("MultiplyPlain, coefficient >= t", lambda L, o: L.rc("Evaluator_MultiplyPlain", o["ev"], o["ct"], new_pt(L, [1, t + 5]), o["dst"], None))
+    both("MultiplyPlain by zero", lambda L, o: L.rc("Evaluator_MultiplyPlain", o["ev"], o["ct"], new_pt(L, [0, 0]), o["dst"], None))
+    both("MultiplyPlain by empty plaintext", lambda L, o: L.rc("Evaluator_MultiplyPlain", o["ev"], o["ct"], o["pt"], o["dst"], None))
+    both("AddPlain with empty plaintext", lambda L, o: (L.rc("Evaluator_AddPlain", o["ev"], o["ct"], o["pt"], o["dst"]), L.save("Ciphertext", o["dst"], 0)))
+    both("SubPlain, too many coefficients", lambda L, o: L.rc("Evaluator_SubPlain", o["ev"], o["ct"], new_pt(L, [1] * (n + 1)), o["dst"]))
+    # plaintext accessors
+    both("Plaintext_CoeffAt out of range", lambda L, o: L.rc("Plaintext_CoeffAt", new_pt(L, [1, 2]), u64(5), C.byref(u64())))
+    both("Plaintext_SetCoeffAt out of range", lambda L, o: L.rc("Plaintext_SetCoeffAt", new_pt(L, [1, 2]), u64(2), u64(1)))
+    both("Plaintext_Resize beyond n then encrypt", lambda L, o: L.rc("Evaluator_AddPlain", o["ev"], o["ct"], new_pt(L, [0] * (2 * n)), o["dst"]))
+    # ciphertext accessors
+    both("Ciphertext_GetDataAt1 out of range", lambda L, o: L.rc("Ciphertext_GetDataAt1", o["ct"], u64(10**9), C.byref(u64())))
+    both("Ciphertext_GetDataAt2 poly out of range", lambda L, o: L.rc("Ciphertext_GetDataAt2", o["ct"], u64(2), u64(0), C.byref(u64())))
+    both("Ciphertext_GetDataAt2 coeff out of range", lambda L, o: L.rc("Ciphertext_GetDataAt2", o["ct"], u64(1), u64(10**9), C.byref(u64())))
+    both("Ciphertext accessors on an empty ciphertext", lambda L, o: tuple(
+        (L.rc(name, o["dst"], C.byref(v)), v.value) for name, v in (("Ciphertext_Size", u64(7)), ("Ciphertext_CoeffModulusSize", u64(7)), ("Ciphertext_PolyModulusDegree", u64(7)))))
+    # evaluator on empty / mismatched operands
+    both("Negate of an empty ciphertext", lambda L, o: L.rc("Evaluator_Negate", o["ev"], o["dst"], L.new("Ciphertext")))
+    both("Square of an empty ciphertext", lambda L, o: L.rc("Evaluator_Square", o["ev"], o["dst"], L.new("Ciphertext"), None))
+    both("Relinearize of a size-2 ciphertext", lambda L, o: (L.rc("Evaluator_Relinearize", o["ev"], o["ct"], o["rlk"], o["dst"], None), L.save("Ciphertext", o["dst"], 0)))
+    both("Relinearize with an empty key object", lambda L, o: L.rc("Evaluator_Relinearize", o["ev"], o["ct"], L.new("KSwitchKeys"), o["dst"], None))
+    both("RotateRows with relinearization keys", lambda L, o: L.rc("Evaluator_RotateRows", o["ev"], o["ct"], C.c_int(1), o["rlk"], o["dst"], None))
+    both("RotateRows by 0", lambda L, o: (L.rc("Evaluator_RotateRows", o["ev"], o["ct"], C.c_int(0), o["rlk"], o["dst"], None),))
+    both("RotateRows by n", lambda L, o: L.rc("Evaluator_RotateRows", o["ev"], o["ct"], C.c_int(n), o["rlk"], o["dst"], None))
+    both("Exponentiate to the power 0", lambda L, o: L.rc("Evaluator_Exponentiate", o["ev"], o["ct"], u64(0), o["rlk"], o["dst"], None))
+    both("Exponentiate to the power 1", lambda L, o: (L.rc("Evaluator_Exponentiate", o["ev"], o["ct"], u64(1), o["rlk"], o["dst"], None), L.save("Ciphertext", o["dst"], 0)))
+    both("MultiplyMany of nothing", lambda L, o: L.rc("Evaluator_MultiplyMany", o["ev"], u64(0), (vp * 1)(), o["rlk"], o["dst"], None))
+    both("AddMany of nothing", lambda L, o: L.rc("Evaluator_AddMany", o["ev"], u64(0), (vp * 1)(), o["dst"]))
+    both("AddMany of one", lambda L, o: (L.rc("Evaluator_AddMany", o["ev"], u64(1), (vp * 1)(o["ct"]), o["dst"]), L.save("Ciphertext", o["dst"], 0)))
+    # keys / encryptor / decryptor
+    def enc_without(L, o, which):
+        e = vp()
+        rc = L.rc("Encryptor_Create", L.ctx, o["pk"] if which == "sk" else None, o["sk"] if which == "pk" else None, C.byref(e))
+        if rc:
+            return ("create", rc)
+        name = "Encryptor_Encrypt" if which == "pk" else "Encryptor_EncryptSymmetric"
+        args = (e, new_pt(L, [1]), o["dst"], None) if which == "pk" else (e, new_pt(L, [1]), C.c_bool(False), o["dst"], None)
+        return ("use", L.rc(name, *args))
+    both("Encrypt without a public key", lambda L, o: enc_without(L, o, "pk"))
+    both("EncryptSymmetric without a secret key", lambda L, o: enc_without(L, o, "sk"))
+    both("Encryptor_Create without any key", lambda L, o: L.rc("Encryptor_Create", L.ctx, None, None, C.byref(vp())))
+    def dec_of(L, o, h):
+        d = vp()
+        L.call("Decryptor_Create", L.ctx, o["sk"], C.byref(d))
+        return (L.rc("Decryptor_Decrypt", d, h, o["pt"]), L.rc("Decryptor_InvariantNoiseBudget", d, h, C.byref(C.c_int())))
+    both("Decrypt an empty ciphertext", lambda L, o: dec_of(L, o, o["dst"]))
+    def ntt_flagged(L, o):
+        L.call("Ciphertext_SetIsNTTForm", o["ct"], C.c_bool(True))
+        return dec_of(L, o, o["ct"])
+    both("Decrypt a ciphertext flagged NTT", ntt_flagged)
+    both("Decryptor_Create with a public key handle's parms (wrong object contents)",
+         lambda L, o: L.rc("Decryptor_Create", L.ctx, L.load("SecretKey", blob["sk"], unsafe=True), C.byref(vp())))
+    both("KeyGenerator_Create2 from a loaded secret key, then relin keys usable",
+         lambda L, o: (lambda kg2: (L.rc("KeyGenerator_Create2", L.ctx, o["sk"], C.byref(kg2)), L.rc("KeyGenerator_CreateRelinKeys", kg2, C.c_bool(False), C.byref(vp()))))(vp()))
+    # (KSwitchKeys_GetKeyList with an index past the end throws through the reference's C layer and aborts the process:
+    #  not comparable)
+    if t % (2 * n) == 1:
+        def be_case(L, o, vals):
+            be = vp()
+            L.call("BatchEncoder_Create", L.ctx, C.byref(be))
+            arr = (u64 * len(vals))(*vals)
+            rc = L.rc("BatchEncoder_Encode1", be, u64(len(vals)), arr, o["pt"])
+            return (rc, L.save("Plaintext", o["pt"], 0) if rc == 0 else None)
+        def be_signed(L, o, vals):
+            be = vp()
+            L.call("BatchEncoder_Create", L.ctx, C.byref(be))
+            arr = (C.c_int64 * len(vals))(*vals)
+            rc = L.rc("BatchEncoder_Encode2", be, u64(len(vals)), arr, o["pt"])
+            return (rc, L.save("Plaintext", o["pt"], 0) if rc == 0 else None)
+        both("BatchEncoder value == t (the reference checks ranges only in debug builds)", lambda L, o: be_case(L, o, [1, t]))
+        both("BatchEncoder signed values beyond +-t/2", lambda L, o: be_signed(L, o, [3, -(t // 2) - 5, t // 2 + 7]))
+        both("BatchEncoder too many values", lambda L, o: be_case(L, o, [1] * (n + 1)))
+    else:
+        both("BatchEncoder_Create without batching", lambda L, o: L.rc("BatchEncoder_Create", L.ctx, C.byref(vp())))
+    assert not mismatches, "HRESULT / value mismatches:\\n  " + "\\n  ".join(mismatches)

@@ -111,3 +111,8 @@ def test_single_prime_chain(S, ref, n, moduli, t):
 @pytest.mark.parametrize("name", ["n4096", "n8192", "n8192_49", "n16384"])
 def test_whole_chain_and_large_sizes(S, ref, name):
     sc.deep_chain_parity(S, *PARAMS[name])
+
+
+@pytest.mark.parametrize("name", ["n4096", "n8192"])
+def test_misuse_hresults(S, ref, name):
+    sc.misuse_hresults(S, *PARAMS[name])
