@@ -539,11 +539,8 @@ long EncParams_SetCoeffModulus(void *p, uint64_t length, void **coeffs)
     for (uint64_t i = 0; i < length; i++)
     {
         NULLRET(coeffs[i]);
-        u64 q = ((Modulus_ *)coeffs[i])->value;
-        int bits = q ? 64 - __builtin_clzll(q) : 0;
-        if (bits > 60 || bits < 2)
-            return E_INVALIDARG_; // "coeff_modulus is invalid" (S/encryptionparams.h:209-225)
-        v.push_back(q);
+        // only the COUNT is checked here (S/encryptionparams.h:188-207); widths are judged by SEALContext_Create
+        v.push_back(((Modulus_ *)coeffs[i])->value);
     }
     e->coeff = v;
     return S_OK_;
@@ -586,7 +583,8 @@ long EncParams_SetPlainModulus2(void *p, uint64_t v)
 {
     NULLRET(p);
     if (v == 1 || (v >> 61))
-        return E_INVALIDARG_;
+        return COR_E_INVALIDOPERATION_; // Modulus::set_value throws; the C layer catches it as logic_error
+                                        // (S/c/encryptionparameters.cpp:190-204)
     ((EncParams_ *)p)->plain = v;
     return S_OK_;
 }
@@ -620,6 +618,9 @@ long SEALContext_Create(void *parms, bool expand_mod_chain, int sec_level, void 
             ok = false;
         for (size_t i = 0; i < e->coeff.size() && ok; i++)
         {
+            const int bits = e->coeff[i] ? 64 - __builtin_clzll(e->coeff[i]) : 0;
+            if (bits < 2 || bits > 60) // SEAL_USER_MOD_BIT_COUNT_MIN / _MAX (S/context.cpp:166-177)
+                ok = false;
             if ((e->coeff[i] - 1) % (2 * e->n))
                 ok = false;
             if (e->plain >= e->coeff[i] && e->coeff.size() == 1)
@@ -656,11 +657,27 @@ long SEALContext_Create(void *parms, bool expand_mod_chain, int sec_level, void 
                 c->ids.push_back(id);
                 c->level_k.push_back(li.k);
             }
-            if (!expand_mod_chain && c->levels > c->first_level + 1)
-            { // only the key level and the first data level exist (S/context.cpp:478-497)
-                c->levels = c->first_level + 1;
-                c->ids.resize(c->levels);
-                c->level_k.resize(c->levels);
+            // the chain ends where the next parameter set would be invalid: the plain modulus must stay below the
+            // coefficient modulus (S/context.cpp:207-215 via create_next_context_data, :478-497)
+            {
+                int keep = c->first_level + 1;
+                for (int l = c->first_level + 1; l < c->levels; l++)
+                {
+                    b200::BigUInt Q(1);
+                    for (int r = 0; r < c->level_k[l]; r++)
+                        Q.mul(e->coeff[r]);
+                    if (Q.w.size() == 1 && Q.w[0] <= e->plain)
+                        break;
+                    keep = l + 1;
+                }
+                if (!expand_mod_chain)
+                    keep = c->first_level + 1; // only the key level and the first data level exist
+                if (keep < c->levels)
+                {
+                    c->levels = keep;
+                    c->ids.resize(keep);
+                    c->level_k.resize(keep);
+                }
             }
         }
     }

@@ -1027,3 +1027,66 @@ def misuse_hresults(S, n, moduli, t):
     else:
         both("BatchEncoder_Create without batching", lambda L, o: L.rc("BatchEncoder_Create", L.ctx, C.byref(vp())))
     assert not mismatches, "HRESULT / value mismatches:\\n  " + "\\n  ".join(mismatches)
+
+
+def context_validation_sweep(S):
+    """SEALContext_Create over valid and invalid parameter sets (S/context.cpp:135-420): both libraries agree on
+    parameters_set, on key switching / batching support and on the three parms_ids."""
+    Rl = refseal.RefLib.get()
+    p27 = [0x7e00001, 0x7d20001, 0x7c80001, 0x7b40001]          # 27-bit primes = 1 mod 8192? (checked by the reference)
+    d4096, d8192 = [0xffffee001, 0xffffc4001, 0x1ffffe0001], [0x7fffffd8001, 0x7fffffc8001, 0xfffffffc001, 0xffffff6c001, 0xfffffebc001]
+    cases = [
+        ("default 4096 / TC128", 4096, d4096, 65537, 128, True), ("default 4096 / TC192 (too many bits)", 4096, d4096, 65537, 192, True),
+        ("default 4096 / no security", 4096, d4096, 65537, 0, True), ("default 8192, no chain expansion", 8192, d8192, 1032193, 128, False),
+        ("default 8192 / TC256 (too many bits)", 8192, d8192, 1032193, 256, True),
+        ("8192 chain used at n = 4096 (too many bits)", 4096, d8192, 65537, 128, True), ("same without security", 4096, d8192, 65537, 0, True),
+        ("27-bit primes", 4096, p27, 65537, 128, True), ("repeated prime", 4096, [d4096[0], d4096[0], d4096[2]], 65537, 128, True),
+        ("composite modulus", 4096, [d4096[0], 0xffffee001 + 2 * 8192, d4096[2]], 65537, 0, True),
+        ("modulus not 1 mod 2n", 4096, [d4096[0], 0xffffee003, d4096[2]], 65537, 0, True),
+        ("n not a power of two", 3000, d4096, 65537, 0, True), ("n = 512 without security", 512, [0x7e00001], 17, 0, True),
+        ("n = 1024 default", 1024, [0x7e00001], 1 << 8, 128, True), ("n = 2048 default", 2048, [0x3fffffff000001], 65537, 128, True),
+        ("t = 2 (smallest)", 4096, d4096, 2, 128, True), ("t = 1", 4096, d4096, 1, 128, True), ("t even, no batching", 4096, d4096, 1 << 18, 128, True),
+        ("t shares a factor with q", 4096, d4096, d4096[0], 128, True), ("t larger than every q_i", 4096, d4096, 0x1ffffe0001 + 2, 0, True),
+        ("t = 1 mod 2n but composite", 4096, d4096, 8193 * 3 if (8193 * 3) % 8192 == 1 else 8192 * 5 + 1, 128, True),
+        ("single small prime, t close to q", 1024, [0x7e00001], 0x7e00001 - 2, 0, True), ("61-bit prime", 8192, [0x1fffffffffe00001, 0xfffffffc001], 65537, 0, True),
+        ("62-bit modulus", 8192, [0x3fffffffffe00001, 0xfffffffc001], 65537, 0, True), ("no coefficient modulus", 4096, [], 65537, 128, True),
+    ]
+    mismatches = []
+    for label, n, moduli, t, sec, expand in cases:
+        res = []
+        for call, rc in ((Rl.call, Rl.call_rc), (S.call, S.rc)):
+            out = []
+            parms = vp()
+            call("EncParams_Create1", C.c_uint8(1), C.byref(parms))
+            out.append(rc("EncParams_SetPolyModulusDegree", parms, u64(n)))
+            arr = (vp * max(len(moduli), 1))()
+            ok = True
+            for i, m in enumerate(moduli):
+                h = vp()
+                r = rc("Modulus_Create1", u64(m), C.byref(h))
+                out.append(r)
+                ok = ok and r == 0
+                arr[i] = h
+            if ok:
+                out.append(rc("EncParams_SetCoeffModulus", parms, u64(len(moduli)), arr))
+                out.append(rc("EncParams_SetPlainModulus2", parms, u64(t)))
+                ctx = vp()
+                r = rc("SEALContext_Create", parms, C.c_bool(expand), C.c_int(sec), C.byref(ctx))
+                out.append(r)
+                if r == 0:
+                    flag = C.c_bool()
+                    call("SEALContext_ParametersSet", ctx, C.byref(flag))
+                    out.append(flag.value)
+                    if flag.value:
+                        call("SEALContext_UsingKeyswitching", ctx, C.byref(flag))
+                        out.append(flag.value)
+                        for name in ("KeyParmsId", "FirstParmsId", "LastParmsId"):
+                            a = (u64 * 4)()
+                            call("SEALContext_" + name, ctx, a)
+                            out.append(tuple(a))
+                        be = vp()
+                        out.append(rc("BatchEncoder_Create", ctx, C.byref(be)) == 0)
+            res.append(out)
+        if res[0] != res[1]:
+            mismatches.append(f"{label}: reference {res[0][-6:]}, ours {res[1][-6:]}")
+    assert not mismatches, "context validation differs:\\n  " + "\\n  ".join(mismatches)

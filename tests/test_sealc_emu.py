@@ -80,3 +80,7 @@ def test_whole_chain_and_large_sizes(S, ref, name):
 @pytest.mark.parametrize("name", ["n4096", "n8192"])
 def test_misuse_hresults(S, ref, name):
     sc.misuse_hresults(S, *PARAMS[name])
+
+
+def test_context_validation_sweep(S, ref):
+    sc.context_validation_sweep(S)
