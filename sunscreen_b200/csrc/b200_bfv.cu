@@ -87,8 +87,10 @@ static int fail(int code, const std::string &msg)
 // ---------------------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------------------
-template <bool FWD, int NT>
-__global__ void __launch_bounds__(NT) ntt_kernel(const NttJob job)
+// MB = CTAs per SM the register allocation is sized for (the 64 KiB + pad of shared memory allow 3 at n = 8192; without a
+// bound ptxas took 192 registers and a single 8-warp CTA ran per SM)
+template <bool FWD, int NT, int MB = (NT <= 256 ? 3 : 1)>
+__global__ void __launch_bounds__(NT, MB) ntt_kernel(const NttJob job)
 {
 #ifdef B200_EMU_HEADER
     u64 *ntt_sm = (u64 *)emu_shared;
@@ -98,6 +100,9 @@ __global__ void __launch_bounds__(NT) ntt_kernel(const NttJob job)
     const long long block = (long long)blockIdx.x;
     const long long item = block / job.slots;
     const int slot = (int)(block - item * job.slots);
+#ifdef B200_EMU_HEADER
+    // the emulation build has no statically scheduled FP64 kernel: FP64-capable primes take the generic FP64 body here, so
+    // that the CPU-side tests cover its arithmetic
     const int pidx = job.slot_prime[slot];
     if (job.fprimes[pidx].enabled)
     {
@@ -105,9 +110,14 @@ __global__ void __launch_bounds__(NT) ntt_kernel(const NttJob job)
         u64 *dst = job.dst + item * job.dst_item_stride + job.slot_dst[slot];
         ntt_fp_block_body<FWD>(job, job.fprimes[pidx], job.primes[pidx], src, dst, reinterpret_cast<double *>(ntt_sm),
                                (int)threadIdx.x, (int)blockDim.x);
+        return;
     }
-    else
-        ntt_block_body<FWD>(job, block, ntt_sm, (int)threadIdx.x, (int)blockDim.x);
+#endif
+    // integer Harvey / Shoup transform: valid for every prime up to 61 bits (jobs whose slots are all FP64-capable are
+    // launched on ntt_fp_kernel instead; keeping the FP64 body out of this kernel saves ~60 registers)
+    (void)item;
+    (void)slot;
+    ntt_block_body<FWD>(job, block, ntt_sm, (int)threadIdx.x, (int)blockDim.x);
 }
 
 // FP64-only statically scheduled kernel (all slots of the job use FP-capable primes)
@@ -1169,8 +1179,9 @@ static int launch_ntt(b200_ctx *ctx, const JobDesc &jd, const u64 *src, long lon
         return 0;
     }
 #endif
+    static const int mb = std::getenv("B200_NTT_INT_MB") ? atoi(std::getenv("B200_NTT_INT_MB")) : 3;
     void (*kfn)(const NttJob) = ctx->ntt_threads == 512   ? ntt_kernel<FWD, 512>
-                                : ctx->ntt_threads == 256 ? ntt_kernel<FWD, 256>
+                                : ctx->ntt_threads == 256 ? (mb == 2 ? ntt_kernel<FWD, 256, 2> : mb == 1 ? ntt_kernel<FWD, 256, 1> : ntt_kernel<FWD, 256>)
                                                           : ntt_kernel<FWD, 64>;
     B200_LAUNCH(kfn, (unsigned)blocks, ctx->ntt_threads, ctx->ntt_smem, s, job);
     ctx->launches++;
@@ -1551,6 +1562,16 @@ int b200_ctx_create(uint64_t n, const uint64_t *coeff_modulus, uint64_t count, u
     CU_TRY(cudaFuncSetAttribute(ntt_kernel<false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
     CU_TRY(cudaFuncSetAttribute(ntt_kernel<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
     CU_TRY(cudaFuncSetAttribute(ntt_kernel<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
+#ifndef B200_EMU_HEADER
+    CU_TRY(cudaFuncSetAttribute(ntt_kernel<true, 256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
+    CU_TRY(cudaFuncSetAttribute(ntt_kernel<false, 256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
+    CU_TRY(cudaFuncSetAttribute(ntt_kernel<true, 256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
+    CU_TRY(cudaFuncSetAttribute(ntt_kernel<false, 256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
+    CU_TRY(cudaFuncSetAttribute(ntt_kernel<true, 256>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CU_TRY(cudaFuncSetAttribute(ntt_kernel<false, 256>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CU_TRY(cudaFuncSetAttribute(ntt_kernel<true, 256, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CU_TRY(cudaFuncSetAttribute(ntt_kernel<false, 256, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+#endif
     CU_TRY(cudaFuncSetAttribute(ntt_kernel<true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
     CU_TRY(cudaFuncSetAttribute(ntt_kernel<false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
     // keep freed scratch cached in the pool instead of returning it to the OS

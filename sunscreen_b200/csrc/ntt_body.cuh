@@ -111,6 +111,73 @@ inline int ntt_schedule(int logn, int *passes)
     return np;
 }
 
+// twiddle pair {w, floor(w 2^64 / p)} number idx of a table
+B200_HD void ntt_load_tw(const u64 *__restrict__ tw, int idx, u64 &w, u64 &wq)
+{
+#if defined(__CUDA_ARCH__)
+    const ulonglong2 t2 = __ldg(reinterpret_cast<const ulonglong2 *>(tw) + idx);
+    w = t2.x;
+    wq = t2.y;
+#else
+    w = tw[2 * idx];
+    wq = tw[2 * idx + 1];
+#endif
+}
+
+// One butterfly stage with a COMPILE-TIME stage index: every x[] index is a constant after unrolling, so the group stays
+// in registers (with a run-time stage loop ptxas kept the inverse group's 16 words in local memory).
+template <int L, int l>
+B200_HD void ntt_fwd_stage(u64 (&x)[1 << L], const u64 *__restrict__ tw, int tw_base, u64 p, u64 two_p)
+{
+    constexpr int half = 1 << (L - 1 - l);
+#pragma unroll
+    for (int grp = 0; grp < (1 << l); grp++)
+    {
+        u64 w, wq;
+        ntt_load_tw(tw, tw_base + grp, w, wq);
+#pragma unroll
+        for (int jj = 0; jj < half; jj++)
+        {
+            const int j = grp * 2 * half + jj;
+            u64 X = x[j];
+            X = X >= two_p ? X - two_p : X;
+            const u64 T = shoup_mul_lazy(x[j + half], w, wq, p);
+            x[j] = X + T;
+            x[j + half] = X - T + two_p;
+        }
+    }
+}
+template <int L, int l>
+B200_HD void ntt_inv_stage(u64 (&x)[1 << L], const u64 *__restrict__ tw, int tw_base, const NttPrime &P, u64 two_p, bool fold)
+{
+    constexpr int R = 1 << L;
+    constexpr int half = 1 << l;
+    const u64 p = P.p;
+#pragma unroll
+    for (int grp = 0; grp < (R >> (l + 1)); grp++)
+    {
+        u64 w, wq;
+        if (fold)
+        {
+            w = P.inv_n_w;
+            wq = P.inv_n_w_q;
+        }
+        else
+            ntt_load_tw(tw, tw_base + grp, w, wq);
+#pragma unroll
+        for (int jj = 0; jj < half; jj++)
+        {
+            const int j = grp * 2 * half + jj;
+            const u64 X = x[j], Y = x[j + half];
+            u64 U = X + Y;
+            U = U >= two_p ? U - two_p : U;
+            const u64 V = shoup_mul_lazy(X - Y + two_p, w, wq, p);
+            x[j] = fold ? shoup_mul_lazy(U, P.inv_n, P.inv_n_q, p) : U;
+            x[j + half] = V;
+        }
+    }
+}
+
 // ---- forward: Cooley-Tukey group of 2^L elements, L stages -------------------------------------------
 template <int L>
 B200_HD void ntt_fwd_group(u64 *sm, int g, int logs /*log2 sub-stride*/, int M /*groups at first stage (times the
@@ -127,33 +194,13 @@ B200_HD void ntt_fwd_group(u64 *sm, int g, int logs /*log2 sub-stride*/, int M /
 #pragma unroll
     for (int j = 0; j < R; j++)
         x[j] = sm[ntt_pad(base + (j << logs))];
-#pragma unroll
-    for (int l = 0; l < L; l++)
-    {
-        const int half = 1 << (L - 1 - l);
-        const int tw_base = (M << l) + (i << l);
-#pragma unroll
-        for (int grp = 0; grp < (1 << l); grp++)
-        {
-            const int idx = tw_base + grp;
-#if defined(__CUDA_ARCH__)
-            const ulonglong2 t2 = __ldg(reinterpret_cast<const ulonglong2 *>(tw) + idx);
-            const u64 w = t2.x, wq = t2.y;
-#else
-            const u64 w = tw[2 * idx], wq = tw[2 * idx + 1];
-#endif
-#pragma unroll
-            for (int jj = 0; jj < half; jj++)
-            {
-                const int j = grp * 2 * half + jj;
-                u64 X = x[j];
-                X = X >= two_p ? X - two_p : X;
-                const u64 T = shoup_mul_lazy(x[j + half], w, wq, p);
-                x[j] = X + T;
-                x[j + half] = X - T + two_p;
-            }
-        }
-    }
+    ntt_fwd_stage<L, 0>(x, tw, M + i, p, two_p);
+    if constexpr (L > 1)
+        ntt_fwd_stage<L, 1>(x, tw, (M << 1) + (i << 1), p, two_p);
+    if constexpr (L > 2)
+        ntt_fwd_stage<L, 2>(x, tw, (M << 2) + (i << 2), p, two_p);
+    if constexpr (L > 3)
+        ntt_fwd_stage<L, 3>(x, tw, (M << 3) + (i << 3), p, two_p);
 #pragma unroll
     for (int j = 0; j < R; j++)
         sm[ntt_pad(base + (j << logs))] = x[j];
@@ -170,53 +217,20 @@ B200_HD void ntt_inv_group(u64 *sm, int g, int logs, int logn, const u64 *__rest
     const int i = g >> logs;
     const int o = g & (s - 1);
     const int base = (i << (logs + L)) + o;
-    const u64 p = P.p, two_p = p << 1;
+    const u64 two_p = P.p << 1;
     u64 x[R];
 #pragma unroll
     for (int j = 0; j < R; j++)
         x[j] = sm[ntt_pad(base + (j << logs))];
-#pragma unroll
-    for (int l = 0; l < L; l++)
-    {
-        const int half = 1 << l;
-        // global gap G = s*2^l, m = n/(2G) groups at this stage
-        const int m = 1 << (logn - 1 - logs - l);
-        const int tw_base = m * mult + (i << (L - l - 1));
-        const bool fold = last && (l == L - 1);
-#pragma unroll
-        for (int grp = 0; grp < (R >> (l + 1)); grp++)
-        {
-            const int idx = tw_base + grp;
-            u64 w, wq;
-            if (fold)
-            {
-                w = P.inv_n_w;
-                wq = P.inv_n_w_q;
-            }
-            else
-            {
-#if defined(__CUDA_ARCH__)
-                const ulonglong2 t2 = __ldg(reinterpret_cast<const ulonglong2 *>(tw) + idx);
-                w = t2.x;
-                wq = t2.y;
-#else
-                w = tw[2 * idx];
-                wq = tw[2 * idx + 1];
-#endif
-            }
-#pragma unroll
-            for (int jj = 0; jj < half; jj++)
-            {
-                const int j = grp * 2 * half + jj;
-                const u64 X = x[j], Y = x[j + half];
-                u64 U = X + Y;
-                U = U >= two_p ? U - two_p : U;
-                const u64 V = shoup_mul_lazy(X - Y + two_p, w, wq, p);
-                x[j] = fold ? shoup_mul_lazy(U, P.inv_n, P.inv_n_q, p) : U;
-                x[j + half] = V;
-            }
-        }
-    }
+    // stage l: global gap s*2^l, m = n/(2 gap) groups; twiddle index m*mult + (i << (L-l-1)) + grp
+    const int m0 = 1 << (logn - 1 - logs);
+    ntt_inv_stage<L, 0>(x, tw, m0 * mult + (i << (L - 1)), P, two_p, last && L == 1);
+    if constexpr (L > 1)
+        ntt_inv_stage<L, 1>(x, tw, (m0 >> 1) * mult + (i << (L - 2)), P, two_p, last && L == 2);
+    if constexpr (L > 2)
+        ntt_inv_stage<L, 2>(x, tw, (m0 >> 2) * mult + (i << (L - 3)), P, two_p, last && L == 3);
+    if constexpr (L > 3)
+        ntt_inv_stage<L, 3>(x, tw, (m0 >> 3) * mult + i, P, two_p, last && L == 4);
 #pragma unroll
     for (int j = 0; j < R; j++)
         sm[ntt_pad(base + (j << logs))] = x[j];
