@@ -1090,3 +1090,55 @@ def context_validation_sweep(S):
         if res[0] != res[1]:
             mismatches.append(f"{label}: reference {res[0][-6:]}, ours {res[1][-6:]}")
     assert not mismatches, "context validation differs:\\n  " + "\\n  ".join(mismatches)
+
+
+def concurrent_evaluator_calls(S, n, moduli, t, threads=8, rounds=6):
+    """sunscreen_runtime drives one Evaluator from rayon workers (run.rs:415-469): shared read-only inputs, fresh
+    destinations, any interleaving.  Eight Python threads (ctypes drops the GIL in the call) replay that against our library;
+    every result must equal the serial one."""
+    import threading
+    R = refseal.RefContext(n, moduli, t)
+    O = S.context(n, moduli, t)
+    RL, OL = _libs(R, O)
+    kg = R.keygen()
+    sk, pk, rlk = R.secret_key(kg), R.public_key(kg), R.relin_keys(kg)
+    enc = R.encryptor(pk, sk)
+    rng = np.random.default_rng(77)
+    cts = [OL.load("Ciphertext", RL.save("Ciphertext", R.encrypt(enc, R.new_pt(rng.integers(0, t, size=16, dtype=np.uint64))), 0)) for _ in range(4)]
+    orlk = OL.load("KSwitchKeys", RL.save("KSwitchKeys", rlk, 0))
+    pl = O.new_pt(rng.integers(1, t, size=9, dtype=np.uint64))
+
+    def work(i):
+        a, b = cts[i % 4], cts[(i + 1) % 4]
+        m = O.relinearize(O.multiply(a, b), orlk)
+        s = O.add(m, a)
+        p = O.multiply_plain(s, pl)
+        return OL.save("Ciphertext", O.sub(p, b), 0)
+
+    serial = [work(i) for i in range(threads)]
+    results = [[None] * rounds for _ in range(threads)]
+    errors = []
+
+    def runner(i):
+        try:
+            for r in range(rounds):
+                results[i][r] = work(i)
+        except Exception as e:  # pragma: no cover
+            errors.append((i, repr(e)))
+
+    ts = [threading.Thread(target=runner, args=(i,)) for i in range(threads)]
+    for th in ts:
+        th.start()
+    for th in ts:
+        th.join()
+    assert not errors, errors
+    for i in range(threads):
+        for r in range(rounds):
+            assert results[i][r] == serial[i], f"thread {i}, round {r}: result differs from the serial evaluation"
+    # and the serial results are the reference's
+    rcts = [RL.load("Ciphertext", OL.save("Ciphertext", h, 0)) for h in cts]
+    rpl = R.new_pt(O.pt_coeffs(pl))
+    for i in range(threads):
+        a, b = rcts[i % 4], rcts[(i + 1) % 4]
+        exp = R.sub(R.multiply_plain(R.add(R.relinearize(R.multiply(a, b), rlk), a), rpl), b)
+        assert RL.save("Ciphertext", exp, 0) == serial[i]

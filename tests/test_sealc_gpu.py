@@ -120,3 +120,7 @@ def test_misuse_hresults(S, ref, name):
 
 def test_context_validation_sweep(S, ref):
     sc.context_validation_sweep(S)
+
+
+def test_concurrent_evaluator_calls(S, ref):
+    sc.concurrent_evaluator_calls(S, *PARAMS["n8192"])
