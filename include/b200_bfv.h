@@ -78,6 +78,13 @@ int b200_galois_elt_from_step(const b200_ctx *ctx, int steps, uint32_t *elt);
 /* device memory helpers so that non-CUDA callers (Rust/C via FFI, Python via ctypes) can stage data */
 int b200_malloc(b200_ctx *ctx, size_t bytes, void **dptr);
 int b200_free(b200_ctx *ctx, void *dptr);
+/* free ordered after the work already enqueued on `stream`; b200_malloc/b200_free use the stream-ordered pool, and
+   b200_free requires that nothing still in flight uses the buffer */
+int b200_free_async(b200_ctx *ctx, void *dptr, void *stream);
+/* non-blocking streams for callers that overlap independent operations (the SEAL-named layer runs each calling thread's
+   operations on its own) */
+int b200_stream_create(b200_ctx *ctx, void **stream);
+int b200_stream_destroy(b200_ctx *ctx, void *stream);
 int b200_malloc_host(size_t bytes, void **hptr); /* pinned */
 int b200_free_host(void *hptr);
 int b200_memcpy_h2d(b200_ctx *ctx, void *dst, const void *src, size_t bytes, void *stream);

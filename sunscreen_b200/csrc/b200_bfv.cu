@@ -682,6 +682,8 @@ struct b200_ctx
     std::mutex mu;
     std::atomic<uint64_t> launches{ 0 };
     cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
+    cudaStream_t s_alloc = nullptr; // b200_malloc / b200_free order their pool operations on this stream
+    std::mutex alloc_mu;
     // side streams for intra-call concurrency: sub-batches of one call run on different streams so that the
     // FP64-bound NTT kernels of one overlap the HBM-bound element-wise kernels of another
     static const int NSIDE = 4;
@@ -1584,6 +1586,7 @@ int b200_ctx_create(uint64_t n, const uint64_t *coeff_modulus, uint64_t count, u
     int rc = build_device(ctx.get());
     if (rc)
         return rc;
+    CU_TRY(cudaStreamCreateWithFlags(&ctx->s_alloc, cudaStreamNonBlocking));
     CU_TRY(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
     CU_TRY(cudaStreamCreateWithFlags(&ctx->s_comp, cudaStreamNonBlocking));
     CU_TRY(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
@@ -1630,6 +1633,8 @@ void b200_ctx_destroy(b200_ctx *ctx)
             cudaEventDestroy(ctx->hp_comp[i]);
             cudaEventDestroy(ctx->hp_out[i]);
         }
+    if (ctx->s_alloc)
+        cudaStreamDestroy(ctx->s_alloc);
     if (ctx->s_h2d)
         cudaStreamDestroy(ctx->s_h2d);
     if (ctx->s_comp)
@@ -1695,19 +1700,56 @@ int b200_galois_elt_from_step(const b200_ctx *ctx, int steps, uint32_t *elt)
     return 0;
 }
 
+// Device memory comes from the stream-ordered pool (release threshold = infinity, set at context creation): an
+// allocation is a pool lookup, not a driver call, and a free does not synchronise the device — the per-handle FFI path
+// allocates a destination per operation, and several host threads do so at once (sunscreen_runtime's rayon workers).
 int b200_malloc(b200_ctx *ctx, size_t bytes, void **dptr)
 {
     if (!ctx || !dptr)
         return fail(B200_E_NULL, "null argument");
     CU_TRY(cudaSetDevice(ctx->device));
-    CU_TRY(cudaMalloc(dptr, bytes ? bytes : 8));
+    std::lock_guard<std::mutex> lk(ctx->alloc_mu);
+    CU_TRY(cudaMallocAsync(dptr, bytes ? bytes : 8, ctx->s_alloc));
+    CU_TRY(cudaStreamSynchronize(ctx->s_alloc)); // usable from every stream on return
     return 0;
 }
+// the caller guarantees that no work using the buffer is still in flight (every layer-2 operation completes before it returns)
 int b200_free(b200_ctx *ctx, void *dptr)
 {
     if (!ctx)
         return fail(B200_E_NULL, "null argument");
-    CU_TRY(cudaFree(dptr));
+    if (!dptr)
+        return 0;
+    std::lock_guard<std::mutex> lk(ctx->alloc_mu);
+    CU_TRY(cudaFreeAsync(dptr, ctx->s_alloc));
+    return 0;
+}
+// free ordered after the work already enqueued on `stream` (an operation replacing a buffer it has just read)
+int b200_free_async(b200_ctx *ctx, void *dptr, void *stream)
+{
+    if (!ctx)
+        return fail(B200_E_NULL, "null argument");
+    if (!dptr)
+        return 0;
+    CU_TRY(cudaFreeAsync(dptr, (cudaStream_t)stream));
+    return 0;
+}
+int b200_stream_create(b200_ctx *ctx, void **stream)
+{
+    if (!ctx || !stream)
+        return fail(B200_E_NULL, "null argument");
+    CU_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t s;
+    CU_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    *stream = (void *)s;
+    return 0;
+}
+int b200_stream_destroy(b200_ctx *ctx, void *stream)
+{
+    if (!ctx)
+        return fail(B200_E_NULL, "null argument");
+    if (stream)
+        CU_TRY(cudaStreamDestroy((cudaStream_t)stream));
     return 0;
 }
 int b200_malloc_host(size_t bytes, void **hptr)

@@ -41,20 +41,20 @@ int data_level(Context_ *c, const Ciphertext_ &ct, const char *what)
 
 void transparent_guard(Context_ *c, int level, Ciphertext_ &dst)
 {
+    OpScope *sc = tl_scope;
+    if (!sc || sc->c != c)
+        throw std::logic_error("internal: transparent_guard outside an operation scope");
     if (!c->check_transparent)
+    {
+        sc->wait();
         return;
+    }
     // SEAL_THROW_ON_TRANSPARENT_CIPHERTEXT (seal_fhe/build.rs:37-42): "result ciphertext is transparent"
-    void *flag = nullptr;
-    dev_check(b200_malloc(c->dev, 8, &flag));
-    uint32_t h = 0;
-    int rc = b200_is_transparent(c->dev, level, dst.dev, (int)dst.size, (uint32_t *)flag, 1, nullptr);
-    if (!rc)
-        rc = b200_memcpy_d2h(c->dev, &h, flag, 4, nullptr);
-    if (!rc)
-        rc = b200_stream_synchronize(c->dev, nullptr);
-    b200_free(c->dev, flag);
-    dev_check(rc);
-    if (h)
+    *sc->lane->hflag = 0;
+    dev_check(b200_is_transparent(c->dev, level, dst.dev, (int)dst.size, (uint32_t *)sc->lane->dflag, 1, sc->stream()));
+    dev_check(b200_memcpy_d2h(c->dev, sc->lane->hflag, sc->lane->dflag, 4, sc->stream()));
+    sc->wait(); // context mutex released while the GPU finishes this operation
+    if (*sc->lane->hflag)
         throw LogicErr("result ciphertext is transparent");
 }
 
@@ -82,6 +82,7 @@ void with_output(Context_ *c, Ciphertext_ &dst, std::initializer_list<const Ciph
     dst.is_ntt_form = false;
     dst.scale = 1.0;
     dst.ctx = c;
+    dst.keep = tmp.keep;
     dst.dev = tmp.dev;
     dst.dev_words = tmp.dev_words;
     dst.dev_valid = true;
@@ -102,7 +103,7 @@ void check_same(const Ciphertext_ &a, const Ciphertext_ &b)
 
 void op_addsub(Context_ *c, Ciphertext_ &a, Ciphertext_ &b, Ciphertext_ &dst, int mode)
 {
-    std::lock_guard<std::mutex> lk(c->mu);
+    OpScope scope(c);
     int lv = data_level(c, a, "encrypted1 is not valid for encryption parameters");
     data_level(c, b, "encrypted2 is not valid for encryption parameters");
     check_same(a, b);
@@ -110,15 +111,15 @@ void op_addsub(Context_ *c, Ciphertext_ &a, Ciphertext_ &b, Ciphertext_ &dst, in
     const u64 mx = std::max(a.size, b.size), mn = std::min(a.size, b.size);
     const u64 *pa = a.dev_ptr(c), *pb = b.dev_ptr(c);
     with_output(c, dst, { &a, &b }, a.parms_id, mx, k, [&](u64 *out) {
-        dev_check((mode == 0 ? b200_add : b200_sub)(c->dev, lv, pa, pb, out, (int)mn, 1, nullptr));
+        dev_check((mode == 0 ? b200_add : b200_sub)(c->dev, lv, pa, pb, out, (int)mn, 1, cur_stream()));
         if (a.size > mn) // tail polys copied from the larger operand
-            dev_check(b200_memcpy_d2d(c->dev, out + mn * k * n, pa + mn * k * n, (a.size - mn) * k * n * sizeof(u64), nullptr));
+            dev_check(b200_memcpy_d2d(c->dev, out + mn * k * n, pa + mn * k * n, (a.size - mn) * k * n * sizeof(u64), cur_stream()));
         else if (b.size > mn)
         {
             if (mode == 0)
-                dev_check(b200_memcpy_d2d(c->dev, out + mn * k * n, pb + mn * k * n, (b.size - mn) * k * n * sizeof(u64), nullptr));
+                dev_check(b200_memcpy_d2d(c->dev, out + mn * k * n, pb + mn * k * n, (b.size - mn) * k * n * sizeof(u64), cur_stream()));
             else
-                dev_check(b200_negate(c->dev, lv, pb + mn * k * n, out + mn * k * n, (int)(b.size - mn), 1, nullptr));
+                dev_check(b200_negate(c->dev, lv, pb + mn * k * n, out + mn * k * n, (int)(b.size - mn), 1, cur_stream()));
         }
     });
     dst.is_ntt_form = a.is_ntt_form;
@@ -127,7 +128,7 @@ void op_addsub(Context_ *c, Ciphertext_ &a, Ciphertext_ &b, Ciphertext_ &dst, in
 
 void op_multiply(Context_ *c, Ciphertext_ &a, Ciphertext_ &b, Ciphertext_ &dst, bool square)
 {
-    std::lock_guard<std::mutex> lk(c->mu);
+    OpScope scope(c);
     int lv = data_level(c, a, "encrypted1 is not valid for encryption parameters");
     if (!square)
     {
@@ -150,9 +151,9 @@ void op_multiply(Context_ *c, Ciphertext_ &a, Ciphertext_ &b, Ciphertext_ &dst, 
         throw InvalidArg("invalid size"); // Ciphertext::resize_internal, SEAL_CIPHERTEXT_SIZE_MAX (S/ciphertext.cpp:100-106)
     with_output(c, dst, { &a, &b }, a.parms_id, ds, k, [&](u64 *out) {
         if (square)
-            dev_check(b200_square(c->dev, lv, pa, out, 1, nullptr));
+            dev_check(b200_square(c->dev, lv, pa, out, 1, cur_stream()));
         else
-            dev_check(b200_multiply(c->dev, lv, pa, (int)a.size, pb, (int)sb, out, 1, nullptr));
+            dev_check(b200_multiply(c->dev, lv, pa, (int)a.size, pb, (int)sb, out, 1, cur_stream()));
     });
     transparent_guard(c, lv, dst);
 }
@@ -169,7 +170,7 @@ void check_keys(Context_ *c, KSwitchKeys_ &keys, size_t index)
 
 void op_relinearize(Context_ *c, Ciphertext_ &a, KSwitchKeys_ &keys, Ciphertext_ &dst)
 {
-    std::lock_guard<std::mutex> lk(c->mu);
+    OpScope scope(c);
     int lv = data_level(c, a, "encrypted is not valid for encryption parameters");
     if (keys.parms_id != c->ids[0])
         throw InvalidArg("relin_keys is not valid for encryption parameters");
@@ -189,26 +190,26 @@ void op_relinearize(Context_ *c, Ciphertext_ &a, KSwitchKeys_ &keys, Ciphertext_
         {
             check_keys(c, keys, 0);
             const u64 *key = keys.flat_dev(c, 0, (int)k);
-            dev_check(b200_relinearize(c->dev, lv, pa, key, out, 1, nullptr));
+            dev_check(b200_relinearize(c->dev, lv, pa, key, out, 1, cur_stream()));
             return;
         }
         // size > 3: peel polynomials from the top, key index = power - 2 (S/evaluator.cpp:1143-1151)
         void *tmp = nullptr;
         dev_check(b200_malloc(c->dev, 3 * k * n * sizeof(u64), &tmp));
         u64 *t3 = (u64 *)tmp;
-        dev_check(b200_memcpy_d2d(c->dev, out, pa, 2 * k * n * sizeof(u64), nullptr));
+        dev_check(b200_memcpy_d2d(c->dev, out, pa, 2 * k * n * sizeof(u64), cur_stream()));
         int rc = 0;
         for (u64 s = a.size - 1; s >= 2 && !rc; s--)
         {
             check_keys(c, keys, s - 2);
             const u64 *key = keys.flat_dev(c, s - 2, (int)k);
-            rc = b200_memcpy_d2d(c->dev, t3, out, 2 * k * n * sizeof(u64), nullptr);
+            rc = b200_memcpy_d2d(c->dev, t3, out, 2 * k * n * sizeof(u64), cur_stream());
             if (!rc)
-                rc = b200_memcpy_d2d(c->dev, t3 + 2 * k * n, pa + s * k * n, k * n * sizeof(u64), nullptr);
+                rc = b200_memcpy_d2d(c->dev, t3 + 2 * k * n, pa + s * k * n, k * n * sizeof(u64), cur_stream());
             if (!rc)
-                rc = b200_relinearize(c->dev, lv, t3, key, out, 1, nullptr);
+                rc = b200_relinearize(c->dev, lv, t3, key, out, 1, cur_stream());
         }
-        b200_stream_synchronize(c->dev, nullptr);
+        b200_stream_synchronize(c->dev, cur_stream());
         b200_free(c->dev, tmp);
         dev_check(rc);
     });
@@ -232,7 +233,7 @@ void op_galois(Context_ *c, Ciphertext_ &a, uint32_t elt, KSwitchKeys_ &keys, Ci
     const u64 *pa = a.dev_ptr(c);
     const u64 *key = keys.flat_dev(c, index, (int)a.k);
     with_output(c, dst, { &a }, a.parms_id, 2, a.k, [&](u64 *out) {
-        dev_check(b200_apply_galois(c->dev, lv, pa, elt, key, out, 1, nullptr));
+        dev_check(b200_apply_galois(c->dev, lv, pa, elt, key, out, 1, cur_stream()));
     });
     transparent_guard(c, lv, dst);
 }
@@ -319,7 +320,7 @@ std::vector<u64> padded_plain(Context_ *c, const Plaintext_ &p, bool check_value
 
 void op_plain(Context_ *c, Ciphertext_ &a, const Plaintext_ &p, Ciphertext_ &dst, int which /*0 add 1 sub 2 mul*/)
 {
-    std::lock_guard<std::mutex> lk(c->mu);
+    OpScope scope(c);
     int lv = data_level(c, a, "encrypted is not valid for encryption parameters");
     if (a.is_ntt_form)
         throw InvalidArg("BFV encrypted cannot be in NTT form");
@@ -334,24 +335,24 @@ void op_plain(Context_ *c, Ciphertext_ &a, const Plaintext_ &p, Ciphertext_ &dst
     }
     void *dp = nullptr;
     dev_check(b200_malloc(c->dev, pv.size() * sizeof(u64), &dp));
-    int rc = b200_memcpy_h2d(c->dev, dp, pv.data(), pv.size() * sizeof(u64), nullptr);
+    int rc = b200_memcpy_h2d(c->dev, dp, pv.data(), pv.size() * sizeof(u64), cur_stream());
     const u64 *pa = a.dev_ptr(c);
     try
     {
         dev_check(rc);
         with_output(c, dst, { &a }, a.parms_id, a.size, a.k, [&](u64 *out) {
             if (which == 0)
-                dev_check(b200_add_plain(c->dev, lv, pa, (int)a.size, (const u64 *)dp, 1, out, 1, nullptr));
+                dev_check(b200_add_plain(c->dev, lv, pa, (int)a.size, (const u64 *)dp, 1, out, 1, cur_stream()));
             else if (which == 1)
-                dev_check(b200_sub_plain(c->dev, lv, pa, (int)a.size, (const u64 *)dp, 1, out, 1, nullptr));
+                dev_check(b200_sub_plain(c->dev, lv, pa, (int)a.size, (const u64 *)dp, 1, out, 1, cur_stream()));
             else
-                dev_check(b200_multiply_plain(c->dev, lv, pa, (int)a.size, (const u64 *)dp, 1, out, 1, nullptr));
+                dev_check(b200_multiply_plain(c->dev, lv, pa, (int)a.size, (const u64 *)dp, 1, out, 1, cur_stream()));
         });
-        b200_stream_synchronize(c->dev, nullptr);
+        b200_stream_synchronize(c->dev, cur_stream());
     }
     catch (...)
     {
-        b200_stream_synchronize(c->dev, nullptr);
+        b200_stream_synchronize(c->dev, cur_stream());
         b200_free(c->dev, dp);
         throw;
     }
@@ -642,6 +643,8 @@ long SEALContext_Create(void *parms, bool expand_mod_chain, int sec_level, void 
         else
         {
             c->dev = dev;
+            c->owner = std::make_shared<DevOwner>();
+            c->owner->dev = dev;
             b200_info info;
             b200_ctx_info(dev, &info);
             c->levels = info.levels;
@@ -688,7 +691,7 @@ long SEALContext_Create(void *parms, bool expand_mod_chain, int sec_level, void 
 long SEALContext_Destroy(void *p)
 {
     NULLRET(p);
-    delete (Context_ *)p;
+    Context_::release((Context_ *)p);
     return S_OK_;
 }
 static long ctx_id(void *p, uint64_t *out, int which)
@@ -1387,6 +1390,7 @@ long Evaluator_Create(void *context, void **out)
         return E_INVALIDARG_; // "encryption parameters are not set correctly" (S/evaluator.cpp:66-71)
     auto *e = new Evaluator_();
     e->ctx = c;
+    e->hold.bind(c);
     *out = e;
     return S_OK_;
 }
@@ -1412,12 +1416,12 @@ long Evaluator_Negate(void *p, void *enc, void *dst)
     auto &a = *(Ciphertext_ *)enc;
     auto &d = *(Ciphertext_ *)dst;
     return guard([&] {
-        std::lock_guard<std::mutex> lk(c->mu);
+        OpScope scope(c);
         int lv = data_level(c, a, "encrypted is not valid for encryption parameters");
         const u64 *pa = a.dev_ptr(c);
         bool ntt = a.is_ntt_form;
         with_output(c, d, { &a }, a.parms_id, a.size, a.k,
-                    [&](u64 *out) { dev_check(b200_negate(c->dev, lv, pa, out, (int)a.size, 1, nullptr)); });
+                    [&](u64 *out) { dev_check(b200_negate(c->dev, lv, pa, out, (int)a.size, 1, cur_stream())); });
         d.is_ntt_form = ntt;
         transparent_guard(c, lv, d);
     });
@@ -1560,7 +1564,7 @@ long Evaluator_ModSwitchToNext1(void *p, void *a, void *dst, void *)
     auto &x = *(Ciphertext_ *)a;
     auto &d = *(Ciphertext_ *)dst;
     return guard([&] {
-        std::lock_guard<std::mutex> lk(c->mu);
+        OpScope scope(c);
         int lv = data_level(c, x, "encrypted is not valid for encryption parameters");
         if (lv + 1 >= c->levels)
             throw InvalidArg("end of modulus switching chain reached");
@@ -1568,7 +1572,7 @@ long Evaluator_ModSwitchToNext1(void *p, void *a, void *dst, void *)
             throw InvalidArg("BFV encrypted cannot be in NTT form");
         const u64 *px = x.dev_ptr(c);
         with_output(c, d, { &x }, c->ids[lv + 1], x.size, x.k - 1,
-                    [&](u64 *out) { dev_check(b200_mod_switch_to_next(c->dev, lv, px, (int)x.size, out, 1, nullptr)); });
+                    [&](u64 *out) { dev_check(b200_mod_switch_to_next(c->dev, lv, px, (int)x.size, out, 1, cur_stream())); });
         transparent_guard(c, lv + 1, d);
     });
 }
@@ -1640,7 +1644,7 @@ long Evaluator_ApplyGalois(void *p, void *a, uint32_t elt, void *keys, void *dst
     NULLRET(dst);
     auto *c = ((Evaluator_ *)p)->ctx;
     return guard([&] {
-        std::lock_guard<std::mutex> lk(c->mu);
+        OpScope scope(c);
         op_galois(c, *(Ciphertext_ *)a, elt, *(KSwitchKeys_ *)keys, *(Ciphertext_ *)dst);
     });
 }
@@ -1652,7 +1656,7 @@ long Evaluator_RotateRows(void *p, void *a, int steps, void *keys, void *dst, vo
     NULLRET(dst);
     auto *c = ((Evaluator_ *)p)->ctx;
     return guard([&] {
-        std::lock_guard<std::mutex> lk(c->mu);
+        OpScope scope(c);
         op_rotate(c, *(Ciphertext_ *)a, steps, *(KSwitchKeys_ *)keys, *(Ciphertext_ *)dst);
     });
 }
@@ -1664,7 +1668,7 @@ long Evaluator_RotateColumns(void *p, void *a, void *keys, void *dst, void *)
     NULLRET(dst);
     auto *c = ((Evaluator_ *)p)->ctx;
     return guard([&] {
-        std::lock_guard<std::mutex> lk(c->mu);
+        OpScope scope(c);
         if (!c->using_batching)
             throw LogicErr("encryption parameters do not support batching");
         op_galois(c, *(Ciphertext_ *)a, (uint32_t)(2 * c->parms.n - 1), *(KSwitchKeys_ *)keys, *(Ciphertext_ *)dst);
@@ -1682,7 +1686,7 @@ long B200_Evaluator_MultiplyRelinBatch(void *p, uint64_t count, void **e1, void 
     return guard([&] {
         if (count == 0)
             return;
-        std::lock_guard<std::mutex> lk(c->mu);
+        OpScope scope(c);
         auto &a0 = *(Ciphertext_ *)e1[0];
         int lv = data_level(c, a0, "encrypted is not valid for encryption parameters");
         const u64 k = a0.k, n = a0.n, w = 2 * k * n;
@@ -1701,28 +1705,28 @@ long B200_Evaluator_MultiplyRelinBatch(void *p, uint64_t count, void **e1, void 
                 if (data_level(c, a, "encrypted1 is not valid") != lv || data_level(c, b, "encrypted2 is not valid") != lv ||
                     a.size != 2 || b.size != 2 || a.is_ntt_form || b.is_ntt_form)
                     throw InvalidArg("batch items must be size-2 ciphertexts at the same level");
-                dev_check(b200_memcpy_d2d(c->dev, (u64 *)da + i * w, a.dev_ptr(c), w * 8, nullptr));
-                dev_check(b200_memcpy_d2d(c->dev, (u64 *)db + i * w, b.dev_ptr(c), w * 8, nullptr));
+                dev_check(b200_memcpy_d2d(c->dev, (u64 *)da + i * w, a.dev_ptr(c), w * 8, cur_stream()));
+                dev_check(b200_memcpy_d2d(c->dev, (u64 *)db + i * w, b.dev_ptr(c), w * 8, cur_stream()));
             }
-            dev_check(b200_multiply_relin(c->dev, lv, (u64 *)da, (u64 *)db, keys.flat_dev(c, 0, (int)k), (u64 *)dout, count, nullptr));
+            dev_check(b200_multiply_relin(c->dev, lv, (u64 *)da, (u64 *)db, keys.flat_dev(c, 0, (int)k), (u64 *)dout, count, cur_stream()));
             for (uint64_t i = 0; i < count; i++)
             {
                 auto &d = *(Ciphertext_ *)dsts[i];
                 u64 *o = d.prepare_output(c, a0.parms_id, 2, k);
-                dev_check(b200_memcpy_d2d(c->dev, o, (u64 *)dout + i * w, w * 8, nullptr));
+                dev_check(b200_memcpy_d2d(c->dev, o, (u64 *)dout + i * w, w * 8, cur_stream()));
             }
         }
         catch (...)
         {
             rc = 1;
-            b200_stream_synchronize(c->dev, nullptr);
+            b200_stream_synchronize(c->dev, cur_stream());
             b200_free(c->dev, da);
             b200_free(c->dev, db);
             b200_free(c->dev, dout);
             throw;
         }
         (void)rc;
-        b200_stream_synchronize(c->dev, nullptr);
+        b200_stream_synchronize(c->dev, cur_stream());
         b200_free(c->dev, da);
         b200_free(c->dev, db);
         b200_free(c->dev, dout);
@@ -1745,6 +1749,7 @@ long Decryptor_Create(void *context, void *secret_key, void **out)
         return E_INVALIDARG_; // "secret key is not valid for encryption parameters" (S/decryptor.cpp:54-77)
     auto *d = new Decryptor_();
     d->ctx = c;
+    d->hold.bind(c);
     d->sk = sk->data.coeffs;
     *out = d;
     return S_OK_;
@@ -1956,6 +1961,7 @@ long KeyGenerator_Create1(void *context, void **out)
         return E_INVALIDARG_;
     auto *kg = new KeyGenerator_();
     kg->ctx = c;
+    kg->hold.bind(c);
     long hr = guard([&] {
         std::lock_guard<std::mutex> lk(c->mu);
         const size_t n = c->parms.n, K = c->parms.coeff.size();
@@ -1986,6 +1992,7 @@ long KeyGenerator_Create2(void *context, void *secret_key, void **out)
         return E_INVALIDARG_;
     auto *kg = new KeyGenerator_();
     kg->ctx = c;
+    kg->hold.bind(c);
     kg->sk = sk->data.coeffs;
     *out = kg;
     return S_OK_;
@@ -2166,6 +2173,7 @@ long Encryptor_Create(void *context, void *public_key, void *secret_key, void **
         return E_INVALIDARG_;
     auto *e = new Encryptor_();
     e->ctx = c;
+    e->hold.bind(c);
     long hr = guard([&] {
         const size_t words = c->parms.coeff.size() * c->parms.n;
         if (public_key)
@@ -2439,6 +2447,7 @@ long BatchEncoder_Create(void *context, void **out)
         return E_INVALIDARG_; // "encryption parameters are not valid for batching"
     auto *b = new BatchEncoder_();
     b->ctx = c;
+    b->hold.bind(c);
     const size_t n = c->parms.n, row = n >> 1, m = n << 1;
     int logn = 0;
     while (((size_t)1 << logn) < n)

@@ -8,6 +8,7 @@
 #include "sampling.h"
 #include <algorithm>
 #include <array>
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -85,22 +86,69 @@ inline int max_bits(u64 n, int sec)
     return 0;
 }
 
+// Shared ownership of the device context: data objects may outlive the SEALContext handle they were created with (Rust
+// drops them in any order), and their device buffers must be returned to a context that still exists.
+struct DevOwner
+{
+    b200_ctx *dev = nullptr;
+    ~DevOwner()
+    {
+        if (dev)
+            b200_ctx_destroy(dev);
+    }
+};
+
 struct Context_
 {
     EncParams_ parms;
     bool parameters_set = false;
     bool using_keyswitching = false;
     bool using_batching = false;
-    b200_ctx *dev = nullptr;
+    b200_ctx *dev = nullptr;         // == owner->dev
+    std::shared_ptr<DevOwner> owner; // keeps the device context alive for every object holding device memory
     int levels = 0, first_level = 0;
     std::vector<ParmsId> ids; // per level
     std::vector<int> level_k;
-    std::mutex mu;            // serialises enqueue on the context's stream (the legacy default stream)
+    std::mutex mu;            // serialises ENQUEUE (layer-1 caches, launch bookkeeping); never held while waiting for the GPU
     bool check_transparent = true;
+    // Evaluator operations of different host threads run on different streams ("lanes") so that their small kernels
+    // overlap on the GPU (sunscreen_runtime calls one Evaluator from rayon workers, run.rs:415-469).  A lane is owned by
+    // one operation at a time; every operation completes before it returns, so results are visible to any thread.
+    struct Lane
+    {
+        std::mutex m;
+        bool ready = false;
+        void *stream = nullptr;
+        void *dflag = nullptr;        // transparent-result flag (device)
+        uint32_t *hflag = nullptr;    // ... and its pinned host copy
+    };
+    static const int NLANE = 8;
+    Lane lanes[NLANE];
+    // The SEALContext handle and every object created from it (Evaluator, Encryptor, Decryptor, KeyGenerator,
+    // BatchEncoder) share the context, as the reference's objects share SEALContext's internals: it goes away with the
+    // last of them, whichever order the caller destroys them in.
+    std::atomic<int> refs{ 1 };
+    static void release(Context_ *c)
+    {
+        if (c && c->refs.fetch_sub(1) == 1)
+            delete c;
+    }
     ~Context_()
     {
         if (dev)
-            b200_ctx_destroy(dev);
+        {
+            for (auto &l : lanes)
+            {
+                if (l.stream)
+                    b200_stream_destroy(dev, l.stream);
+                if (l.dflag)
+                    b200_free(dev, l.dflag);
+                if (l.hflag)
+                    b200_free_host(l.hflag);
+            }
+            if (!owner)
+                b200_ctx_destroy(dev);
+        }
     }
     int level_of(const ParmsId &id) const
     {
@@ -124,6 +172,95 @@ inline void dev_check(int rc)
     throw std::runtime_error(b200_last_error());
 }
 
+struct CtxHold
+{
+    Context_ *c = nullptr;
+    void bind(Context_ *ctx)
+    {
+        if (c == ctx)
+            return;
+        Context_::release(c);
+        c = ctx;
+        if (c)
+            c->refs.fetch_add(1);
+    }
+    ~CtxHold() { Context_::release(c); }
+    CtxHold() = default;
+    CtxHold(const CtxHold &) = delete;
+    CtxHold &operator=(const CtxHold &) = delete;
+};
+
+// One Evaluator operation: owns a lane (stream) for its whole duration and the context mutex while it enqueues.
+struct OpScope;
+inline thread_local OpScope *tl_scope = nullptr;
+struct OpScope
+{
+    Context_ *c;
+    Context_::Lane *lane = nullptr;
+    std::unique_lock<std::mutex> lane_lk, ctx_lk;
+    OpScope *outer;
+    explicit OpScope(Context_ *ctx) : c(ctx), outer(tl_scope)
+    {
+        if (outer && outer->c == ctx)
+        { // nested helper inside an operation of the same context: share its lane and its lock
+            lane = outer->lane;
+            tl_scope = this;
+            return;
+        }
+        static std::atomic<unsigned> next{ 0 };
+        static thread_local unsigned pref = next++;
+        for (unsigned probe = 0;; probe++)
+        {
+            Context_::Lane &l = ctx->lanes[(pref + probe) % Context_::NLANE];
+            std::unique_lock<std::mutex> lk(l.m, std::defer_lock);
+            if (probe < (unsigned)Context_::NLANE ? lk.try_lock() : (lk.lock(), true))
+            {
+                lane = &l;
+                lane_lk = std::move(lk);
+                break;
+            }
+        }
+        ctx_lk = std::unique_lock<std::mutex>(ctx->mu);
+        if (!lane->ready)
+        {
+            lane->ready = true;
+            dev_check(b200_stream_create(ctx->dev, &lane->stream));
+            dev_check(b200_malloc(ctx->dev, 8, &lane->dflag));
+            void *h = nullptr;
+            dev_check(b200_malloc_host(8, &h));
+            lane->hflag = (uint32_t *)h;
+        }
+        tl_scope = this;
+    }
+    void *stream() const { return lane->stream; }
+    // wait for everything this operation enqueued, without holding the context mutex
+    void wait()
+    {
+        OpScope *root = this;
+        while (root->outer && root->outer->c == c)
+            root = root->outer;
+        const bool held = root->ctx_lk.owns_lock();
+        if (held)
+            root->ctx_lk.unlock();
+        int rc = b200_stream_synchronize(c->dev, lane->stream);
+        if (held)
+            root->ctx_lk.lock();
+        dev_check(rc);
+    }
+    ~OpScope()
+    {
+        tl_scope = outer;
+        if (outer && outer->c == c)
+            return;
+        if (ctx_lk.owns_lock())
+            ctx_lk.unlock();
+        b200_stream_synchronize(c->dev, lane->stream); // the operation is complete when the call returns
+    }
+    OpScope(const OpScope &) = delete;
+};
+// stream of the Evaluator operation this thread is executing (the legacy default stream outside of one)
+inline void *cur_stream() { return tl_scope ? tl_scope->stream() : nullptr; }
+
 // Ciphertext: device-resident words with a lazily materialised host mirror.
 struct Ciphertext_
 {
@@ -132,7 +269,8 @@ struct Ciphertext_
     u64 size = 0, n = 0, k = 0;
     double scale = 1.0;
     u64 correction_factor = 1;
-    Context_ *ctx = nullptr; // owner of the device buffer (set once data exists)
+    Context_ *ctx = nullptr;          // context the device buffer belongs to (identity only: it may be gone already)
+    std::shared_ptr<DevOwner> keep;   // ... and what keeps its device alive
     mutable std::vector<u64> host;
     mutable bool host_valid = true;
     u64 *dev = nullptr;
@@ -143,8 +281,13 @@ struct Ciphertext_
     ~Ciphertext_() { release_dev(); }
     void release_dev()
     {
-        if (dev && ctx && ctx->dev)
-            b200_free(ctx->dev, dev);
+        if (dev && keep && keep->dev)
+        { // inside an operation the buffer may still be read by kernels enqueued on its stream: free in stream order
+            if (tl_scope && tl_scope->c == ctx)
+                b200_free_async(keep->dev, dev, tl_scope->stream());
+            else
+                b200_free(keep->dev, dev);
+        }
         dev = nullptr;
         dev_words = 0;
         dev_valid = false;
@@ -155,6 +298,7 @@ struct Ciphertext_
         {
             release_dev();
             ctx = c;
+            keep = c->owner;
             void *p = nullptr;
             dev_check(b200_malloc(c->dev, std::max<size_t>(words(), 1) * sizeof(u64), &p));
             dev = (u64 *)p;
@@ -181,10 +325,10 @@ struct Ciphertext_
         if (host_valid)
             return;
         host.resize(words());
-        if (words() && dev && ctx)
+        if (words() && dev && keep)
         {
-            dev_check(b200_memcpy_d2h(ctx->dev, host.data(), dev, words() * sizeof(u64), nullptr));
-            dev_check(b200_stream_synchronize(ctx->dev, nullptr));
+            dev_check(b200_memcpy_d2h(keep->dev, host.data(), dev, words() * sizeof(u64), nullptr));
+            dev_check(b200_stream_synchronize(keep->dev, nullptr));
         }
         host_valid = true;
     }
@@ -237,7 +381,7 @@ struct KSwitchKeys_
     ParmsId parms_id = kZeroId;
     std::vector<std::vector<PublicKey_ *>> keys; // owned
     // device cache of flattened key lists
-    struct Flat { u64 *dev = nullptr; Context_ *ctx = nullptr; };
+    struct Flat { u64 *dev = nullptr; Context_ *ctx = nullptr; std::shared_ptr<DevOwner> keep; };
     std::vector<Flat> flat;
     ~KSwitchKeys_() { clear(); }
     void clear()
@@ -251,8 +395,8 @@ struct KSwitchKeys_
     void drop_flat()
     {
         for (auto &f : flat)
-            if (f.dev && f.ctx && f.ctx->dev)
-                b200_free(f.ctx->dev, f.dev);
+            if (f.dev && f.keep && f.keep->dev)
+                b200_free(f.keep->dev, f.dev);
         flat.clear();
     }
     const u64 *flat_dev(Context_ *c, size_t index, int decomp)
@@ -279,6 +423,7 @@ struct KSwitchKeys_
         dev_check(b200_stream_synchronize(c->dev, nullptr));
         f.dev = (u64 *)p;
         f.ctx = c;
+        f.keep = c->owner;
         return f.dev;
     }
 };
@@ -316,26 +461,29 @@ struct PolynomialArray_
     }
 };
 
-struct Evaluator_ { Context_ *ctx; };
+struct Evaluator_ { Context_ *ctx; CtxHold hold; };
 
 struct BatchEncoder_
 {
     Context_ *ctx;
+    CtxHold hold;
     std::vector<size_t> index_map; // populate_matrix_reps_index_map (S/batchencoder.cpp:62-80)
 };
 
 struct Decryptor_
 {
     Context_ *ctx;
+    CtxHold hold;
     std::vector<u64> sk; // key level NTT form [K][n]
     // device cache: powers s^1..s^m packed per (level, terms)
     struct Pow { int level, terms; u64 *dev; };
     std::vector<Pow> cache;
+    std::shared_ptr<DevOwner> keep;
     ~Decryptor_()
     {
         for (auto &p : cache)
-            if (p.dev)
-                b200_free(ctx->dev, p.dev);
+            if (p.dev && keep && keep->dev)
+                b200_free(keep->dev, p.dev);
     }
     const u64 *powers(int level, int terms)
     {
@@ -363,6 +511,7 @@ struct Decryptor_
         dev_check(b200_malloc(ctx->dev, buf.size() * sizeof(u64), &p));
         dev_check(b200_memcpy_h2d(ctx->dev, p, buf.data(), buf.size() * sizeof(u64), nullptr));
         dev_check(b200_stream_synchronize(ctx->dev, nullptr));
+        keep = ctx->owner;
         cache.push_back({ level, terms, (u64 *)p });
         return (u64 *)p;
     }
@@ -421,6 +570,7 @@ inline std::vector<u64> encrypt_zero_symmetric_key_level(Context_ *c, const std:
 struct KeyGenerator_
 {
     Context_ *ctx;
+    CtxHold hold;
     std::vector<u64> sk; // key level, NTT form [K][n]
     // generate_one_kswitch_key (S/keygenerator.cpp:303-337): new_key = [K][n] NTT form
     void one_kswitch_key(const std::vector<u64> &new_key, std::vector<PublicKey_ *> &dest)
@@ -457,6 +607,7 @@ struct KeyGenerator_
 struct Encryptor_
 {
     Context_ *ctx;
+    CtxHold hold;
     bool has_pk = false, has_sk = false;
     std::vector<u64> pk; // [2][K][n] NTT form, key level
     std::vector<u64> sk; // [K][n]

@@ -1142,3 +1142,32 @@ def concurrent_evaluator_calls(S, n, moduli, t, threads=8, rounds=6):
         a, b = rcts[i % 4], rcts[(i + 1) % 4]
         exp = R.sub(R.multiply_plain(R.add(R.relinearize(R.multiply(a, b), rlk), a), rpl), b)
         assert RL.save("Ciphertext", exp, 0) == serial[i]
+
+
+def handle_lifetime_order(S, n, moduli, t):
+    """Rust drops handles in whatever order the program's scopes dictate.  The reference's objects share the context's
+    internals, so an Evaluator / Decryptor / ciphertext stays usable after SEALContext_Destroy; ours must too (the device
+    context is reference-counted).  The same out-of-order sequence runs against both libraries."""
+    inp = refseal.appendix_b_inputs(n, moduli, t)
+    outs = []
+    for which in ("ref", "ours"):
+        if which == "ref":
+            R = refseal.RefContext(n, moduli, t)
+            L, ctx, ev = _Lib(R.ref.call, R.ref.call_rc, R.ctx), R.ctx, R.ev
+            a, b = R.new_ct(inp["a"]), R.new_ct(inp["b"])
+        else:
+            O = S.context(n, moduli, t)
+            L, ctx, ev = _Lib(O.S.call, O.S.rc, O.ctx), O.ctx, O.ev
+            a, b = O.new_ct(inp["a"]), O.new_ct(inp["b"])
+        prod = L.new("Ciphertext")
+        L.call("Evaluator_Multiply", ev, a, b, prod, None)          # device-resident result
+        L.call("SEALContext_Destroy", ctx)                          # the context handle goes first
+        s = L.new("Ciphertext")
+        L.call("Evaluator_Add", ev, prod, prod, s)                  # the evaluator still works
+        words = L.save("Ciphertext", s, 0)
+        L.call("Evaluator_Destroy", ev)                             # then the evaluator
+        after = L.save("Ciphertext", prod, 0)                       # ciphertexts outlive both
+        for h in (a, b, prod, s):
+            L.call("Ciphertext_Destroy", h)
+        outs.append((words, after))
+    assert outs[0] == outs[1]

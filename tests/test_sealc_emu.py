@@ -84,3 +84,7 @@ def test_misuse_hresults(S, ref, name):
 
 def test_context_validation_sweep(S, ref):
     sc.context_validation_sweep(S)
+
+
+def test_handle_lifetime_order(S, ref):
+    sc.handle_lifetime_order(S, *PARAMS["n4096"])

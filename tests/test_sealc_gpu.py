@@ -124,3 +124,7 @@ def test_context_validation_sweep(S, ref):
 
 def test_concurrent_evaluator_calls(S, ref):
     sc.concurrent_evaluator_calls(S, *PARAMS["n8192"])
+
+
+def test_handle_lifetime_order(S, ref):
+    sc.handle_lifetime_order(S, *PARAMS["n4096"])
