@@ -34,7 +34,7 @@ using namespace b200c;
 int data_level(Context_ *c, const Ciphertext_ &ct, const char *what)
 {
     int lv = c->level_of(ct.parms_id);
-    if (lv < 0 || (lv == 0 && c->first_level == 1) || ct.n != c->parms.n || (int)ct.k != c->level_k[lv] || ct.size < 2 || ct.size > 16)
+    if (lv < 0 || (lv == 0 && c->first_level == 1) || ct.n != c->parms.n || ct.k != (u64)c->level_k[lv] || ct.size < 2 || ct.size > 16)
         throw InvalidArg(what);
     return lv;
 }

@@ -383,7 +383,7 @@ bool ct_metadata_valid(Context_ *c, const Ciphertext_ &ct, bool allow_pure_key_l
         return false;
     if (!allow_pure_key_levels && lv < c->first_level)
         return false;
-    if ((int)ct.k != c->level_k[lv] || ct.n != c->parms.n)
+    if (ct.k != (u64)c->level_k[lv] || ct.n != c->parms.n)
         return false;
     if ((ct.size < 2 && ct.size != 0) || ct.size > 16) // SEAL_CIPHERTEXT_SIZE_MIN / _MAX (S/util/defines.h)
         return false;

@@ -1171,3 +1171,63 @@ def handle_lifetime_order(S, n, moduli, t):
             L.call("Ciphertext_Destroy", h)
         outs.append((words, after))
     assert outs[0] == outs[1]
+
+
+def wire_fuzz(S, n, moduli, t, trials=160, seed=1234):
+    """Corrupted and truncated serialisations: our loader never crashes and answers with the reference's HRESULT (and, when both
+    accept, holds the same object afterwards)."""
+    R = refseal.RefContext(n, moduli, t)
+    O = S.context(n, moduli, t)
+    RL, OL = _libs(R, O)
+    kg = R.keygen()
+    sk, pk, rlk = R.secret_key(kg), R.public_key(kg), R.relin_keys(kg)
+    ct = R.encrypt(R.encryptor(pk), R.new_pt(np.arange(3, 40, dtype=np.uint64) % t))
+    sct = R.new_ct()
+    R.ref.call("Encryptor_EncryptSymmetric", R.encryptor(pk, sk), R.new_pt(np.array([5, 6], dtype=np.uint64)), C.c_bool(True), sct, None)
+    blobs = [("Ciphertext", RL.save("Ciphertext", ct, 0)), ("Ciphertext", RL.save("Ciphertext", sct, 0)),
+             ("Plaintext", RL.save("Plaintext", R.new_pt(np.arange(9, dtype=np.uint64)), 0)), ("SecretKey", RL.save("SecretKey", sk, 0)),
+             ("PublicKey", RL.save("PublicKey", pk, 0)), ("KSwitchKeys", RL.save("KSwitchKeys", rlk, 0)),
+             ("Ciphertext", RL.save("Ciphertext", ct, COMPR_ZLIB)), ("Ciphertext", RL.save("Ciphertext", ct, COMPR_ZSTD))]
+    rng = np.random.default_rng(seed)
+    mismatches = []
+    for trial in range(trials):
+        kind, raw = blobs[trial % len(blobs)]
+        data = bytearray(raw)
+        mode = trial % 6
+        compressed = raw[5] != 0
+        if mode == 0:      # one byte in the headers / metadata region
+            i = int(rng.integers(0, min(len(data), 140)))
+            data[i] ^= int(rng.integers(1, 256))
+        elif mode == 1:    # one byte anywhere
+            i = int(rng.integers(0, len(data)))
+            data[i] ^= 1 << int(rng.integers(0, 8))
+        elif mode == 2:    # truncate
+            data = data[: int(rng.integers(0, len(data)))]
+        elif mode == 3:    # a size / count field set to something else (moderate: the reference allocates what it is told)
+            i = int(rng.integers(0, min(len(data) - 8, 140)))
+            data[i:i + 8] = int(rng.integers(0, 2**20)).to_bytes(8, "little")
+        elif mode == 5:    # ... or to something absurd: the reference dies of an uncaught bad_alloc here, so only OUR loader is
+            i = int(rng.integers(0, min(len(data) - 8, 140)))   # asked — it must refuse without allocating
+            data[i:i + 8] = int(rng.integers(2**40, 2**63)).to_bytes(8, "little")
+            for unsafe in (False, True):
+                OL.load_rc(kind, OL.new(kind), bytes(data), unsafe)
+            continue
+        else:              # trailing garbage after a valid object
+            data = data + bytes(rng.integers(0, 256, size=int(rng.integers(1, 64)), dtype=np.uint8))
+        data = bytes(data)
+        if kind == "KSwitchKeys" and mode in (0, 1, 3) and data[48:64] != raw[48:64]:
+            # the two list-length fields: the reference reserves whatever they say and aborts on bad_alloc; ours only
+            for unsafe in (False, True):
+                OL.load_rc(kind, OL.new(kind), data, unsafe)
+            continue
+        for unsafe in (False, True):
+            rh, oh = RL.new(kind), OL.new(kind)
+            r_rc, r_n = RL.load_rc(kind, rh, data, unsafe)
+            o_rc, o_n = OL.load_rc(kind, oh, data, unsafe)
+            if compressed and mode in (0, 1, 3) and r_rc != 0 and o_rc != 0:
+                continue  # both reject a damaged compressed stream; which layer notices first is the compressor's business
+            if (r_rc, r_n if r_rc == 0 else 0) != (o_rc, o_n if o_rc == 0 else 0):
+                mismatches.append(f"trial {trial} ({kind}, mode {mode}, unsafe={unsafe}): reference 0x{r_rc:08x}/{r_n}, ours 0x{o_rc:08x}/{o_n}")
+            elif r_rc == 0 and RL.save(kind, rh, 0) != OL.save(kind, oh, 0):
+                mismatches.append(f"trial {trial} ({kind}, mode {mode}): both accept but hold different objects")
+    assert not mismatches, "\\n  ".join(["wire fuzz mismatches:"] + mismatches[:12])

@@ -88,3 +88,7 @@ def test_context_validation_sweep(S, ref):
 
 def test_handle_lifetime_order(S, ref):
     sc.handle_lifetime_order(S, *PARAMS["n4096"])
+
+
+def test_wire_fuzz(S, ref):
+    sc.wire_fuzz(S, *PARAMS["n4096"])
