@@ -267,6 +267,16 @@ SEAL_C_FUNC B200_SEALContext_Synchronize(void *context);
 SEAL_C_FUNC B200_Evaluator_MultiplyRelinBatch(void *thisptr, uint64_t count, void **encrypteds1, void **encrypteds2,
                                               void *relin_keys, void **destinations);
 
+/* the other DAG node kinds as batches of independent size-2 ciphertexts at one level (same words as the per-handle calls) */
+SEAL_C_FUNC B200_Evaluator_AddSubBatch(void *thisptr, uint64_t count, void **encrypteds1, void **encrypteds2, bool subtract,
+                                       void **destinations);
+/* which: 0 add_plain, 1 sub_plain, 2 multiply_plain; plains[i] goes with encrypteds[i] */
+SEAL_C_FUNC B200_Evaluator_PlainBatch(void *thisptr, int which, uint64_t count, void **encrypteds, void **plains,
+                                      void **destinations);
+/* one row rotation for all items; the Galois key for `steps` must be present */
+SEAL_C_FUNC B200_Evaluator_RotateRowsBatch(void *thisptr, uint64_t count, void **encrypteds, int steps, void *galois_keys,
+                                           void **destinations);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1733,6 +1733,159 @@ long B200_Evaluator_MultiplyRelinBatch(void *p, uint64_t count, void **e1, void 
     });
 }
 
+// The other DAG node kinds of sunscreen_runtime (run.rs:160-341) as batches of independent items: same results as the
+// per-handle calls, one launch sequence per batch.  All items must be size-2 ciphertexts at one level.
+namespace
+{
+struct BatchSlab
+{
+    Context_ *c;
+    void *p = nullptr;
+    BatchSlab(Context_ *ctx, size_t words) : c(ctx) { dev_check(b200_malloc(c->dev, std::max<size_t>(words, 1) * 8, &p)); }
+    ~BatchSlab()
+    {
+        b200_stream_synchronize(c->dev, cur_stream());
+        b200_free(c->dev, p);
+    }
+    u64 *w() const { return (u64 *)p; }
+    BatchSlab(const BatchSlab &) = delete;
+};
+int batch_gather(Context_ *c, uint64_t count, void **cts, BatchSlab &slab, u64 &k_out)
+{
+    auto &a0 = *(Ciphertext_ *)cts[0];
+    const int lv = data_level(c, a0, "encrypted is not valid for encryption parameters");
+    const u64 w = 2 * a0.k * a0.n;
+    for (uint64_t i = 0; i < count; i++)
+    {
+        auto &a = *(Ciphertext_ *)cts[i];
+        if (data_level(c, a, "encrypted is not valid for encryption parameters") != lv || a.size != 2 || a.is_ntt_form)
+            throw InvalidArg("batch items must be size-2 ciphertexts at the same level");
+        dev_check(b200_memcpy_d2d(c->dev, slab.w() + i * w, a.dev_ptr(c), w * 8, cur_stream()));
+    }
+    k_out = a0.k;
+    return lv;
+}
+void batch_scatter(Context_ *c, uint64_t count, void **dsts, const BatchSlab &slab, const ParmsId &id, u64 k, int level)
+{
+    const u64 w = 2 * k * c->parms.n;
+    for (uint64_t i = 0; i < count; i++)
+    {
+        auto &d = *(Ciphertext_ *)dsts[i];
+        u64 *o = d.prepare_output(c, id, 2, k);
+        dev_check(b200_memcpy_d2d(c->dev, o, slab.w() + i * w, w * 8, cur_stream()));
+    }
+    if (c->check_transparent)
+    { // one flag per item
+        BatchSlab flags(c, count);
+        std::vector<uint32_t> h(count);
+        dev_check(b200_is_transparent(c->dev, level, slab.w(), 2, (uint32_t *)flags.p, count, cur_stream()));
+        dev_check(b200_memcpy_d2h(c->dev, h.data(), flags.p, count * 4, cur_stream()));
+        dev_check(b200_stream_synchronize(c->dev, cur_stream()));
+        for (uint32_t f : h)
+            if (f)
+                throw LogicErr("result ciphertext is transparent");
+    }
+}
+} // namespace
+
+long B200_Evaluator_AddSubBatch(void *p, uint64_t count, void **e1, void **e2, bool subtract, void **dsts)
+{
+    NULLRET(p);
+    NULLRET(e1);
+    NULLRET(e2);
+    NULLRET(dsts);
+    auto *c = ((Evaluator_ *)p)->ctx;
+    return guard([&] {
+        if (count == 0)
+            return;
+        OpScope scope(c);
+        const u64 w = 2 * ((Ciphertext_ *)e1[0])->k * c->parms.n;
+        BatchSlab A(c, count * w), B(c, count * w);
+        u64 k = 0, kb = 0;
+        const int lv = batch_gather(c, count, e1, A, k);
+        if (batch_gather(c, count, e2, B, kb) != lv)
+            throw InvalidArg("encrypted1 and encrypted2 parameter mismatch");
+        dev_check((subtract ? b200_sub : b200_add)(c->dev, lv, A.w(), B.w(), A.w(), 2, count, cur_stream()));
+        batch_scatter(c, count, dsts, A, ((Ciphertext_ *)e1[0])->parms_id, k, lv);
+    });
+}
+// which: 0 add_plain, 1 sub_plain, 2 multiply_plain; one plaintext per item
+long B200_Evaluator_PlainBatch(void *p, int which, uint64_t count, void **encs, void **plains, void **dsts)
+{
+    NULLRET(p);
+    NULLRET(encs);
+    NULLRET(plains);
+    NULLRET(dsts);
+    if (which < 0 || which > 2)
+        return E_INVALIDARG_;
+    auto *c = ((Evaluator_ *)p)->ctx;
+    return guard([&] {
+        if (count == 0)
+            return;
+        OpScope scope(c);
+        const size_t n = c->parms.n;
+        const u64 w = 2 * ((Ciphertext_ *)encs[0])->k * n;
+        BatchSlab A(c, count * w), O(c, count * w), P(c, count * n);
+        u64 k = 0;
+        const int lv = batch_gather(c, count, encs, A, k);
+        std::vector<u64> host(count * n);
+        for (uint64_t i = 0; i < count; i++)
+        {
+            NULLRET_THROW(plains[i]);
+            std::vector<u64> pv = padded_plain(c, *(Plaintext_ *)plains[i], false);
+            if (which == 2 && c->check_transparent && std::all_of(pv.begin(), pv.end(), [](u64 x) { return x == 0; }))
+                throw LogicErr("result ciphertext is transparent");
+            std::copy(pv.begin(), pv.end(), host.begin() + i * n);
+        }
+        dev_check(b200_memcpy_h2d(c->dev, P.p, host.data(), host.size() * 8, cur_stream()));
+        if (which == 0)
+            dev_check(b200_add_plain(c->dev, lv, A.w(), 2, P.w(), count, O.w(), count, cur_stream()));
+        else if (which == 1)
+            dev_check(b200_sub_plain(c->dev, lv, A.w(), 2, P.w(), count, O.w(), count, cur_stream()));
+        else
+            dev_check(b200_multiply_plain(c->dev, lv, A.w(), 2, P.w(), count, O.w(), count, cur_stream()));
+        dev_check(b200_stream_synchronize(c->dev, cur_stream())); // `host` is read by the copy above
+        batch_scatter(c, count, dsts, O, ((Ciphertext_ *)encs[0])->parms_id, k, lv);
+    });
+}
+// the same row rotation applied to every item (the Galois key for `steps` must be present: no NAF fallback here)
+long B200_Evaluator_RotateRowsBatch(void *p, uint64_t count, void **encs, int steps, void *galois_keys, void **dsts)
+{
+    NULLRET(p);
+    NULLRET(encs);
+    NULLRET(galois_keys);
+    NULLRET(dsts);
+    auto *c = ((Evaluator_ *)p)->ctx;
+    auto &keys = *(KSwitchKeys_ *)galois_keys;
+    return guard([&] {
+        if (count == 0)
+            return;
+        if (!c->using_batching)
+            throw LogicErr("encryption parameters do not support batching");
+        OpScope scope(c);
+        const u64 w = 2 * ((Ciphertext_ *)encs[0])->k * c->parms.n;
+        BatchSlab A(c, count * w), O(c, count * w);
+        u64 k = 0;
+        const int lv = batch_gather(c, count, encs, A, k);
+        if (steps == 0)
+        {
+            batch_scatter(c, count, dsts, A, ((Ciphertext_ *)encs[0])->parms_id, k, lv);
+            return;
+        }
+        uint32_t elt = 0;
+        if (b200_galois_elt_from_step(c->dev, steps, &elt))
+            throw InvalidArg("step count too large");
+        const size_t index = (elt - 1) >> 1;
+        if (keys.parms_id != c->ids[0])
+            throw InvalidArg("galois_keys is not valid for encryption parameters");
+        if (index >= keys.keys.size() || keys.keys[index].empty())
+            throw InvalidArg("Galois key not present");
+        check_keys(c, keys, index);
+        dev_check(b200_apply_galois(c->dev, lv, A.w(), elt, keys.flat_dev(c, index, (int)k), O.w(), count, cur_stream()));
+        batch_scatter(c, count, dsts, O, ((Ciphertext_ *)encs[0])->parms_id, k, lv);
+    });
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Decryptor
 // ---------------------------------------------------------------------------------------------------------

@@ -647,6 +647,9 @@ long guard(F f)
     }
 }
 
+#define NULLRET_THROW(p)                                                                                               \
+    if (!(p))                                                                                                          \
+    throw InvalidArg("null handle in batch")
 #define NULLRET(p)                                                                                                     \
     if (!(p))                                                                                                          \
     return E_POINTER_

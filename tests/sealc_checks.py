@@ -1231,3 +1231,67 @@ def wire_fuzz(S, n, moduli, t, trials=160, seed=1234):
             elif r_rc == 0 and RL.save(kind, rh, 0) != OL.save(kind, oh, 0):
                 mismatches.append(f"trial {trial} ({kind}, mode {mode}): both accept but hold different objects")
     assert not mismatches, "\\n  ".join(["wire fuzz mismatches:"] + mismatches[:12])
+
+
+def batch_seams(S, n, moduli, t, count=5):
+    """B200_Evaluator_{MultiplyRelin,AddSub,Plain,RotateRows}Batch give, item by item, the words of the per-handle calls
+    (which the other checks pin to the reference), including in-place destinations and the error cases."""
+    R = refseal.RefContext(n, moduli, t)
+    O = S.context(n, moduli, t)
+    RL, OL = _libs(R, O)
+    kg = R.keygen()
+    sk, pk, rlk = R.secret_key(kg), R.public_key(kg), R.relin_keys(kg)
+    batching = t % (2 * n) == 1
+    glk = R.galois_keys_steps(kg, [2]) if batching else None
+    enc = R.encryptor(pk)
+    rng = np.random.default_rng(41)
+    msgs = [rng.integers(0, t, size=int(rng.integers(1, n)), dtype=np.uint64) for _ in range(2 * count)]
+    rcts = [R.encrypt(enc, R.new_pt(m)) for m in msgs]
+    octs = [OL.load("Ciphertext", RL.save("Ciphertext", h, 0)) for h in rcts]
+    A, B = octs[:count], octs[count:]
+    orlk = OL.load("KSwitchKeys", RL.save("KSwitchKeys", rlk, 0))
+    words = lambda h: OL.save("Ciphertext", h, 0)
+    arr = lambda hs: (vp * len(hs))(*hs)
+    fresh = lambda: [OL.new("Ciphertext") for _ in range(count)]
+    # multiply + relinearize
+    d = fresh()
+    O.S.call("B200_Evaluator_MultiplyRelinBatch", O.ev, u64(count), arr(A), arr(B), orlk, arr(d))
+    for i in range(count):
+        assert words(d[i]) == words(O.relinearize(O.multiply(A[i], B[i]), orlk)), f"MultiplyRelinBatch item {i}"
+    assert words(d[0]) == RL.save("Ciphertext", R.relinearize(R.multiply(rcts[0], rcts[count]), rlk), 0)
+    # add / sub
+    for sub in (False, True):
+        d = fresh()
+        O.S.call("B200_Evaluator_AddSubBatch", O.ev, u64(count), arr(A), arr(B), C.c_bool(sub), arr(d))
+        for i in range(count):
+            assert words(d[i]) == words((O.sub if sub else O.add)(A[i], B[i])), f"AddSubBatch(sub={sub}) item {i}"
+    # plain operations, one plaintext per item
+    pls = [rng.integers(1, t, size=int(rng.integers(1, n)), dtype=np.uint64) for _ in range(count)]
+    opl = [O.new_pt(p) for p in pls]
+    for which, fn in ((0, O.add_plain), (1, O.sub_plain), (2, O.multiply_plain)):
+        d = fresh()
+        O.S.call("B200_Evaluator_PlainBatch", O.ev, C.c_int(which), u64(count), arr(A), arr(opl), arr(d))
+        for i in range(count):
+            assert words(d[i]) == words(fn(A[i], opl[i])), f"PlainBatch({which}) item {i}"
+    assert S.rc("B200_Evaluator_PlainBatch", O.ev, C.c_int(7), u64(count), arr(A), arr(opl), arr(fresh())) == E_INVALIDARG
+    zero = [O.new_pt(np.zeros(3, dtype=np.uint64))] + opl[1:]
+    assert S.rc("B200_Evaluator_PlainBatch", O.ev, C.c_int(2), u64(count), arr(A), arr(zero), arr(fresh())) == COR_E_INVALIDOPERATION
+    # rotations
+    if batching:
+        oglk = OL.load("KSwitchKeys", RL.save("KSwitchKeys", glk, 0))
+        d = fresh()
+        O.S.call("B200_Evaluator_RotateRowsBatch", O.ev, u64(count), arr(A), C.c_int(2), oglk, arr(d))
+        for i in range(count):
+            assert words(d[i]) == words(O.rotate_rows(A[i], 2, oglk)), f"RotateRowsBatch item {i}"
+        assert words(d[1]) == RL.save("Ciphertext", R.rotate_rows(rcts[1], 2, glk), 0)
+        assert S.rc("B200_Evaluator_RotateRowsBatch", O.ev, u64(count), arr(A), C.c_int(3), oglk, arr(fresh())) == E_INVALIDARG
+    # in place: destinations are the first operands
+    mine = [OL.load("Ciphertext", RL.save("Ciphertext", h, 0)) for h in rcts[:count]]
+    exp = [words(O.add(A[i], B[i])) for i in range(count)]
+    O.S.call("B200_Evaluator_AddSubBatch", O.ev, u64(count), arr(mine), arr(B), C.c_bool(False), arr(mine))
+    assert [words(h) for h in mine] == exp
+    # items at different levels are rejected
+    lower = O.mod_switch_to_next(A[1])
+    assert S.rc("B200_Evaluator_AddSubBatch", O.ev, u64(2), arr([A[0], lower]), arr([B[0], B[1]]), C.c_bool(False), arr(fresh()[:2])) == E_INVALIDARG
+    # transparent items are reported
+    assert S.rc("B200_Evaluator_AddSubBatch", O.ev, u64(2), arr([A[0], A[1]]), arr([B[0], A[1]]), C.c_bool(True), arr(fresh()[:2])) == COR_E_INVALIDOPERATION

@@ -92,3 +92,8 @@ def test_handle_lifetime_order(S, ref):
 
 def test_wire_fuzz(S, ref):
     sc.wire_fuzz(S, *PARAMS["n4096"])
+
+
+@pytest.mark.parametrize("name", ["n4096", "n8192"])
+def test_batch_seams(S, ref, name):
+    sc.batch_seams(S, *PARAMS[name], count=3)

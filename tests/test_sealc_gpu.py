@@ -128,3 +128,8 @@ def test_concurrent_evaluator_calls(S, ref):
 
 def test_handle_lifetime_order(S, ref):
     sc.handle_lifetime_order(S, *PARAMS["n4096"])
+
+
+@pytest.mark.parametrize("name", ["n4096", "n8192"])
+def test_batch_seams(S, ref, name):
+    sc.batch_seams(S, *PARAMS[name], count=9)
