@@ -147,6 +147,12 @@ int b200_multiply_relin_host(b200_ctx *ctx, int level, const uint64_t *a_host, c
                              const uint64_t *relin_key_dev, uint64_t *out_host, uint64_t batch);
 int b200_ntt_roundtrip_host(b200_ctx *ctx, int level, const uint64_t *in_host, uint64_t *out_host, uint64_t items);
 
+/* gather (`gather` != 0: slab[i*words..] <- *host_ptrs[i]) or scatter (*host_ptrs[i] <- slab[i*words..]) of `count` device
+   buffers of `words` words in one launch; `host_ptrs` is a HOST array of device pointers and must stay valid until the
+   stream has consumed it (pageable memory is copied at call time) */
+int b200_gather_scatter(b200_ctx *ctx, uint64_t *const *host_ptrs, uint64_t count, uint64_t *slab, uint64_t words, int gather,
+                        void *stream);
+
 /* number of kernel launches issued by this library since the context was created (bench.py: gpu_launches) */
 uint64_t b200_launch_count(const b200_ctx *ctx);
 /* developer aid: with B200_TRACE=1 in the environment every kernel launch is bracketed by CUDA events;

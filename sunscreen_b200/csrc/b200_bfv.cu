@@ -1828,6 +1828,44 @@ void b200_trace_dump(void)
 #endif
 }
 
+// dst[i*words .. ) <- *srcs[i]   (gather = 1)   or   *ptrs[i] <- slab[i*words ..)   (gather = 0); ptrs is a DEVICE array
+__global__ void gather_scatter_kernel(u64 *const *ptrs, u64 *slab, long long words, int gather)
+{
+    const long long i = blockIdx.y;
+    u64 *p = ptrs[i];
+    u64 *s = slab + i * words;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < words; e += (long long)gridDim.x * blockDim.x)
+    {
+        if (gather)
+            s[e] = p[e];
+        else
+            p[e] = s[e];
+    }
+}
+// Move `count` equally sized word arrays between individually allocated device buffers (host array of device pointers)
+// and one contiguous slab, in ONE launch: the batch seams of the SEAL-named layer gather operands and scatter results
+// this way instead of issuing a memcpy per ciphertext.
+int b200_gather_scatter(b200_ctx *ctx, uint64_t *const *host_ptrs, uint64_t count, uint64_t *slab, uint64_t words, int gather,
+                        void *stream)
+{
+    if (!ctx || !host_ptrs || !slab)
+        return fail(B200_E_NULL, "null argument");
+    if (count == 0 || words == 0)
+        return 0;
+    if (count > 65535)
+        return fail(B200_E_INVALID, "at most 65535 items per gather/scatter");
+    cudaStream_t s = (cudaStream_t)stream;
+    void *dptrs = nullptr;
+    CU_TRY(cudaMallocAsync(&dptrs, count * sizeof(void *), s));
+    CU_TRY(cudaMemcpyAsync(dptrs, host_ptrs, count * sizeof(void *), cudaMemcpyHostToDevice, s));
+    dim3 grid((unsigned)std::min<long long>(64, (long long)(words + 255) / 256), (unsigned)count);
+    B200_LAUNCH(gather_scatter_kernel, grid, 256, 0, s, (u64 *const *)dptrs, (u64 *)slab, (long long)words, gather);
+    ctx->launches++;
+    CU_TRY(cudaFreeAsync(dptrs, s));
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
 uint64_t b200_launch_count(const b200_ctx *ctx) { return ctx ? ctx->launches.load() : 0; }
 
 // ---- NTT ----

@@ -1674,64 +1674,7 @@ long Evaluator_RotateColumns(void *p, void *a, void *keys, void *dst, void *)
         op_galois(c, *(Ciphertext_ *)a, (uint32_t)(2 * c->parms.n - 1), *(KSwitchKeys_ *)keys, *(Ciphertext_ *)dst);
     });
 }
-long B200_Evaluator_MultiplyRelinBatch(void *p, uint64_t count, void **e1, void **e2, void *relin_keys, void **dsts)
-{
-    NULLRET(p);
-    NULLRET(e1);
-    NULLRET(e2);
-    NULLRET(relin_keys);
-    NULLRET(dsts);
-    auto *c = ((Evaluator_ *)p)->ctx;
-    auto &keys = *(KSwitchKeys_ *)relin_keys;
-    return guard([&] {
-        if (count == 0)
-            return;
-        OpScope scope(c);
-        auto &a0 = *(Ciphertext_ *)e1[0];
-        int lv = data_level(c, a0, "encrypted is not valid for encryption parameters");
-        const u64 k = a0.k, n = a0.n, w = 2 * k * n;
-        check_keys(c, keys, 0);
-        void *da = nullptr, *db = nullptr, *dout = nullptr;
-        dev_check(b200_malloc(c->dev, count * w * 8, &da));
-        dev_check(b200_malloc(c->dev, count * w * 8, &db));
-        dev_check(b200_malloc(c->dev, count * w * 8, &dout));
-        int rc = 0;
-        try
-        {
-            for (uint64_t i = 0; i < count; i++)
-            {
-                auto &a = *(Ciphertext_ *)e1[i];
-                auto &b = *(Ciphertext_ *)e2[i];
-                if (data_level(c, a, "encrypted1 is not valid") != lv || data_level(c, b, "encrypted2 is not valid") != lv ||
-                    a.size != 2 || b.size != 2 || a.is_ntt_form || b.is_ntt_form)
-                    throw InvalidArg("batch items must be size-2 ciphertexts at the same level");
-                dev_check(b200_memcpy_d2d(c->dev, (u64 *)da + i * w, a.dev_ptr(c), w * 8, cur_stream()));
-                dev_check(b200_memcpy_d2d(c->dev, (u64 *)db + i * w, b.dev_ptr(c), w * 8, cur_stream()));
-            }
-            dev_check(b200_multiply_relin(c->dev, lv, (u64 *)da, (u64 *)db, keys.flat_dev(c, 0, (int)k), (u64 *)dout, count, cur_stream()));
-            for (uint64_t i = 0; i < count; i++)
-            {
-                auto &d = *(Ciphertext_ *)dsts[i];
-                u64 *o = d.prepare_output(c, a0.parms_id, 2, k);
-                dev_check(b200_memcpy_d2d(c->dev, o, (u64 *)dout + i * w, w * 8, cur_stream()));
-            }
-        }
-        catch (...)
-        {
-            rc = 1;
-            b200_stream_synchronize(c->dev, cur_stream());
-            b200_free(c->dev, da);
-            b200_free(c->dev, db);
-            b200_free(c->dev, dout);
-            throw;
-        }
-        (void)rc;
-        b200_stream_synchronize(c->dev, cur_stream());
-        b200_free(c->dev, da);
-        b200_free(c->dev, db);
-        b200_free(c->dev, dout);
-    });
-}
+long B200_Evaluator_MultiplyRelinBatch(void *p, uint64_t count, void **e1, void **e2, void *relin_keys, void **dsts);
 
 // The other DAG node kinds of sunscreen_runtime (run.rs:160-341) as batches of independent items: same results as the
 // per-handle calls, one launch sequence per batch.  All items must be size-2 ciphertexts at one level.
@@ -1755,25 +1698,25 @@ int batch_gather(Context_ *c, uint64_t count, void **cts, BatchSlab &slab, u64 &
     auto &a0 = *(Ciphertext_ *)cts[0];
     const int lv = data_level(c, a0, "encrypted is not valid for encryption parameters");
     const u64 w = 2 * a0.k * a0.n;
+    std::vector<u64 *> ptrs(count);
     for (uint64_t i = 0; i < count; i++)
     {
         auto &a = *(Ciphertext_ *)cts[i];
         if (data_level(c, a, "encrypted is not valid for encryption parameters") != lv || a.size != 2 || a.is_ntt_form)
             throw InvalidArg("batch items must be size-2 ciphertexts at the same level");
-        dev_check(b200_memcpy_d2d(c->dev, slab.w() + i * w, a.dev_ptr(c), w * 8, cur_stream()));
+        ptrs[i] = const_cast<u64 *>(a.dev_ptr(c));
     }
+    dev_check(b200_gather_scatter(c->dev, ptrs.data(), count, slab.w(), w, 1, cur_stream())); // one launch for all items
     k_out = a0.k;
     return lv;
 }
 void batch_scatter(Context_ *c, uint64_t count, void **dsts, const BatchSlab &slab, const ParmsId &id, u64 k, int level)
 {
     const u64 w = 2 * k * c->parms.n;
+    std::vector<u64 *> ptrs(count);
     for (uint64_t i = 0; i < count; i++)
-    {
-        auto &d = *(Ciphertext_ *)dsts[i];
-        u64 *o = d.prepare_output(c, id, 2, k);
-        dev_check(b200_memcpy_d2d(c->dev, o, slab.w() + i * w, w * 8, cur_stream()));
-    }
+        ptrs[i] = ((Ciphertext_ *)dsts[i])->prepare_output(c, id, 2, k);
+    dev_check(b200_gather_scatter(c->dev, ptrs.data(), count, slab.w(), w, 0, cur_stream()));
     if (c->check_transparent)
     { // one flag per item
         BatchSlab flags(c, count);
@@ -1788,6 +1731,30 @@ void batch_scatter(Context_ *c, uint64_t count, void **dsts, const BatchSlab &sl
 }
 } // namespace
 
+long B200_Evaluator_MultiplyRelinBatch(void *p, uint64_t count, void **e1, void **e2, void *relin_keys, void **dsts)
+{
+    NULLRET(p);
+    NULLRET(e1);
+    NULLRET(e2);
+    NULLRET(relin_keys);
+    NULLRET(dsts);
+    auto *c = ((Evaluator_ *)p)->ctx;
+    auto &keys = *(KSwitchKeys_ *)relin_keys;
+    return guard([&] {
+        if (count == 0)
+            return;
+        OpScope scope(c);
+        const u64 w = 2 * ((Ciphertext_ *)e1[0])->k * c->parms.n;
+        BatchSlab A(c, count * w), B(c, count * w), D(c, count * w);
+        u64 k = 0, kb = 0;
+        const int lv = batch_gather(c, count, e1, A, k);
+        if (batch_gather(c, count, e2, B, kb) != lv)
+            throw InvalidArg("encrypted1 and encrypted2 parameter mismatch");
+        check_keys(c, keys, 0);
+        dev_check(b200_multiply_relin(c->dev, lv, A.w(), B.w(), keys.flat_dev(c, 0, (int)k), D.w(), count, cur_stream()));
+        batch_scatter(c, count, dsts, D, ((Ciphertext_ *)e1[0])->parms_id, k, lv);
+    });
+}
 long B200_Evaluator_AddSubBatch(void *p, uint64_t count, void **e1, void **e2, bool subtract, void **dsts)
 {
     NULLRET(p);
