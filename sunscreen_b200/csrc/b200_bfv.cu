@@ -177,6 +177,12 @@ __global__ void ntt_outer_kernel(const NttJob job, long long total)
     const long long idx = GLOBAL_IDX();
     if (idx >= total)
         return;
+    if (job.split == 2)
+    {
+        const int q4 = 1 << (job.logn - 2);
+        ntt_outer_quad<FWD>(job, idx / q4, (int)(idx % q4));
+        return;
+    }
     const int halfn = 1 << (job.logn - 1);
     ntt_outer_pair<FWD>(job, idx / halfn, (int)(idx % halfn));
 }
@@ -703,7 +709,7 @@ struct b200_ctx
     struct HostPool *pool = nullptr;
     int ntt_threads = 256;
     size_t ntt_smem = 0;
-    int ntt_split = 0; // 1: n > 16384 -> two-level transform (ntt_outer_kernel + half-size sub-transforms)
+    int ntt_split = 0; // n > 16384: two-level transform, ntt_outer_kernel + 2^split sub-transforms of n >> split points
 };
 
 template <class T>
@@ -1132,11 +1138,11 @@ static int launch_ntt(b200_ctx *ctx, const JobDesc &jd, const u64 *src, long lon
     job.npass = ctx->npass;
     for (int i = 0; i < 8; i++)
         job.pass_L[i] = ctx->pass_L[i];
-    const long long blocks = items * jd.slots * (ctx->ntt_split ? 2 : 1);
+    const long long blocks = items * jd.slots * (1LL << ctx->ntt_split);
     if (ctx->ntt_split)
     {
         // two-level transform: the stage over the whole polynomial runs in global memory, the halves in shared memory
-        const long long pairs = items * jd.slots * (long long)(ctx->n >> 1);
+        const long long pairs = items * jd.slots * (long long)(ctx->n >> ctx->ntt_split); // butterflies (split 1) / quads (2)
         void (*kin)(const NttJob) = ctx->ntt_threads == 512 ? ntt_kernel<FWD, 512> : ntt_kernel<FWD, 256>;
         if (FWD)
         {
@@ -1541,7 +1547,13 @@ int b200_ctx_create(uint64_t n, const uint64_t *coeff_modulus, uint64_t count, u
     CU_TRY(cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
     // NTT launch configuration
-    ctx->ntt_split = ctx->logn >= 15 ? 1 : 0;
+    // n = 32768: two global stages + quarter-size sub-transforms (69.6 KB of shared memory: three CTAs per SM); B200_NTT_SPLIT=1
+    // selects the older one-stage / half-size split (139 KB: one CTA per SM)
+    ctx->ntt_split = ctx->logn >= 15 ? (std::getenv("B200_NTT_SPLIT") ? atoi(std::getenv("B200_NTT_SPLIT")) : 2) : 0;
+    if (ctx->ntt_split < 1 && ctx->logn >= 15)
+        ctx->ntt_split = 1;
+    if (ctx->ntt_split > 2)
+        ctx->ntt_split = 2;
     if (ctx->logn > 15)
         return fail(B200_E_INVALID, "poly_modulus_degree above 32768 is not supported");
     const int local_logn = ctx->logn - ctx->ntt_split;

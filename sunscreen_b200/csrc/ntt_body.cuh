@@ -268,11 +268,13 @@ template <bool FWD>
 B200_HD void ntt_block_body(const NttJob &job, long long block, u64 *sm, int tid, int nthreads)
 {
     // split transforms: CTA (poly, half) works on n/2 coefficients with twiddle multiplier 2 + half
-    const int half = job.split ? (int)(block & 1) : 0;
-    const long long poly = job.split ? block >> 1 : block;
-    const int logn = job.split ? job.logn - 1 : job.logn;
+    // job.split = log2 of the number of parts: 1 -> halves after one global stage, 2 -> quarters after two
+    const int parts = 1 << job.split;
+    const int half = (int)(block & (parts - 1));
+    const long long poly = block >> job.split;
+    const int logn = job.logn - job.split;
     const int n = 1 << logn;
-    const int mult = job.split ? 2 + half : 1;
+    const int mult = job.split ? parts + half : 1; // part `half` of stage s covers groups [half*2^(s-split), ...)
     const long long item = poly / job.slots;
     const int slot = (int)(poly - item * job.slots);
     const NttPrime P = job.primes[job.slot_prime[slot]];
@@ -335,6 +337,49 @@ B200_HD void ntt_block_body(const NttJob &job, long long block, u64 *sm, int tid
 // The butterfly stage a split transform performs over the whole polynomial in global memory:
 //   forward : first stage (m = 1, gap n/2, twiddle fwd[1]), canonical output, src -> dst
 //   inverse : last stage (m = 1) with n^-1 folded in, in place on dst (input = the two inverse sub-transforms, < p)
+// Two global stages at once for a transform split in four (n = 32768: the quarters then fit three CTAs per SM):
+//   forward : stages m = 1 (gap n/2, twiddle 1) and m = 2 (gap n/4, twiddles 2 and 3), canonical output, src -> dst
+//   inverse : the mirrored Gentleman-Sande stages with n^-1 folded into the last one, in place on dst
+template <bool FWD>
+B200_HD void ntt_outer_quad(const NttJob &job, long long poly, int j)
+{
+    const int n = 1 << job.logn, q4 = n >> 2;
+    const long long item = poly / job.slots;
+    const int slot = (int)(poly - item * job.slots);
+    const NttPrime P = job.primes[job.slot_prime[slot]];
+    const u64 p = P.p;
+    u64 *dst = job.dst + item * job.dst_item_stride + job.slot_dst[slot];
+    if (FWD)
+    {
+        const u64 *src = job.src + item * job.src_item_stride + job.slot_src[slot];
+        u64 a0 = src[j], a1 = src[j + q4], a2 = src[j + 2 * q4], a3 = src[j + 3 * q4];
+        if (job.reduce_input)
+        {
+            a0 = barrett64(a0, p, P.ratio1);
+            a1 = barrett64(a1, p, P.ratio1);
+            a2 = barrett64(a2, p, P.ratio1);
+            a3 = barrett64(a3, p, P.ratio1);
+        }
+        const u64 t2 = shoup_mul(a2, P.fwd[2], P.fwd[3], p), t3 = shoup_mul(a3, P.fwd[2], P.fwd[3], p);
+        const u64 b0 = add_mod(a0, t2, p), b2 = sub_mod(a0, t2, p), b1 = add_mod(a1, t3, p), b3 = sub_mod(a1, t3, p);
+        const u64 u1 = shoup_mul(b1, P.fwd[4], P.fwd[5], p), u3 = shoup_mul(b3, P.fwd[6], P.fwd[7], p);
+        dst[j] = add_mod(b0, u1, p);
+        dst[j + q4] = sub_mod(b0, u1, p);
+        dst[j + 2 * q4] = add_mod(b2, u3, p);
+        dst[j + 3 * q4] = sub_mod(b2, u3, p);
+    }
+    else
+    {
+        const u64 a0 = dst[j], a1 = dst[j + q4], a2 = dst[j + 2 * q4], a3 = dst[j + 3 * q4];
+        const u64 b0 = add_mod(a0, a1, p), b1 = shoup_mul(sub_mod(a0, a1, p), P.inv[4], P.inv[5], p);
+        const u64 b2 = add_mod(a2, a3, p), b3 = shoup_mul(sub_mod(a2, a3, p), P.inv[6], P.inv[7], p);
+        dst[j] = shoup_mul(add_mod(b0, b2, p), P.inv_n, P.inv_n_q, p);
+        dst[j + 2 * q4] = shoup_mul(sub_mod(b0, b2, p), P.inv_n_w, P.inv_n_w_q, p);
+        dst[j + q4] = shoup_mul(add_mod(b1, b3, p), P.inv_n, P.inv_n_q, p);
+        dst[j + 3 * q4] = shoup_mul(sub_mod(b1, b3, p), P.inv_n_w, P.inv_n_w_q, p);
+    }
+}
+
 template <bool FWD>
 B200_HD void ntt_outer_pair(const NttJob &job, long long poly, int j)
 {
