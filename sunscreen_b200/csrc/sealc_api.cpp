@@ -1978,51 +1978,71 @@ static void noise_norm(Decryptor_ *d, Ciphertext_ &ct, std::vector<u64> &norm_ou
             for (size_t i = 0; i < tmp.size(); i++)
                 half[i] = (tmp[i] >> 1) | (i + 1 < tmp.size() ? tmp[i + 1] << 63 : 0);
         }
-        auto ge = [&](const std::vector<u64> &a, const std::vector<u64> &b) {
-            for (size_t i = a.size(); i-- > 0;)
+        // Per coefficient: v = sum_i [x_i * t * (Q/q_i)^-1]_{q_i} * (Q/q_i) mod Q, centred, and the running maximum.
+        // Tight loops over fixed-size word arrays (no allocation, no 128-bit division): c_i = t (Q/q_i)^-1 mod q_i is
+        // applied with a Shoup quotient, the sum is reduced once at the end (it is below k Q).
+        const size_t MAXW = 18;
+        if (W + 1 > MAXW)
+            throw LogicErr("internal: coefficient modulus too wide for the noise-budget accumulator");
+        std::vector<u64> cmul(k), cmul_q(k);
+        const u64 t = c->parms.plain;
+        for (int i = 0; i < k; i++)
+        {
+            cmul[i] = (u64)((u128)(t % q[i]) * inv[i] % q[i]);
+            cmul_q[i] = (u64)(((u128)cmul[i] << 64) / q[i]);
+        }
+        auto ge_w = [W](const u64 *a, const u64 *b) {
+            for (size_t i = W + 1; i-- > 0;)
                 if (a[i] != b[i])
                     return a[i] > b[i];
             return true;
         };
-        auto sub = [&](std::vector<u64> &a, const std::vector<u64> &b) {
+        auto sub_w = [W](u64 *a, const u64 *b) {
             u64 borrow = 0;
-            for (size_t i = 0; i < a.size(); i++)
+            for (size_t i = 0; i <= W; i++)
             {
-                u64 bi = b[i] + borrow;
-                u64 nb = (bi < borrow) || (a[i] < bi);
+                const u64 bi = b[i] + borrow;
+                const u64 nb = (bi < borrow) || (a[i] < bi);
                 a[i] -= bi;
                 borrow = nb;
             }
         };
-        std::vector<u64> norm(W + 1, 0);
-        const u64 t = c->parms.plain;
+        u64 norm_w[MAXW] = { 0 }, acc[MAXW], neg[MAXW];
+        const u64 *Qp = Qw.data(), *halfp = half.data();
         for (size_t cidx = 0; cidx < n; cidx++)
         {
-            std::vector<u64> acc(W + 1, 0);
+            for (size_t w = 0; w <= W; w++)
+                acc[w] = 0;
             for (int i = 0; i < k; i++)
             {
-                u64 x = (u64)((u128)ph[(size_t)i * n + cidx] * (t % q[i]) % q[i]);
-                u64 y = (u64)((u128)x * inv[i] % q[i]);
+                const u64 x = ph[(size_t)i * n + cidx];
+                u64 y = x * cmul[i] - (u64)(((u128)x * cmul_q[i]) >> 64) * q[i];
+                y = y >= q[i] ? y - q[i] : y;
+                const u64 *pw = punc[i].data();
                 u64 carry = 0;
                 for (size_t w = 0; w < W; w++)
                 {
-                    u128 m = (u128)punc[i][w] * y + acc[w] + carry;
+                    const u128 m = (u128)pw[w] * y + acc[w] + carry;
                     acc[w] = (u64)m;
                     carry = (u64)(m >> 64);
                 }
                 acc[W] += carry;
-                while (ge(acc, Qw))
-                    sub(acc, Qw);
             }
-            if (ge(acc, half))
+            while (ge_w(acc, Qp))
+                sub_w(acc, Qp);
+            if (ge_w(acc, halfp))
             { // centred magnitude = Q - acc
-                std::vector<u64> m(Qw);
-                sub(m, acc);
-                acc = m;
+                for (size_t w = 0; w <= W; w++)
+                    neg[w] = Qp[w];
+                sub_w(neg, acc);
+                for (size_t w = 0; w <= W; w++)
+                    acc[w] = neg[w];
             }
-            if (ge(acc, norm))
-                norm = acc;
+            if (ge_w(acc, norm_w))
+                for (size_t w = 0; w <= W; w++)
+                    norm_w[w] = acc[w];
         }
+        std::vector<u64> norm(norm_w, norm_w + W + 1);
         norm_out = norm;
         k_out = k;
         q_bits_out = Q.bit_length();
