@@ -188,7 +188,7 @@ __global__ void ntt_outer_kernel(const NttJob job, long long total)
 }
 
 template <int K>
-__global__ void lift_kernel(const LevelDev L, const u64 *a, int sa, const u64 *b, int sb, u64 *ext, long long n,
+__global__ void lift_kernel(const LiftIntC<K> L, const u64 *a, int sa, const u64 *b, int sb, u64 *ext, long long n,
                             long long total)
 {
     const long long idx = GLOBAL_IDX();
@@ -244,7 +244,7 @@ __global__ void tensor_kernel(const LevelDev L, const u64 *ext, int sa, int sb, 
 }
 
 template <int K>
-__global__ void scale_kernel(const LevelDev L, const u64 *D, int Dn, u64 *dst0, int split, u64 *dst1, long long n,
+__global__ void scale_kernel(const ScaleIntC<K> L, const u64 *D, int Dn, u64 *dst0, int split, u64 *dst1, long long n,
                              long long total)
 {
     const long long idx = GLOBAL_IDX();
@@ -1220,6 +1220,66 @@ static int launch_ntt(b200_ctx *ctx, const JobDesc &jd, const u64 *src, long lon
     }
 
 template <int K>
+static LiftIntC<K> make_lift_intc(const b200_ctx *ctx, int level)
+{
+    const auto &Lh = ctx->host->levels[level];
+    LiftIntC<K> C;
+    memset(&C, 0, sizeof(C));
+    C.nBsk = Lh.nBsk;
+    C.neg_inv_q_mod_mt = Lh.neg_inv_q_mod_mt;
+    for (int i = 0; i < K; i++)
+    {
+        C.q[i] = ctx->host->primes[Lh.q_idx[i]].mod.p;
+        C.c[2 * i] = Lh.lift_c[i].w;
+        C.c[2 * i + 1] = Lh.lift_c[i].wq;
+        C.mt[i] = Lh.lift_mt[i];
+    }
+    for (int j = 0; j < Lh.nBsk; j++)
+    {
+        const auto &M = ctx->host->primes[Lh.bsk_idx[j]].mod;
+        C.bsk[j] = PrimeC{ M.p, M.r0, M.r1 };
+        C.qm[j] = Lh.lift_qm[j];
+        for (int i = 0; i < K; i++)
+            C.mat[j * K + i] = Lh.lift_mat[(size_t)j * K + i];
+    }
+    return C;
+}
+template <int K>
+static ScaleIntC<K> make_scale_intc(const b200_ctx *ctx, int level)
+{
+    const auto &Lh = ctx->host->levels[level];
+    ScaleIntC<K> C;
+    memset(&C, 0, sizeof(C));
+    C.nB = Lh.nB;
+    C.nBsk = Lh.nBsk;
+    for (int i = 0; i < K; i++)
+    {
+        const auto &M = ctx->host->primes[Lh.q_idx[i]].mod;
+        C.q[i] = PrimeC{ M.p, M.r0, M.r1 };
+        C.c[2 * i] = Lh.scale_c[i].w;
+        C.c[2 * i + 1] = Lh.scale_c[i].wq;
+        C.sk_prod_b_q[i] = Lh.sk_prod_b_q[i];
+        for (int b = 0; b < Lh.nB; b++)
+            C.sk_mat_q[i * (K + 1) + b] = Lh.sk_mat_q[(size_t)i * Lh.nB + b];
+    }
+    for (int j = 0; j < Lh.nBsk; j++)
+    {
+        const auto &M = ctx->host->primes[Lh.bsk_idx[j]].mod;
+        C.bsk[j] = PrimeC{ M.p, M.r0, M.r1 };
+        C.tq[j] = Lh.scale_tq[j];
+        for (int i = 0; i < K; i++)
+            C.mat[j * K + i] = Lh.scale_mat[(size_t)j * K + i];
+    }
+    for (int b = 0; b < Lh.nB; b++)
+    {
+        C.sk_c[2 * b] = Lh.sk_c[b].w;
+        C.sk_c[2 * b + 1] = Lh.sk_c[b].wq;
+        C.sk_mat_msk[b] = Lh.sk_mat_msk[b];
+    }
+    C.sk_inv_b_msk = Lh.sk_inv_b_msk;
+    return C;
+}
+template <int K>
 static LiftFpC<K> make_lift_fpc(const b200_ctx *ctx, int level)
 {
     const LevelFpHost &H = ctx->fp_levels[level];
@@ -1321,8 +1381,8 @@ static int multiply_core(b200_ctx *ctx, int level, const u64 *a, int sa, const u
         else
         {
             const long long total = batch * P * n;
-            DISPATCH_K(k, B200_LAUNCH(lift_kernel<KK>, blocks_for(total, EB), EB, 0, s, L, a, sa, square ? a : b, square ? 0 : sb, ext,
-                                      n, total));
+            DISPATCH_K(k, B200_LAUNCH(lift_kernel<KK>, blocks_for(total, EB), EB, 0, s, make_lift_intc<KK>(ctx, level), a, sa,
+                                      square ? a : b, square ? 0 : sb, ext, n, total));
         }
         ctx->launches++;
     }
@@ -1413,7 +1473,8 @@ static int multiply_core(b200_ctx *ctx, int level, const u64 *a, int sa, const u
         else
         {
             const long long total = batch * Dn * n;
-            DISPATCH_K(k, B200_LAUNCH(scale_kernel<KK>, blocks_for(total, EB), EB, 0, s, L, D, Dn, dst0, split, dst1, n, total));
+            DISPATCH_K(k, B200_LAUNCH(scale_kernel<KK>, blocks_for(total, EB), EB, 0, s, make_scale_intc<KK>(ctx, level), D, Dn, dst0,
+                                      split, dst1, n, total));
         }
         ctx->launches++;
     }

@@ -86,8 +86,41 @@ B200_HD PrimeDev ld_prime(const PrimeDev *p)
 // ---------------------------------------------------------------------------------------------------------
 // BEHZ lift: x (k residues, coeff form) -> z (nBsk residues, coeff form)
 // ---------------------------------------------------------------------------------------------------------
+// BEHZ constants of the integer path as kernel PARAMETERS (constant bank), like LiftFpC / ScaleFpC further down: the
+// pointer-based tables cost one L1 transaction per use (up to ~550 per coefficient in scale at k = 15).
+struct PrimeC
+{
+    u64 p, r0, r1;
+};
 template <int K>
-B200_HD void lift_coeff(const LevelDev &L, const u64 *__restrict__ src /*[K][n]*/, u64 *__restrict__ dst /*[nBsk][n]*/,
+struct LiftIntC
+{
+    int nBsk;
+    u64 neg_inv_q_mod_mt;
+    u64 q[K];                  // q_i
+    u64 c[2 * K];              // Shoup pair of m~ (Q/q_i)^-1 mod q_i
+    u64 mt[K];                 // (Q/q_i) mod m~
+    PrimeC bsk[K + 2];
+    u64 mat[(K + 2) * K];      // (Q/q_i) m~^-1 mod p_j
+    u64 qm[K + 2];             // Q m~^-1 mod p_j
+};
+template <int K>
+struct ScaleIntC
+{
+    int nB, nBsk;
+    PrimeC q[K], bsk[K + 2];
+    u64 c[2 * K];                  // Shoup pair of t (Q/q_i)^-1 mod q_i
+    u64 tq[K + 2];                 // t Q^-1 mod p_j
+    u64 mat[(K + 2) * K];          // -(Q/q_i) Q^-1 mod p_j
+    u64 sk_c[2 * (K + 1)];         // Shoup pair of (B/b)^-1 mod b
+    u64 sk_mat_q[K * (K + 1)];     // (B/b) mod q_i   (row i, column b; row stride K+1)
+    u64 sk_mat_msk[K + 1];         // (B/b) mod m_sk
+    u64 sk_prod_b_q[K];
+    u64 sk_inv_b_msk;
+};
+
+template <int K>
+B200_HD void lift_coeff(const LiftIntC<K> &L, const u64 *__restrict__ src /*[K][n]*/, u64 *__restrict__ dst /*[nBsk][n]*/,
                         long long n, long long c)
 {
     u64 y[K];
@@ -95,9 +128,8 @@ B200_HD void lift_coeff(const LevelDev &L, const u64 *__restrict__ src /*[K][n]*
 #pragma unroll
     for (int i = 0; i < K; i++)
     {
-        const u64 q = B200_LDG(&L.q[i].p);
-        y[i] = shoup_mul(src[i * n + c], B200_LDG(&L.lift_c[2 * i]), B200_LDG(&L.lift_c[2 * i + 1]), q);
-        ymt += y[i] * B200_LDG(&L.lift_mt[i]); // only the low 32 bits matter (mod m~ = 2^32)
+        y[i] = shoup_mul(src[i * n + c], L.c[2 * i], L.c[2 * i + 1], L.q[i]);
+        ymt += y[i] * L.mt[i]; // only the low 32 bits matter (mod m~ = 2^32)
     }
     const u64 r = ((ymt & 0xffffffffULL) * L.neg_inv_q_mod_mt) & 0xffffffffULL;
 #pragma unroll
@@ -105,14 +137,14 @@ B200_HD void lift_coeff(const LevelDev &L, const u64 *__restrict__ src /*[K][n]*
     {
         if (j < L.nBsk)
         {
-            const PrimeDev P = ld_prime(&L.bsk[j]);
+            const PrimeC P = L.bsk[j];
             // centred representative of r modulo p_j
             const u64 rc = (r >= 0x80000000ULL) ? r + P.p - 0x100000000ULL : r;
             u64 lo = 0, hi = 0;
 #pragma unroll
             for (int i = 0; i < K; i++)
-                mac128(y[i], B200_LDG(&L.lift_mat[j * K + i]), lo, hi);
-            mac128(rc, B200_LDG(&L.lift_qm[j]), lo, hi);
+                mac128(y[i], L.mat[j * K + i], lo, hi);
+            mac128(rc, L.qm[j], lo, hi);
             dst[j * n + c] = barrett128(lo, hi, P.p, P.r0, P.r1);
         }
     }
@@ -188,48 +220,48 @@ B200_HD void square_coeff(const PrimeDev &P, const u64 *__restrict__ A, long lon
 // src rows: [K q-rows][nBsk Bsk-rows], n words apart.
 // ---------------------------------------------------------------------------------------------------------
 template <int K>
-B200_HD void scale_coeff(const LevelDev &L, const u64 *__restrict__ src, u64 *__restrict__ dst, long long n, long long c)
+B200_HD void scale_coeff(const ScaleIntC<K> &L, const u64 *__restrict__ src, u64 *__restrict__ dst, long long n, long long c)
 {
     u64 y[K];
 #pragma unroll
     for (int i = 0; i < K; i++)
-    {
-        const u64 q = B200_LDG(&L.q[i].p);
-        y[i] = shoup_mul(src[i * n + c], B200_LDG(&L.scale_c[2 * i]), B200_LDG(&L.scale_c[2 * i + 1]), q);
-    }
+        y[i] = shoup_mul(src[i * n + c], L.c[2 * i], L.c[2 * i + 1], L.q[i].p);
     // w_j = (t*v_j - FBC_{q->p_j}(t*u)) * Q^-1 mod p_j ; then y'_b = [w_b * (B/b)^-1]_b for b in B
     u64 yb[K + 1];
     u64 w_sk = 0;
+    PrimeC MS = L.bsk[0];
 #pragma unroll
     for (int j = 0; j < K + 2; j++)
     {
         if (j < L.nBsk)
         {
-            const PrimeDev P = ld_prime(&L.bsk[j]);
+            const PrimeC P = L.bsk[j];
             u64 lo = 0, hi = 0;
-            mac128(src[(K + j) * n + c], B200_LDG(&L.scale_tq[j]), lo, hi);
+            mac128(src[(K + j) * n + c], L.tq[j], lo, hi);
 #pragma unroll
             for (int i = 0; i < K; i++)
-                mac128(y[i], B200_LDG(&L.scale_mat[j * K + i]), lo, hi);
+                mac128(y[i], L.mat[j * K + i], lo, hi);
             const u64 w = barrett128(lo, hi, P.p, P.r0, P.r1);
             if (j < L.nB)
             {
                 if (j < K + 1)
-                    yb[j < K + 1 ? j : 0] = shoup_mul(w, B200_LDG(&L.sk_c[2 * j]), B200_LDG(&L.sk_c[2 * j + 1]), P.p);
+                    yb[j < K + 1 ? j : 0] = shoup_mul(w, L.sk_c[2 * (j < K + 1 ? j : 0)], L.sk_c[2 * (j < K + 1 ? j : 0) + 1], P.p);
             }
             else
+            {
                 w_sk = w;
+                MS = P; // m_sk is the last prime of Bsk
+            }
         }
     }
     // alpha_sk = (FBC_{B->m_sk}(w) - w_sk) * B^-1 mod m_sk
-    const PrimeDev MS = ld_prime(&L.bsk[L.nB]);
     u64 alpha;
     {
         u64 lo = 0, hi = 0;
 #pragma unroll
         for (int b = 0; b < K + 1; b++)
             if (b < L.nB)
-                mac128(yb[b], B200_LDG(&L.sk_mat_msk[b]), lo, hi);
+                mac128(yb[b], L.sk_mat_msk[b], lo, hi);
         mac128(MS.p - w_sk, L.sk_inv_b_msk, lo, hi);
         alpha = barrett128(lo, hi, MS.p, MS.r0, MS.r1);
     }
@@ -238,13 +270,13 @@ B200_HD void scale_coeff(const LevelDev &L, const u64 *__restrict__ src, u64 *__
 #pragma unroll
     for (int i = 0; i < K; i++)
     {
-        const PrimeDev Q = ld_prime(&L.q[i]);
+        const PrimeC Q = L.q[i];
         u64 lo = 0, hi = 0;
 #pragma unroll
         for (int b = 0; b < K + 1; b++)
             if (b < L.nB)
-                mac128(yb[b], B200_LDG(&L.sk_mat_q[i * L.nB + b]), lo, hi);
-        const u64 pb = B200_LDG(&L.sk_prod_b_q[i]);
+                mac128(yb[b], L.sk_mat_q[i * (K + 1) + b], lo, hi);
+        const u64 pb = L.sk_prod_b_q[i];
         // alpha negative: + |alpha| * B ; alpha positive: + alpha * (q - B)
         mac128(mag, neg ? pb : Q.p - pb, lo, hi);
         dst[i * n + c] = barrett128(lo, hi, Q.p, Q.r0, Q.r1);
