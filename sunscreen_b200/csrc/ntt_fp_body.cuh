@@ -214,10 +214,12 @@ B200_HD int fp_elem_index(int pbase, int base, int j, int logs)
 }
 
 template <int L, bool FWD, bool SRC_GLOBAL, bool DST_GLOBAL, bool TW16 = false, bool RENORM = true, bool REDUCE = true, bool PRELOADED = false,
-          bool RAW_IN = false /* shared memory holds the raw input words (landed by cp.async): convert on read */>
+          bool RAW_IN = false /* shared memory holds the raw input words (landed by cp.async): convert on read */,
+          bool TW_PRE = false /* the group's twiddles were prefetched by the caller (twpre) */>
 B200_HD void ntt_fp_group(double *sm, const u64 *__restrict__ gsrc, u64 *__restrict__ gdst, int g, int logs, int logn, int M,
                           const NttPrimeFp &P, bool renorm, bool last_inv, bool reduce_input, u64 pint, u64 ratio1,
-                          const u64 *pre = nullptr /* PRELOADED: the group's 2^L raw input words, already in registers */)
+                          const u64 *pre = nullptr /* PRELOADED: the group's 2^L raw input words, already in registers */,
+                          const double *twpre = nullptr)
 {
     constexpr int R = 1 << L;
     const int s = 1 << logs;
@@ -229,7 +231,14 @@ B200_HD void ntt_fp_group(double *sm, const u64 *__restrict__ gsrc, u64 *__restr
     const double *__restrict__ tw = TW16 ? (FWD ? P.fwd16 : P.inv16) : (FWD ? P.fwd : P.inv);
     const int n16 = 1 << (logn - 4); // groups of the radix-16 pass (TW16 layout: [slot][group])
     double tws[R - 1];
-    fp_load_group_tw<L, FWD, TW16>(tws, tw, g, i, logs, logn, M, n16, P, last_inv);
+    if (TW_PRE)
+    {
+#pragma unroll
+        for (int j = 0; j < R - 1; j++)
+            tws[j] = twpre[j];
+    }
+    else
+        fp_load_group_tw<L, FWD, TW16>(tws, tw, g, i, logs, logn, M, n16, P, last_inv);
     double x[R];
 #pragma unroll
     for (int j = 0; j < R; j++)
@@ -388,6 +397,9 @@ struct NttFpStaticPass
         // sub-stride-1 pass would make every lane touch its own 128-byte line (32 L1 wavefronts per request), so
         // its global side is staged through shared memory with coalesced copies instead.
         constexpr bool EDGE_IN = STEP == 0, EDGE_OUT = STEP == NP - 1;
+#ifndef B200_NTT_TW_PREFETCH
+#define B200_NTT_TW_PREFETCH 1
+#endif
 #ifndef B200_NTT_DIRECT_IN
 #define B200_NTT_DIRECT_IN 1
 #endif
@@ -503,13 +515,37 @@ struct NttFpStaticPass
             else
             {
                 auto run = [&](auto RAWF) {
-#pragma unroll
-                    for (int it = 0; it < ITERS; it++)
+                    if constexpr (L <= 3 && NGROUPS % NT == 0 && ITERS > 1 && B200_NTT_TW_PREFETCH)
                     {
-                        const int g = tid + it * NT;
-                        if (NGROUPS % NT == 0 || g < NGROUPS)
-                            ntt_fp_group<L, FWD, SG, DG, TW16, decltype(RN)::value, decltype(RD)::value, false, decltype(RAWF)::value>(
-                                smd, src, dst, g, LOGS, LOGN, M, P, true, !FWD && EDGE_OUT, true, PI_.p, PI_.ratio1);
+                        // the twiddles of group it+1 are requested before group `it` is transformed: their L1/L2 latency
+                        // (the largest stall reason of the kernel, profiles/r1_ncu_ntt_v6.txt) overlaps the butterflies
+                        constexpr int R = 1 << L;
+                        const double *__restrict__ twt = FWD ? P.fwd : P.inv;
+                        double twc[R - 1], twn[R - 1];
+                        fp_load_group_tw<L, FWD, false>(twc, twt, tid, tid >> LOGS, LOGS, LOGN, M, 0, P, !FWD && EDGE_OUT);
+#pragma unroll
+                        for (int it = 0; it < ITERS; it++)
+                        {
+                            const int g = tid + it * NT;
+                            if (it + 1 < ITERS)
+                                fp_load_group_tw<L, FWD, false>(twn, twt, g + NT, (g + NT) >> LOGS, LOGS, LOGN, M, 0, P, !FWD && EDGE_OUT);
+                            ntt_fp_group<L, FWD, SG, DG, TW16, decltype(RN)::value, decltype(RD)::value, false, decltype(RAWF)::value, true>(
+                                smd, src, dst, g, LOGS, LOGN, M, P, true, !FWD && EDGE_OUT, true, PI_.p, PI_.ratio1, nullptr, twc);
+#pragma unroll
+                            for (int j = 0; j < R - 1; j++)
+                                twc[j] = twn[j];
+                        }
+                    }
+                    else
+                    {
+#pragma unroll
+                        for (int it = 0; it < ITERS; it++)
+                        {
+                            const int g = tid + it * NT;
+                            if (NGROUPS % NT == 0 || g < NGROUPS)
+                                ntt_fp_group<L, FWD, SG, DG, TW16, decltype(RN)::value, decltype(RD)::value, false, decltype(RAWF)::value>(
+                                    smd, src, dst, g, LOGS, LOGN, M, P, true, !FWD && EDGE_OUT, true, PI_.p, PI_.ratio1);
+                        }
                     }
                 };
                 if constexpr (RAW)
