@@ -136,6 +136,11 @@ int b200_decrypt(b200_ctx *ctx, int level, const uint64_t *ct, int size, const u
 /* phase = c0 + sum_j c_j * s^j in coefficient form: [batch][k][n] (Decryptor::dot_product_ct_sk_array, S/decryptor.cpp:340-422) */
 int b200_ct_sk_phase(b200_ctx *ctx, int level, const uint64_t *ct, int size, const uint64_t *sk_powers_ntt, uint64_t *phase_out,
                      uint64_t batch, void *stream);
+/* infinity norm of the centred t * phase mod Q of each item, as little-endian multi-precision words; norm_out is a HOST
+   array [batch][words], words >= ceil(bits(Q)/64) + 1; returns after completion (Decryptor::invariant_noise_internal,
+   S/decryptor.cpp:424-485: the quantity behind invariant_noise_budget and the fork's invariant_noise) */
+int b200_noise_norm(b200_ctx *ctx, int level, const uint64_t *ct, int size, const uint64_t *sk_powers_ntt, uint64_t *norm_out,
+                    int words, uint64_t batch, void *stream);
 /* any-nonzero test over polys [1, size) of each item (transparent-ciphertext guard, S/ciphertext.h:451-456);
    flags_out: device array [batch] of 0/1 ("is transparent") */
 int b200_is_transparent(b200_ctx *ctx, int level, const uint64_t *ct, int size, uint32_t *flags_out, uint64_t batch,

@@ -621,6 +621,102 @@ __global__ void phase_add_kernel(const PrimeDev *primes, int size, const u64 *ct
         ph[i * n + c] = add_mod(ph[i * n + c], c0[i * n + c], __ldg(&primes[i].p));
 }
 
+// Decryptor::invariant_noise_internal (S/decryptor.cpp:424-485) on the device: per coefficient the phase c0 + dot, times t,
+// CRT-composed to a multi-precision integer mod Q, centred (poly_infty_norm_coeffmod, S/util/polyarithsmallmod.cpp:292-322),
+// and the maximum over the coefficients of a chunk.  One block = `chunk` consecutive coefficients of one item; the
+// block maxima ([item][block][W + 1] little-endian words) are merged by the caller.
+// consts: q[k] | c[k] | cq[k] | Q[W+1] | half[W+1] | punc[k][W]   with c_i = t (Q/q_i)^-1 mod q_i and its Shoup quotient
+static const int NOISE_MAXW = 18;
+B200_HD bool mp_ge(const u64 *a, const u64 *b, int words)
+{
+    for (int i = words; i-- > 0;)
+        if (a[i] != b[i])
+            return a[i] > b[i];
+    return true;
+}
+__global__ void noise_norm_kernel(const u64 *consts, int k, int W, int size, const u64 *ct, const u64 *dot, long long n, int chunk,
+                                  u64 *blockmax)
+{
+#ifdef B200_EMU_HEADER
+    u64 *sm = (u64 *)emu_shared;
+#else
+    extern __shared__ u64 sm[];
+#endif
+    const int WW = W + 1;
+    const u64 *q = consts, *cm = consts + k, *cq = consts + 2 * k, *Qw = consts + 3 * k, *half = Qw + WW, *punc = half + WW;
+    const long long item = blockIdx.y;
+    const u64 *c0 = ct + item * size * k * n;
+    const u64 *dp = dot + item * k * n;
+    u64 best[NOISE_MAXW], acc[NOISE_MAXW];
+    for (int w = 0; w < WW; w++)
+        best[w] = 0;
+    for (int cc = (int)threadIdx.x; cc < chunk; cc += (int)blockDim.x)
+    {
+        const long long c = (long long)blockIdx.x * chunk + cc;
+        if (c >= n)
+            break;
+        for (int w = 0; w < WW; w++)
+            acc[w] = 0;
+        for (int i = 0; i < k; i++)
+        {
+            const u64 qi = q[i];
+            const u64 x = add_mod(dp[i * n + c], c0[i * n + c], qi);
+            const u64 y = shoup_mul(x, cm[i], cq[i], qi);
+            const u64 *pw = punc + (size_t)i * W;
+            u64 carry = 0;
+            for (int w = 0; w < W; w++)
+            {
+                u64 lo, hi;
+                mul128(pw[w], y, lo, hi);
+                lo += carry;
+                hi += lo < carry;
+                acc[w] += lo;
+                hi += acc[w] < lo;
+                carry = hi;
+            }
+            acc[W] += carry;
+        }
+        while (mp_ge(acc, Qw, WW))
+        { // the sum is below k Q
+            u64 borrow = 0;
+            for (int w = 0; w < WW; w++)
+            {
+                const u64 b = Qw[w] + borrow;
+                const u64 nb = (b < borrow) || (acc[w] < b);
+                acc[w] -= b;
+                borrow = nb;
+            }
+        }
+        if (mp_ge(acc, half, WW))
+        { // centred magnitude Q - acc
+            u64 borrow = 0;
+            for (int w = 0; w < WW; w++)
+            {
+                const u64 b = acc[w] + borrow;
+                const u64 nb = (b < borrow) || (Qw[w] < b);
+                acc[w] = Qw[w] - b;
+                borrow = nb;
+            }
+        }
+        if (mp_ge(acc, best, WW))
+            for (int w = 0; w < WW; w++)
+                best[w] = acc[w];
+    }
+    for (int w = 0; w < WW; w++)
+        sm[(size_t)threadIdx.x * WW + w] = best[w];
+    B200_SYNC();
+    for (int s = (int)blockDim.x >> 1; s > 0; s >>= 1)
+    {
+        if ((int)threadIdx.x < s && mp_ge(sm + (size_t)(threadIdx.x + s) * WW, sm + (size_t)threadIdx.x * WW, WW))
+            for (int w = 0; w < WW; w++)
+                sm[(size_t)threadIdx.x * WW + w] = sm[(size_t)(threadIdx.x + s) * WW + w];
+        B200_SYNC();
+    }
+    if (threadIdx.x == 0)
+        for (int w = 0; w < WW; w++)
+            blockmax[(item * gridDim.x + blockIdx.x) * WW + w] = sm[w];
+}
+
 __global__ void transparent_kernel(const u64 *ct, long long item_words, long long skip_words, u32 *flags)
 {
     const long long item = blockIdx.y;
@@ -685,6 +781,7 @@ struct b200_ctx
     int npass = 0;
     int pass_L[8];
     std::map<std::string, JobDesc> jobs;
+    std::map<int, std::pair<u64 *, int>> noise_consts; // per level: device constants of noise_norm_kernel, words of Q
     std::mutex mu;
     std::atomic<uint64_t> launches{ 0 };
     cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
@@ -862,16 +959,24 @@ static int build_device(b200_ctx *ctx)
                 }
                 return b;
             };
-            double B = p; // canonical (or Barrett-reduced) input
+            // the pass schedule that will run: the statically scheduled kernel's where it is used, else the generic one
+            int sched_np = ctx->npass, sched_L[8];
             for (int pi = 0; pi < ctx->npass; pi++)
+                sched_L[pi] = ctx->pass_L[pi];
+#ifndef B200_EMU_HEADER
+            if (ctx->logn >= 12 && ctx->logn <= 14 && !std::getenv("B200_NO_STATIC_NTT"))
+                sched_np = ntt_static_schedule(ctx->logn, sched_L);
+#endif
+            double B = p; // canonical (or Barrett-reduced) input
+            for (int pi = 0; pi < sched_np; pi++)
             {
                 bool ok = true;
-                double nb = fwd_pass(B, ctx->pass_L[pi], ok);
+                double nb = fwd_pass(B, sched_L[pi], ok);
                 if (!ok)
                 {
                     fp[i].renorm_fwd |= 1u << pi;
                     ok = true;
-                    nb = fwd_pass(RENORMED, ctx->pass_L[pi], ok);
+                    nb = fwd_pass(RENORMED, sched_L[pi], ok);
                     if (!ok)
                         return fail(B200_E_LOGIC, "internal: FP64 NTT bound analysis failed (forward)");
                 }
@@ -879,15 +984,15 @@ static int build_device(b200_ctx *ctx)
             }
             B = p;
             int step = 0;
-            for (int pi = ctx->npass - 1; pi >= 0; pi--, step++)
+            for (int pi = sched_np - 1; pi >= 0; pi--, step++)
             {
                 bool ok = true;
-                double nb = inv_pass(B, ctx->pass_L[pi], ok);
+                double nb = inv_pass(B, sched_L[pi], ok);
                 if (!ok)
                 {
                     fp[i].renorm_inv |= 1u << step;
                     ok = true;
-                    nb = inv_pass(RENORMED, ctx->pass_L[pi], ok);
+                    nb = inv_pass(RENORMED, sched_L[pi], ok);
                     if (!ok)
                         return fail(B200_E_LOGIC, "internal: FP64 NTT bound analysis failed (inverse)");
                 }
@@ -2402,6 +2507,144 @@ int b200_ct_sk_phase(b200_ctx *ctx, int level, const uint64_t *ct, int size, con
         ctx->launches++;
     }
     CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+// infinity norm of the centred t * (c0 + sum_j c_j s^j) mod Q of each item as a little-endian multi-precision integer
+// (Decryptor::invariant_noise_internal, S/decryptor.cpp:424-485).  norm_out: HOST array [batch][words]; the call returns
+// after the result has arrived.
+int b200_noise_norm(b200_ctx *ctx, int level, const uint64_t *ct, int size, const uint64_t *sk_powers_ntt, uint64_t *norm_out,
+                    int words, uint64_t batch, void *stream)
+{
+    int rc = check_level(ctx, level);
+    if (rc)
+        return rc;
+    if (!ct || !sk_powers_ntt || !norm_out)
+        return fail(B200_E_NULL, "null pointer");
+    if (size < 2)
+        return fail(B200_E_INVALID, "ciphertext size must be >= 2");
+    CU_TRY(cudaSetDevice(ctx->device));
+    const long long n = (long long)ctx->n;
+    const LevelDev &L = ctx->levels[level];
+    const LevelHost &Lh = ctx->host->levels[level];
+    const int k = L.k, terms = size - 1;
+    u64 *consts = nullptr;
+    int W = 0;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        auto it = ctx->noise_consts.find(level);
+        if (it == ctx->noise_consts.end())
+        {
+            std::vector<u64> q(k);
+            for (int i = 0; i < k; i++)
+                q[i] = ctx->host->primes[Lh.q_idx[i]].mod.p;
+            b200::BigUInt Q(1);
+            for (u64 v : q)
+                Q.mul(v);
+            W = (int)Q.w.size();
+            if (W + 1 > NOISE_MAXW)
+                return fail(B200_E_INVALID, "coefficient modulus too wide for the noise-norm kernel");
+            std::vector<u64> h((size_t)3 * k + 2 * (W + 1) + (size_t)k * W, 0);
+            for (int i = 0; i < k; i++)
+            {
+                h[i] = q[i];
+                h[k + i] = Lh.scale_c[i].w;
+                h[2 * k + i] = Lh.scale_c[i].wq;
+                b200::BigUInt P(1);
+                for (int j = 0; j < k; j++)
+                    if (j != i)
+                        P.mul(q[j]);
+                std::copy(P.w.begin(), P.w.end(), h.begin() + 3 * k + 2 * (W + 1) + (size_t)i * W);
+            }
+            u64 *Qw = h.data() + 3 * k, *half = Qw + W + 1;
+            std::copy(Q.w.begin(), Q.w.end(), Qw);
+            { // half = (Q + 1) / 2: value >= half  <=>  centred negative
+                std::vector<u64> tmp(Qw, Qw + W + 1);
+                u64 carry = 1;
+                for (auto &x : tmp)
+                {
+                    const u64 s = x + carry;
+                    carry = s < x;
+                    x = s;
+                }
+                for (int i = 0; i <= W; i++)
+                    half[i] = (tmp[i] >> 1) | (i < W ? tmp[i + 1] << 63 : 0);
+            }
+            if ((rc = upload(ctx, h, &consts)))
+                return rc;
+            ctx->noise_consts[level] = std::make_pair(consts, W);
+        }
+        else
+        {
+            consts = it->second.first;
+            W = it->second.second;
+        }
+    }
+    if (words < W + 1)
+        return fail(B200_E_INVALID, "norm_out holds fewer words than the coefficient modulus");
+    for (size_t i = 0; i < (size_t)batch * words; i++)
+        norm_out[i] = 0;
+    if (batch == 0)
+        return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    Scratch scr(s);
+    u64 *X = nullptr, *acc = nullptr, *bm = nullptr;
+    const int NT = 128, CHUNK = 128, WW = W + 1;
+    const int blocks = (int)((n + CHUNK - 1) / CHUNK);
+    if ((rc = scr.get((size_t)batch * terms * k * n, &X)))
+        return rc;
+    if ((rc = scr.get((size_t)batch * k * n, &acc)))
+        return rc;
+    if ((rc = scr.get((size_t)batch * blocks * WW, &bm)))
+        return rc;
+    {
+        std::vector<int> prime;
+        std::vector<long long> so, dof;
+        for (int j = 0; j < terms; j++)
+            for (int r = 0; r < k; r++)
+            {
+                prime.push_back(Lh.q_idx[r]);
+                so.push_back(((long long)(j + 1) * k + r) * n);
+                dof.push_back(((long long)j * k + r) * n);
+            }
+        JobDesc jd;
+        if ((rc = get_job(ctx, "dec:" + std::to_string(level) + ":" + std::to_string(size), prime, so, dof, &jd)))
+            return rc;
+        if ((rc = launch_ntt<true>(ctx, jd, (const u64 *)ct, (long long)size * k * n, X, (long long)terms * k * n,
+                                   (long long)batch, 0, s)))
+            return rc;
+    }
+    {
+        const long long total = (long long)batch * k * n;
+        B200_LAUNCH(dot_sk_kernel, blocks_for(total, EB), EB, 0, s, ctx->d_primes, k, terms, X, (const u64 *)sk_powers_ntt, acc,
+                    ctx->logn, total);
+        ctx->launches++;
+    }
+    JobDesc jd;
+    if ((rc = dense_job(ctx, "slab:" + std::to_string(level), row_primes(ctx, level, false), &jd)))
+        return rc;
+    if ((rc = launch_ntt<false>(ctx, jd, acc, (long long)k * n, acc, (long long)k * n, (long long)batch, 0, s)))
+        return rc;
+    {
+        dim3 grid((unsigned)blocks, (unsigned)batch);
+        B200_LAUNCH(noise_norm_kernel, grid, NT, (size_t)NT * WW * 8, s, (const u64 *)consts, k, W, size, (const u64 *)ct,
+                    (const u64 *)acc, n, CHUNK, bm);
+        ctx->launches++;
+    }
+    CU_TRY(cudaGetLastError());
+    std::vector<u64> hb((size_t)batch * blocks * WW);
+    CU_TRY(cudaMemcpyAsync(hb.data(), bm, hb.size() * 8, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    for (uint64_t b = 0; b < batch; b++)
+    {
+        u64 *best = (u64 *)norm_out + b * words;
+        for (int j = 0; j < blocks; j++)
+        {
+            const u64 *v = hb.data() + (b * blocks + j) * WW;
+            if (mp_ge(v, best, WW))
+                std::copy(v, v + WW, best);
+        }
+    }
     return 0;
 }
 

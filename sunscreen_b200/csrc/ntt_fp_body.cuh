@@ -369,6 +369,18 @@ template <> struct NttSched<12> { static constexpr int NP = 3; static constexpr 
 template <> struct NttSched<13> { static constexpr int NP = 4; static constexpr int L0 = 3, L1 = 3, L2 = 3, L3 = 4; };
 template <> struct NttSched<14> { static constexpr int NP = 4; static constexpr int L0 = 3, L1 = 3, L2 = 4, L3 = 4; };
 
+// the same schedules for the host's magnitude bookkeeping (renorm masks are per pass of the schedule that runs)
+inline int ntt_static_schedule(int logn, int *L)
+{
+    auto fill = [&](int np, int a, int b, int c_, int d) { L[0] = a; L[1] = b; L[2] = c_; L[3] = d; return np; };
+    if (logn == 12)
+        return fill(NttSched<12>::NP, NttSched<12>::L0, NttSched<12>::L1, NttSched<12>::L2, NttSched<12>::L3);
+    if (logn == 13)
+        return fill(NttSched<13>::NP, NttSched<13>::L0, NttSched<13>::L1, NttSched<13>::L2, NttSched<13>::L3);
+    if (logn == 14)
+        return fill(NttSched<14>::NP, NttSched<14>::L0, NttSched<14>::L1, NttSched<14>::L2, NttSched<14>::L3);
+    return 0;
+}
 template <int LOGN, int PI> struct NttSchedL
 {
     static constexpr int value = PI == 0 ? NttSched<LOGN>::L0 : PI == 1 ? NttSched<LOGN>::L1 : PI == 2 ? NttSched<LOGN>::L2 : NttSched<LOGN>::L3;

@@ -1927,122 +1927,17 @@ static void noise_norm(Decryptor_ *d, Ciphertext_ &ct, std::vector<u64> &norm_ou
         int lv = data_level(c, ct, "encrypted is not valid for encryption parameters");
         if (ct.is_ntt_form)
             throw InvalidArg("encrypted cannot be in NTT form");
-        const size_t n = c->parms.n;
         const int k = c->level_k[lv];
         const u64 *pc = ct.dev_ptr(c);
         const u64 *pw = d->powers(lv, (int)ct.size - 1);
-        void *dp = nullptr;
-        dev_check(b200_malloc(c->dev, (size_t)k * n * 8, &dp));
-        std::vector<u64> ph((size_t)k * n);
-        int rc = b200_ct_sk_phase(c->dev, lv, pc, (int)ct.size, pw, (u64 *)dp, 1, nullptr);
-        if (!rc)
-            rc = b200_memcpy_d2h(c->dev, ph.data(), dp, ph.size() * 8, nullptr);
-        if (!rc)
-            rc = b200_stream_synchronize(c->dev, nullptr);
-        b200_free(c->dev, dp);
-        dev_check(rc);
-        // CRT-compose each coefficient (Garner-free: sum_i [x_i * t * (Q/q_i)^-1]_{q_i} * (Q/q_i) mod Q) and take
-        // the infinity norm of the centred values.  Multi-precision on the host, like the reference.
-        typedef unsigned __int128 u128;
-        std::vector<u64> q(c->parms.coeff.begin(), c->parms.coeff.begin() + k);
+        // phase on the GPU, then per coefficient t * phase CRT-composed mod Q, centred, and the maximum — also on the GPU
+        // (noise_norm_kernel); only the norm's words come back
         b200::BigUInt Q(1);
-        for (u64 v : q)
-            Q.mul(v);
+        for (int i = 0; i < k; i++)
+            Q.mul(c->parms.coeff[i]);
         const size_t W = Q.w.size();
-        std::vector<std::vector<u64>> punc(k, std::vector<u64>(W, 0));
-        std::vector<u64> inv(k);
-        for (int i = 0; i < k; i++)
-        {
-            b200::BigUInt P(1);
-            u64 pm = 1;
-            for (int j = 0; j < k; j++)
-                if (j != i)
-                {
-                    P.mul(q[j]);
-                    pm = (u64)((u128)pm * (q[j] % q[i]) % q[i]);
-                }
-            std::copy(P.w.begin(), P.w.end(), punc[i].begin());
-            inv[i] = b200::inv_mod(pm, q[i]);
-        }
-        std::vector<u64> Qw(W + 1, 0), half(W + 1, 0);
-        std::copy(Q.w.begin(), Q.w.end(), Qw.begin());
-        { // half = (Q + 1) / 2 comparison threshold: value >= half  <=>  centred negative (poly_infty_norm_coeffmod)
-            std::vector<u64> tmp(Qw);
-            u64 carry = 1;
-            for (auto &x : tmp)
-            {
-                u64 s = x + carry;
-                carry = s < x;
-                x = s;
-            }
-            for (size_t i = 0; i < tmp.size(); i++)
-                half[i] = (tmp[i] >> 1) | (i + 1 < tmp.size() ? tmp[i + 1] << 63 : 0);
-        }
-        // Per coefficient: v = sum_i [x_i * t * (Q/q_i)^-1]_{q_i} * (Q/q_i) mod Q, centred, and the running maximum.
-        // Tight loops over fixed-size word arrays (no allocation, no 128-bit division): c_i = t (Q/q_i)^-1 mod q_i is
-        // applied with a Shoup quotient, the sum is reduced once at the end (it is below k Q).
-        const size_t MAXW = 18;
-        if (W + 1 > MAXW)
-            throw LogicErr("internal: coefficient modulus too wide for the noise-budget accumulator");
-        std::vector<u64> cmul(k), cmul_q(k);
-        const u64 t = c->parms.plain;
-        for (int i = 0; i < k; i++)
-        {
-            cmul[i] = (u64)((u128)(t % q[i]) * inv[i] % q[i]);
-            cmul_q[i] = (u64)(((u128)cmul[i] << 64) / q[i]);
-        }
-        auto ge_w = [W](const u64 *a, const u64 *b) {
-            for (size_t i = W + 1; i-- > 0;)
-                if (a[i] != b[i])
-                    return a[i] > b[i];
-            return true;
-        };
-        auto sub_w = [W](u64 *a, const u64 *b) {
-            u64 borrow = 0;
-            for (size_t i = 0; i <= W; i++)
-            {
-                const u64 bi = b[i] + borrow;
-                const u64 nb = (bi < borrow) || (a[i] < bi);
-                a[i] -= bi;
-                borrow = nb;
-            }
-        };
-        u64 norm_w[MAXW] = { 0 }, acc[MAXW], neg[MAXW];
-        const u64 *Qp = Qw.data(), *halfp = half.data();
-        for (size_t cidx = 0; cidx < n; cidx++)
-        {
-            for (size_t w = 0; w <= W; w++)
-                acc[w] = 0;
-            for (int i = 0; i < k; i++)
-            {
-                const u64 x = ph[(size_t)i * n + cidx];
-                u64 y = x * cmul[i] - (u64)(((u128)x * cmul_q[i]) >> 64) * q[i];
-                y = y >= q[i] ? y - q[i] : y;
-                const u64 *pw = punc[i].data();
-                u64 carry = 0;
-                for (size_t w = 0; w < W; w++)
-                {
-                    const u128 m = (u128)pw[w] * y + acc[w] + carry;
-                    acc[w] = (u64)m;
-                    carry = (u64)(m >> 64);
-                }
-                acc[W] += carry;
-            }
-            while (ge_w(acc, Qp))
-                sub_w(acc, Qp);
-            if (ge_w(acc, halfp))
-            { // centred magnitude = Q - acc
-                for (size_t w = 0; w <= W; w++)
-                    neg[w] = Qp[w];
-                sub_w(neg, acc);
-                for (size_t w = 0; w <= W; w++)
-                    acc[w] = neg[w];
-            }
-            if (ge_w(acc, norm_w))
-                for (size_t w = 0; w <= W; w++)
-                    norm_w[w] = acc[w];
-        }
-        std::vector<u64> norm(norm_w, norm_w + W + 1);
+        std::vector<u64> norm(W + 1, 0);
+        dev_check(b200_noise_norm(c->dev, lv, pc, (int)ct.size, pw, norm.data(), (int)norm.size(), 1, nullptr));
         norm_out = norm;
         k_out = k;
         q_bits_out = Q.bit_length();

@@ -64,6 +64,8 @@ _SIGS = {
     "b200_sub_plain": [vp, C.c_int, vp, C.c_int, vp, u64, vp, u64, vp],
     "b200_mod_switch_to_next": [vp, C.c_int, vp, C.c_int, vp, u64, vp],
     "b200_decrypt": [vp, C.c_int, vp, C.c_int, vp, vp, u64, vp],
+    "b200_ct_sk_phase": [vp, C.c_int, vp, C.c_int, vp, vp, u64, vp],
+    "b200_noise_norm": [vp, C.c_int, vp, C.c_int, vp, vp, C.c_int, u64, vp],
     "b200_is_transparent": [vp, C.c_int, vp, C.c_int, vp, u64, vp],
     "b200_multiply_relin_host": [vp, C.c_int, vp, vp, vp, vp, u64],
     "b200_ntt_roundtrip_host": [vp, C.c_int, vp, vp, u64],
@@ -257,6 +259,15 @@ class B200Context:
     def decrypt(self, ct, size, sk_powers, plain_out, batch, level=None, stream=None):
         self.L.call("b200_decrypt", self.h, self._lv(level), vp(ptr(ct)), C.c_int(size), vp(ptr(sk_powers)),
                     vp(ptr(plain_out)), u64(batch), vp(stream))
+
+    def ct_sk_phase(self, ct, size, sk_powers, phase_out, batch, level=None, stream=None):
+        self.L.call("b200_ct_sk_phase", self.h, self._lv(level), vp(ptr(ct)), C.c_int(size), vp(ptr(sk_powers)),
+                    vp(ptr(phase_out)), u64(batch), vp(stream))
+
+    def noise_norm(self, ct, size, sk_powers, norm_out_host, words, batch, level=None, stream=None):
+        """norm_out_host: HOST uint64 array [batch][words] (little-endian multi-precision)."""
+        self.L.call("b200_noise_norm", self.h, self._lv(level), vp(ptr(ct)), C.c_int(size), vp(ptr(sk_powers)),
+                    vp(ptr(norm_out_host)), C.c_int(words), u64(batch), vp(stream))
 
     def is_transparent(self, ct, size, flags, batch, level=None, stream=None):
         self.L.call("b200_is_transparent", self.h, self._lv(level), vp(ptr(ct)), C.c_int(size), vp(ptr(flags)), u64(batch),

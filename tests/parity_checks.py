@@ -258,6 +258,35 @@ def check_encrypted_roundtrip(P, seed=3):
     return dict(dec=dec, sk=sk, ct=got, expect_plain=R.pt_coeffs(R.decrypt(dec, back)))
 
 
+def check_noise_norm(P, batch=3, seed=23):
+    """b200_noise_norm (the quantity behind invariant_noise_budget, S/decryptor.cpp:424-485): for random ciphertexts of
+    size 2 and 3 and random key powers, the device's multi-precision infinity norm of the centred t * phase mod Q equals
+    the same computed with Python integers from the phase words."""
+    from functools import reduce
+    rng = np.random.default_rng(seed)
+    q = [int(m) for m in P.moduli[: P.k]]
+    Q = reduce(lambda a, b: a * b, q)
+    words = (Q.bit_length() + 63) // 64 + 1
+    for size in (2, 3):
+        ct = rand_ct(rng, P.moduli, P.k, P.n, size=size, batch=batch)
+        skp = np.stack([np.stack([rng.integers(0, q[i], size=P.n, dtype=np.uint64) for i in range(P.k)]) for _ in range(size - 1)])
+        dct, dsk = P.dev(ct), P.dev(skp)
+        ph = P.out(batch, P.k, P.n)
+        P.ctx.ct_sk_phase(dct, size, dsk, ph, batch)
+        phase = P.host(ph).reshape(batch, P.k, P.n)
+        got = np.zeros((batch, words), dtype=np.uint64)
+        P.ctx.noise_norm(dct, size, dsk, got, words, batch)
+        coef = [(Q // qi) * pow(Q // qi, -1, qi) * P.t % Q for qi in q]
+        for b in range(batch):
+            best = 0
+            for c in range(P.n):
+                v = sum(int(phase[b, i, c]) * coef[i] for i in range(P.k)) % Q
+                v = Q - v if v >= (Q + 1) // 2 else v
+                best = max(best, v)
+            mine = sum(int(got[b, w]) << (64 * w) for w in range(words))
+            assert mine == best, f"noise norm, size {size}, item {b}: {mine:#x} != {best:#x}"
+
+
 def check_host_pipeline(P, batch=5, seed=17):
     """b200_multiply_relin_host (host buffers in, host buffers out; chunked, overlapped, packed 6-byte transfers when the
     level's primes fit 48 bits) returns the same words as the device-resident entry point, also when the ring of staging

@@ -57,6 +57,12 @@ def test_host_buffer_pipeline(pair):
     pc.check_host_pipeline(pair)
 
 
+def test_noise_norm(pair):
+    if pair.n > 4096:
+        pytest.skip("noise norm test runs on the smallest set only (emulation speed)")
+    pc.check_noise_norm(pair)
+
+
 def test_encrypted_roundtrip(pair):
     if not pair.ctx.using_batching:
         pytest.skip("needs a batching plain modulus")
