@@ -1,9 +1,14 @@
 // sampling.cpp — see sampling.h.
 #include "sampling.h"
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <random>
 #include <stdexcept>
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+#define B200_X86_SIMD 1
+#endif
 
 namespace b200
 {
@@ -110,6 +115,132 @@ void final(B2State &S, unsigned char *out, size_t outlen)
     std::memcpy(out, full, outlen);
 }
 void store32(unsigned char *p, uint32_t v) { std::memcpy(p, &v, 4); }
+
+#ifdef B200_X86_SIMD
+// BLAKE2Xb expansion nodes are independent BLAKE2b compressions of the same 64-byte root that differ only in the node
+// offset of their parameter block, so W of them run side by side in the 64-bit lanes of one vector register (the
+// generator behind every key and every encryption is otherwise the host-side bottleneck: one scalar compression per 64
+// output bytes).  h1_xor = the parameter word that carries the node offset, for lane 0; lane j adds j to the offset.
+#define B200_G(a, b, c, d, x, y)                                                                                       \
+    a = ADD(ADD(a, b), x);                                                                                             \
+    d = ROR(XOR(d, a), 32);                                                                                            \
+    c = ADD(c, d);                                                                                                     \
+    b = ROR(XOR(b, c), 24);                                                                                            \
+    a = ADD(ADD(a, b), y);                                                                                             \
+    d = ROR(XOR(d, a), 16);                                                                                            \
+    c = ADD(c, d);                                                                                                     \
+    b = ROR(XOR(b, c), 63);
+#define B200_ROUNDS()                                                                                                  \
+    for (int r = 0; r < 12; r++)                                                                                       \
+    {                                                                                                                  \
+        const unsigned char *s = SIGMA[r];                                                                             \
+        B200_G(v0, v4, v8, v12, m[s[0]], m[s[1]])                                                                       \
+        B200_G(v1, v5, v9, v13, m[s[2]], m[s[3]])                                                                       \
+        B200_G(v2, v6, v10, v14, m[s[4]], m[s[5]])                                                                      \
+        B200_G(v3, v7, v11, v15, m[s[6]], m[s[7]])                                                                      \
+        B200_G(v0, v5, v10, v15, m[s[8]], m[s[9]])                                                                      \
+        B200_G(v1, v6, v11, v12, m[s[10]], m[s[11]])                                                                    \
+        B200_G(v2, v7, v8, v13, m[s[12]], m[s[13]])                                                                     \
+        B200_G(v3, v4, v9, v14, m[s[14]], m[s[15]])                                                                     \
+    }
+
+__attribute__((target("avx512f"))) void expand_nodes_avx512(const uint64_t h0[8], const uint64_t root[8], uint64_t node0,
+                                                            unsigned char *out)
+{
+    typedef __m512i V;
+#define ADD _mm512_add_epi64
+#define XOR _mm512_xor_si512
+#define ROR(x, n) _mm512_ror_epi64(x, n)
+    V m[16];
+    for (int i = 0; i < 8; i++)
+        m[i] = _mm512_set1_epi64((long long)root[i]);
+    for (int i = 8; i < 16; i++)
+        m[i] = _mm512_setzero_si512();
+    // node offset: low 32 bits of parameter word 1 (bytes 8..11)
+    const V lane = _mm512_set_epi64(7, 6, 5, 4, 3, 2, 1, 0);
+    V h[8];
+    for (int i = 0; i < 8; i++)
+        h[i] = _mm512_set1_epi64((long long)h0[i]);
+    h[1] = XOR(h[1], ADD(_mm512_set1_epi64((long long)node0), lane));
+    V v0 = h[0], v1 = h[1], v2 = h[2], v3 = h[3], v4 = h[4], v5 = h[5], v6 = h[6], v7 = h[7];
+    V v8 = _mm512_set1_epi64((long long)IV[0]), v9 = _mm512_set1_epi64((long long)IV[1]), v10 = _mm512_set1_epi64((long long)IV[2]),
+      v11 = _mm512_set1_epi64((long long)IV[3]), v12 = _mm512_set1_epi64((long long)(IV[4] ^ 64)),
+      v13 = _mm512_set1_epi64((long long)IV[5]), v14 = _mm512_set1_epi64((long long)~IV[6]), v15 = _mm512_set1_epi64((long long)IV[7]);
+    B200_ROUNDS()
+    alignas(64) uint64_t t[8][8];
+    _mm512_store_si512((void *)t[0], XOR(h[0], XOR(v0, v8)));
+    _mm512_store_si512((void *)t[1], XOR(h[1], XOR(v1, v9)));
+    _mm512_store_si512((void *)t[2], XOR(h[2], XOR(v2, v10)));
+    _mm512_store_si512((void *)t[3], XOR(h[3], XOR(v3, v11)));
+    _mm512_store_si512((void *)t[4], XOR(h[4], XOR(v4, v12)));
+    _mm512_store_si512((void *)t[5], XOR(h[5], XOR(v5, v13)));
+    _mm512_store_si512((void *)t[6], XOR(h[6], XOR(v6, v14)));
+    _mm512_store_si512((void *)t[7], XOR(h[7], XOR(v7, v15)));
+    for (int j = 0; j < 8; j++)
+    {
+        uint64_t w[8];
+        for (int i = 0; i < 8; i++)
+            w[i] = t[i][j];
+        std::memcpy(out + j * 64, w, 64);
+    }
+#undef ADD
+#undef XOR
+#undef ROR
+}
+
+__attribute__((target("avx2"))) void expand_nodes_avx2(const uint64_t h0[8], const uint64_t root[8], uint64_t node0, unsigned char *out)
+{
+    typedef __m256i V;
+#define ADD _mm256_add_epi64
+#define XOR _mm256_xor_si256
+#define ROR(x, n) _mm256_or_si256(_mm256_srli_epi64(x, n), _mm256_slli_epi64(x, 64 - (n)))
+    V m[16];
+    for (int i = 0; i < 8; i++)
+        m[i] = _mm256_set1_epi64x((long long)root[i]);
+    for (int i = 8; i < 16; i++)
+        m[i] = _mm256_setzero_si256();
+    const V lane = _mm256_set_epi64x(3, 2, 1, 0);
+    V h[8];
+    for (int i = 0; i < 8; i++)
+        h[i] = _mm256_set1_epi64x((long long)h0[i]);
+    h[1] = XOR(h[1], ADD(_mm256_set1_epi64x((long long)node0), lane));
+    V v0 = h[0], v1 = h[1], v2 = h[2], v3 = h[3], v4 = h[4], v5 = h[5], v6 = h[6], v7 = h[7];
+    V v8 = _mm256_set1_epi64x((long long)IV[0]), v9 = _mm256_set1_epi64x((long long)IV[1]), v10 = _mm256_set1_epi64x((long long)IV[2]),
+      v11 = _mm256_set1_epi64x((long long)IV[3]), v12 = _mm256_set1_epi64x((long long)(IV[4] ^ 64)),
+      v13 = _mm256_set1_epi64x((long long)IV[5]), v14 = _mm256_set1_epi64x((long long)~IV[6]), v15 = _mm256_set1_epi64x((long long)IV[7]);
+    B200_ROUNDS()
+    alignas(32) uint64_t t[8][4];
+    _mm256_store_si256((__m256i *)t[0], XOR(h[0], XOR(v0, v8)));
+    _mm256_store_si256((__m256i *)t[1], XOR(h[1], XOR(v1, v9)));
+    _mm256_store_si256((__m256i *)t[2], XOR(h[2], XOR(v2, v10)));
+    _mm256_store_si256((__m256i *)t[3], XOR(h[3], XOR(v3, v11)));
+    _mm256_store_si256((__m256i *)t[4], XOR(h[4], XOR(v4, v12)));
+    _mm256_store_si256((__m256i *)t[5], XOR(h[5], XOR(v5, v13)));
+    _mm256_store_si256((__m256i *)t[6], XOR(h[6], XOR(v6, v14)));
+    _mm256_store_si256((__m256i *)t[7], XOR(h[7], XOR(v7, v15)));
+    for (int j = 0; j < 4; j++)
+    {
+        uint64_t w[8];
+        for (int i = 0; i < 8; i++)
+            w[i] = t[i][j];
+        std::memcpy(out + j * 64, w, 64);
+    }
+#undef ADD
+#undef XOR
+#undef ROR
+}
+int simd_width()
+{
+    static const int w = [] {
+        __builtin_cpu_init();
+        const int hw = __builtin_cpu_supports("avx512f") ? 8 : __builtin_cpu_supports("avx2") ? 4 : 1;
+        const char *e = std::getenv("B200_PRNG_SIMD"); // developer/test knob: cap the width (1 = scalar, 4 = AVX2)
+        const int cap = e ? std::atoi(e) : 8;
+        return hw >= 8 && cap >= 8 ? 8 : hw >= 4 && cap >= 4 ? 4 : 1;
+    }();
+    return w;
+}
+#endif
 } // namespace
 
 void blake2xb(void *out_, size_t outlen, const void *in, size_t inlen, const void *key, size_t keylen)
@@ -144,7 +275,30 @@ void blake2xb(void *out_, size_t outlen, const void *in, size_t inlen, const voi
     store32(P + 12, (uint32_t)outlen);
     P[16] = 0;  // node_depth
     P[17] = 64; // inner_length
-    for (size_t i = 0; outlen > 0; i++)
+    size_t i = 0;
+#ifdef B200_X86_SIMD
+    if (const int W = simd_width(); W > 1)
+    { // full 64-byte nodes, W at a time
+        P[0] = 64;
+        store32(P + 8, 0);
+        uint64_t h0[8], rootw[8];
+        for (int j = 0; j < 8; j++)
+        {
+            uint64_t w;
+            std::memcpy(&w, P + 8 * j, 8);
+            h0[j] = IV[j] ^ w;
+        }
+        std::memcpy(rootw, root, 64);
+        for (; outlen >= (size_t)W * 64; i += W, outlen -= (size_t)W * 64)
+        {
+            if (W == 8)
+                expand_nodes_avx512(h0, rootw, i, out + i * 64);
+            else
+                expand_nodes_avx2(h0, rootw, i, out + i * 64);
+        }
+    }
+#endif
+    for (; outlen > 0; i++)
     {
         size_t block = outlen < 64 ? outlen : 64;
         P[0] = (unsigned char)block;
@@ -234,12 +388,16 @@ void sample_poly_uniform(Blake2xbPrng &prng, size_t n, const std::vector<uint64_
     {
         const uint64_t q = moduli[j];
         const uint64_t max_multiple = max_random - (max_random % q) - 1;
+        const uint64_t qinv = (uint64_t)(((u128)1 << 64) / q); // floor(2^64 / q): r % q without a division per word
         for (size_t c = 0; c < n; c++)
         {
             uint64_t r = out[j * n + c];
             while (r >= max_multiple)
                 prng.generate(sizeof(r), &r);
-            out[j * n + c] = r % q;
+            uint64_t rem = r - (uint64_t)(((u128)r * qinv) >> 64) * q; // quotient estimate is at most 1 too small
+            while (rem >= q)
+                rem -= q;
+            out[j * n + c] = rem;
         }
     }
 }

@@ -26,6 +26,12 @@ public:
     uint32_t generate32()
     {
         uint32_t r;
+        if (head_ + sizeof(r) <= buffer_.size())
+        { // the common case inline: the distributions draw one 32-bit word at a time
+            __builtin_memcpy(&r, buffer_.data() + head_, sizeof(r));
+            head_ += sizeof(r);
+            return r;
+        }
         generate(sizeof(r), &r);
         return r;
     }
