@@ -127,6 +127,9 @@ int b200_sub_plain(b200_ctx *ctx, int level, const uint64_t *a, int size, const 
 /* out = x (*) y coefficient-wise mod q_r, y broadcast over polys (and over items when y_batch == 1) */
 int b200_dyadic_product(b200_ctx *ctx, int level, const uint64_t *x, int size, const uint64_t *y, uint64_t y_batch,
                         uint64_t *out, uint64_t batch, void *stream);
+/* residues of small signed values (host-sampled ternary secrets / clipped-normal noise, S/util/rlwe.cpp:23-67):
+   vals [polys][n] int64 (device) -> out [polys][k][n], out = v < 0 ? v + q_r : v */
+int b200_expand_signed(b200_ctx *ctx, int level, const int64_t *vals, int polys, uint64_t *out, void *stream);
 /* [batch][size][k][n] at `level` -> [batch][size][k-1][n] at level+1 */
 int b200_mod_switch_to_next(b200_ctx *ctx, int level, const uint64_t *a, int size, uint64_t *out, uint64_t batch,
                             void *stream);

@@ -512,6 +512,21 @@ __global__ void addsub_kernel(const PrimeDev *primes, int k, const u64 *a, const
     out[idx] = v;
 }
 
+// small signed values (ternary secrets, clipped-normal noise: host samples, S/util/rlwe.cpp:23-67) -> their residues:
+// out[poly][r][c] = v < 0 ? v + q_r : v
+__global__ void expand_signed_kernel(const PrimeDev *primes, int k, const long long *vals, u64 *out, int logn, long long total)
+{
+    const long long idx = GLOBAL_IDX();
+    if (idx >= total)
+        return;
+    const long long c = idx & ((1LL << logn) - 1);
+    const long long row = idx >> logn;
+    const int r = (int)(row % k);
+    const long long poly = row / k;
+    const long long v = vals[(poly << logn) + c];
+    out[idx] = v < 0 ? __ldg(&primes[r].p) + (u64)v : (u64)v;
+}
+
 // dyadic out[item][poly][r][c] = x * y[(item % pb)][r][c] mod q_r   (x, y canonical)
 __global__ void dyadic_plain_kernel(const PrimeDev *primes, int k, int size, const u64 *x, const u64 *y, long long pb,
                                     u64 *out, int logn, long long total)
@@ -2124,6 +2139,26 @@ int b200_sub(b200_ctx *ctx, int level, const uint64_t *a, const uint64_t *b, uin
 int b200_negate(b200_ctx *ctx, int level, const uint64_t *a, uint64_t *out, int size, uint64_t batch, void *stream)
 {
     return addsub(ctx, level, (const u64 *)a, nullptr, (u64 *)out, size, batch, stream, 2);
+}
+
+// residues of small signed host samples: vals [polys][n] (int64, device) -> out [polys][k][n]
+int b200_expand_signed(b200_ctx *ctx, int level, const int64_t *vals, int polys, uint64_t *out, void *stream)
+{
+    int rc = check_level(ctx, level);
+    if (rc)
+        return rc;
+    if (!vals || !out)
+        return fail(B200_E_NULL, "null pointer");
+    if (polys < 1)
+        return 0;
+    CU_TRY(cudaSetDevice(ctx->device));
+    const int k = ctx->levels[level].k;
+    const long long total = (long long)polys * k * (long long)ctx->n;
+    B200_LAUNCH(expand_signed_kernel, blocks_for(total, EB), EB, 0, (cudaStream_t)stream, ctx->d_primes, k, (const long long *)vals,
+                (u64 *)out, ctx->logn, total);
+    ctx->launches++;
+    CU_TRY(cudaGetLastError());
+    return 0;
 }
 
 // ---- multiply / square ----

@@ -2059,7 +2059,7 @@ long KeyGenerator_CreatePublicKey(void *p, bool /*save_seed*/, void **out)
     long hr = guard([&] {
         std::lock_guard<std::mutex> lk(c->mu);
         b200::Blake2xbPrng bootstrap(b200::random_seed());
-        pk->data.host = encrypt_zero_symmetric_key_level(c, kg->sk, bootstrap); // generate_pk (S/keygenerator.cpp:94-122)
+        pk->data.host = encrypt_zero_symmetric_key_level(c, kg->dev_sk(), bootstrap); // generate_pk (S/keygenerator.cpp:94-122)
         pk->data.host_valid = true;
         pk->data.parms_id = c->ids[0];
         pk->data.size = 2;
@@ -2280,30 +2280,31 @@ static void encrypt_asymmetric(Encryptor_ *e, const Plaintext_ &plain, b200::Bla
     const int enc_lv = drop ? 0 : c->first_level;
     const size_t ke = (size_t)c->level_k[enc_lv];
     const std::vector<u64> mods(c->parms.coeff.begin(), c->parms.coeff.begin() + ke);
-    std::vector<u64> u(ke * n), ee(2 * ke * n);
-    b200::sample_poly_ternary(prng, n, mods, u.data());
-    b200::sample_poly_normal(prng, n, mods, ee.data());
-    b200::sample_poly_normal(prng, n, mods, ee.data() + ke * n);
+    // u, e_0, e_1 as small signed values; their residues are formed on the device
+    std::vector<u64> us(n), es(2 * n);
+    b200::sample_poly_ternary(prng, n, signed_only(), us.data());
+    b200::sample_poly_normal(prng, n, signed_only(), es.data());
+    b200::sample_poly_normal(prng, n, signed_only(), es.data() + n);
     if (comp)
     {
         if (comp->u)
         {
             comp->u->reserve(1, n, mods);
-            comp->u->insert(0, u.data());
+            comp->u->insert(0, expand_signed_host(us.data(), n, mods).data());
         }
         if (comp->e)
         {
             comp->e->reserve(2, n, mods);
-            comp->e->insert(0, ee.data());
-            comp->e->insert(1, ee.data() + ke * n);
+            comp->e->insert(0, expand_signed_host(es.data(), n, mods).data());
+            comp->e->insert(1, expand_signed_host(es.data() + n, n, mods).data());
         }
     }
-    std::vector<u64> pk(2 * ke * n); // first ke residues of both public-key polynomials
-    for (int j = 0; j < 2; j++)
-        std::copy_n(e->pk.begin() + (size_t)j * K * n, ke * n, pk.begin() + (size_t)j * ke * n);
-    DevBuf du(c, u), dpk(c, pk), de(c, ee), dct(c, 2 * ke * n), dpl(c, pv);
+    const u64 *dpk = e->dev_pk(enc_lv); // first ke residues of both public-key polynomials, resident
+    DevBuf dus(c, us), des(c, es), du(c, ke * n), de(c, 2 * ke * n), dct(c, 2 * ke * n), dpl(c, pv);
+    dev_check(b200_expand_signed(c->dev, enc_lv, (const int64_t *)dus.p, 1, du.p, nullptr));
+    dev_check(b200_expand_signed(c->dev, enc_lv, (const int64_t *)des.p, 2, de.p, nullptr));
     dev_check(b200_ntt_forward(c->dev, enc_lv, du.p, 1, nullptr));
-    dev_check(b200_dyadic_product(c->dev, enc_lv, dpk.p, 2, du.p, 1, dct.p, 1, nullptr)); // pk_j (*) NTT(u)
+    dev_check(b200_dyadic_product(c->dev, enc_lv, dpk, 2, du.p, 1, dct.p, 1, nullptr)); // pk_j (*) NTT(u)
     dev_check(b200_ntt_inverse(c->dev, enc_lv, dct.p, 2, nullptr));                       // two polys = two slab items
     dev_check(b200_add(c->dev, enc_lv, dct.p, de.p, dct.p, 2, 1, nullptr));               // + e_j
     const int lv = c->first_level;
@@ -2337,18 +2338,19 @@ static void encrypt_symmetric(Encryptor_ *e, const Plaintext_ &plain, b200::Blak
     b200::PrngSeed pub;
     bootstrap.generate(sizeof(pub), pub.data());
     b200::Blake2xbPrng ct_prng(pub);
-    std::vector<u64> c1((size_t)k * n), noise((size_t)k * n);
+    std::vector<u64> c1((size_t)k * n), noise(n);
     b200::sample_poly_uniform(ct_prng, n, mods, c1.data());
-    b200::sample_poly_normal(bootstrap, n, mods, noise.data());
+    b200::sample_poly_normal(bootstrap, n, signed_only(), noise.data());
     if (comp && comp->e)
     {
         comp->e->reserve(1, n, mods);
-        comp->e->insert(0, noise.data());
+        comp->e->insert(0, expand_signed_host(noise.data(), n, mods).data());
     }
-    std::vector<u64> skl(e->sk.begin(), e->sk.begin() + (size_t)k * n);
-    DevBuf d1(c, c1), de(c, noise), ds(c, skl), d0(c, (size_t)2 * k * n), dpl(c, pv);
+    const u64 *dsk = e->dev_sk(); // [K][n] resident; the first k residues are this level's
+    DevBuf d1(c, c1), dn(c, noise), de(c, (size_t)k * n), d0(c, (size_t)2 * k * n), dpl(c, pv);
+    dev_check(b200_expand_signed(c->dev, lv, (const int64_t *)dn.p, 1, de.p, nullptr));
     // c0 = -(INTT(s (*) c1) + e); c1 is sampled in the NTT domain and converted back at the end
-    dev_check(b200_dyadic_product(c->dev, lv, ds.p, 1, d1.p, 1, d0.p, 1, nullptr));
+    dev_check(b200_dyadic_product(c->dev, lv, dsk, 1, d1.p, 1, d0.p, 1, nullptr));
     dev_check(b200_ntt_inverse(c->dev, lv, d0.p, 1, nullptr));
     dev_check(b200_add(c->dev, lv, d0.p, de.p, d0.p, 1, 1, nullptr));
     dev_check(b200_negate(c->dev, lv, d0.p, d0.p, 1, 1, nullptr));

@@ -546,19 +546,67 @@ struct DevBuf
     DevBuf(const DevBuf &) = delete;
 };
 
+// device-resident copies of key material (public key / secret key residues), created on first use, freed with their owner
+struct DevCache
+{
+    std::shared_ptr<DevOwner> keep;
+    std::vector<std::pair<int, u64 *>> bufs;
+    ~DevCache()
+    {
+        for (auto &b : bufs)
+            if (b.second && keep && keep->dev)
+                b200_free(keep->dev, b.second);
+    }
+    u64 *find(int key) const
+    {
+        for (auto &b : bufs)
+            if (b.first == key)
+                return b.second;
+        return nullptr;
+    }
+    u64 *put(Context_ *c, int key, const std::vector<u64> &h)
+    {
+        void *p = nullptr;
+        dev_check(b200_malloc(c->dev, std::max<size_t>(h.size(), 1) * sizeof(u64), &p));
+        dev_check(b200_memcpy_h2d(c->dev, p, h.data(), h.size() * sizeof(u64), nullptr));
+        dev_check(b200_stream_synchronize(c->dev, nullptr));
+        keep = c->owner;
+        bufs.emplace_back(key, (u64 *)p);
+        return (u64 *)p;
+    }
+};
+
+// The samplers of sampling.h write one row per modulus; with this single zero "modulus" they return the small signed value
+// itself (two's complement), which b200_expand_signed turns into residues on the device — n words cross PCIe instead of k n.
+inline const std::vector<u64> &signed_only()
+{
+    static const std::vector<u64> z(1, 0);
+    return z;
+}
+// host-side residues of such signed samples (only where the caller wants the components back: PolynomialArray)
+inline std::vector<u64> expand_signed_host(const u64 *vals, size_t n, const std::vector<u64> &mods)
+{
+    std::vector<u64> out(mods.size() * n);
+    for (size_t i = 0; i < mods.size(); i++)
+        for (size_t c = 0; c < n; c++)
+            out[i * n + c] = (int64_t)vals[c] < 0 ? vals[c] + mods[i] : vals[c];
+    return out;
+}
+
 // encrypt_zero_symmetric at the key level, NTT form, no seed saving (S/util/rlwe.cpp:312-459): returns [2][K][n]
-// c1 <- uniform (a fresh PRNG seeded from the bootstrap PRNG), c0 = -(s*c1 + e)
-inline std::vector<u64> encrypt_zero_symmetric_key_level(Context_ *c, const std::vector<u64> &sk, b200::Blake2xbPrng &bootstrap)
+// c1 <- uniform (a fresh PRNG seeded from the bootstrap PRNG), c0 = -(s*c1 + e); dsk = the secret key on the device
+inline std::vector<u64> encrypt_zero_symmetric_key_level(Context_ *c, const u64 *dsk, b200::Blake2xbPrng &bootstrap)
 {
     const size_t n = c->parms.n, K = c->parms.coeff.size();
     b200::PrngSeed pub;
     bootstrap.generate(sizeof(pub), pub.data());
     b200::Blake2xbPrng ct_prng(pub);
-    std::vector<u64> c1(K * n), noise(K * n);
+    std::vector<u64> c1(K * n), noise(n);
     b200::sample_poly_uniform(ct_prng, n, c->parms.coeff, c1.data());
-    b200::sample_poly_normal(bootstrap, n, c->parms.coeff, noise.data());
-    DevBuf d1(c, c1), de(c, noise), ds(c, sk), d0(c, K * n);
-    dev_check(b200_dyadic_product(c->dev, 0, ds.p, 1, d1.p, 1, d0.p, 1, nullptr)); // s (*) c1
+    b200::sample_poly_normal(bootstrap, n, signed_only(), noise.data());
+    DevBuf d1(c, c1), dn(c, noise), de(c, K * n), d0(c, K * n);
+    dev_check(b200_expand_signed(c->dev, 0, (const int64_t *)dn.p, 1, de.p, nullptr));
+    dev_check(b200_dyadic_product(c->dev, 0, dsk, 1, d1.p, 1, d0.p, 1, nullptr)); // s (*) c1
     dev_check(b200_ntt_forward(c->dev, 0, de.p, 1, nullptr));                      // NTT(e)
     dev_check(b200_add(c->dev, 0, d0.p, de.p, d0.p, 1, 1, nullptr));
     dev_check(b200_negate(c->dev, 0, d0.p, d0.p, 1, 1, nullptr));
@@ -572,6 +620,12 @@ struct KeyGenerator_
     Context_ *ctx;
     CtxHold hold;
     std::vector<u64> sk; // key level, NTT form [K][n]
+    DevCache dev_cache;
+    const u64 *dev_sk()
+    {
+        u64 *p = dev_cache.find(0);
+        return p ? p : dev_cache.put(ctx, 0, sk);
+    }
     // generate_one_kswitch_key (S/keygenerator.cpp:303-337): new_key = [K][n] NTT form
     void one_kswitch_key(const std::vector<u64> &new_key, std::vector<PublicKey_ *> &dest)
     {
@@ -582,14 +636,18 @@ struct KeyGenerator_
         b200::Blake2xbPrng bootstrap(b200::random_seed());
         for (int J = 0; J < decomp; J++)
         {
-            std::vector<u64> w = encrypt_zero_symmetric_key_level(c, sk, bootstrap);
+            std::vector<u64> w = encrypt_zero_symmetric_key_level(c, dev_sk(), bootstrap);
             const u64 qj = c->parms.coeff[J];
             const u64 factor = qsp % qj;
+            const u64 factor_q = (u64)(((unsigned __int128)factor << 64) / qj); // Shoup quotient: no division per word
             for (size_t i = 0; i < n; i++)
-            { // c0[J] += factor * new_key[J]  (S/keygenerator.cpp:330-334)
-                u64 t = (u64)((unsigned __int128)new_key[(size_t)J * n + i] * factor % qj);
+            { // c0[J] += factor * new_key[J]  (S/keygenerator.cpp:330-334); all operands canonical
+                const u64 nk = new_key[(size_t)J * n + i];
+                u64 t = nk * factor - (u64)(((unsigned __int128)nk * factor_q) >> 64) * qj;
+                t = t >= qj ? t - qj : t;
                 u64 &d = w[(size_t)J * n + i];
-                d = (u64)(((unsigned __int128)d + t) % qj);
+                const u64 s = d + t;
+                d = s >= qj ? s - qj : s;
             }
             auto *pk = new PublicKey_();
             pk->data.parms_id = c->ids[0];
@@ -611,6 +669,22 @@ struct Encryptor_
     bool has_pk = false, has_sk = false;
     std::vector<u64> pk; // [2][K][n] NTT form, key level
     std::vector<u64> sk; // [K][n]
+    DevCache dev_cache;  // key 0: secret key [K][n]; key 1 + level: the level's residues of both public-key polynomials
+    const u64 *dev_sk()
+    {
+        u64 *p = dev_cache.find(0);
+        return p ? p : dev_cache.put(ctx, 0, sk);
+    }
+    const u64 *dev_pk(int level)
+    {
+        if (u64 *p = dev_cache.find(1 + level))
+            return p;
+        const size_t n = ctx->parms.n, K = ctx->parms.coeff.size(), ke = (size_t)ctx->level_k[level];
+        std::vector<u64> part(2 * ke * n);
+        for (int j = 0; j < 2; j++)
+            std::copy_n(pk.begin() + (size_t)j * K * n, ke * n, part.begin() + (size_t)j * ke * n);
+        return dev_cache.put(ctx, 1 + level, part);
+    }
 };
 
 template <class F>
