@@ -149,6 +149,10 @@ int b200_noise_norm(b200_ctx *ctx, int level, const uint64_t *ct, int size, cons
 int b200_is_transparent(b200_ctx *ctx, int level, const uint64_t *ct, int size, uint32_t *flags_out, uint64_t batch,
                         void *stream);
 
+/* the same test without clearing: flags[item] = 1 when polys [1, size) of the item hold a nonzero word; the caller zeroes
+   `flags` beforehand, and `flags` may be pinned host memory from b200_malloc_host (no fill kernel, no copy back) */
+int b200_any_nonzero(b200_ctx *ctx, int level, const uint64_t *ct, int size, uint32_t *flags, uint64_t batch, void *stream);
+
 /* ---- host-buffer (end-to-end) variants: pinned or pageable host memory in, host memory out;
         H2D / compute / D2H are chunked and overlapped on internal streams; returns after completion ---- */
 int b200_multiply_relin_host(b200_ctx *ctx, int level, const uint64_t *a_host, const uint64_t *b_host,

@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(NT, MB) ntt_kernel(const NttJob job)
     const int pidx = job.slot_prime[slot];
     if (job.fprimes[pidx].enabled)
     {
-        const u64 *src = job.src + item * job.src_item_stride + job.slot_src[slot];
+        const u64 *src = ntt_src_ptr(job, item, slot);
         u64 *dst = job.dst + item * job.dst_item_stride + job.slot_dst[slot];
         ntt_fp_block_body<FWD>(job, job.fprimes[pidx], job.primes[pidx], src, dst, reinterpret_cast<double *>(ntt_sm),
                                (int)threadIdx.x, (int)blockDim.x);
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(NT, (LOGN <= 13 ? (NT <= 256 ? 3 : 2) : 1)) nt
     const int pidx = job.slot_prime[slot];
     const NttPrimeFp PF = job.fprimes[pidx];
     const NttPrime PI_ = job.primes[pidx];
-    const u64 *src = job.src + item * job.src_item_stride + job.slot_src[slot];
+    const u64 *src = ntt_src_ptr(job, item, slot);
     u64 *dst = job.dst + item * job.dst_item_stride + job.slot_dst[slot];
     if (job.timeline && threadIdx.x == 0)
     {
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(NT, (LOGN <= 13 ? (NT <= 256 ? 3 : 2) : 1)) nt
         {
             const int nslot = job.slot_major ? (int)(nb / job.items) : (int)(nb % job.slots);
             const long long nitem = job.slot_major ? nb - (long long)nslot * job.items : nb / job.slots;
-            const char *np_ = reinterpret_cast<const char *>(job.src + nitem * job.src_item_stride + job.slot_src[nslot]);
+            const char *np_ = reinterpret_cast<const char *>(ntt_src_ptr(job, nitem, nslot));
             constexpr int LINES = (8 << LOGN) / 128;
 #pragma unroll
             for (int l = (int)threadIdx.x; l < LINES; l += NT)
@@ -1222,13 +1222,27 @@ static bool static_fp_ok(b200_ctx *ctx, const JobDesc &jd)
 #endif
 }
 
+// alternative sources of the leading slots (NttJob::alt_*)
+struct NttAlt
+{
+    int end[2] = { 0, 0 };
+    const u64 *src[2] = { nullptr, nullptr };
+    long long stride[2] = { 0, 0 };
+};
+
 template <bool FWD>
 static int launch_ntt(b200_ctx *ctx, const JobDesc &jd, const u64 *src, long long src_stride, u64 *dst, long long dst_stride,
-                      long long items, int reduce_input, cudaStream_t s, const TensorArgs *ta = nullptr)
+                      long long items, int reduce_input, cudaStream_t s, const TensorArgs *ta = nullptr, const NttAlt *alt = nullptr)
 {
     if (items == 0 || jd.slots == 0)
         return 0;
     NttJob job;
+    for (int i = 0; i < 2; i++)
+    {
+        job.alt_end[i] = alt ? alt->end[i] : 0;
+        job.alt_src[i] = alt ? alt->src[i] : nullptr;
+        job.alt_stride[i] = alt ? alt->stride[i] : 0;
+    }
     job.logn = ctx->logn;
     job.slots = jd.slots;
     job.slot_prime = jd.d_prime;
@@ -1268,6 +1282,7 @@ static int launch_ntt(b200_ctx *ctx, const JobDesc &jd, const u64 *src, long lon
         {
             B200_LAUNCH(ntt_outer_kernel<true>, blocks_for(pairs, 256), 256, 0, s, job, pairs);
             NttJob inner = job; // sub-transforms run in place on the destination
+            inner.alt_end[0] = inner.alt_end[1] = 0;
             inner.src = job.dst;
             inner.slot_src = job.slot_dst;
             inner.src_item_stride = job.dst_item_stride;
@@ -1506,41 +1521,40 @@ static int multiply_core(b200_ctx *ctx, int level, const u64 *a, int sa, const u
         }
         ctx->launches++;
     }
-    // (3) forward NTTs: q rows straight from the inputs, Bsk rows in place
-    for (int which = 0; which < (square ? 1 : 2); which++)
+    // (3) forward NTTs in ONE launch: q rows straight from the inputs (alternative sources a, b), Bsk rows in place in ext
     {
-        const int sz = which == 0 ? sa : sb;
-        const int p0 = which == 0 ? 0 : sa;
         std::vector<int> prime;
         std::vector<long long> so, dof;
-        for (int p = 0; p < sz; p++)
-            for (int r = 0; r < k; r++)
-            {
-                prime.push_back(Lh.q_idx[r]);
-                so.push_back(((long long)p * k + r) * n);
-                dof.push_back(((long long)(p0 + p) * R + r) * n);
-            }
-        JobDesc jd;
-        std::string key = "mulq:" + std::to_string(level) + ":" + std::to_string(sz) + ":" + std::to_string(p0) + ":" +
-                          std::to_string(P);
-        if ((rc = get_job(ctx, key, prime, so, dof, &jd)))
-            return rc;
-        if ((rc = launch_ntt<true>(ctx, jd, which == 0 ? a : b, (long long)sz * k * n, ext, (long long)P * R * n, batch, 0, s)))
-            return rc;
-    }
-    {
-        std::vector<int> prime;
-        std::vector<long long> off;
+        NttAlt alt;
+        for (int which = 0; which < (square ? 1 : 2); which++)
+        {
+            const int sz = which == 0 ? sa : sb;
+            const int p0 = which == 0 ? 0 : sa;
+            for (int p = 0; p < sz; p++)
+                for (int r = 0; r < k; r++)
+                {
+                    prime.push_back(Lh.q_idx[r]);
+                    so.push_back(((long long)p * k + r) * n);
+                    dof.push_back(((long long)(p0 + p) * R + r) * n);
+                }
+            alt.end[which] = (int)prime.size();
+            alt.src[which] = which == 0 ? a : b;
+            alt.stride[which] = (long long)sz * k * n;
+        }
+        if (square)
+            alt.end[1] = alt.end[0];
         for (int p = 0; p < P; p++)
             for (int j = 0; j < L.nBsk; j++)
             {
                 prime.push_back(Lh.bsk_idx[j]);
-                off.push_back(((long long)p * R + k + j) * n);
+                so.push_back(((long long)p * R + k + j) * n);
+                dof.push_back(((long long)p * R + k + j) * n);
             }
         JobDesc jd;
-        if ((rc = get_job(ctx, "mulbsk:" + std::to_string(level) + ":" + std::to_string(P), prime, off, off, &jd)))
+        std::string key = "mulfwd:" + std::to_string(level) + ":" + std::to_string(sa) + ":" + std::to_string(square ? 0 : sb);
+        if ((rc = get_job(ctx, key, prime, so, dof, &jd)))
             return rc;
-        if ((rc = launch_ntt<true>(ctx, jd, ext, (long long)P * R * n, ext, (long long)P * R * n, batch, 0, s)))
+        if ((rc = launch_ntt<true>(ctx, jd, ext, (long long)P * R * n, ext, (long long)P * R * n, batch, 0, s, nullptr, &alt)))
             return rc;
     }
     // (4) tensor + (5) inverse NTTs.  Optionally (FP64 path) the dyadic products are formed inside the inverse
@@ -2704,6 +2718,40 @@ int b200_is_transparent(b200_ctx *ctx, int level, const uint64_t *ct, int size, 
         B200_LAUNCH(transparent_kernel, grid, 256, 0, s, (const u64 *)ct, (long long)size * k * n, (long long)k * n, flags_out);
         ctx->launches++;
     }
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+// flags[item] = 1 when polys [1, size) of the item hold a nonzero word; flags are NOT cleared here (the caller zeroes them)
+// and may live in pinned host memory (b200_malloc_host; device-accessible under UVA), which saves the per-call path a fill
+// kernel and a device-to-host copy per operation
+__global__ void any_nonzero_kernel(const u64 *ct, long long item_words, long long skip_words, u32 *flags)
+{
+    const long long item = blockIdx.y;
+    const u64 *p = ct + item * item_words + skip_words;
+    const long long cnt = item_words - skip_words;
+    bool nz = false;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += (long long)gridDim.x * blockDim.x)
+        nz |= p[i] != 0;
+    if (nz)
+        flags[item] = 1; // every writer stores the same value
+}
+int b200_any_nonzero(b200_ctx *ctx, int level, const uint64_t *ct, int size, uint32_t *flags, uint64_t batch, void *stream)
+{
+    int rc = check_level(ctx, level);
+    if (rc)
+        return rc;
+    if (!ct || !flags)
+        return fail(B200_E_NULL, "null pointer");
+    if (batch == 0 || size < 2)
+        return 0;
+    const long long n = (long long)ctx->n;
+    const int k = ctx->levels[level].k;
+    const long long words = (long long)(size - 1) * k * n;
+    dim3 grid((unsigned)std::max<long long>(1, std::min<long long>(64, words / 512)), (unsigned)batch);
+    B200_LAUNCH(any_nonzero_kernel, grid, 256, 0, (cudaStream_t)stream, (const u64 *)ct, (long long)size * k * n, (long long)k * n,
+                flags);
+    ctx->launches++;
     CU_TRY(cudaGetLastError());
     return 0;
 }

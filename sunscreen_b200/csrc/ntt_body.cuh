@@ -64,7 +64,22 @@ struct NttJob
                                //    the remaining butterfly stage over the whole polynomial runs in ntt_outer_kernel
     int npass;                 // forward pass schedule (host: ntt_schedule); inverse runs it mirrored
     int pass_L[8];
+    // up to two alternative sources: slots [0, alt_end[0]) read from alt_src[0], slots [alt_end[0], alt_end[1]) from
+    // alt_src[1], the rest from `src` (one launch transforms rows that live in different buffers — the inputs of a
+    // multiply and its lifted rows — instead of one latency-bound launch per buffer); alt_end = {0, 0}: off
+    int alt_end[2];
+    const u64 *alt_src[2];
+    long long alt_stride[2];
 };
+
+B200_HD const u64 *ntt_src_ptr(const NttJob &job, long long item, int slot)
+{
+    if (slot < job.alt_end[0])
+        return job.alt_src[0] + item * job.alt_stride[0] + job.slot_src[slot];
+    if (slot < job.alt_end[1])
+        return job.alt_src[1] + item * job.alt_stride[1] + job.slot_src[slot];
+    return job.src + item * job.src_item_stride + job.slot_src[slot];
+}
 
 B200_HD int ntt_pad(int e) { return e + (e >> 4); }
 B200_HD int ntt_smem_words(int n) { return n + (n >> 4); }
@@ -278,7 +293,7 @@ B200_HD void ntt_block_body(const NttJob &job, long long block, u64 *sm, int tid
     const long long item = poly / job.slots;
     const int slot = (int)(poly - item * job.slots);
     const NttPrime P = job.primes[job.slot_prime[slot]];
-    const u64 *src = job.src + item * job.src_item_stride + job.slot_src[slot] + (long long)half * n;
+    const u64 *src = ntt_src_ptr(job, item, slot) + (long long)half * n;
     u64 *dst = job.dst + item * job.dst_item_stride + job.slot_dst[slot] + (long long)half * n;
     const u64 p = P.p;
 
@@ -351,7 +366,7 @@ B200_HD void ntt_outer_quad(const NttJob &job, long long poly, int j)
     u64 *dst = job.dst + item * job.dst_item_stride + job.slot_dst[slot];
     if (FWD)
     {
-        const u64 *src = job.src + item * job.src_item_stride + job.slot_src[slot];
+        const u64 *src = ntt_src_ptr(job, item, slot);
         u64 a0 = src[j], a1 = src[j + q4], a2 = src[j + 2 * q4], a3 = src[j + 3 * q4];
         if (job.reduce_input)
         {
@@ -390,7 +405,7 @@ B200_HD void ntt_outer_pair(const NttJob &job, long long poly, int j)
     const u64 p = P.p;
     if (FWD)
     {
-        const u64 *src = job.src + item * job.src_item_stride + job.slot_src[slot];
+        const u64 *src = ntt_src_ptr(job, item, slot);
         u64 *dst = job.dst + item * job.dst_item_stride + job.slot_dst[slot];
         u64 X = src[j], Y = src[j + (n >> 1)];
         if (job.reduce_input)

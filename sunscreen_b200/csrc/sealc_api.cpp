@@ -50,11 +50,11 @@ void transparent_guard(Context_ *c, int level, Ciphertext_ &dst)
         return;
     }
     // SEAL_THROW_ON_TRANSPARENT_CIPHERTEXT (seal_fhe/build.rs:37-42): "result ciphertext is transparent"
-    *sc->lane->hflag = 0;
-    dev_check(b200_is_transparent(c->dev, level, dst.dev, (int)dst.size, (uint32_t *)sc->lane->dflag, 1, sc->stream()));
-    dev_check(b200_memcpy_d2h(c->dev, sc->lane->hflag, sc->lane->dflag, 4, sc->stream()));
+    // one kernel, writing "a nonzero word exists" straight into the lane's pinned flag
+    *(volatile uint32_t *)sc->lane->hflag = 0;
+    dev_check(b200_any_nonzero(c->dev, level, dst.dev, (int)dst.size, sc->lane->hflag, 1, sc->stream()));
     sc->wait(); // context mutex released while the GPU finishes this operation
-    if (*sc->lane->hflag)
+    if (!*(volatile uint32_t *)sc->lane->hflag)
         throw LogicErr("result ciphertext is transparent");
 }
 
