@@ -1303,7 +1303,10 @@ static int launch_ntt(b200_ctx *ctx, const JobDesc &jd, const u64 *src, long lon
 #ifndef B200_EMU_HEADER
     if (static_fp_ok(ctx, jd))
     {
-        static const int nt13 = std::getenv("B200_NTT_NT") ? atoi(std::getenv("B200_NTT_NT")) : 256;
+        // n = 8192: 256 threads x 3 CTAs/SM is the throughput configuration; a launch that cannot fill the SMs anyway (the
+        // per-handle path: at most 36 polynomials) is latency-bound and finishes sooner with 512 threads per polynomial
+        static const int nt_env = std::getenv("B200_NTT_NT") ? atoi(std::getenv("B200_NTT_NT")) : 0;
+        const int nt13 = nt_env ? nt_env : (blocks <= 2LL * ctx->sm_count ? 512 : 256);
         void (*sfn)(const NttJob) = ctx->logn == 12   ? ntt_fp_kernel<12, FWD, 256>
                                     : ctx->logn == 13 ? (nt13 == 256 ? ntt_fp_kernel<13, FWD, 256> : ntt_fp_kernel<13, FWD, 512>)
                                                       : ntt_fp_kernel<14, FWD, 1024>;
