@@ -67,6 +67,8 @@ _SIGS = {
     "b200_ct_sk_phase": [vp, C.c_int, vp, C.c_int, vp, vp, u64, vp],
     "b200_noise_norm": [vp, C.c_int, vp, C.c_int, vp, vp, C.c_int, u64, vp],
     "b200_is_transparent": [vp, C.c_int, vp, C.c_int, vp, u64, vp],
+    "b200_any_nonzero": [vp, C.c_int, vp, C.c_int, vp, u64, vp],
+    "b200_expand_signed": [vp, C.c_int, vp, C.c_int, vp, vp],
     "b200_multiply_relin_host": [vp, C.c_int, vp, vp, vp, vp, u64],
     "b200_ntt_roundtrip_host": [vp, C.c_int, vp, vp, u64],
 }
@@ -272,6 +274,14 @@ class B200Context:
     def is_transparent(self, ct, size, flags, batch, level=None, stream=None):
         self.L.call("b200_is_transparent", self.h, self._lv(level), vp(ptr(ct)), C.c_int(size), vp(ptr(flags)), u64(batch),
                     vp(stream))
+
+    def any_nonzero(self, ct, size, flags, batch, level=None, stream=None):
+        """flags (uint32 per item, zeroed by the caller; device or pinned host memory) <- 1 where polys [1, size) are not all zero."""
+        self.L.call("b200_any_nonzero", self.h, self._lv(level), vp(ptr(ct)), C.c_int(size), vp(ptr(flags)), u64(batch),
+                    vp(stream))
+
+    def expand_signed(self, vals, polys, out, level=None, stream=None):
+        self.L.call("b200_expand_signed", self.h, self._lv(level), vp(ptr(vals)), C.c_int(polys), vp(ptr(out)), vp(stream))
 
     def multiply_relin_host(self, a_host, b_host, rlk_dev, out_host, batch, level=None):
         self.L.call("b200_multiply_relin_host", self.h, self._lv(level), vp(ptr(a_host)), vp(ptr(b_host)), vp(ptr(rlk_dev)),

@@ -258,6 +258,36 @@ def check_encrypted_roundtrip(P, seed=3):
     return dict(dec=dec, sk=sk, ct=got, expect_plain=R.pt_coeffs(R.decrypt(dec, back)))
 
 
+def check_small_kernels(P, seed=29):
+    """b200_is_transparent / b200_any_nonzero (the transparent-result guard, S/ciphertext.h:451-456) on a batch with one
+    transparent item and one whose only nonzero word is the very last; b200_expand_signed (residues of the host-sampled
+    ternary / clipped-normal values, S/util/rlwe.cpp:23-67) against v mod q_i."""
+    rng = np.random.default_rng(seed)
+    batch = 4
+    ct = rand_ct(rng, P.moduli, P.k, P.n, batch=batch)
+    ct[1, 1:] = 0                      # transparent: c1 == 0 (c0 arbitrary)
+    ct[2, 1:] = 0
+    ct[2, 1, P.k - 1, P.n - 1] = 1     # a single nonzero word at the very end
+    d = P.dev(ct)
+    words = (batch + 1) // 2
+    flags = P.dev(np.zeros(words, dtype=np.uint64))
+    P.ctx.is_transparent(d, 2, flags, batch)
+    got = P.host(flags).view(np.uint32)[:batch]
+    assert list(got) == [0, 1, 0, 0], f"is_transparent flags {list(got)}"
+    flags = P.dev(np.zeros(words, dtype=np.uint64))
+    P.ctx.any_nonzero(d, 2, flags, batch)
+    got = P.host(flags).view(np.uint32)[:batch]
+    assert list(got) == [1, 0, 1, 1], f"any_nonzero flags {list(got)}"
+    vals = rng.integers(-19, 20, size=(3, P.n), dtype=np.int64)
+    vals[0, :4] = (-1, 0, 1, -19)
+    out = P.out(3, P.k, P.n)
+    P.ctx.expand_signed(P.dev(vals.view(np.uint64)), 3, out)
+    got = P.host(out).reshape(3, P.k, P.n)
+    for i in range(P.k):
+        want = (vals.astype(object) % int(P.moduli[i])).astype(np.uint64)
+        eq(got[:, i, :], want, f"expand_signed residue {i}")
+
+
 def check_noise_norm(P, batch=3, seed=23):
     """b200_noise_norm (the quantity behind invariant_noise_budget, S/decryptor.cpp:424-485): for random ciphertexts of
     size 2 and 3 and random key powers, the device's multi-precision infinity norm of the centred t * phase mod Q equals

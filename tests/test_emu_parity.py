@@ -57,6 +57,12 @@ def test_host_buffer_pipeline(pair):
     pc.check_host_pipeline(pair)
 
 
+def test_small_kernels(pair):
+    if pair.n > 4096:
+        pytest.skip("runs on the smallest set only (emulation speed)")
+    pc.check_small_kernels(pair)
+
+
 def test_noise_norm(pair):
     if pair.n > 4096:
         pytest.skip("noise norm test runs on the smallest set only (emulation speed)")

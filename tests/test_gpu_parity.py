@@ -68,6 +68,10 @@ def test_batch_strides(pair):
     pc.check_batch(pair, batch=5 if pair.n <= 16384 else 2)
 
 
+def test_small_kernels(pair):
+    pc.check_small_kernels(pair)
+
+
 def test_noise_norm(pair):
     pc.check_noise_norm(pair)
 
