@@ -2268,13 +2268,14 @@ static void export_remainder(Context_ *c, const Plaintext_ &plain, Plaintext_ &d
 // special prime, then add round(q m / t) (S/util/rlwe.cpp:193-310, S/encryptor.cpp:160-208,300-312).  With
 // `disable_special_modulus` the zero encryption is made directly at the first data level from the first k residues
 // of the public key and no modulus switch follows (S/encryptor.cpp:160-163,210-224).
+// `lk` (the context mutex, not yet held) is taken only after the host-side sampling, which touches nothing shared: threads
+// that encrypt concurrently sample in parallel and serialise only for the device part
 static void encrypt_asymmetric(Encryptor_ *e, const Plaintext_ &plain, b200::Blake2xbPrng &prng, Ciphertext_ &dst,
-                               bool disable_special_modulus = false, EncComponents *comp = nullptr)
+                               std::unique_lock<std::mutex> &lk, bool disable_special_modulus = false, EncComponents *comp = nullptr)
 {
     Context_ *c = e->ctx;
     if (!e->has_pk)
         throw LogicErr("public key is not set");
-    std::vector<u64> pv = padded_plain(c, plain);
     const size_t n = c->parms.n, K = c->parms.coeff.size();
     const bool drop = c->first_level == 1 && !disable_special_modulus; // encrypt at the key level, then switch down
     const int enc_lv = drop ? 0 : c->first_level;
@@ -2285,6 +2286,8 @@ static void encrypt_asymmetric(Encryptor_ *e, const Plaintext_ &plain, b200::Bla
     b200::sample_poly_ternary(prng, n, signed_only(), us.data());
     b200::sample_poly_normal(prng, n, signed_only(), es.data());
     b200::sample_poly_normal(prng, n, signed_only(), es.data() + n);
+    lk.lock();
+    std::vector<u64> pv = padded_plain(c, plain);
     if (comp)
     {
         if (comp->u)
@@ -2325,12 +2328,11 @@ static void encrypt_asymmetric(Encryptor_ *e, const Plaintext_ &plain, b200::Bla
 // sk encryption: encrypt_zero_symmetric at the first data level, coefficient form (S/util/rlwe.cpp:312-459), then
 // add round(q m / t).  `bootstrap` supplies the public seed of the uniform polynomial and the noise.
 static void encrypt_symmetric(Encryptor_ *e, const Plaintext_ &plain, b200::Blake2xbPrng &bootstrap, Ciphertext_ &dst,
-                              EncComponents *comp = nullptr)
+                              std::unique_lock<std::mutex> &lk, EncComponents *comp = nullptr)
 {
     Context_ *c = e->ctx;
     if (!e->has_sk)
         throw LogicErr("secret key is not set");
-    std::vector<u64> pv = padded_plain(c, plain);
     const int lv = c->first_level;
     const size_t n = c->parms.n;
     const int k = c->level_k[lv];
@@ -2341,6 +2343,8 @@ static void encrypt_symmetric(Encryptor_ *e, const Plaintext_ &plain, b200::Blak
     std::vector<u64> c1((size_t)k * n), noise(n);
     b200::sample_poly_uniform(ct_prng, n, mods, c1.data());
     b200::sample_poly_normal(bootstrap, n, signed_only(), noise.data());
+    lk.lock();
+    std::vector<u64> pv = padded_plain(c, plain);
     if (comp && comp->e)
     {
         comp->e->reserve(1, n, mods);
@@ -2370,7 +2374,7 @@ static long encrypt_components(void *p, void *plaintext, bool asymmetric, bool d
 {
     auto *e = (Encryptor_ *)p;
     return guard([&] {
-        std::lock_guard<std::mutex> lk(e->ctx->mu);
+        std::unique_lock<std::mutex> lk(e->ctx->mu, std::defer_lock);
         b200::PrngSeed sd = seed8 ? b200::PrngSeed{} : b200::random_seed();
         if (seed8)
             std::copy_n(seed8, 8, sd.begin());
@@ -2380,9 +2384,9 @@ static long encrypt_components(void *p, void *plaintext, bool asymmetric, bool d
         if ((comp.u && comp.u->reserved) || (comp.e && comp.e->reserved))
             throw LogicErr("PolynomialArray can only be reserved once.");
         if (asymmetric)
-            encrypt_asymmetric(e, *(Plaintext_ *)plaintext, prng, *(Ciphertext_ *)destination, disable_special_modulus, &comp);
+            encrypt_asymmetric(e, *(Plaintext_ *)plaintext, prng, *(Ciphertext_ *)destination, lk, disable_special_modulus, &comp);
         else
-            encrypt_symmetric(e, *(Plaintext_ *)plaintext, prng, *(Ciphertext_ *)destination, &comp);
+            encrypt_symmetric(e, *(Plaintext_ *)plaintext, prng, *(Ciphertext_ *)destination, lk, &comp);
     });
 }
 long Encryptor_EncryptReturnComponents(void *p, void *plaintext, bool disable_special_modulus, void *destination, void *u_dst,
@@ -2436,9 +2440,9 @@ long Encryptor_Encrypt(void *p, void *plaintext, void *destination, void *)
     NULLRET(destination);
     auto *e = (Encryptor_ *)p;
     return guard([&] {
-        std::lock_guard<std::mutex> lk(e->ctx->mu);
+        std::unique_lock<std::mutex> lk(e->ctx->mu, std::defer_lock);
         b200::Blake2xbPrng prng(b200::random_seed());
-        encrypt_asymmetric(e, *(Plaintext_ *)plaintext, prng, *(Ciphertext_ *)destination);
+        encrypt_asymmetric(e, *(Plaintext_ *)plaintext, prng, *(Ciphertext_ *)destination, lk);
     });
 }
 // deterministic variant: same stream as the reference's Encryptor_EncryptReturnComponentsSetSeed (S/c/encryptor.cpp:185-240)
@@ -2450,11 +2454,11 @@ long B200_Encryptor_EncryptSetSeed(void *p, void *plaintext, const uint64_t *see
     NULLRET(destination);
     auto *e = (Encryptor_ *)p;
     return guard([&] {
-        std::lock_guard<std::mutex> lk(e->ctx->mu);
+        std::unique_lock<std::mutex> lk(e->ctx->mu, std::defer_lock);
         b200::PrngSeed sd;
         std::copy_n(seed8, 8, sd.begin());
         b200::Blake2xbPrng prng(sd);
-        encrypt_asymmetric(e, *(Plaintext_ *)plaintext, prng, *(Ciphertext_ *)destination);
+        encrypt_asymmetric(e, *(Plaintext_ *)plaintext, prng, *(Ciphertext_ *)destination, lk);
     });
 }
 long Encryptor_EncryptSymmetric(void *p, void *plaintext, bool /*save_seed*/, void *destination, void *)
@@ -2466,9 +2470,9 @@ long Encryptor_EncryptSymmetric(void *p, void *plaintext, bool /*save_seed*/, vo
     NULLRET(destination);
     auto *e = (Encryptor_ *)p;
     return guard([&] {
-        std::lock_guard<std::mutex> lk(e->ctx->mu);
+        std::unique_lock<std::mutex> lk(e->ctx->mu, std::defer_lock);
         b200::Blake2xbPrng bootstrap(b200::random_seed());
-        encrypt_symmetric(e, *(Plaintext_ *)plaintext, bootstrap, *(Ciphertext_ *)destination);
+        encrypt_symmetric(e, *(Plaintext_ *)plaintext, bootstrap, *(Ciphertext_ *)destination, lk);
     });
 }
 
