@@ -313,7 +313,7 @@ def main():
                 traffic = json.load(open(tf)).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
-        roof = {"bound": "hbm", "kernel": "ntt_kernel<fwd> (4096 polys x 4 residues, n=8192)", "achieved": achieved,
+        roof = {"bound": "hbm", "kernel": "ntt_fp_kernel<13, fwd, 256> (4096 polys x 4 residues, n=8192; FP64 butterflies)", "achieved": achieved,
                 "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "algorithmic_bytes_per_launch": alg_bytes, "fwd_ms": fwd_ms, "inv_ms": inv_ms,
                 "inverse_achieved": alg_bytes / (inv_ms / 1000.0) / 1e9,
