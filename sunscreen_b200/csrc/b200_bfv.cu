@@ -1792,6 +1792,13 @@ int b200_ctx_create(uint64_t n, const uint64_t *coeff_modulus, uint64_t count, u
     {
         unsigned long long thr = ~0ULL;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        // a block freed on one stream must not be handed to another stream by making that stream WAIT for the first one:
+        // the per-handle path runs one operation per lane stream, and such a wait would chain independent operations
+        if (!std::getenv("B200_POOL_INTERNAL_DEPS"))
+        {
+            int off = 0;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolReuseAllowInternalDependencies, &off);
+        }
     }
     int rc = build_device(ctx.get());
     if (rc)
