@@ -119,8 +119,7 @@ struct Context_
         std::mutex m;
         bool ready = false;
         void *stream = nullptr;
-        void *dflag = nullptr;        // transparent-result flag (device)
-        uint32_t *hflag = nullptr;    // ... and its pinned host copy
+        uint32_t *hflag = nullptr;    // transparent-result flag: pinned host memory the check kernel writes directly
     };
     static const int NLANE = 8;
     Lane lanes[NLANE];
@@ -141,8 +140,6 @@ struct Context_
             {
                 if (l.stream)
                     b200_stream_destroy(dev, l.stream);
-                if (l.dflag)
-                    b200_free(dev, l.dflag);
                 if (l.hflag)
                     b200_free_host(l.hflag);
             }
@@ -225,7 +222,6 @@ struct OpScope
         {
             lane->ready = true;
             dev_check(b200_stream_create(ctx->dev, &lane->stream));
-            dev_check(b200_malloc(ctx->dev, 8, &lane->dflag));
             void *h = nullptr;
             dev_check(b200_malloc_host(8, &h));
             lane->hflag = (uint32_t *)h;
