@@ -90,6 +90,8 @@ int b200_free_host(void *hptr);
 int b200_memcpy_h2d(b200_ctx *ctx, void *dst, const void *src, size_t bytes, void *stream);
 int b200_memcpy_d2h(b200_ctx *ctx, void *dst, const void *src, size_t bytes, void *stream);
 int b200_memcpy_d2d(b200_ctx *ctx, void *dst, const void *src, size_t bytes, void *stream);
+/* zero a device buffer (secret material is wiped before its memory returns to the pool; S/memorymanager.h clear_on_destruction) */
+int b200_memzero(b200_ctx *ctx, void *dst, size_t bytes, void *stream);
 int b200_stream_synchronize(b200_ctx *ctx, void *stream);
 
 /* ---- NTT over a slab [items][k(level)][n], in place, canonical in -> canonical out ---- */

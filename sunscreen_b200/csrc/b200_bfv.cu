@@ -801,6 +801,7 @@ struct b200_ctx
     std::atomic<uint64_t> launches{ 0 };
     cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
     cudaStream_t s_alloc = nullptr; // b200_malloc / b200_free order their pool operations on this stream
+    cudaMemPool_t mempool = nullptr; // private stream-ordered pool of this context
     std::mutex alloc_mu;
     // side streams for intra-call concurrency: sub-batches of one call run on different streams so that the
     // FP64-bound NTT kernels of one overlap the HBM-bound element-wise kernels of another
@@ -1161,12 +1162,13 @@ static int build_device(b200_ctx *ctx)
 struct Scratch
 {
     cudaStream_t s;
+    cudaMemPool_t pool;
     std::vector<void *> ptrs;
-    explicit Scratch(cudaStream_t st) : s(st) {}
+    Scratch(b200_ctx *ctx, cudaStream_t st) : s(st), pool(ctx->mempool) {}
     int get(size_t words, u64 **out)
     {
         void *p = nullptr;
-        cudaError_t e = cudaMallocAsync(&p, std::max<size_t>(words, 1) * sizeof(u64), s);
+        cudaError_t e = cudaMallocFromPoolAsync(&p, std::max<size_t>(words, 1) * sizeof(u64), pool, s);
         if (e != cudaSuccess)
             return fail(B200_E_NOMEM, std::string("cudaMallocAsync: ") + cudaGetErrorString(e));
         ptrs.push_back(p);
@@ -1501,7 +1503,7 @@ static int multiply_core(b200_ctx *ctx, int level, const u64 *a, int sa, const u
     const int k = L.k, R = k + L.nBsk;
     const int P = square ? sa : sa + sb;
     const int Dn = square ? 3 : sa + sb - 1;
-    Scratch scr(s);
+    Scratch scr(ctx, s);
     u64 *ext = nullptr, *D = nullptr;
     int rc;
     if ((rc = scr.get((size_t)batch * P * R * n, &ext)))
@@ -1632,7 +1634,7 @@ static int keyswitch_core(b200_ctx *ctx, int level, const u64 *d, long long d_st
     const int k = L.k;
     const int Kkey = ctx->host->K;
     const int special = Kkey - 1;
-    Scratch scr(s);
+    Scratch scr(ctx, s);
     u64 *ks1 = nullptr, *ks2 = nullptr;
     int rc;
     if ((rc = scr.get((size_t)batch * (k + 1) * k * n, &ks1)))
@@ -1786,10 +1788,18 @@ int b200_ctx_create(uint64_t n, const uint64_t *coeff_modulus, uint64_t count, u
 #endif
     CU_TRY(cudaFuncSetAttribute(ntt_kernel<true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
     CU_TRY(cudaFuncSetAttribute(ntt_kernel<false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
-    // keep freed scratch cached in the pool instead of returning it to the OS
+    // A PRIVATE stream-ordered pool (the device's default pool is shared with every other user of the process, e.g. torch:
+    // its attributes are not ours to change).  Freed scratch stays cached in it instead of returning to the OS.
     cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess)
     {
+        cudaMemPoolProps props;
+        std::memset(&props, 0, sizeof(props));
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        CU_TRY(cudaMemPoolCreate(&pool, &props));
+        ctx->mempool = pool;
         unsigned long long thr = ~0ULL;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
         // a block freed on one stream must not be handed to another stream by making that stream WAIT for the first one:
@@ -1858,6 +1868,8 @@ void b200_ctx_destroy(b200_ctx *ctx)
         cudaStreamDestroy(ctx->s_comp);
     if (ctx->s_d2h)
         cudaStreamDestroy(ctx->s_d2h);
+    if (ctx->mempool)
+        cudaMemPoolDestroy(ctx->mempool);
     delete ctx;
 }
 
@@ -1926,7 +1938,7 @@ int b200_malloc(b200_ctx *ctx, size_t bytes, void **dptr)
         return fail(B200_E_NULL, "null argument");
     CU_TRY(cudaSetDevice(ctx->device));
     std::lock_guard<std::mutex> lk(ctx->alloc_mu);
-    CU_TRY(cudaMallocAsync(dptr, bytes ? bytes : 8, ctx->s_alloc));
+    CU_TRY(cudaMallocFromPoolAsync(dptr, bytes ? bytes : 8, ctx->mempool, ctx->s_alloc));
     CU_TRY(cudaStreamSynchronize(ctx->s_alloc)); // usable from every stream on return
     return 0;
 }
@@ -2002,6 +2014,15 @@ int b200_memcpy_d2d(b200_ctx *ctx, void *dst, const void *src, size_t bytes, voi
     CU_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return 0;
 }
+int b200_memzero(b200_ctx *ctx, void *dst, size_t bytes, void *stream)
+{
+    if (!ctx)
+        return fail(B200_E_NULL, "null argument");
+    if (!dst || !bytes)
+        return 0;
+    CU_TRY(cudaMemsetAsync(dst, 0, bytes, (cudaStream_t)stream));
+    return 0;
+}
 int b200_stream_synchronize(b200_ctx *ctx, void *stream)
 {
     if (!ctx)
@@ -2073,7 +2094,7 @@ int b200_gather_scatter(b200_ctx *ctx, uint64_t *const *host_ptrs, uint64_t coun
         return fail(B200_E_INVALID, "at most 65535 items per gather/scatter");
     cudaStream_t s = (cudaStream_t)stream;
     void *dptrs = nullptr;
-    CU_TRY(cudaMallocAsync(&dptrs, count * sizeof(void *), s));
+    CU_TRY(cudaMallocFromPoolAsync(&dptrs, count * sizeof(void *), ctx->mempool, s));
     CU_TRY(cudaMemcpyAsync(dptrs, host_ptrs, count * sizeof(void *), cudaMemcpyHostToDevice, s));
     dim3 grid((unsigned)std::min<long long>(64, (long long)(words + 255) / 256), (unsigned)count);
     B200_LAUNCH(gather_scatter_kernel, grid, 256, 0, s, (u64 *const *)dptrs, (u64 *)slab, (long long)words, gather);
@@ -2252,7 +2273,7 @@ static int multiply_relin_one(b200_ctx *ctx, int level, const uint64_t *a, const
     const long long n = (long long)ctx->n;
     const int k = ctx->levels[level].k;
     cudaStream_t s = (cudaStream_t)stream;
-    Scratch scr(s);
+    Scratch scr(ctx, s);
     u64 *c2 = nullptr;
     if ((rc = scr.get((size_t)batch * k * n, &c2)))
         return rc;
@@ -2308,7 +2329,7 @@ int b200_apply_galois(b200_ctx *ctx, int level, const uint64_t *in2, uint32_t ga
     const LevelDev &L = ctx->levels[level];
     const int k = L.k;
     cudaStream_t s = (cudaStream_t)stream;
-    Scratch scr(s);
+    Scratch scr(ctx, s);
     u64 *tmp = nullptr;
     if ((rc = scr.get((size_t)batch * k * n, &tmp)))
         return rc;
@@ -2338,7 +2359,7 @@ int b200_multiply_plain(b200_ctx *ctx, int level, const uint64_t *a, int size, c
     const LevelDev &L = ctx->levels[level];
     const int k = L.k;
     cudaStream_t s = (cudaStream_t)stream;
-    Scratch scr(s);
+    Scratch scr(ctx, s);
     u64 *pl = nullptr;
     if ((rc = scr.get((size_t)pb * k * n, &pl)))
         return rc;
@@ -2463,7 +2484,7 @@ int b200_decrypt(b200_ctx *ctx, int level, const uint64_t *ct, int size, const u
     const LevelHost &Lh = ctx->host->levels[level];
     const int k = L.k, terms = size - 1;
     cudaStream_t s = (cudaStream_t)stream;
-    Scratch scr(s);
+    Scratch scr(ctx, s);
     u64 *X = nullptr, *acc = nullptr;
     if ((rc = scr.get((size_t)batch * terms * k * n, &X)))
         return rc;
@@ -2526,7 +2547,7 @@ int b200_ct_sk_phase(b200_ctx *ctx, int level, const uint64_t *ct, int size, con
     const LevelHost &Lh = ctx->host->levels[level];
     const int k = L.k, terms = size - 1;
     cudaStream_t s = (cudaStream_t)stream;
-    Scratch scr(s);
+    Scratch scr(ctx, s);
     u64 *X = nullptr;
     u64 *acc = (u64 *)phase_out;
     if ((rc = scr.get((size_t)batch * terms * k * n, &X)))
@@ -2646,7 +2667,7 @@ int b200_noise_norm(b200_ctx *ctx, int level, const uint64_t *ct, int size, cons
     if (batch == 0)
         return 0;
     cudaStream_t s = (cudaStream_t)stream;
-    Scratch scr(s);
+    Scratch scr(ctx, s);
     u64 *X = nullptr, *acc = nullptr, *bm = nullptr;
     const int NT = 128, CHUNK = 128, WW = W + 1;
     const int blocks = (int)((n + CHUNK - 1) / CHUNK);

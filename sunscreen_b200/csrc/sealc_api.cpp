@@ -820,7 +820,7 @@ long Ciphertext_Resize1(void *p, void *context, uint64_t *parms_id, uint64_t siz
         int lv = c->level_of(id);
         if (lv < 0)
             throw InvalidArg("parms_id is not valid for encryption parameters");
-        if ((size < 2 && size != 0) || size > 6)
+        if ((size < 2 && size != 0) || size > 16)
             throw InvalidArg("invalid size");
         ct->sync_host();
         std::vector<u64> old = ct->host;
@@ -1693,6 +1693,22 @@ struct BatchSlab
     u64 *w() const { return (u64 *)p; }
     BatchSlab(const BatchSlab &) = delete;
 };
+// every handle of a batch argument must be non-null BEFORE anything is read through it (E_INVALIDARG)
+void batch_handles(uint64_t count, std::initializer_list<void **> arrays)
+{
+    for (void **arr : arrays)
+        for (uint64_t i = 0; i < count; i++)
+            NULLRET_THROW(arr[i]);
+}
+// slab words of one batch item, from the first (validated) handle
+u64 batch_item_words(Context_ *c, void **cts)
+{
+    auto &a0 = *(Ciphertext_ *)cts[0];
+    data_level(c, a0, "encrypted is not valid for encryption parameters");
+    if (a0.size != 2 || a0.n != c->parms.n || a0.k == 0 || a0.k > c->parms.coeff.size())
+        throw InvalidArg("batch items must be size-2 ciphertexts at the same level");
+    return 2 * a0.k * c->parms.n;
+}
 int batch_gather(Context_ *c, uint64_t count, void **cts, BatchSlab &slab, u64 &k_out)
 {
     auto &a0 = *(Ciphertext_ *)cts[0];
@@ -1743,8 +1759,9 @@ long B200_Evaluator_MultiplyRelinBatch(void *p, uint64_t count, void **e1, void 
     return guard([&] {
         if (count == 0)
             return;
+        batch_handles(count, { e1, e2, dsts });
         OpScope scope(c);
-        const u64 w = 2 * ((Ciphertext_ *)e1[0])->k * c->parms.n;
+        const u64 w = batch_item_words(c, e1);
         BatchSlab A(c, count * w), B(c, count * w), D(c, count * w);
         u64 k = 0, kb = 0;
         const int lv = batch_gather(c, count, e1, A, k);
@@ -1765,8 +1782,9 @@ long B200_Evaluator_AddSubBatch(void *p, uint64_t count, void **e1, void **e2, b
     return guard([&] {
         if (count == 0)
             return;
+        batch_handles(count, { e1, e2, dsts });
         OpScope scope(c);
-        const u64 w = 2 * ((Ciphertext_ *)e1[0])->k * c->parms.n;
+        const u64 w = batch_item_words(c, e1);
         BatchSlab A(c, count * w), B(c, count * w);
         u64 k = 0, kb = 0;
         const int lv = batch_gather(c, count, e1, A, k);
@@ -1789,9 +1807,10 @@ long B200_Evaluator_PlainBatch(void *p, int which, uint64_t count, void **encs, 
     return guard([&] {
         if (count == 0)
             return;
+        batch_handles(count, { encs, plains, dsts });
         OpScope scope(c);
         const size_t n = c->parms.n;
-        const u64 w = 2 * ((Ciphertext_ *)encs[0])->k * n;
+        const u64 w = batch_item_words(c, encs);
         BatchSlab A(c, count * w), O(c, count * w), P(c, count * n);
         u64 k = 0;
         const int lv = batch_gather(c, count, encs, A, k);
@@ -1829,8 +1848,9 @@ long B200_Evaluator_RotateRowsBatch(void *p, uint64_t count, void **encs, int st
             return;
         if (!c->using_batching)
             throw LogicErr("encryption parameters do not support batching");
+        batch_handles(count, { encs, dsts });
         OpScope scope(c);
-        const u64 w = 2 * ((Ciphertext_ *)encs[0])->k * c->parms.n;
+        const u64 w = batch_item_words(c, encs);
         BatchSlab A(c, count * w), O(c, count * w);
         u64 k = 0;
         const int lv = batch_gather(c, count, encs, A, k);
@@ -2003,6 +2023,7 @@ long KeyGenerator_Create1(void *context, void **out)
         // generate_sk (S/keygenerator.cpp:57-92): ternary sample, then NTT at the key level
         b200::Blake2xbPrng prng(b200::random_seed());
         std::vector<u64> s(K * n);
+        WipeGuard wg(s);
         b200::sample_poly_ternary(prng, n, c->parms.coeff, s.data());
         DevBuf d(c, s);
         dev_check(b200_ntt_forward(c->dev, 0, d.p, 1, nullptr));
@@ -2283,6 +2304,7 @@ static void encrypt_asymmetric(Encryptor_ *e, const Plaintext_ &plain, b200::Bla
     const std::vector<u64> mods(c->parms.coeff.begin(), c->parms.coeff.begin() + ke);
     // u, e_0, e_1 as small signed values; their residues are formed on the device
     std::vector<u64> us(n), es(2 * n);
+    WipeGuard wgu(us), wge(es);
     b200::sample_poly_ternary(prng, n, signed_only(), us.data());
     b200::sample_poly_normal(prng, n, signed_only(), es.data());
     b200::sample_poly_normal(prng, n, signed_only(), es.data() + n);
@@ -2341,6 +2363,7 @@ static void encrypt_symmetric(Encryptor_ *e, const Plaintext_ &plain, b200::Blak
     bootstrap.generate(sizeof(pub), pub.data());
     b200::Blake2xbPrng ct_prng(pub);
     std::vector<u64> c1((size_t)k * n), noise(n);
+    WipeGuard wgn(noise);
     b200::sample_poly_uniform(ct_prng, n, mods, c1.data());
     b200::sample_poly_normal(bootstrap, n, signed_only(), noise.data());
     lk.lock();

@@ -16,6 +16,7 @@
 #include <mutex>
 #include <stdexcept>
 #include <vector>
+#include <string.h> // explicit_bzero
 
 namespace b200c
 {
@@ -268,7 +269,8 @@ struct Ciphertext_
     Context_ *ctx = nullptr;          // context the device buffer belongs to (identity only: it may be gone already)
     std::shared_ptr<DevOwner> keep;   // ... and what keeps its device alive
     mutable std::vector<u64> host;
-    mutable bool host_valid = true;
+    mutable std::atomic<bool> host_valid{ true };
+    mutable std::mutex mirror_mu; // the reference allows concurrent const reads: mirror materialisation is serialised
     u64 *dev = nullptr;
     size_t dev_words = 0;
     bool dev_valid = false;
@@ -318,7 +320,10 @@ struct Ciphertext_
     }
     void sync_host() const
     {
-        if (host_valid)
+        if (host_valid.load(std::memory_order_acquire))
+            return;
+        std::lock_guard<std::mutex> lk(mirror_mu);
+        if (host_valid.load(std::memory_order_relaxed))
             return;
         host.resize(words());
         if (words() && dev && keep)
@@ -326,7 +331,7 @@ struct Ciphertext_
             dev_check(b200_memcpy_d2h(keep->dev, host.data(), dev, words() * sizeof(u64), nullptr));
             dev_check(b200_stream_synchronize(keep->dev, nullptr));
         }
-        host_valid = true;
+        host_valid.store(true, std::memory_order_release);
     }
     // prepare as an output of shape (size, k) for context c; contents undefined, device copy becomes the valid one
     u64 *prepare_output(Context_ *c, const ParmsId &id, u64 new_size, u64 new_k)
@@ -369,6 +374,28 @@ struct Plaintext_
     double scale = 1.0;
 };
 
+// Secret material (secret-key residues, the sampled u / e, buffers derived from them) is zeroed before its memory goes back
+// to the heap or the device pool — the reference keeps such data in clear-on-destruction pools (S/memorymanager.h, `clear_on_destruction`).
+inline void wipe(std::vector<u64> &v)
+{
+    if (!v.empty())
+        explicit_bzero(v.data(), v.size() * sizeof(u64));
+}
+struct WipeGuard
+{
+    std::vector<u64> &v;
+    explicit WipeGuard(std::vector<u64> &x) : v(x) {}
+    ~WipeGuard() { wipe(v); }
+};
+inline void wipe_dev_free(b200_ctx *dev, void *p, size_t bytes)
+{
+    if (!p || !dev)
+        return;
+    b200_memzero(dev, p, bytes, nullptr);
+    b200_stream_synchronize(dev, nullptr);
+    b200_free(dev, p);
+}
+
 struct PublicKey_ { Ciphertext_ data; };
 struct SecretKey_ { Plaintext_ data; };
 
@@ -377,7 +404,7 @@ struct KSwitchKeys_
     ParmsId parms_id = kZeroId;
     std::vector<std::vector<PublicKey_ *>> keys; // owned
     // device cache of flattened key lists
-    struct Flat { u64 *dev = nullptr; Context_ *ctx = nullptr; std::shared_ptr<DevOwner> keep; };
+    struct Flat { u64 *dev = nullptr; Context_ *ctx = nullptr; int count = 0; std::shared_ptr<DevOwner> keep; };
     std::vector<Flat> flat;
     ~KSwitchKeys_() { clear(); }
     void clear()
@@ -395,17 +422,27 @@ struct KSwitchKeys_
                 b200_free(f.keep->dev, f.dev);
         flat.clear();
     }
+    // The cached buffer always holds EVERY component of the key list (the first level's decomposition count): a lower
+    // level reads a prefix of it, so one key object can serve ciphertexts at any level in any order.
     const u64 *flat_dev(Context_ *c, size_t index, int decomp)
     {
+        if (index >= keys.size() || keys[index].size() < (size_t)decomp)
+            throw InvalidArg("kswitch_keys is not valid for encryption parameters");
         if (flat.size() <= index)
             flat.resize(index + 1);
         Flat &f = flat[index];
-        if (f.dev && f.ctx == c)
+        if (f.dev && f.ctx == c && f.count >= decomp)
             return f.dev;
+        if (f.dev && f.keep && f.keep->dev)
+        {
+            b200_free(f.keep->dev, f.dev);
+            f.dev = nullptr;
+        }
         const size_t K = c->parms.coeff.size(), n = c->parms.n;
         const size_t per = 2 * K * n;
-        std::vector<u64> buf(per * decomp);
-        for (int j = 0; j < decomp; j++)
+        const int all = (int)keys[index].size();
+        std::vector<u64> buf(per * all);
+        for (int j = 0; j < all; j++)
         {
             Ciphertext_ &ct = keys[index][j]->data;
             ct.sync_host();
@@ -419,6 +456,7 @@ struct KSwitchKeys_
         dev_check(b200_stream_synchronize(c->dev, nullptr));
         f.dev = (u64 *)p;
         f.ctx = c;
+        f.count = all;
         f.keep = c->owner;
         return f.dev;
     }
@@ -472,15 +510,10 @@ struct Decryptor_
     CtxHold hold;
     std::vector<u64> sk; // key level NTT form [K][n]
     // device cache: powers s^1..s^m packed per (level, terms)
-    struct Pow { int level, terms; u64 *dev; };
+    struct Pow { int level, terms; u64 *dev; size_t bytes; };
     std::vector<Pow> cache;
     std::shared_ptr<DevOwner> keep;
-    ~Decryptor_()
-    {
-        for (auto &p : cache)
-            if (p.dev && keep && keep->dev)
-                b200_free(keep->dev, p.dev);
-    }
+    ~Decryptor_();
     const u64 *powers(int level, int terms)
     {
         for (auto &p : cache)
@@ -489,6 +522,7 @@ struct Decryptor_
         const size_t n = ctx->parms.n;
         const int k = ctx->level_k[level];
         std::vector<u64> buf((size_t)terms * k * n);
+        WipeGuard wg(buf);
         for (int r = 0; r < k; r++)
         {
             const u64 q = ctx->parms.coeff[r];
@@ -508,7 +542,7 @@ struct Decryptor_
         dev_check(b200_memcpy_h2d(ctx->dev, p, buf.data(), buf.size() * sizeof(u64), nullptr));
         dev_check(b200_stream_synchronize(ctx->dev, nullptr));
         keep = ctx->owner;
-        cache.push_back({ level, terms, (u64 *)p });
+        cache.push_back({ level, terms, (u64 *)p, buf.size() * sizeof(u64) });
         return (u64 *)p;
     }
 };
@@ -527,9 +561,9 @@ struct DevBuf
     }
     DevBuf(Context_ *ctx, const std::vector<u64> &h) : DevBuf(ctx, h.size()) { upload(h); }
     ~DevBuf()
-    {
+    { // the E-row temporaries hold u, e and products with the secret key: always wiped
         b200_stream_synchronize(c->dev, nullptr);
-        b200_free(c->dev, p);
+        wipe_dev_free(c->dev, p, std::max<size_t>(words, 1) * 8);
     }
     void upload(const std::vector<u64> &h) { dev_check(b200_memcpy_h2d(c->dev, p, h.data(), h.size() * 8, nullptr)); }
     std::vector<u64> download()
@@ -547,11 +581,12 @@ struct DevCache
 {
     std::shared_ptr<DevOwner> keep;
     std::vector<std::pair<int, u64 *>> bufs;
+    std::vector<size_t> bytes;
     ~DevCache()
     {
-        for (auto &b : bufs)
-            if (b.second && keep && keep->dev)
-                b200_free(keep->dev, b.second);
+        for (size_t i = 0; i < bufs.size(); i++)
+            if (bufs[i].second && keep && keep->dev)
+                wipe_dev_free(keep->dev, bufs[i].second, bytes[i]);
     }
     u64 *find(int key) const
     {
@@ -568,9 +603,18 @@ struct DevCache
         dev_check(b200_stream_synchronize(c->dev, nullptr));
         keep = c->owner;
         bufs.emplace_back(key, (u64 *)p);
+        bytes.push_back(std::max<size_t>(h.size(), 1) * sizeof(u64));
         return (u64 *)p;
     }
 };
+
+inline Decryptor_::~Decryptor_()
+{
+    for (auto &p : cache)
+        if (p.dev && keep && keep->dev)
+            wipe_dev_free(keep->dev, p.dev, p.bytes);
+    wipe(sk);
+}
 
 // The samplers of sampling.h write one row per modulus; with this single zero "modulus" they return the small signed value
 // itself (two's complement), which b200_expand_signed turns into residues on the device — n words cross PCIe instead of k n.
@@ -598,6 +642,7 @@ inline std::vector<u64> encrypt_zero_symmetric_key_level(Context_ *c, const u64 
     bootstrap.generate(sizeof(pub), pub.data());
     b200::Blake2xbPrng ct_prng(pub);
     std::vector<u64> c1(K * n), noise(n);
+    WipeGuard wg(noise);
     b200::sample_poly_uniform(ct_prng, n, c->parms.coeff, c1.data());
     b200::sample_poly_normal(bootstrap, n, signed_only(), noise.data());
     DevBuf d1(c, c1), dn(c, noise), de(c, K * n), d0(c, K * n);
@@ -617,6 +662,7 @@ struct KeyGenerator_
     CtxHold hold;
     std::vector<u64> sk; // key level, NTT form [K][n]
     DevCache dev_cache;
+    ~KeyGenerator_() { wipe(sk); }
     const u64 *dev_sk()
     {
         u64 *p = dev_cache.find(0);
@@ -665,6 +711,7 @@ struct Encryptor_
     bool has_pk = false, has_sk = false;
     std::vector<u64> pk; // [2][K][n] NTT form, key level
     std::vector<u64> sk; // [K][n]
+    ~Encryptor_() { wipe(sk); }
     DevCache dev_cache;  // key 0: secret key [K][n]; key 1 + level: the level's residues of both public-key polynomials
     const u64 *dev_sk()
     {

@@ -36,6 +36,10 @@ inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) { *p = cudaDe
 template <class F> inline cudaError_t cudaFuncSetAttribute(F, int, int) { return 0; }
 inline cudaError_t cudaDeviceGetDefaultMemPool(cudaMemPool_t *p, int) { *p = nullptr; return 0; }
 inline cudaError_t cudaMemPoolSetAttribute(cudaMemPool_t, int, void *) { return 0; }
+enum { cudaMemAllocationTypePinned = 1, cudaMemHandleTypeNone = 0, cudaMemLocationTypeDevice = 1 };
+struct cudaMemPoolProps { int allocType, handleTypes; struct { int type, id; } location; };
+inline cudaError_t cudaMemPoolCreate(cudaMemPool_t *p, const cudaMemPoolProps *) { *p = nullptr; return 0; }
+inline cudaError_t cudaMemPoolDestroy(cudaMemPool_t) { return 0; }
 inline cudaError_t cudaDeviceSynchronize() { return 0; }
 inline cudaError_t cudaGetLastError() { return 0; }
 inline cudaError_t cudaMalloc(void **p, size_t b) { *p = std::malloc(b ? b : 8); return *p ? 0 : 2; }
@@ -43,9 +47,11 @@ inline cudaError_t cudaFree(void *p) { std::free(p); return 0; }
 inline cudaError_t cudaMallocHost(void **p, size_t b) { return cudaMalloc(p, b); }
 inline cudaError_t cudaFreeHost(void *p) { return cudaFree(p); }
 inline cudaError_t cudaMallocAsync(void **p, size_t b, cudaStream_t) { return cudaMalloc(p, b); }
+inline cudaError_t cudaMallocFromPoolAsync(void **p, size_t b, cudaMemPool_t, cudaStream_t) { return cudaMalloc(p, b); }
 inline cudaError_t cudaFreeAsync(void *p, cudaStream_t) { return cudaFree(p); }
 inline cudaError_t cudaMemcpy(void *d, const void *s, size_t b, cudaMemcpyKind) { std::memmove(d, s, b); return 0; }
 inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t b, cudaMemcpyKind, cudaStream_t) { std::memmove(d, s, b); return 0; }
+inline cudaError_t cudaMemsetAsync(void *d, int v, size_t b, cudaStream_t) { std::memset(d, v, b); return 0; }
 inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, int) { *s = nullptr; return 0; }
 inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }

@@ -363,7 +363,7 @@ def batch_encoder_parity(S, n, moduli, t):
 # wire format, PolynomialArray, component-returning encryption, small leftovers of the seal_fhe surface
 # ------------------------------------------------------------------------------------------------------------
 COMPR_NONE, COMPR_ZLIB, COMPR_ZSTD = 0, 1, 2
-E_INVALIDARG, COR_E_INVALIDOPERATION, COR_E_IO = 0x80070057, 0x80131509, 0x80131620
+E_INVALIDARG, COR_E_INVALIDOPERATION, COR_E_IO, E_POINTER = 0x80070057, 0x80131509, 0x80131620, 0x80004003
 _CREATE = {"Ciphertext": ("Ciphertext_Create1", True), "Plaintext": ("Plaintext_Create1", True),
            "PublicKey": ("PublicKey_Create1", False), "SecretKey": ("SecretKey_Create1", False),
            "KSwitchKeys": ("KSwitchKeys_Create1", False)}
@@ -916,6 +916,41 @@ def deep_chain_parity(S, n, moduli, t):
     assert level == len(moduli) - 2, "the chain should end at a single residue"
 
 
+def key_level_order(S, n, moduli, t):
+    """One RelinKeys / GaloisKeys object used FIRST at the lowest level that still key-switches and THEN at the first level
+    (and through the batch seam): the cached device copy of a key must serve every level in any order (a cache sized
+    by the first use returned garbage for the later, higher-level use)."""
+    R = refseal.RefContext(n, moduli, t)
+    O = S.context(n, moduli, t)
+    RL, OL = _libs(R, O)
+    kg = R.keygen()
+    sk, pk, rlk = R.secret_key(kg), R.public_key(kg), R.relin_keys(kg)
+    batching = t % (2 * n) == 1
+    glk = R.galois_keys_steps(kg, [1]) if batching else None
+    enc = R.encryptor(pk)
+    orlk = OL.load("KSwitchKeys", RL.save("KSwitchKeys", rlk, 0))
+    oglk = OL.load("KSwitchKeys", RL.save("KSwitchKeys", glk, 0)) if batching else None
+    rng = np.random.default_rng(77)
+    ra = R.encrypt(enc, R.new_pt(rng.integers(0, t, size=n, dtype=np.uint64)))
+    rb = R.encrypt(enc, R.new_pt(rng.integers(0, t, size=n, dtype=np.uint64)))
+    oa, ob = (OL.load("Ciphertext", RL.save("Ciphertext", h, 0)) for h in (ra, rb))
+    same = lambda rh, oh, what: eq(np.frombuffer(OL.save("Ciphertext", oh, 0), dtype=np.uint8),
+                                   np.frombuffer(RL.save("Ciphertext", rh, 0), dtype=np.uint8), what)
+    # walk both operands down to the last level
+    chain = [(ra, rb, oa, ob)]
+    for _ in range(len(moduli) - 2):
+        ra_, rb_, oa_, ob_ = chain[-1]
+        chain.append((R.mod_switch_to_next(ra_), R.mod_switch_to_next(rb_), O.mod_switch_to_next(oa_), O.mod_switch_to_next(ob_)))
+    for idx in list(range(len(chain) - 1, -1, -1)) + [len(chain) - 1, 0]:
+        ra_, rb_, oa_, ob_ = chain[idx]
+        same(R.relinearize(R.multiply(ra_, rb_), rlk), O.relinearize(O.multiply(oa_, ob_), orlk), f"relinearize, level +{idx}")
+        if batching:
+            same(R.rotate_rows(ra_, 1, glk), O.rotate_rows(oa_, 1, oglk), f"rotate_rows, level +{idx}")
+        d = OL.new("Ciphertext")
+        O.S.call("B200_Evaluator_MultiplyRelinBatch", O.ev, u64(1), (vp * 1)(oa_), (vp * 1)(ob_), orlk, (vp * 1)(d))
+        same(R.relinearize(R.multiply(ra_, rb_), rlk), d, f"MultiplyRelinBatch, level +{idx}")
+
+
 def misuse_hresults(S, n, moduli, t):
     """A sweep of calls the Rust wrappers can make with bad arguments: both libraries must answer every one of them with
     the same HRESULT (and leave the same values where there are any)."""
@@ -1295,3 +1330,19 @@ def batch_seams(S, n, moduli, t, count=5):
     assert S.rc("B200_Evaluator_AddSubBatch", O.ev, u64(2), arr([A[0], lower]), arr([B[0], B[1]]), C.c_bool(False), arr(fresh()[:2])) == E_INVALIDARG
     # transparent items are reported
     assert S.rc("B200_Evaluator_AddSubBatch", O.ev, u64(2), arr([A[0], A[1]]), arr([B[0], A[1]]), C.c_bool(True), arr(fresh()[:2])) == COR_E_INVALIDOPERATION
+    # a null handle anywhere in an argument array, a size-3 item, an NTT-form... : rejected before anything is launched
+    holes = (vp * 2)(A[0], None)
+    assert S.rc("B200_Evaluator_AddSubBatch", O.ev, u64(2), holes, arr(B[:2]), C.c_bool(False), arr(fresh()[:2])) == E_INVALIDARG
+    assert S.rc("B200_Evaluator_MultiplyRelinBatch", O.ev, u64(2), arr(A[:2]), holes, orlk, arr(fresh()[:2])) == E_INVALIDARG
+    assert S.rc("B200_Evaluator_MultiplyRelinBatch", O.ev, u64(2), arr(A[:2]), arr(B[:2]), orlk, holes) == E_INVALIDARG
+    assert S.rc("B200_Evaluator_MultiplyRelinBatch", O.ev, u64(2), None, arr(B[:2]), orlk, arr(fresh()[:2])) == E_POINTER
+    size3 = O.multiply(A[0], B[0])
+    assert S.rc("B200_Evaluator_MultiplyRelinBatch", O.ev, u64(2), arr([size3, A[1]]), arr(B[:2]), orlk, arr(fresh()[:2])) == E_INVALIDARG
+    assert S.rc("B200_Evaluator_AddSubBatch", O.ev, u64(2), arr([A[0], size3]), arr(B[:2]), C.c_bool(False), arr(fresh()[:2])) == E_INVALIDARG
+    if batching:
+        assert S.rc("B200_Evaluator_RotateRowsBatch", O.ev, u64(1), arr([size3]), C.c_int(2), oglk, arr(fresh()[:1])) == E_INVALIDARG
+    # relinearization keys of another context / an empty key object
+    empty = OL.new("KSwitchKeys")
+    assert S.rc("B200_Evaluator_MultiplyRelinBatch", O.ev, u64(2), arr(A[:2]), arr(B[:2]), empty, arr(fresh()[:2])) == E_INVALIDARG
+    # count == 0 is a no-op
+    assert S.rc("B200_Evaluator_MultiplyRelinBatch", O.ev, u64(0), arr(A[:1]), arr(B[:1]), orlk, arr(fresh()[:1])) == 0

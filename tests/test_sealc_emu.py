@@ -95,5 +95,10 @@ def test_wire_fuzz(S, ref):
 
 
 @pytest.mark.parametrize("name", ["n4096", "n8192"])
+def test_key_level_order(S, ref, name):
+    sc.key_level_order(S, *PARAMS[name])
+
+
+@pytest.mark.parametrize("name", ["n4096", "n8192"])
 def test_batch_seams(S, ref, name):
     sc.batch_seams(S, *PARAMS[name], count=3)

@@ -130,6 +130,11 @@ def test_handle_lifetime_order(S, ref):
     sc.handle_lifetime_order(S, *PARAMS["n4096"])
 
 
+@pytest.mark.parametrize("name", ["n4096", "n8192", "n16384"])
+def test_key_level_order(S, ref, name):
+    sc.key_level_order(S, *PARAMS[name])
+
+
 @pytest.mark.parametrize("name", ["n4096", "n8192"])
 def test_batch_seams(S, ref, name):
     sc.batch_seams(S, *PARAMS[name], count=9)
