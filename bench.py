@@ -6,11 +6,19 @@
   python bench.py --impl reference --steps K --warmup W  # the reference's own CPU implementation (oracle/_ref)
 
 One "step" = one pass of the hot path (Evaluator::multiply then ::relinearize) over the whole batch.
-`value` = device-resident throughput (inputs already in HBM), `e2e` = the same metric through the host-buffer
-C-ABI entry point (pinned host memory in, host memory out, copies inside the timed region).
-`roofline` is measured live on the dominant kernel (the batched NTT, BASELINE config 2: 4096 polynomials x 4
-residues) with CUDA events on the launching stream; `cpu_baseline` times the unmodified reference on this box's
-host cores on a bounded sample of the same workload.
+`value` = device-resident throughput (inputs already in HBM).
+`e2e`   = the same metric through the reference-facing PLUGIN calls (the SEAL-named C ABI, include/b200_sealc.h) with HOST
+          buffers: pinned host words -> B200_Ciphertext_SetWordsBatch -> B200_Evaluator_MultiplyRelinBatch ->
+          B200_Ciphertext_GetWordsBatch -> pinned host words, copies inside the timed region, a few worker threads each
+          driving chunks of the batch (the call pattern of sunscreen_runtime's rayon workers, run.rs:237-282,415-469).
+`e2e_host_slab`     = the layer-1 host-buffer entry point b200_multiply_relin_host (last round's `e2e`).
+`plugin_per_handle` = Evaluator_Multiply + Evaluator_Relinearize per ciphertext handle from 8 threads (what unmodified
+          sunscreen_runtime issues today), handles device-resident.
+`roofline` is measured live on the dominant kernel (the batched NTT, BASELINE config 2: 4096 polynomials x 4 residues) with
+CUDA events on the launching stream, `roofline_keyswitch` on the batched relinearisation (key-switch inner product);
+`cpu_baseline` times the unmodified reference on this box's host cores on a bounded sample of the same workload and says how
+many cores the box actually grants.  Under torchrun (N > 1) a `sharded` leg runs the north-star split: rank 0 holds the batch,
+NCCL scatter -> every rank computes -> NCCL gather, checked against the 1-GPU words.
 """
 import argparse
 import json
@@ -37,6 +45,30 @@ def peaks():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_quota():
+    """What the box really grants: CPUs in the affinity mask and the cgroup CPU bandwidth limit (cores' worth), if any."""
+    info = {"logical_cpus": os.cpu_count(), "affinity_cpus": None, "cgroup_quota_cores": None}
+    try:
+        info["affinity_cpus"] = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    try:
+        txt = open("/sys/fs/cgroup/cpu.max").read().split()
+        if txt and txt[0] != "max":
+            info["cgroup_quota_cores"] = float(txt[0]) / float(txt[1])
+    except Exception:
+        try:
+            q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                info["cgroup_quota_cores"] = q / per
+        except Exception:
+            pass
+    eff = [v for v in (info["affinity_cpus"], info["cgroup_quota_cores"], info["logical_cpus"]) if v]
+    info["effective_cores"] = min(eff) if eff else None
+    return info
 
 
 class ClockSampler:
@@ -168,6 +200,104 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+class PluginLegs:
+    """The reference-facing plugin calls of OUR library (include/b200_sealc.h), driven the way seal_fhe's wrappers do:
+    opaque handles, one Evaluator, relinearization keys as a KSwitchKeys handle."""
+
+    def __init__(self, ctx, device, k, n, rlk_dev):
+        import ctypes as C
+        import numpy as np
+        from sealc_driver import Sealc
+        from sunscreen_b200.lib import B200Lib
+        self.C, self.np = C, np
+        self.vp, self.u64 = C.c_void_p, C.c_uint64
+        self.S = Sealc(B200Lib.default().lib)
+        self.O = self.S.context(N_POLY, MODULI, PLAIN)
+        self.k, self.n = k, n
+        key = rlk_dev.cpu().numpy().view(np.uint64)  # (k, 2, K, n) key-level NTT-form words
+        self.rlk = self.O.new_ksk({0: key})
+        self.threads = int(os.environ.get("B200_BENCH_E2E_THREADS", "4"))
+        self.chunk = int(os.environ.get("B200_BENCH_E2E_CHUNK", "128"))
+        self.pool = {}
+
+    def _handles(self, tag, count):
+        hs = self.pool.get(tag)
+        if hs is None or len(hs) < count:
+            hs = [self.O._dst() for _ in range(count)]
+            self.pool[tag] = hs
+        return hs[:count]
+
+    def _arr(self, hs):
+        return (self.vp * len(hs))(*hs)
+
+    def _ptr(self, t):
+        return self.C.cast(t.data_ptr(), self.C.POINTER(self.u64))
+
+    def batch_step(self, ah, bh, oh, B):
+        """host words -> handles -> MultiplyRelinBatch -> host words, chunks of the batch driven by worker threads"""
+        S, O, u64, C = self.S, self.O, self.u64, self.C
+        chunks = [(lo, min(lo + self.chunk, B)) for lo in range(0, B, self.chunk)]
+        errs = []
+
+        def work(tid):
+            try:
+                for ci in range(tid, len(chunks), self.threads):
+                    lo, hi = chunks[ci]
+                    cnt = hi - lo
+                    A = self._arr(self._handles(("a", ci), cnt))
+                    Bh = self._arr(self._handles(("b", ci), cnt))
+                    D = self._arr(self._handles(("d", ci), cnt))
+                    S.call("B200_Ciphertext_SetWordsBatch", O.ctx, u64(cnt), A, O.first_id, u64(2), C.c_bool(False), self._ptr(ah[lo]))
+                    S.call("B200_Ciphertext_SetWordsBatch", O.ctx, u64(cnt), Bh, O.first_id, u64(2), C.c_bool(False), self._ptr(bh[lo]))
+                    S.call("B200_Evaluator_MultiplyRelinBatch", O.ev, u64(cnt), A, Bh, self.rlk, D)
+                    S.call("B200_Ciphertext_GetWordsBatch", O.ctx, u64(cnt), D, self._ptr(oh[lo]), u64(cnt * 2 * self.k * self.n))
+            except Exception as ex:  # surfaced by the caller
+                errs.append(ex)
+
+        ts = [threading.Thread(target=work, args=(t,)) for t in range(self.threads)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        if errs:
+            raise errs[0]
+
+    def per_handle_prepare(self, ah, bh, pairs):
+        S, O, u64, C = self.S, self.O, self.u64, self.C
+        self.pa, self.pb = self._handles("pa", pairs), self._handles("pb", pairs)
+        self.pm, self.pr = self._handles("pm", pairs), self._handles("pr", pairs)
+        S.call("B200_Ciphertext_SetWordsBatch", O.ctx, u64(pairs), self._arr(self.pa), O.first_id, u64(2), C.c_bool(False), self._ptr(ah))
+        S.call("B200_Ciphertext_SetWordsBatch", O.ctx, u64(pairs), self._arr(self.pb), O.first_id, u64(2), C.c_bool(False), self._ptr(bh))
+
+    def per_handle_run(self, threads, pairs):
+        S, O = self.S, self.O
+        errs = []
+
+        def work(tid):
+            try:
+                for i in range(tid, pairs, threads):
+                    S.call("Evaluator_Multiply", O.ev, self.pa[i], self.pb[i], self.pm[i], None)
+                    S.call("Evaluator_Relinearize", O.ev, self.pm[i], self.rlk, self.pr[i], None)
+            except Exception as ex:
+                errs.append(ex)
+
+        ts = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        if errs:
+            raise errs[0]
+
+    def per_handle_check(self, out_dev, pairs):
+        import torch
+        ok = True
+        for i in (0, pairs // 2, pairs - 1):
+            w = self.O.ct_words(self.pr[i])
+            ok = ok and bool(torch.equal(torch.from_numpy(w.view(self.np.int64)), out_dev[i].cpu()))
+        return ok
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -254,7 +384,7 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     value = world * B * args.steps / (ms / 1000.0)
 
-    # ---- e2e: host buffers through the C ABI (H2D + compute + D2H in the timed region) ----
+    # ---- e2e legs (host buffers; H2D + compute + D2H inside the timed region) ----
     ct_bytes = 2 * k * n * 8
     ah = torch.empty((B, 2, k, n), dtype=torch.int64).pin_memory()
     bh = torch.empty((B, 2, k, n), dtype=torch.int64).pin_memory()
@@ -262,23 +392,110 @@ def main():
     ah.copy_(a)
     bh.copy_(b)
     e2e_steps = max(2, min(args.steps, 5))
+
+    def wall_max(seconds):
+        if dist is None:
+            return seconds
+        ts = torch.tensor([seconds], device=dev, dtype=torch.float64)
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        return float(ts.item())
+
+    # (a) layer-1 host-slab entry point
     ctx.multiply_relin_host(ah, bh, rlk, oh, B)  # warm
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         ctx.multiply_relin_host(ah, bh, rlk, oh, B)
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    if dist is not None:
-        ts = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
-        e2e_s = float(ts.item())
-    e2e_value = world * B * e2e_steps / e2e_s
-    same = bool(torch.equal(oh.to(dev), out))
+    slab_s = wall_max(time.perf_counter() - t0)
+    slab_value = world * B * e2e_steps / slab_s
+    slab_same = bool(torch.equal(oh.to(dev), out))
     pack_num = 6 if (max(MODULI[:k]) < 2 ** 48 and os.environ.get("B200_HOST_PACK", "0") not in ("", "0")) else 8
+
+    # (b) the plugin calls (SEAL-named C ABI): handles, batch seam, bulk word access
+    os.environ["B200_DEVICE"] = str(local)  # the SEAL-named layer creates its own device context: same GPU as this rank
+    plug = PluginLegs(ctx, local, k, n, rlk)
+    oh.zero_()
+    plug.batch_step(ah, bh, oh, B)  # warm (allocates the handles' device buffers)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        plug.batch_step(ah, bh, oh, B)
+    plug_s = wall_max(time.perf_counter() - t0)
+    e2e_value = world * B * e2e_steps / plug_s
+    same = bool(torch.equal(oh.to(dev), out))
+    # (c) per-handle calls from 8 threads, handles device-resident
+    ph_threads = int(os.environ.get("B200_BENCH_PH_THREADS", "8"))
+    ph_pairs = min(B, 256)
+    plug.per_handle_prepare(ah, bh, ph_pairs)
+    plug.per_handle_run(ph_threads, ph_pairs)  # warm
+    barrier()
+    t0 = time.perf_counter()
+    plug.per_handle_run(ph_threads, ph_pairs)
+    ph_s = wall_max(time.perf_counter() - t0)
+    ph_value = world * ph_pairs / ph_s
+    ph_same = plug.per_handle_check(out, ph_pairs)
+    t0 = time.perf_counter()
+    plug.per_handle_run(1, min(ph_pairs, 64))
+    ph1_value = min(ph_pairs, 64) / (time.perf_counter() - t0)
+
+    # ---- north-star multi-GPU split (N > 1): rank 0 holds the whole batch, NCCL scatter -> compute -> NCCL gather ----
+    sharded = None
+    if dist is not None:
+        Bt = B  # total pairs held by rank 0 (strong scaling: fixed total work)
+        per = Bt // world
+        a_loc = torch.empty((per, 2, k, n), dtype=torch.int64, device=dev)
+        b_loc = torch.empty_like(a_loc)
+        o_loc = torch.zeros_like(a_loc)
+        gathered = [torch.empty_like(o_loc) for _ in range(world)] if rank == 0 else None
+        a_chunks = list(a[: per * world].chunk(world)) if rank == 0 else None  # rank 0's own batch is the job
+        b_chunks = list(b[: per * world].chunk(world)) if rank == 0 else None
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+
+        def sharded_step():
+            ev[0].record()
+            dist.scatter(a_loc, a_chunks, src=0)
+            dist.scatter(b_loc, b_chunks, src=0)
+            ev[1].record()
+            ctx.multiply_relin(a_loc, b_loc, rlk_shared, o_loc, per, stream=stream)
+            ev[2].record()
+            dist.gather(o_loc, gathered, dst=0)
+            ev[3].record()
+
+        # every rank needs rank 0's relinearization key (replicated once, outside the timed region)
+        rlk_shared = rlk.clone()
+        dist.broadcast(rlk_shared, src=0)
+        for _ in range(2):
+            sharded_step()
+        barrier()
+        reps_s = max(2, min(args.steps, 5))
+        phase = torch.zeros(4, dtype=torch.float64, device=dev)
+        for _ in range(reps_s):
+            barrier()
+            sharded_step()
+            torch.cuda.synchronize()
+            phase += torch.tensor([ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3]),
+                                   ev[0].elapsed_time(ev[3])], dtype=torch.float64, device=dev)
+        phase /= reps_s
+        dist.all_reduce(phase, op=dist.ReduceOp.MAX)
+        ok = None
+        if rank == 0:
+            whole = torch.cat(gathered)
+            ok = bool(torch.equal(whole, out[: per * world]))  # `out` = the same pairs computed on one GPU (timed loop above)
+        sc_ms, comp_ms, ga_ms, tot_ms = (float(x) for x in phase.tolist())
+        moved_out = (world - 1) * per * 2 * ct_bytes  # bytes leaving rank 0 in the scatter
+        moved_in = (world - 1) * per * ct_bytes
+        sharded = {"scaling": "strong", "total_pairs": per * world, "scatter_ms": sc_ms, "compute_ms": comp_ms, "gather_ms": ga_ms,
+                   "total_ms": tot_ms, "ops_per_s": per * world / (tot_ms / 1000.0),
+                   "ops_per_s_compute_only": per * world / (comp_ms / 1000.0),
+                   "scatter_gbs_out_of_rank0": moved_out / (sc_ms / 1000.0) / 1e9 if sc_ms else None,
+                   "gather_gbs_into_rank0": moved_in / (ga_ms / 1000.0) / 1e9 if ga_ms else None,
+                   "equals_one_gpu_words": ok, "timing": "CUDA events per phase, max over ranks, mean of %d steps" % reps_s,
+                   "collectives": "torch.distributed scatter x2 / gather (NCCL over NVLink), none inside the compute"}
 
     # ---- roofline of the dominant kernel: batched forward NTT, 4096 polys x 4 residues (1 GiB slab > L2) ----
     roof = None
+    roof_ks = None
     cpu = None
     if rank == 0:
         peak, peak_src = peaks()
@@ -319,16 +536,46 @@ def main():
                 "inverse_achieved": alg_bytes / (inv_ms / 1000.0) / 1e9,
                 "mul_relin_algorithmic_gbs": (8 * n * k * 6) * value / world / 1e9}
         del slab
+        # key switch (relinearize 3 -> 2 over the batch): digit NTTs + inner product against the key + inverse NTTs + mod-down.
+        # algorithmic bytes: 8nk*5 per item + the key once per batch
+        c3 = rand_rows((B, 3), MODULI[:k])
+        o2 = torch.zeros((B, 2, k, n), dtype=torch.int64, device=dev)
+        for _ in range(3):
+            ctx.relinearize(c3, rlk, o2, B, stream=stream)
+        torch.cuda.synchronize()
+        ks_ms = 0.0
+        for _ in range(reps):
+            ef0.record()
+            ctx.relinearize(c3, rlk, o2, B, stream=stream)
+            ef1.record()
+            torch.cuda.synchronize()
+            ks_ms += ef0.elapsed_time(ef1)
+        ks_ms /= reps
+        ks_bytes = 8 * n * k * 5 * B + 16 * n * k * (k + 1)
+        roof_ks = {"bound": "hbm", "kernel": "relinearize = ntt_fp_kernel<fwd> (k(k+1) digit rows) + ksmac + ntt_fp_kernel<inv> + ksmoddown",
+                   "achieved": ks_bytes / (ks_ms / 1000.0) / 1e9, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                   "frac": ks_bytes / (ks_ms / 1000.0) / 1e9 / peak, "ms_per_batch": ks_ms, "batch": B,
+                   "algorithmic_bytes_per_launch": ks_bytes, "ops_per_s": B / (ks_ms / 1000.0),
+                   "note": "the key switch is bound by its 30 transforms per item (FP64 pipe), not by HBM: see DESIGN.md"}
+        del c3, o2
         if not args.no_cpu and world == 1:  # the CPU baseline is an N=1 leg (the reference arm covers every N)
             try:
-                os.sched_setaffinity(0, range(os.cpu_count() or 1))
+                try:
+                    os.sched_setaffinity(0, range(os.cpu_count() or 1))
+                except Exception:
+                    pass
+                quota = cpu_quota()
                 cores = os.cpu_count() or 1
-                iters = 32
+                iters = 32 if (quota["effective_cores"] or cores) >= 32 else 8
                 rate, secs = cpu_reference_rate(cores, iters)
                 rate1, secs1 = cpu_reference_rate(1, 16)
                 cpu = {"value": rate, "unit": "ops/s", "cores": cores, "kind": "reference",
                        "sample": f"{cores} threads x {iters} multiply+relinearize_inplace (uniform-random words), {secs:.2f}s",
-                       "single_thread_ops_per_s": rate1}
+                       "single_thread_ops_per_s": rate1,
+                       # a CPU-quota'd lease shows up here: threads >> the cores' worth of time the box grants
+                       "box": quota, "parallel_speedup_over_one_thread": rate / rate1 if rate1 else None,
+                       "build": "unmodified reference sources, -O3, Intel HEXL off (not buildable offline), one MemoryPool per thread",
+                       "full_node_reference": "round-1 SCALE run, same arm on an unquota'd 8-GPU node (128 threads): 3509 ops/s"}
             except Exception as ex:  # reference .so missing on this box
                 cpu = {"value": None, "unit": "ops/s", "cores": os.cpu_count(), "kind": "reference",
                        "sample": f"unavailable: {ex}"}
@@ -344,13 +591,20 @@ def main():
                        "l2": "inputs (1 GiB per GPU) exceed the 126 MB L2; no explicit flush"},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "ops/s",
-                    # bytes that actually cross PCIe per step (with B200_HOST_PACK=1 the library narrows each residue word
-                    # to 6 bytes on the host and widens it again on the device; off by default: measured slower)
-                    "h2d_bytes_per_step": 2 * B * ct_bytes * pack_num // 8, "d2h_bytes_per_step": B * ct_bytes * pack_num // 8,
-                    "host_buffer_bytes_in_per_step": 2 * B * ct_bytes, "host_buffer_bytes_out_per_step": B * ct_bytes,
-                    "transfer": "6-byte packed residues" if pack_num == 6 else "8-byte words",
-                    "steps": e2e_steps, "matches_device_path": same, "host_numa_node": numa_node},
-            "roofline": roof, "cpu_baseline": cpu,
+                    "path": "pinned host words -> B200_Ciphertext_SetWordsBatch -> B200_Evaluator_MultiplyRelinBatch -> "
+                            "B200_Ciphertext_GetWordsBatch -> pinned host words (SEAL-named plugin ABI, include/b200_sealc.h)",
+                    "h2d_bytes_per_step": 2 * B * ct_bytes, "d2h_bytes_per_step": B * ct_bytes,
+                    "threads": plug.threads, "chunk_pairs": plug.chunk, "steps": e2e_steps, "matches_device_path": same,
+                    "host_numa_node": numa_node, "pcie_gbs": 3 * B * ct_bytes * e2e_steps / plug_s / 1e9},
+            "e2e_host_slab": {"value": slab_value, "unit": "ops/s", "path": "b200_multiply_relin_host (layer-1 C ABI, include/b200_bfv.h)",
+                              "h2d_bytes_per_step": 2 * B * ct_bytes * pack_num // 8, "d2h_bytes_per_step": B * ct_bytes * pack_num // 8,
+                              "transfer": "6-byte packed residues" if pack_num == 6 else "8-byte words",
+                              "matches_device_path": slab_same},
+            "plugin_per_handle": {"value": ph_value, "unit": "ops/s", "threads": ph_threads, "pairs": ph_pairs,
+                                  "path": "Evaluator_Multiply + Evaluator_Relinearize per handle (device-resident handles; what "
+                                          "unmodified sunscreen_runtime issues, run.rs:243,279)",
+                                  "one_thread_ops_per_s": ph1_value, "matches_device_path": ph_same},
+            "roofline": roof, "roofline_keyswitch": roof_ks, "cpu_baseline": cpu, "sharded": sharded,
         }
         print(json.dumps(line))
     if dist is not None:

@@ -175,6 +175,9 @@ void b200_trace_dump(void);
 /* developer aid: per-CTA phase timestamps of the next NTT launches ({smid, t_start, t_pass..., t_end} x 8 u64 per CTA,
    globaltimer ns) into a caller-provided device buffer; NULL detaches */
 void b200_ntt_timeline(b200_ctx *ctx, unsigned long long *device_buffer);
+/* developer aid: select the FP64 NTT kernel variant for subsequent launches (bit 0: twiddle table in shared memory; the
+   other bits are timing ablations whose RESULTS ARE MEANINGLESS — tools/ntt_ablate.py); returns the previous value */
+int b200_debug_ntt_variant(int variant);
 
 #ifdef __cplusplus
 }

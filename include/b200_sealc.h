@@ -256,6 +256,12 @@ SEAL_C_FUNC B200_Encryptor_EncryptSetSeed(void *thisptr, void *plaintext, const 
 SEAL_C_FUNC B200_Ciphertext_SetWords(void *thisptr, void *context, uint64_t *parms_id, uint64_t size, bool is_ntt_form,
                                      const uint64_t *words);
 SEAL_C_FUNC B200_Ciphertext_GetWords(void *thisptr, uint64_t *words, uint64_t capacity_words);
+/* the same for `count` handles at once: `words` is one contiguous host buffer [count][size][k][n] (pinned memory moves
+   asynchronously at link speed); one transfer + one device-side scatter / gather instead of a copy per handle */
+SEAL_C_FUNC B200_Ciphertext_SetWordsBatch(void *context, uint64_t count, void **ciphertexts, uint64_t *parms_id, uint64_t size,
+                                          bool is_ntt_form, const uint64_t *words);
+SEAL_C_FUNC B200_Ciphertext_GetWordsBatch(void *context, uint64_t count, void **ciphertexts, uint64_t *words,
+                                          uint64_t capacity_words);
 SEAL_C_FUNC B200_Plaintext_SetCoeffs(void *thisptr, uint64_t count, const uint64_t *coeffs);
 /* Key list `index` <- `decomp` size-2 key-level NTT-form ciphertexts given as one flat word array */
 SEAL_C_FUNC B200_KSwitchKeys_SetKeyWords(void *thisptr, void *context, uint64_t index, uint64_t decomp, const uint64_t *words);

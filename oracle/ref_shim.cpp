@@ -199,6 +199,67 @@ int refshim_behz_floor_sk(void *ctx, const uint64_t *in, uint64_t *out)
     catch (...) { return -1; }
 }
 
+// --- full-size parity: `count` independent (a, b) pairs of size-2 first-level ciphertexts given as raw words
+// ([count][2][k][n]) -> relinearize(multiply(a, b)) words ([count][2][k][n]), items split over `threads` workers.
+int refshim_mul_relin_batch(void *ctx, const uint64_t *a, const uint64_t *b, void *rlk, uint64_t *out, uint64_t count,
+                            int threads)
+{
+    try
+    {
+        auto &context = *reinterpret_cast<SEALContext *>(ctx);
+        auto &keys = *reinterpret_cast<RelinKeys *>(rlk);
+        auto cd = context.first_context_data();
+        const size_t words = 2 * cd->parms().coeff_modulus().size() * cd->parms().poly_modulus_degree();
+        Evaluator ev(context);
+        std::vector<int> bad(threads, 0);
+        std::vector<std::thread> ws;
+        for (int t = 0; t < threads; t++)
+            ws.emplace_back([&, t]() {
+                try
+                {
+                    auto pool = MemoryPoolHandle::New();
+                    Ciphertext ca(pool), cb(pool), d(pool);
+                    ca.resize(context, context.first_parms_id(), 2);
+                    cb.resize(context, context.first_parms_id(), 2);
+                    for (uint64_t i = t; i < count; i += threads)
+                    {
+                        std::memcpy(ca.data(), a + i * words, words * sizeof(uint64_t));
+                        std::memcpy(cb.data(), b + i * words, words * sizeof(uint64_t));
+                        ev.multiply(ca, cb, d, pool);
+                        ev.relinearize_inplace(d, keys, pool);
+                        std::memcpy(out + i * words, d.data(), words * sizeof(uint64_t));
+                    }
+                }
+                catch (...) { bad[t] = 1; }
+            });
+        for (auto &w : ws)
+            w.join();
+        for (int v : bad)
+            if (v)
+                return -1;
+        return 0;
+    }
+    catch (...) { return -1; }
+}
+// forward transforms of `count` polynomials modulo `modulus`, split over `threads` workers (fully reduced output)
+int refshim_ntt_forward_mt(uint64_t modulus, int logn, uint64_t *data, uint64_t count, int threads)
+{
+    try
+    {
+        auto *t = get_tables(modulus, logn);
+        std::vector<std::thread> ws;
+        for (int w = 0; w < threads; w++)
+            ws.emplace_back([=]() {
+                for (uint64_t i = w; i < count; i += threads)
+                    ntt_negacyclic_harvey(CoeffIter(data + (i << logn)), *t);
+            });
+        for (auto &w : ws)
+            w.join();
+        return 0;
+    }
+    catch (...) { return -1; }
+}
+
 // --- CPU baseline: `threads` workers, each `iters` x (multiply + relinearize_inplace) on its own pool ------
 // Returns wall seconds for the whole job (threads*iters operations) or <0 on error.
 double refshim_time_mul_relin(void *ctx, void *a, void *b, void *rlk, int threads, int iters, int warmup)

@@ -120,54 +120,11 @@ __global__ void __launch_bounds__(NT, MB) ntt_kernel(const NttJob job)
     ntt_block_body<FWD>(job, block, ntt_sm, (int)threadIdx.x, (int)blockDim.x);
 }
 
-// FP64-only statically scheduled kernel (all slots of the job use FP-capable primes)
-template <int LOGN, bool FWD, int NT>
-__global__ void __launch_bounds__(NT, (LOGN <= 13 ? (NT <= 256 ? 3 : 2) : 1)) ntt_fp_kernel(const NttJob job)
-{
+// The FP64 statically scheduled kernels (ntt_fp_kernel<LOGN, FWD, NT, VAR>) live in their own translation unit,
+// ntt_fp_kernels.cu; this file only fetches the function pointer of the instantiation it wants to launch.
 #ifndef B200_EMU_HEADER
-    extern __shared__ u64 ntt_sm[];
-    const long long block = (long long)blockIdx.x;
-    // slot-major order: CTAs that run at the same time work on the same prime, so the early-pass twiddles stay in L1
-    const int slot = job.slot_major ? (int)(block / job.items) : (int)(block % job.slots);
-    const long long item = job.slot_major ? block - (long long)slot * job.items : block / job.slots;
-    const int pidx = job.slot_prime[slot];
-    const NttPrimeFp PF = job.fprimes[pidx];
-    const NttPrime PI_ = job.primes[pidx];
-    const u64 *src = ntt_src_ptr(job, item, slot);
-    u64 *dst = job.dst + item * job.dst_item_stride + job.slot_dst[slot];
-    if (job.timeline && threadIdx.x == 0)
-    {
-        unsigned long long t;
-        unsigned smid;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        job.timeline[block * 8] = smid;
-        job.timeline[block * 8 + 1] = t;
-    }
-    if (job.prefetch_dist > 0 && !job.tensor_mode)
-    {
-        // pull the polynomial that the CTA one wave later will transform into L2 (its pass-1 loads then hit L2)
-        const long long nb = block + job.prefetch_dist;
-        if (nb < (long long)gridDim.x)
-        {
-            const int nslot = job.slot_major ? (int)(nb / job.items) : (int)(nb % job.slots);
-            const long long nitem = job.slot_major ? nb - (long long)nslot * job.items : nb / job.slots;
-            const char *np_ = reinterpret_cast<const char *>(ntt_src_ptr(job, nitem, nslot));
-            constexpr int LINES = (8 << LOGN) / 128;
-#pragma unroll
-            for (int l = (int)threadIdx.x; l < LINES; l += NT)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(np_ + (size_t)l * 128));
-        }
-    }
-    NttFpStaticPass<LOGN, NT, FWD, 0>::run(job, PF, PI_, src, dst, reinterpret_cast<double *>(ntt_sm), (int)threadIdx.x, item, slot);
-    if (job.timeline && threadIdx.x == 0)
-    {
-        unsigned long long t;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        job.timeline[block * 8 + 7] = t;
-    }
+#include "ntt_fp_kernels.h"
 #endif
-}
 
 #define GLOBAL_IDX() ((long long)blockIdx.x * blockDim.x + threadIdx.x)
 
@@ -1213,6 +1170,10 @@ struct TensorArgs
     const u64 *src = nullptr;
 };
 
+#ifndef B200_EMU_HEADER
+// FP64 NTT kernel variant (ntt_fp_body.cuh: NttFpStaticPass VAR); B200_NTT_VAR or b200_debug_ntt_variant() override the default
+static std::atomic<int> g_ntt_var{ std::getenv("B200_NTT_VAR") ? atoi(std::getenv("B200_NTT_VAR")) : B200_NTT_DEFAULT_VAR };
+#endif
 static bool static_fp_ok(b200_ctx *ctx, const JobDesc &jd)
 {
 #ifdef B200_EMU_HEADER
@@ -1308,11 +1269,24 @@ static int launch_ntt(b200_ctx *ctx, const JobDesc &jd, const u64 *src, long lon
         // n = 8192: 256 threads x 3 CTAs/SM is the throughput configuration; a launch that cannot fill the SMs anyway (the
         // per-handle path: at most 36 polynomials) is latency-bound and finishes sooner with 512 threads per polynomial
         static const int nt_env = std::getenv("B200_NTT_NT") ? atoi(std::getenv("B200_NTT_NT")) : 0;
+        const int var_env = g_ntt_var.load(std::memory_order_relaxed);
         const int nt13 = nt_env ? nt_env : (blocks <= 2LL * ctx->sm_count ? 512 : 256);
-        void (*sfn)(const NttJob) = ctx->logn == 12   ? ntt_fp_kernel<12, FWD, 256>
-                                    : ctx->logn == 13 ? (nt13 == 256 ? ntt_fp_kernel<13, FWD, 256> : ntt_fp_kernel<13, FWD, 512>)
-                                                      : ntt_fp_kernel<14, FWD, 1024>;
         const int nt = ctx->logn == 12 ? 256 : ctx->logn == 13 ? (nt13 == 256 ? 256 : 512) : 1024;
+        int var = ta && ta->mode ? (var_env & 1) : var_env; // the fused-tensor copy-in exists in the plain variants only
+        b200_ntt_fp_fn sfn = b200_ntt_fp_kernel(ctx->logn, FWD, nt, var);
+        if (!sfn)
+        {
+            var &= 1;
+            sfn = b200_ntt_fp_kernel(ctx->logn, FWD, nt, var);
+        }
+        if (!sfn)
+        {
+            var = 0;
+            sfn = b200_ntt_fp_kernel(ctx->logn, FWD, nt, 0);
+        }
+        if (!sfn)
+            return fail(B200_E_LOGIC, "internal: no FP64 NTT kernel for this size");
+        const size_t smem = ctx->ntt_smem + ((var & 1) ? B200_NTT_TWS_ENTRIES * sizeof(double) : 0);
         if (trace_on())
         {
             static char labels[2][128][40];
@@ -1321,7 +1295,7 @@ static int launch_ntt(b200_ctx *ctx, const JobDesc &jd, const u64 *src, long lon
                      job.tensor_mode ? " +tensor" : "");
             g_trace_name = labels[FWD ? 1 : 0][sl];
         }
-        B200_LAUNCH(sfn, (unsigned)blocks, nt, ctx->ntt_smem, s, job);
+        B200_LAUNCH(sfn, (unsigned)blocks, nt, smem, s, job);
         ctx->launches++;
         CU_TRY(cudaGetLastError());
         return 0;
@@ -1763,14 +1737,11 @@ int b200_ctx_create(uint64_t n, const uint64_t *coeff_modulus, uint64_t count, u
         return fail(B200_E_INVALID, "poly_modulus_degree too large for the shared-memory NTT");
     ctx->ntt_threads = local_logn >= 14 ? 512 : (local_logn >= 10 ? 256 : 64);
 #ifndef B200_EMU_HEADER
-#define SET_SMEM(fn)                                                                                                   \
-    CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));   \
-    CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    SET_SMEM((ntt_fp_kernel<12, true, 256>)) SET_SMEM((ntt_fp_kernel<12, false, 256>))
-    SET_SMEM((ntt_fp_kernel<13, true, 512>)) SET_SMEM((ntt_fp_kernel<13, false, 512>))
-    SET_SMEM((ntt_fp_kernel<13, true, 256>)) SET_SMEM((ntt_fp_kernel<13, false, 256>))
-    SET_SMEM((ntt_fp_kernel<14, true, 1024>)) SET_SMEM((ntt_fp_kernel<14, false, 1024>))
-#undef SET_SMEM
+    {
+        const int frc = b200_ntt_fp_setup((int)prop.sharedMemPerBlockOptin);
+        if (frc)
+            return fail(B200_E_CUDA, std::string("cudaFuncSetAttribute (FP64 NTT kernels): ") + cudaGetErrorString((cudaError_t)frc));
+    }
 #endif
     CU_TRY(cudaFuncSetAttribute(ntt_kernel<true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
     CU_TRY(cudaFuncSetAttribute(ntt_kernel<false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
@@ -2033,6 +2004,15 @@ int b200_stream_synchronize(b200_ctx *ctx, void *stream)
 
 // developer aid: attach a device buffer of 8 u64 per CTA that the NEXT static NTT launches fill with
 // {smid, t_start, t_after_each_pass (<=5), t_end} (globaltimer ns); pass nullptr to detach
+int b200_debug_ntt_variant(int variant)
+{
+#ifndef B200_EMU_HEADER
+    return g_ntt_var.exchange(variant);
+#else
+    (void)variant;
+    return 0;
+#endif
+}
 void b200_ntt_timeline(b200_ctx *ctx, unsigned long long *device_buffer)
 {
     if (ctx)

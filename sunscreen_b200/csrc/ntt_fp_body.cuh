@@ -121,7 +121,18 @@ B200_HD double fp_load_tw(const double *__restrict__ tw, int idx)
 // All R-1 twiddles of a radix-2^L group, loaded up front so that their (L2) latency is paid once per group and
 // overlaps the data loads.  Slot order: forward stage l, sub-group grp -> (2^l - 1) + grp;
 // inverse stage l, sub-group grp -> R - (R >> l) + grp  (the TW16 tables use the same slot order).
-template <int L, bool FWD, bool TW16>
+// TWSRC: 0 = read-only global path (__ldg), 1 = `tw` points at the CTA's shared-memory copy of the table's first 512
+// entries (plain load), 2 = developer ablation (no load at all: a constant stands in; results are meaningless)
+template <int TWSRC>
+B200_HD double fp_load_tw_src(const double *__restrict__ tw, int idx, const NttPrimeFp &P)
+{
+    if (TWSRC == 2)
+        return B200_DADD(P.inv_n[0], (double)(idx & 7));
+    if (TWSRC == 1)
+        return tw[idx];
+    return fp_load_tw(tw, idx);
+}
+template <int L, bool FWD, bool TW16, int TWSRC = 0>
 B200_HD void fp_load_group_tw(double (&tws)[(1 << L) - 1], const double *__restrict__ tw, int g, int i, int logs, int logn, int M,
                               int n16, const NttPrimeFp &P, bool last_inv)
 {
@@ -136,7 +147,7 @@ B200_HD void fp_load_group_tw(double (&tws)[(1 << L) - 1], const double *__restr
             for (int grp = 0; grp < (1 << l); grp++)
             {
                 const int slot = (1 << l) - 1 + grp;
-                tws[slot] = fp_load_tw(tw, TW16 ? slot * n16 + g : tw_base + grp);
+                tws[slot] = fp_load_tw_src<TWSRC>(tw, TW16 ? slot * n16 + g : tw_base + grp, P);
             }
         }
         else
@@ -150,14 +161,22 @@ B200_HD void fp_load_group_tw(double (&tws)[(1 << L) - 1], const double *__restr
                 if (last_inv && l == L - 1)
                     tws[slot] = P.inv_n_w[0]; // final stage of the whole inverse: twiddle pre-multiplied by n^-1
                 else
-                    tws[slot] = fp_load_tw(tw, TW16 ? slot * n16 + g : tw_base + grp);
+                    tws[slot] = fp_load_tw_src<TWSRC>(tw, TW16 ? slot * n16 + g : tw_base + grp, P);
             }
         }
     }
 }
 
 // one butterfly stage `l` of a radix-2^L group (compile-time stage index so everything stays in registers)
-template <int L, int l, bool FWD>
+// ABL bit 0 (developer ablation): the modular product is replaced by one DMUL (results are meaningless)
+template <int ABL>
+B200_HD double fp_mulmod_abl(double a, double b, double p, double pinv)
+{
+    if (ABL & 1)
+        return B200_DMUL(a, b);
+    return fp_mulmod2(a, b, p, pinv);
+}
+template <int L, int l, bool FWD, int ABL = 0>
 B200_HD void fp_stage(double (&x)[1 << L], const double (&tws)[(1 << L) - 1], const NttPrimeFp &P, bool last_inv)
 {
     constexpr int R = 1 << L;
@@ -173,7 +192,7 @@ B200_HD void fp_stage(double (&x)[1 << L], const double (&tws)[(1 << L) - 1], co
             for (int jj = 0; jj < half; jj++)
             {
                 const int j = grp * 2 * half + jj;
-                const double T = fp_mulmod2(x[j + half], w, p, pinv);
+                const double T = fp_mulmod_abl<ABL>(x[j + half], w, p, pinv);
                 const double X = x[j];
                 x[j] = B200_DADD(X, T);
                 x[j + half] = B200_DADD(X, -T);
@@ -194,7 +213,7 @@ B200_HD void fp_stage(double (&x)[1 << L], const double (&tws)[(1 << L) - 1], co
                 const int j = grp * 2 * half + jj;
                 const double X = x[j], Y = x[j + half];
                 const double U = B200_DADD(X, Y);
-                x[j + half] = fp_mulmod2(B200_DADD(X, -Y), w, p, pinv);
+                x[j + half] = fp_mulmod_abl<ABL>(B200_DADD(X, -Y), w, p, pinv);
                 x[j] = fold ? fp_mulmod2(U, P.inv_n[0], p, pinv) : U;
             }
         }
@@ -215,11 +234,12 @@ B200_HD int fp_elem_index(int pbase, int base, int j, int logs)
 
 template <int L, bool FWD, bool SRC_GLOBAL, bool DST_GLOBAL, bool TW16 = false, bool RENORM = true, bool REDUCE = true, bool PRELOADED = false,
           bool RAW_IN = false /* shared memory holds the raw input words (landed by cp.async): convert on read */,
-          bool TW_PRE = false /* the group's twiddles were prefetched by the caller (twpre) */>
+          bool TW_PRE = false /* the group's twiddles were prefetched by the caller (twpre) */,
+          int TWSRC = 0 /* fp_load_tw_src */, int ABL = 0 /* developer ablations: 1 cheap product, 2 no global I/O */>
 B200_HD void ntt_fp_group(double *sm, const u64 *__restrict__ gsrc, u64 *__restrict__ gdst, int g, int logs, int logn, int M,
                           const NttPrimeFp &P, bool renorm, bool last_inv, bool reduce_input, u64 pint, u64 ratio1,
                           const u64 *pre = nullptr /* PRELOADED: the group's 2^L raw input words, already in registers */,
-                          const double *twpre = nullptr)
+                          const double *twpre = nullptr, const double *stw = nullptr /* TWSRC == 1: shared-memory table */)
 {
     constexpr int R = 1 << L;
     const int s = 1 << logs;
@@ -228,7 +248,7 @@ B200_HD void ntt_fp_group(double *sm, const u64 *__restrict__ gsrc, u64 *__restr
     const int base = (i << (logs + L)) + o;
     const int pbase = ntt_pad(base);
     const double p = P.p;
-    const double *__restrict__ tw = TW16 ? (FWD ? P.fwd16 : P.inv16) : (FWD ? P.fwd : P.inv);
+    const double *__restrict__ tw = TWSRC == 1 ? stw : TW16 ? (FWD ? P.fwd16 : P.inv16) : (FWD ? P.fwd : P.inv);
     const int n16 = 1 << (logn - 4); // groups of the radix-16 pass (TW16 layout: [slot][group])
     double tws[R - 1];
     if (TW_PRE)
@@ -238,14 +258,14 @@ B200_HD void ntt_fp_group(double *sm, const u64 *__restrict__ gsrc, u64 *__restr
             tws[j] = twpre[j];
     }
     else
-        fp_load_group_tw<L, FWD, TW16>(tws, tw, g, i, logs, logn, M, n16, P, last_inv);
+        fp_load_group_tw<L, FWD, TW16, TWSRC>(tws, tw, g, i, logs, logn, M, n16, P, last_inv);
     double x[R];
 #pragma unroll
     for (int j = 0; j < R; j++)
     {
         if (SRC_GLOBAL)
         {
-            u64 v = PRELOADED ? pre[j] : gsrc[base + (j << logs)];
+            u64 v = PRELOADED ? pre[j] : (ABL & 2) ? (u64)(base + j) : gsrc[base + (j << logs)];
             if (REDUCE && reduce_input)
                 v = barrett64(v, pint, ratio1);
             x[j] = fp_from_u64(v);
@@ -264,17 +284,23 @@ B200_HD void ntt_fp_group(double *sm, const u64 *__restrict__ gsrc, u64 *__restr
         if (RENORM && renorm)
             x[j] = fp_renorm_x(x[j], p, P.pinv);
     }
-    fp_stage<L, 0, FWD>(x, tws, P, last_inv);
+    fp_stage<L, 0, FWD, ABL>(x, tws, P, last_inv);
     if constexpr (L > 1)
-        fp_stage<L, 1, FWD>(x, tws, P, last_inv);
+        fp_stage<L, 1, FWD, ABL>(x, tws, P, last_inv);
     if constexpr (L > 2)
-        fp_stage<L, 2, FWD>(x, tws, P, last_inv);
+        fp_stage<L, 2, FWD, ABL>(x, tws, P, last_inv);
     if constexpr (L > 3)
-        fp_stage<L, 3, FWD>(x, tws, P, last_inv);
+        fp_stage<L, 3, FWD, ABL>(x, tws, P, last_inv);
 #pragma unroll
     for (int j = 0; j < R; j++)
     {
-        if (DST_GLOBAL)
+        if (DST_GLOBAL && (ABL & 2))
+        {
+            const u64 v = fp_to_canonical<true>(x[j], p, P.pinv);
+            if (v == 0xFFFFFFFFFFFFFFFFULL) // never: keeps the value live without the store traffic
+                gdst[base + (j << logs)] = v;
+        }
+        else if (DST_GLOBAL)
             gdst[base + (j << logs)] = fp_to_canonical<true>(x[j], p, P.pinv);
         else
             sm[fp_elem_index(pbase, base, j, logs)] = x[j];
@@ -391,7 +417,12 @@ template <int LOGN, int PI> struct NttSchedDone // stages completed before forwa
 };
 template <int LOGN> struct NttSchedDone<LOGN, 0> { static constexpr int value = 0; };
 
-template <int LOGN, int NT, bool FWD, int STEP /*0..NP-1 in execution order*/>
+// VAR (bit mask): 1 = the table's first 512 twiddles (every stage whose butterflies span >= n/256 points) are copied into
+// shared memory once per CTA and read from there (short latency, no L2 round trip per group); 2 / 4 / 8 = developer
+// ablations for tools/ntt_ablate.py (no twiddle loads / one-DMUL products / no global traffic): results are meaningless,
+// they only measure what each component costs.
+#define B200_NTT_TWS_ENTRIES 512
+template <int LOGN, int NT, bool FWD, int STEP /*0..NP-1 in execution order*/, int VAR = 0>
 struct NttFpStaticPass
 {
     static __device__ __forceinline__ void run(const NttJob &job, const NttPrimeFp &P, const NttPrime &PI_, const u64 *src, u64 *dst,
@@ -421,6 +452,17 @@ struct NttFpStaticPass
         // a CTA's 18.4 us; the kernel is co-limited by the FP64 pipe (52 %) and the shared-memory pipe (55-58 %).
         constexpr bool SG = EDGE_IN && LOGS >= 5 && B200_NTT_DIRECT_IN, DG = EDGE_OUT && LOGS >= 5;
         constexpr bool TW16 = (L == 4 && LOGS == 0);
+        constexpr int TWSRC = (VAR & 2) ? 2 : ((VAR & 1) && !TW16 && (1 << (DONE + L)) <= B200_NTT_TWS_ENTRIES) ? 1 : 0;
+        constexpr int ABL = ((VAR & 4) ? 1 : 0) | ((VAR & 8) ? 2 : 0);
+        double *stw = smd + ntt_smem_words(N); // VAR & 1: B200_NTT_TWS_ENTRIES doubles behind the polynomial
+        if (STEP == 0 && (VAR & 1))
+        {
+            const double *__restrict__ twg = FWD ? P.fwd : P.inv;
+            for (int e = tid; e < B200_NTT_TWS_ENTRIES; e += NT)
+                stw[e] = fp_load_tw(twg, e);
+            if (SG)
+                __syncthreads(); // (the staged copy-in below has its own barrier)
+        }
         constexpr int NGROUPS = N >> L;
         constexpr int ITERS = (NGROUPS + NT - 1) / NT;
         const bool rn = (((FWD ? P.renorm_fwd : P.renorm_inv) >> STEP) & 1) || (!FWD && STEP == 0 && job.tensor_mode);
@@ -473,12 +515,21 @@ struct NttFpStaticPass
                 // asynchronous copy (LDGSTS): no registers are held, so all N/NT requests of a thread are in flight at
                 // once; the words land raw and the first pass converts them when it reads (RAW_IN)
                 const unsigned sbase = (unsigned)__cvta_generic_to_shared(smd + ptid);
+                if (ABL & 2)
+                {
 #pragma unroll
-                for (int it = 0; it < N / NT; it++)
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sbase + (unsigned)(it * PNT * 8)), "l"(src + tid + it * NT)
-                                 : "memory");
-                asm volatile("cp.async.commit_group;" ::: "memory");
-                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    for (int it = 0; it < N / NT; it++)
+                        smd[ptid + it * PNT] = __longlong_as_double((long long)(tid + it * NT));
+                }
+                else
+                {
+#pragma unroll
+                    for (int it = 0; it < N / NT; it++)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sbase + (unsigned)(it * PNT * 8)), "l"(src + tid + it * NT)
+                                     : "memory");
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                }
             }
             __syncthreads();
             if (job.timeline && tid == 0)
@@ -503,7 +554,7 @@ struct NttFpStaticPass
                     const int b0 = (i0 << (LOGS + L)) + o0;
 #pragma unroll
                     for (int j = 0; j < R; j++)
-                        cur[j] = src[b0 + (j << LOGS)];
+                        cur[j] = (ABL & 2) ? (u64)(b0 + j) : src[b0 + (j << LOGS)];
                 }
 #pragma unroll
                 for (int it = 0; it < ITERS; it++)
@@ -515,10 +566,10 @@ struct NttFpStaticPass
                         const int bn = (in_ << (LOGS + L)) + on;
 #pragma unroll
                         for (int j = 0; j < R; j++)
-                            nxt[j] = src[bn + (j << LOGS)];
+                            nxt[j] = (ABL & 2) ? (u64)(bn + j) : src[bn + (j << LOGS)];
                     }
-                    ntt_fp_group<L, FWD, SG, DG, TW16, decltype(RN)::value, decltype(RD)::value, true>(
-                        smd, src, dst, g, LOGS, LOGN, M, P, true, !FWD && EDGE_OUT, true, PI_.p, PI_.ratio1, cur);
+                    ntt_fp_group<L, FWD, SG, DG, TW16, decltype(RN)::value, decltype(RD)::value, true, false, false, TWSRC, ABL>(
+                        smd, src, dst, g, LOGS, LOGN, M, P, true, !FWD && EDGE_OUT, true, PI_.p, PI_.ratio1, cur, nullptr, stw);
 #pragma unroll
                     for (int j = 0; j < R; j++)
                         cur[j] = nxt[j];
@@ -527,7 +578,7 @@ struct NttFpStaticPass
             else
             {
                 auto run = [&](auto RAWF) {
-                    if constexpr (L <= 3 && NGROUPS % NT == 0 && ITERS > 1 && B200_NTT_TW_PREFETCH)
+                    if constexpr (L <= 3 && NGROUPS % NT == 0 && ITERS > 1 && B200_NTT_TW_PREFETCH && TWSRC == 0)
                     {
                         // the twiddles of group it+1 are requested before group `it` is transformed: their L1/L2 latency
                         // (the largest stall reason of the kernel, profiles/r1_ncu_ntt_v6.txt) overlaps the butterflies
@@ -541,7 +592,7 @@ struct NttFpStaticPass
                             const int g = tid + it * NT;
                             if (it + 1 < ITERS)
                                 fp_load_group_tw<L, FWD, false>(twn, twt, g + NT, (g + NT) >> LOGS, LOGS, LOGN, M, 0, P, !FWD && EDGE_OUT);
-                            ntt_fp_group<L, FWD, SG, DG, TW16, decltype(RN)::value, decltype(RD)::value, false, decltype(RAWF)::value, true>(
+                            ntt_fp_group<L, FWD, SG, DG, TW16, decltype(RN)::value, decltype(RD)::value, false, decltype(RAWF)::value, true, 0, ABL>(
                                 smd, src, dst, g, LOGS, LOGN, M, P, true, !FWD && EDGE_OUT, true, PI_.p, PI_.ratio1, nullptr, twc);
 #pragma unroll
                             for (int j = 0; j < R - 1; j++)
@@ -555,8 +606,8 @@ struct NttFpStaticPass
                         {
                             const int g = tid + it * NT;
                             if (NGROUPS % NT == 0 || g < NGROUPS)
-                                ntt_fp_group<L, FWD, SG, DG, TW16, decltype(RN)::value, decltype(RD)::value, false, decltype(RAWF)::value>(
-                                    smd, src, dst, g, LOGS, LOGN, M, P, true, !FWD && EDGE_OUT, true, PI_.p, PI_.ratio1);
+                                ntt_fp_group<L, FWD, SG, DG, TW16, decltype(RN)::value, decltype(RD)::value, false, decltype(RAWF)::value, false, TWSRC, ABL>(
+                                    smd, src, dst, g, LOGS, LOGN, M, P, true, !FWD && EDGE_OUT, true, PI_.p, PI_.ratio1, nullptr, nullptr, stw);
                         }
                     }
                 };
@@ -596,10 +647,14 @@ struct NttFpStaticPass
         { // coalesced copy-out: lazy double -> canonical u64
 #pragma unroll
             for (int it = 0; it < N / NT; it++)
-                dst[tid + it * NT] = fp_to_canonical<true>(smd[ptid + it * PNT], P.p, P.pinv);
+            {
+                const u64 v = fp_to_canonical<true>(smd[ptid + it * PNT], P.p, P.pinv);
+                if (!(ABL & 2) || v == 0xFFFFFFFFFFFFFFFFULL)
+                    dst[tid + it * NT] = v;
+            }
         }
         if (STEP + 1 < NP)
-            NttFpStaticPass<LOGN, NT, FWD, (STEP + 1 < NP ? STEP + 1 : STEP)>::run(job, P, PI_, src, dst, smd, tid, item, slot);
+            NttFpStaticPass<LOGN, NT, FWD, (STEP + 1 < NP ? STEP + 1 : STEP), VAR>::run(job, P, PI_, src, dst, smd, tid, item, slot);
 #endif
     }
 };

@@ -1747,6 +1747,78 @@ void batch_scatter(Context_ *c, uint64_t count, void **dsts, const BatchSlab &sl
 }
 } // namespace
 
+// Bulk word access for a batch of handles: `words` is ONE contiguous host buffer [count][size][k][n] (pinned memory moves at
+// link speed and asynchronously); one copy + one scatter/gather launch instead of a host memcpy and a transfer per handle.
+// Same validation as B200_Ciphertext_SetWords.
+long B200_Ciphertext_SetWordsBatch(void *context, uint64_t count, void **cts, uint64_t *parms_id, uint64_t size, bool ntt,
+                                   const uint64_t *words)
+{
+    NULLRET(context);
+    NULLRET(cts);
+    NULLRET(parms_id);
+    NULLRET(words);
+    auto *c = (Context_ *)context;
+    return guard([&] {
+        if (!c->parameters_set)
+            throw InvalidArg("encryption parameters are not set correctly");
+        ParmsId id;
+        std::copy_n(parms_id, 4, id.begin());
+        const int lv = c->level_of(id);
+        if (lv < 0)
+            throw InvalidArg("parms_id is not valid for encryption parameters");
+        if (size < 2 || size > 16)
+            throw InvalidArg("invalid size");
+        if (count == 0)
+            return;
+        batch_handles(count, { cts });
+        OpScope scope(c);
+        const u64 k = (u64)c->level_k[lv];
+        const u64 w = size * k * c->parms.n;
+        BatchSlab S(c, count * w);
+        dev_check(b200_memcpy_h2d(c->dev, S.p, words, count * w * sizeof(u64), cur_stream()));
+        std::vector<u64 *> ptrs(count);
+        for (uint64_t i = 0; i < count; i++)
+        {
+            auto *ct = (Ciphertext_ *)cts[i];
+            ptrs[i] = ct->prepare_output(c, id, size, k);
+            ct->is_ntt_form = ntt;
+        }
+        dev_check(b200_gather_scatter(c->dev, ptrs.data(), count, S.w(), w, 0, cur_stream()));
+    });
+}
+// all handles must have the same shape; `words` receives [count][size][k][n]
+long B200_Ciphertext_GetWordsBatch(void *context, uint64_t count, void **cts, uint64_t *words, uint64_t cap)
+{
+    NULLRET(context);
+    NULLRET(cts);
+    NULLRET(words);
+    auto *c = (Context_ *)context;
+    return guard([&] {
+        if (count == 0)
+            return;
+        batch_handles(count, { cts });
+        auto &a0 = *(Ciphertext_ *)cts[0];
+        const u64 w = a0.words();
+        if (cap < count * w)
+            throw InvalidArg("capacity too small");
+        OpScope scope(c);
+        std::vector<u64 *> ptrs(count);
+        for (uint64_t i = 0; i < count; i++)
+        {
+            auto &a = *(Ciphertext_ *)cts[i];
+            if (a.size != a0.size || a.k != a0.k || a.n != a0.n)
+                throw InvalidArg("batch items must have the same shape");
+            ptrs[i] = const_cast<u64 *>(a.dev_ptr(c));
+        }
+        if (w == 0)
+            return;
+        BatchSlab S(c, count * w);
+        dev_check(b200_gather_scatter(c->dev, ptrs.data(), count, S.w(), w, 1, cur_stream()));
+        dev_check(b200_memcpy_d2h(c->dev, words, S.p, count * w * sizeof(u64), cur_stream()));
+        dev_check(b200_stream_synchronize(c->dev, cur_stream()));
+    });
+}
+
 long B200_Evaluator_MultiplyRelinBatch(void *p, uint64_t count, void **e1, void **e2, void *relin_keys, void **dsts)
 {
     NULLRET(p);

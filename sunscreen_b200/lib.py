@@ -49,6 +49,7 @@ _SIGS = {
     "b200_memcpy_d2h": [vp, vp, vp, C.c_size_t, vp],
     "b200_memcpy_d2d": [vp, vp, vp, C.c_size_t, vp],
     "b200_memzero": [vp, vp, C.c_size_t, vp],
+    "b200_debug_ntt_variant": [C.c_int],
     "b200_stream_synchronize": [vp, vp],
     "b200_ntt_forward": [vp, C.c_int, vp, u64, vp],
     "b200_ntt_inverse": [vp, C.c_int, vp, u64, vp],

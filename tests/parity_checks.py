@@ -355,3 +355,84 @@ def check_host_pipeline(P, batch=5, seed=17):
                 os.environ.pop(name, None)
             else:
                 os.environ[name] = val
+
+
+# ---------------------------------------------------------------------------------------------------------
+# adversarial operands: the extremes of every lazy range (signed FP64 values up to 2^53, Harvey [0, 4q), the substituted
+# 47..49-bit auxiliary base of the FP64 BEHZ path) — all q-1, alternating 0 / q-1, a +-1 pattern, a single nonzero word
+# ---------------------------------------------------------------------------------------------------------
+ADVERSARIAL = ("qm1", "alt", "pm1", "single", "one")
+
+
+def adversarial_ct(P, kind, size=2):
+    q = np.array([int(m) for m in P.moduli[: P.k]], dtype=np.uint64)[None, :, None]
+    x = np.zeros((size, P.k, P.n), dtype=np.uint64)
+    if kind == "qm1":
+        x[:] = q - np.uint64(1)
+    elif kind == "alt":
+        x[:, :, ::2] = np.broadcast_to(q - np.uint64(1), (size, P.k, (P.n + 1) // 2))
+    elif kind == "pm1":
+        x[:] = 1
+        x[:, :, 1::3] = np.broadcast_to(q - np.uint64(1), x[:, :, 1::3].shape)
+    elif kind == "single":
+        x[:, :, P.n - 1] = np.broadcast_to((q - np.uint64(1))[:, :, 0], (size, P.k))
+    elif kind == "one":
+        x[:, :, 0] = 1
+    else:
+        raise ValueError(kind)
+    return x
+
+
+def check_adversarial_multiply(P, pairs=None, with_size5=True):
+    """multiply / square / multiply_relin of adversarial operands, word for word against the reference (which runs its own
+    61-bit auxiliary base and integer arithmetic throughout)."""
+    R = P.ref
+    rlk = R.new_ksk({0: P.inp["rlk"]})
+    dk = P.dev(P.inp["rlk"])
+    pairs = pairs or [("qm1", "qm1"), ("qm1", "alt"), ("alt", "pm1"), ("pm1", "pm1"), ("single", "qm1"), ("single", "single"),
+                      ("one", "qm1"), ("alt", "alt")]
+    for ka, kb in pairs:
+        a, b = adversarial_ct(P, ka), adversarial_ct(P, kb)
+        ra, rb = R.new_ct(a), R.new_ct(b)
+        da, db = P.dev(a), P.dev(b)
+        rm = R.multiply(ra, rb)
+        o3 = P.out(3, P.k, P.n)
+        P.ctx.multiply(da, 2, db, 2, o3, 1)
+        eq(P.host(o3), R.ct_words(rm), f"multiply({ka},{kb})")
+        o2 = P.out(2, P.k, P.n)
+        P.ctx.multiply_relin(da, db, dk, o2, 1)
+        eq(P.host(o2), R.ct_words(R.relinearize(rm, rlk)), f"multiply_relin({ka},{kb})")
+        if ka == kb:
+            P.ctx.square(da, o3, 1)
+            eq(P.host(o3), R.ct_words(R.square(ra)), f"square({ka})")
+        for h in (ra, rb, rm):
+            R.free_ct(h)
+    if with_size5:
+        for kind in ("qm1", "alt"):
+            a3, b3 = adversarial_ct(P, kind, 3), adversarial_ct(P, "pm1" if kind == "alt" else "qm1", 3)
+            o5 = P.out(5, P.k, P.n)
+            P.ctx.multiply(P.dev(a3), 3, P.dev(b3), 3, o5, 1)
+            ra, rb = R.new_ct(a3), R.new_ct(b3)
+            eq(P.host(o5), R.ct_words(R.multiply(ra, rb)), f"multiply (3,3) -> 5 of {kind}")
+
+
+def check_adversarial_keyswitch(P):
+    """relinearize / rotate on adversarial targets with an all-(p-1) key: the key-switch accumulators at their largest."""
+    R = P.ref
+    K = len(P.moduli)
+    key = np.empty((P.k, 2, K, P.n), dtype=np.uint64)
+    for i in range(K):
+        key[:, :, i, :] = np.uint64(int(P.moduli[i]) - 1)
+    rlk = R.new_ksk({0: key})
+    dk = P.dev(key)
+    for kind in ("qm1", "alt", "single"):
+        m3 = adversarial_ct(P, kind, 3)
+        o2 = P.out(2, P.k, P.n)
+        P.ctx.relinearize(P.dev(m3), dk, o2, 1)
+        eq(P.host(o2), R.ct_words(R.relinearize(R.new_ct(m3), rlk)), f"relinearize({kind}) with an all-(p-1) key")
+    if P.ctx.using_batching:
+        glk = R.new_ksk({1: key})
+        a = adversarial_ct(P, "qm1")
+        o2 = P.out(2, P.k, P.n)
+        P.ctx.apply_galois(P.dev(a), 3, dk, o2, 1)
+        eq(P.host(o2), R.ct_words(R.rotate_rows(R.new_ct(a), 1, glk)), "rotate_rows(qm1) with an all-(p-1) key")

@@ -107,6 +107,9 @@ class RefLib:
         L.refshim_time_mul_relin.restype = C.c_double
         L.refshim_time_ntt_roundtrip.argtypes = [u64, C.c_int, vp, u64, C.c_int]
         L.refshim_time_ntt_roundtrip.restype = C.c_double
+        if hasattr(L, "refshim_mul_relin_batch"):
+            L.refshim_mul_relin_batch.argtypes = [vp, vp, vp, vp, vp, u64, C.c_int]
+            L.refshim_ntt_forward_mt.argtypes = [u64, C.c_int, vp, u64, C.c_int]
 
     def call(self, name, *args):
         fn = getattr(self.lib, name)
@@ -125,6 +128,13 @@ class RefLib:
         a = np.ascontiguousarray(polys, dtype=np.uint64).copy()
         n = a.shape[-1]
         rc = self.lib.refshim_ntt_forward(modulus, n.bit_length() - 1, a.ctypes.data, a.size // n)
+        assert rc == 0
+        return a
+
+    def ntt_forward_mt(self, modulus, polys, threads):
+        a = np.ascontiguousarray(polys, dtype=np.uint64).copy()
+        n = a.shape[-1]
+        rc = self.lib.refshim_ntt_forward_mt(modulus, n.bit_length() - 1, a.ctypes.data, a.size // n, threads)
         assert rc == 0
         return a
 
@@ -296,6 +306,16 @@ class RefContext:
 
     def multiply(self, a, b):
         d = self.new_ct(); self.ref.call("Evaluator_Multiply", self.ev, a, b, d, None); return d
+
+    def mul_relin_batch(self, A, B, rlk, threads):
+        """relinearize(multiply(A[i], B[i])) for raw first-level words A, B: (count, 2, k, n) -> (count, 2, k, n)."""
+        A = np.ascontiguousarray(A, dtype=np.uint64)
+        B = np.ascontiguousarray(B, dtype=np.uint64)
+        assert A.shape == B.shape and A.shape[1:] == (2, self.k, self.n)
+        out = np.empty_like(A)
+        rc = self.ref.lib.refshim_mul_relin_batch(self.ctx, A.ctypes.data, B.ctypes.data, rlk, out.ctypes.data, A.shape[0], threads)
+        assert rc == 0
+        return out
 
     def square(self, a):
         d = self.new_ct(); self.ref.call("Evaluator_Square", self.ev, a, d, None); return d

@@ -1346,3 +1346,21 @@ def batch_seams(S, n, moduli, t, count=5):
     assert S.rc("B200_Evaluator_MultiplyRelinBatch", O.ev, u64(2), arr(A[:2]), arr(B[:2]), empty, arr(fresh()[:2])) == E_INVALIDARG
     # count == 0 is a no-op
     assert S.rc("B200_Evaluator_MultiplyRelinBatch", O.ev, u64(0), arr(A[:1]), arr(B[:1]), orlk, arr(fresh()[:1])) == 0
+    # bulk word access: one contiguous buffer <-> `count` handles
+    slab = np.stack([O.ct_words(h) for h in A])                                       # (count, 2, k, n)
+    hs = fresh()
+    O.S.call("B200_Ciphertext_SetWordsBatch", O.ctx, u64(count), arr(hs), O.first_id, u64(2), C.c_bool(False),
+             slab.ctypes.data_as(C.POINTER(u64)))
+    for i in range(count):
+        assert words(hs[i]) == words(A[i]), f"SetWordsBatch item {i}"
+    back = np.zeros_like(slab)
+    O.S.call("B200_Ciphertext_GetWordsBatch", O.ctx, u64(count), arr(hs), back.ctypes.data_as(C.POINTER(u64)), u64(back.size))
+    eq(back, slab, "GetWordsBatch")
+    d = fresh()
+    O.S.call("B200_Evaluator_MultiplyRelinBatch", O.ev, u64(count), arr(hs), arr(B), orlk, arr(d))
+    O.S.call("B200_Ciphertext_GetWordsBatch", O.ctx, u64(count), arr(d), back.ctypes.data_as(C.POINTER(u64)), u64(back.size))
+    eq(back[0], R.ct_words(R.relinearize(R.multiply(rcts[0], rcts[count]), rlk)), "SetWordsBatch -> MultiplyRelinBatch -> GetWordsBatch")
+    assert S.rc("B200_Ciphertext_GetWordsBatch", O.ctx, u64(count), arr(d), back.ctypes.data_as(C.POINTER(u64)), u64(back.size - 1)) == E_INVALIDARG
+    assert S.rc("B200_Ciphertext_SetWordsBatch", O.ctx, u64(count), arr(hs), O.first_id, u64(1), C.c_bool(False),
+                slab.ctypes.data_as(C.POINTER(u64))) == E_INVALIDARG
+    assert S.rc("B200_Ciphertext_GetWordsBatch", O.ctx, u64(2), arr([d[0], size3]), back.ctypes.data_as(C.POINTER(u64)), u64(back.size)) == E_INVALIDARG

@@ -45,6 +45,12 @@ def test_mod_switch(pair):
     pc.check_modswitch(pair)
 
 
+def test_adversarial_operands(pair):
+    pc.check_adversarial_multiply(pair, with_size5=pair.n <= 4096,
+                                  pairs=None if pair.n <= 4096 else [("qm1", "qm1"), ("alt", "pm1"), ("single", "qm1")])
+    pc.check_adversarial_keyswitch(pair)
+
+
 def test_batch_strides(pair):
     if pair.n > 4096:
         pytest.skip("batch stride test runs on the smallest set only (emulation speed)")

@@ -82,6 +82,81 @@ def test_encrypted_roundtrip(pair):
     pc.check_encrypted_roundtrip(pair)
 
 
+def test_adversarial_operands(pair):
+    """all-(q-1), alternating, +-1 and single-nonzero operands through multiply / square / multiply_relin / (3,3)->5 and the
+    key switch (the 2^53 bound bookkeeping of the FP64 path and its substituted auxiliary base are exercised at their limits)."""
+    pc.check_adversarial_multiply(pair, with_size5=pair.n <= 16384,
+                                  pairs=None if pair.n <= 16384 else [("qm1", "qm1"), ("alt", "pm1")])
+    pc.check_adversarial_keyswitch(pair)
+
+
+def _threads():
+    import os
+    return max(1, min(64, len(os.sched_getaffinity(0))))
+
+
+@pytest.mark.parametrize("name,level", [("n8192", None), ("n8192_54", 0)])
+def test_config2_all_16384_transforms_vs_reference(be, ref, name, level):
+    """BASELINE config 2 at FULL size: every one of the 4096 x 4 forward transforms equals the reference's
+    ntt_negacyclic_harvey (S/util/ntt.cpp:393-436) word for word (inputs: the fixed-seed splitmix64(0xB200) % q_i generator of
+    SURVEY.md App. B); then the inverse returns the input.  Both prime sets of SURVEY.md 8(d): the four default data primes
+    (FP64 kernel) and the four 54-bit primes (integer kernel; key level of the {54 x 4} chain)."""
+    import refseal
+    n, moduli, t = PARAMS[name]
+    from sunscreen_b200.lib import B200Context
+    ctx = B200Context(n, moduli, t)
+    k = ctx.k(level)
+    assert k == 4
+    items = 4096
+    x = np.empty((items, k, n), dtype=np.uint64)
+    state = 0xB200
+    for i in range(k):
+        w, state = refseal.splitmix64_words(items * n, int(moduli[i]), state)
+        x[:, i, :] = w.reshape(items, n)
+    d = be.to_dev(x)
+    ctx.ntt_forward(d, items, level=level)
+    got = be.to_host(d)
+    R = refseal.RefLib.get()
+    for i in range(k):
+        exp = R.ntt_forward_mt(int(moduli[i]), x[:, i, :], _threads())
+        pc.eq(got[:, i, :], exp, f"all {items} forward transforms, prime {i}")
+    ctx.ntt_inverse(d, items, level=level)
+    pc.eq(be.to_host(d), x, "inverse of all transforms")
+
+
+def test_config3_all_1024_pairs_vs_reference(be, ref):
+    """BASELINE config 3 at FULL size: 1024 independent pairs of fresh public-key encryptions of batch-encoded uniform
+    vectors (reference Encryptor), one relinearization key; multiply + relinearize through b200_multiply_relin (the entry
+    point bench.py times) equals the reference's Evaluator::multiply + relinearize_inplace for ALL 1024 pairs, word for word."""
+    import refseal
+    n, moduli, t = PARAMS["n8192"]
+    from sunscreen_b200.lib import B200Context
+    ctx = B200Context(n, moduli, t)
+    k = ctx.k()
+    R = refseal.RefContext(n, moduli, t)
+    kg = R.keygen()
+    pk, rlk = R.public_key(kg), R.relin_keys(kg)
+    enc = R.encryptor(pk)
+    benc = R.batch_encoder()
+    rng = np.random.default_rng(2024)
+    B = 1024
+    A = np.empty((B, 2, k, n), dtype=np.uint64)
+    Bc = np.empty_like(A)
+    for arr in (A, Bc):
+        for i in range(B):
+            h = R.encrypt(enc, R.batch_encode(benc, rng.integers(0, t, size=n, dtype=np.uint64)))
+            arr[i] = R.ct_words(h)
+            R.free_ct(h)
+    exp = R.mul_relin_batch(A, Bc, rlk, _threads())
+    key = R.ksk_words(rlk)[0]
+    out = be.empty((B, 2, k, n))
+    ctx.multiply_relin(be.to_dev(A), be.to_dev(Bc), be.to_dev(key), out, B)
+    got = be.to_host(out)
+    for i in range(B):
+        if not np.array_equal(got[i], exp[i]):
+            pc.eq(got[i], exp[i], f"pair {i} of {B}")
+
+
 def test_full_size_properties(be):
     """BASELINE config 2/3 sizes through size-independent properties: NTT round trip over 4096x4 polynomials,
     and multiply_relin over a 256-item batch equal to the same items computed one by one."""
