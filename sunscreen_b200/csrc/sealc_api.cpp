@@ -126,9 +126,139 @@ void op_addsub(Context_ *c, Ciphertext_ &a, Ciphertext_ &b, Ciphertext_ &dst, in
     transparent_guard(c, lv, dst);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Flat combining (Context_::Combiner).  A caller validates its own arguments, then submits a request.  If nobody holds the
+// combiner it becomes the leader: it repeatedly takes the compatible requests that are pending (its own included), runs
+// them as ONE batch through the layer-1 batch entry points (gather -> compute -> scatter, one transparent-result check for
+// all items), marks them done and wakes their owners; requests that arrive meanwhile form the next batch.  A batch of one
+// runs the direct per-handle path (no gather / scatter).  Every call still completes before it returns and reports its
+// own error (an item whose result is transparent fails alone).
+// ---------------------------------------------------------------------------------------------------------
+using CombineReq = Context_::CombineReq;
+
+void multiply_direct(Context_ *c, Ciphertext_ &a, Ciphertext_ &b, Ciphertext_ &dst, bool square, int lv);
+void relinearize_direct(Context_ *c, Ciphertext_ &a, KSwitchKeys_ &keys, Ciphertext_ &dst, int lv);
+
+static void combine_run_one(Context_ *c, CombineReq &r)
+{
+    try
+    {
+        if (r.kind == 0)
+            multiply_direct(c, *r.a, *r.b, *r.dst, false, r.lv);
+        else
+            relinearize_direct(c, *r.a, *r.keys, *r.dst, r.lv);
+    }
+    catch (...)
+    {
+        r.err = std::current_exception();
+    }
+}
+
+static void combine_run_batch(Context_ *c, std::vector<CombineReq *> &batch)
+{
+    const size_t N = batch.size();
+    if (N == 1)
+        return combine_run_one(c, *batch[0]);
+    CombineReq &r0 = *batch[0];
+    try
+    {
+        OpScope scope(c);
+        const int lv = r0.lv;
+        const u64 k = (u64)c->level_k[lv], n = c->parms.n;
+        const u64 in_polys = r0.kind == 1 ? 3 : 2, out_polys = r0.kind == 0 ? 3 : 2;
+        const u64 win = in_polys * k * n, wout = out_polys * k * n;
+        const size_t operands = r0.kind == 0 ? 2 : 1;
+        // gather: all first operands, then (multiply) all second operands, in ONE launch
+        std::vector<u64 *> ptrs(operands * N);
+        for (size_t i = 0; i < N; i++)
+        {
+            ptrs[i] = const_cast<u64 *>(batch[i]->a->dev_ptr(c));
+            if (operands == 2)
+                ptrs[N + i] = const_cast<u64 *>(batch[i]->b->dev_ptr(c));
+        }
+        void *pin = nullptr, *pout = nullptr;
+        dev_check(b200_malloc(c->dev, operands * N * win * sizeof(u64), &pin));
+        struct Free
+        {
+            Context_ *c;
+            void *p;
+            ~Free() { b200_free_async(c->dev, p, cur_stream()); }
+        } f_in{ c, pin };
+        dev_check(b200_malloc(c->dev, N * wout * sizeof(u64), &pout));
+        Free f_out{ c, pout };
+        u64 *in = (u64 *)pin, *out = (u64 *)pout;
+        dev_check(b200_gather_scatter(c->dev, ptrs.data(), operands * N, in, win, 1, cur_stream()));
+        if (r0.kind == 0)
+            dev_check(b200_multiply(c->dev, lv, in, 2, in + N * win, 2, out, N, cur_stream()));
+        else
+            dev_check(b200_relinearize(c->dev, lv, in, r0.keys->flat_dev(c, 0, (int)k), out, N, cur_stream()));
+        // scatter into the destinations (gathered above, so a destination may alias an operand)
+        std::vector<u64 *> dptrs(N);
+        for (size_t i = 0; i < N; i++)
+            dptrs[i] = batch[i]->dst->prepare_output(c, c->ids[lv], out_polys, k);
+        dev_check(b200_gather_scatter(c->dev, dptrs.data(), N, out, wout, 0, cur_stream()));
+        uint32_t *flags = scope.lane->hflag;
+        if (c->check_transparent)
+        {
+            for (size_t i = 0; i < N; i++)
+                ((volatile uint32_t *)flags)[i] = 0;
+            dev_check(b200_any_nonzero(c->dev, lv, out, (int)out_polys, flags, N, cur_stream()));
+        }
+        scope.wait();
+        if (c->check_transparent)
+            for (size_t i = 0; i < N; i++)
+                if (!((volatile uint32_t *)flags)[i])
+                    batch[i]->err = std::make_exception_ptr(LogicErr("result ciphertext is transparent"));
+    }
+    catch (...)
+    {
+        for (auto *r : batch)
+            if (!r->err)
+                r->err = std::current_exception();
+    }
+}
+
+static void combine_submit(Context_ *c, CombineReq &req)
+{
+    Context_::Combiner &cb = c->comb[req.kind];
+    std::unique_lock<std::mutex> lk(cb.m);
+    cb.pending.push_back(&req);
+    while (!req.done)
+    {
+        if (cb.busy)
+        {
+            cb.cv.wait(lk);
+            continue;
+        }
+        cb.busy = true; // leader
+        while (!cb.pending.empty() && !req.done)
+        {
+            std::vector<CombineReq *> batch, rest;
+            for (auto *r : cb.pending)
+            {
+                if ((int)batch.size() < Context_::COMBINE_MAX && (batch.empty() || r->compatible(*batch[0])))
+                    batch.push_back(r);
+                else
+                    rest.push_back(r);
+            }
+            cb.pending.swap(rest);
+            lk.unlock();
+            combine_run_batch(c, batch);
+            lk.lock();
+            for (auto *r : batch)
+                r->done = true;
+            cb.cv.notify_all();
+        }
+        cb.busy = false;
+        cb.cv.notify_all(); // a waiter whose request is still pending takes over
+    }
+    lk.unlock();
+    if (req.err)
+        std::rethrow_exception(req.err);
+}
+
 void op_multiply(Context_ *c, Ciphertext_ &a, Ciphertext_ &b, Ciphertext_ &dst, bool square)
 {
-    OpScope scope(c);
     int lv = data_level(c, a, "encrypted1 is not valid for encryption parameters");
     if (!square)
     {
@@ -138,6 +268,22 @@ void op_multiply(Context_ *c, Ciphertext_ &a, Ciphertext_ &b, Ciphertext_ &dst, 
     }
     if (a.is_ntt_form || (!square && b.is_ntt_form))
         throw InvalidArg("encrypted1 or encrypted2 cannot be in NTT form");
+    if (c->combine && !square && a.size == 2 && b.size == 2 && !tl_scope)
+    {
+        CombineReq r;
+        r.kind = 0;
+        r.a = &a;
+        r.b = &b;
+        r.dst = &dst;
+        r.lv = lv;
+        return combine_submit(c, r);
+    }
+    multiply_direct(c, a, b, dst, square, lv);
+}
+
+void multiply_direct(Context_ *c, Ciphertext_ &a, Ciphertext_ &b, Ciphertext_ &dst, bool square, int lv)
+{
+    OpScope scope(c);
     const u64 k = a.k;
     const u64 *pa = a.dev_ptr(c), *pb = square ? pa : b.dev_ptr(c);
     if (square && a.size != 2)
@@ -170,20 +316,39 @@ void check_keys(Context_ *c, KSwitchKeys_ &keys, size_t index)
 
 void op_relinearize(Context_ *c, Ciphertext_ &a, KSwitchKeys_ &keys, Ciphertext_ &dst)
 {
-    OpScope scope(c);
     int lv = data_level(c, a, "encrypted is not valid for encryption parameters");
     if (keys.parms_id != c->ids[0])
         throw InvalidArg("relin_keys is not valid for encryption parameters");
     if (a.is_ntt_form)
         throw InvalidArg("BFV encrypted cannot be in NTT form");
-    const u64 k = a.k, n = a.n;
     if (a.size == 2)
     { // nothing to do (S/evaluator.cpp:1131-1135)
+        OpScope scope(c);
         dst.assign(a);
         return;
     }
     if (keys.keys.size() < a.size - 2)
         throw InvalidArg("not enough relinearization keys");
+    if (c->combine && a.size == 3 && !tl_scope)
+    {
+        check_keys(c, keys, 0);
+        if (keys.keys[0].size() < (size_t)a.k)
+            throw InvalidArg("kswitch_keys is not valid for encryption parameters");
+        CombineReq r;
+        r.kind = 1;
+        r.a = &a;
+        r.dst = &dst;
+        r.keys = &keys;
+        r.lv = lv;
+        return combine_submit(c, r);
+    }
+    relinearize_direct(c, a, keys, dst, lv);
+}
+
+void relinearize_direct(Context_ *c, Ciphertext_ &a, KSwitchKeys_ &keys, Ciphertext_ &dst, int lv)
+{
+    OpScope scope(c);
+    const u64 k = a.k, n = a.n;
     const u64 *pa = a.dev_ptr(c);
     with_output(c, dst, { &a }, a.parms_id, 2, k, [&](u64 *out) {
         if (a.size == 3)
@@ -604,6 +769,7 @@ long SEALContext_Create(void *parms, bool expand_mod_chain, int sec_level, void 
     c->parms = *e;
     const char *nt = getenv("B200_SKIP_TRANSPARENT_CHECK");
     c->check_transparent = !(nt && nt[0] == '1');
+    c->combine = !std::getenv("B200_NO_COMBINE");
     // validation (S/context.cpp:135-420): anything failing leaves parameters_set = false, it is not an error here
     bool ok = e->n >= 2 && e->n <= 131072 && !(e->n & (e->n - 1)) && !e->coeff.empty() && e->plain >= 2;
     if (ok)

@@ -9,9 +9,11 @@
 #include <algorithm>
 #include <array>
 #include <atomic>
+#include <condition_variable>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <memory>
 #include <mutex>
 #include <stdexcept>
@@ -99,6 +101,8 @@ struct DevOwner
     }
 };
 
+struct Ciphertext_;
+struct KSwitchKeys_;
 struct Context_
 {
     EncParams_ parms;
@@ -124,6 +128,35 @@ struct Context_
     };
     static const int NLANE = 8;
     Lane lanes[NLANE];
+    // Flat combining of concurrent per-handle calls (sealc_api.cpp: combine_submit): calls of the same kind that arrive
+    // while one is executing are run TOGETHER as one batched launch sequence by whichever caller holds the combiner, so
+    // N rayon workers cost one sequence of launches per round instead of N (sunscreen_runtime/src/run.rs:415-469).
+    struct CombineReq
+    {
+        int kind = 0;             // index into Context_::comb
+        Ciphertext_ *a = nullptr, *b = nullptr, *dst = nullptr;
+        KSwitchKeys_ *keys = nullptr;
+        size_t key_index = 0;
+        uint32_t elt = 0;
+        int lv = 0;
+        bool done = false;
+        std::exception_ptr err;
+        bool compatible(const CombineReq &o) const
+        {
+            return kind == o.kind && lv == o.lv && keys == o.keys && key_index == o.key_index && elt == o.elt;
+        }
+    };
+    struct Combiner
+    {
+        std::mutex m;
+        std::condition_variable cv;
+        std::vector<CombineReq *> pending;
+        bool busy = false;
+    };
+    static const int NCOMB = 3;       // multiply (2,2) | relinearize (3 -> 2) | apply_galois
+    static const int COMBINE_MAX = 64; // items per combined batch (= entries of a lane's pinned flag array)
+    Combiner comb[NCOMB];
+    bool combine = true;              // B200_NO_COMBINE=1 switches it off (every call runs alone, as before)
     // The SEALContext handle and every object created from it (Evaluator, Encryptor, Decryptor, KeyGenerator,
     // BatchEncoder) share the context, as the reference's objects share SEALContext's internals: it goes away with the
     // last of them, whichever order the caller destroys them in.
@@ -224,7 +257,7 @@ struct OpScope
             lane->ready = true;
             dev_check(b200_stream_create(ctx->dev, &lane->stream));
             void *h = nullptr;
-            dev_check(b200_malloc_host(8, &h));
+            dev_check(b200_malloc_host(sizeof(uint32_t) * Context_::COMBINE_MAX, &h));
             lane->hflag = (uint32_t *)h;
         }
         tl_scope = this;

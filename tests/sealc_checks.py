@@ -1179,6 +1179,52 @@ def concurrent_evaluator_calls(S, n, moduli, t, threads=8, rounds=6):
         assert RL.save("Ciphertext", exp, 0) == serial[i]
 
 
+def combined_calls_isolation(S, n, moduli, t, threads=8, rounds=8):
+    """Concurrent Evaluator_Multiply / Evaluator_Relinearize calls are run together as one batch by whichever caller holds
+    the combiner (sealc_api.cpp: combine_submit).  Each call must still behave as if it ran alone: in-place destinations,
+    operands shared between callers, and a caller whose result is transparent (its product with an all-zero ciphertext)
+    gets COR_E_INVALIDOPERATION every time while the calls batched with it succeed with the serial words."""
+    import threading
+    R = refseal.RefContext(n, moduli, t)
+    O = S.context(n, moduli, t)
+    RL, OL = _libs(R, O)
+    kg = R.keygen()
+    sk, pk, rlk = R.secret_key(kg), R.public_key(kg), R.relin_keys(kg)
+    enc = R.encryptor(pk, sk)
+    rng = np.random.default_rng(5)
+    rcts = [R.encrypt(enc, R.new_pt(rng.integers(0, t, size=8, dtype=np.uint64))) for _ in range(3)]
+    cts = [OL.load("Ciphertext", RL.save("Ciphertext", h, 0)) for h in rcts]
+    orlk = OL.load("KSwitchKeys", RL.save("KSwitchKeys", rlk, 0))
+    zero = O.new_ct(np.zeros((2, O.k, n), dtype=np.uint64))
+    words = lambda h: OL.save("Ciphertext", h, 0)
+    expect = {i: RL.save("Ciphertext", R.relinearize(R.multiply(rcts[i % 3], rcts[(i + 1) % 3]), rlk), 0) for i in range(threads)}
+    errors, bad = [], []
+
+    def runner(i):
+        try:
+            for r in range(rounds):
+                if i == 0:  # transparent result, every round
+                    rc = S.rc("Evaluator_Multiply", O.ev, cts[0], zero, OL.new("Ciphertext"), None)
+                    if rc != COR_E_INVALIDOPERATION:
+                        bad.append((i, r, hex(rc)))
+                    continue
+                mine = OL.load("Ciphertext", words(cts[i % 3]))  # private copy, multiplied IN PLACE
+                S.call("Evaluator_Multiply", O.ev, mine, cts[(i + 1) % 3], mine, None)
+                S.call("Evaluator_Relinearize", O.ev, mine, orlk, mine, None)
+                if words(mine) != expect[i]:
+                    bad.append((i, r, "words"))
+        except Exception as e:  # pragma: no cover
+            errors.append((i, repr(e)))
+
+    ts = [threading.Thread(target=runner, args=(i,)) for i in range(threads)]
+    for th in ts:
+        th.start()
+    for th in ts:
+        th.join()
+    assert not errors, errors
+    assert not bad, bad
+
+
 def handle_lifetime_order(S, n, moduli, t):
     """Rust drops handles in whatever order the program's scopes dictate.  The reference's objects share the context's
     internals, so an Evaluator / Decryptor / ciphertext stays usable after SEALContext_Destroy; ours must too (the device

@@ -86,6 +86,14 @@ def test_context_validation_sweep(S, ref):
     sc.context_validation_sweep(S)
 
 
+def test_concurrent_evaluator_calls(S, ref):
+    sc.concurrent_evaluator_calls(S, *PARAMS["n4096"], threads=6, rounds=3)
+
+
+def test_combined_calls_isolation(S, ref):
+    sc.combined_calls_isolation(S, *PARAMS["n4096"])
+
+
 def test_handle_lifetime_order(S, ref):
     sc.handle_lifetime_order(S, *PARAMS["n4096"])
 

@@ -126,6 +126,10 @@ def test_concurrent_evaluator_calls(S, ref):
     sc.concurrent_evaluator_calls(S, *PARAMS["n8192"])
 
 
+def test_combined_calls_isolation(S, ref):
+    sc.combined_calls_isolation(S, *PARAMS["n4096"])
+
+
 def test_handle_lifetime_order(S, ref):
     sc.handle_lifetime_order(S, *PARAMS["n4096"])
 
