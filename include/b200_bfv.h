@@ -166,6 +166,17 @@ int b200_ntt_roundtrip_host(b200_ctx *ctx, int level, const uint64_t *in_host, u
    stream has consumed it (pageable memory is copied at call time) */
 int b200_gather_scatter(b200_ctx *ctx, uint64_t *const *host_ptrs, uint64_t count, uint64_t *slab, uint64_t words, int gather,
                         void *stream);
+/* the same with the pointer table already in device-accessible memory (pinned host memory qualifies): one launch, no copy */
+int b200_gather_scatter_table(b200_ctx *ctx, uint64_t *const *table, uint64_t count, uint64_t *slab, uint64_t words, int gather,
+                              void *stream);
+/* CUDA-graph capture of a fixed launch sequence on `stream` (kernels by value, stream-ordered allocations as memory nodes);
+   capture_end instantiates and returns an executable handle for b200_graph_launch / b200_graph_destroy */
+int b200_capture_begin(b200_ctx *ctx, void *stream);
+int b200_capture_end(b200_ctx *ctx, void *stream, void **graph_exec);
+int b200_graph_launch(b200_ctx *ctx, void *graph_exec, void *stream);
+int b200_graph_destroy(b200_ctx *ctx, void *graph_exec);
+/* stream-ordered allocation for work enqueued on `stream` afterwards (release with b200_free_async on the same stream) */
+int b200_malloc_async(b200_ctx *ctx, size_t bytes, void **dptr, void *stream);
 
 /* number of kernel launches issued by this library since the context was created (bench.py: gpu_launches) */
 uint64_t b200_launch_count(const b200_ctx *ctx);
@@ -178,6 +189,8 @@ void b200_ntt_timeline(b200_ctx *ctx, unsigned long long *device_buffer);
 /* developer aid: select the FP64 NTT kernel variant for subsequent launches (bit 0: twiddle table in shared memory; the
    other bits are timing ablations whose RESULTS ARE MEANINGLESS — tools/ntt_ablate.py); returns the previous value */
 int b200_debug_ntt_variant(int variant);
+/* developer aid: start-up stagger (clock cycles per resident CTA slot) of the streaming NTT kernel; returns the previous value */
+int b200_debug_ntt_stagger(int cycles);
 
 #ifdef __cplusplus
 }

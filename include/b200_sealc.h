@@ -251,6 +251,8 @@ SEAL_C_FUNC PolynomialArray_Drop(void *thisptr, void **poly_array);
 /* ---- extensions (not in the reference) ---- */
 /* deterministic pk-encryption from a 64-byte seed: the same random stream (and therefore the same ciphertext words)
    as the reference's Encryptor_EncryptReturnComponentsSetSeed (S/c/encryptor.cpp:185-240) */
+/* 1: Zstandard 1.4.5 is compiled in (compressed bytes == the reference's); 0: system libzstd bound at run time */
+SEAL_C_FUNC B200_VendoredZstd(void);
 SEAL_C_FUNC B200_Encryptor_EncryptSetSeed(void *thisptr, void *plaintext, const uint64_t *seed8, void *destination);
 /* bulk word access: the reference only offers word-at-a-time accessors */
 SEAL_C_FUNC B200_Ciphertext_SetWords(void *thisptr, void *context, uint64_t *parms_id, uint64_t size, bool is_ntt_form,

@@ -124,6 +124,7 @@ __global__ void __launch_bounds__(NT, MB) ntt_kernel(const NttJob job)
 // ntt_fp_kernels.cu; this file only fetches the function pointer of the instantiation it wants to launch.
 #ifndef B200_EMU_HEADER
 #include "ntt_fp_kernels.h"
+#include "ksmac_tma.h"
 #endif
 
 #define GLOBAL_IDX() ((long long)blockIdx.x * blockDim.x + threadIdx.x)
@@ -1172,6 +1173,7 @@ struct TensorArgs
 
 #ifndef B200_EMU_HEADER
 // FP64 NTT kernel variant (ntt_fp_body.cuh: NttFpStaticPass VAR); B200_NTT_VAR or b200_debug_ntt_variant() override the default
+static std::atomic<int> g_ntt_stagger{ std::getenv("B200_NTT_STAGGER") ? atoi(std::getenv("B200_NTT_STAGGER")) : 0 };
 static std::atomic<int> g_ntt_var{ std::getenv("B200_NTT_VAR") ? atoi(std::getenv("B200_NTT_VAR")) : B200_NTT_DEFAULT_VAR };
 #endif
 static bool static_fp_ok(b200_ctx *ctx, const JobDesc &jd)
@@ -1224,6 +1226,12 @@ static int launch_ntt(b200_ctx *ctx, const JobDesc &jd, const u64 *src, long lon
     job.timeline = ctx->ntt_timeline;
     static const int slot_major = std::getenv("B200_NTT_ITEM_MAJOR") ? 0 : 1;
     job.slot_major = slot_major;
+#ifndef B200_EMU_HEADER
+    job.stagger = g_ntt_stagger.load(std::memory_order_relaxed);
+#else
+    job.stagger = 0;
+#endif
+    job.sm_count = ctx->sm_count;
     job.tensor_mode = ta ? ta->mode : 0;
     job.t_sa = ta ? ta->sa : 0;
     job.t_sb = ta ? ta->sb : 0;
@@ -1273,6 +1281,8 @@ static int launch_ntt(b200_ctx *ctx, const JobDesc &jd, const u64 *src, long lon
         const int nt13 = nt_env ? nt_env : (blocks <= 2LL * ctx->sm_count ? 512 : 256);
         const int nt = ctx->logn == 12 ? 256 : ctx->logn == 13 ? (nt13 == 256 ? 256 : 512) : 1024;
         int var = ta && ta->mode ? (var_env & 1) : var_env; // the fused-tensor copy-in exists in the plain variants only
+        if ((var & 16) && nt == 512)
+            var &= ~16; // the streaming variant exists for the throughput configuration; small launches stay latency-optimised
         b200_ntt_fp_fn sfn = b200_ntt_fp_kernel(ctx->logn, FWD, nt, var);
         if (!sfn)
         {
@@ -1295,7 +1305,22 @@ static int launch_ntt(b200_ctx *ctx, const JobDesc &jd, const u64 *src, long lon
                      job.tensor_mode ? " +tensor" : "");
             g_trace_name = labels[FWD ? 1 : 0][sl];
         }
-        B200_LAUNCH(sfn, (unsigned)blocks, nt, smem, s, job);
+        unsigned grid = (unsigned)blocks;
+        if (var & 16)
+        { // persistent: one CTA per resident slot, each walking its share of the polynomials
+            static std::map<b200_ntt_fp_fn, int> occ;
+            static std::mutex occ_mu;
+            int per_sm;
+            {
+                std::lock_guard<std::mutex> lk(occ_mu);
+                auto it = occ.find(sfn);
+                if (it == occ.end())
+                    it = occ.emplace(sfn, b200_ntt_fp_ctas_per_sm(sfn, nt, smem)).first;
+                per_sm = it->second;
+            }
+            grid = (unsigned)std::min<long long>(blocks, (long long)per_sm * ctx->sm_count);
+        }
+        B200_LAUNCH(sfn, grid, nt, smem, s, job);
         ctx->launches++;
         CU_TRY(cudaGetLastError());
         return 0;
@@ -1632,7 +1657,41 @@ static int keyswitch_core(b200_ctx *ctx, int level, const u64 *d, long long d_st
             return rc;
     }
     {
-        if (L.fp)
+        bool done = false;
+#ifndef B200_EMU_HEADER
+        // key tile resident in shared memory (one tiled TMA load per CTA), batch walked inside the CTA: the key is read from
+        // HBM once per batch chunk instead of once per item (B200_KSMAC_TMA=0 selects the item-major kernels below)
+        static const bool want_tma = !(std::getenv("B200_KSMAC_TMA") && std::getenv("B200_KSMAC_TMA")[0] == '0');
+        if (want_tma && b200_ksmac_tma_supported(n, k))
+        {
+            if (trace_on())
+                g_trace_name = "ksmac_tma_kernel";
+            cudaEvent_t t0 = nullptr, t1 = nullptr;
+            if (trace_on())
+            {
+                cudaEventCreate(&t0);
+                cudaEventCreate(&t1);
+                cudaEventRecord(t0, s);
+            }
+            const int rc2 = b200_ksmac_tma(k, L.fp ? 1 : 0, ctx->d_primes, ctx->d_fp_primes, special, Kkey, ks1, key, ks2, n, batch,
+                                           ctx->sm_count, s);
+            if (rc2 > 0)
+                return fail(B200_E_CUDA, std::string("ksmac_tma_kernel: ") + cudaGetErrorString((cudaError_t)rc2));
+            if (rc2 == 0)
+            {
+                done = true;
+                if (t0)
+                {
+                    cudaEventRecord(t1, s);
+                    g_trace.push_back(B200TraceRec{ "ksmac_tma_kernel", t0, t1 });
+                    g_trace_name = nullptr;
+                }
+            }
+        }
+#endif
+        if (done)
+            ;
+        else if (L.fp)
         {
             const long long total = batch * (k + 1) * (n >> 1);
             DISPATCH_K(k, B200_LAUNCH(ksmac_kernel_v2<KK>, blocks_for(total, EB), EB, 0, s, ctx->d_fp_primes, special, Kkey, ks1, key,
@@ -2004,6 +2063,15 @@ int b200_stream_synchronize(b200_ctx *ctx, void *stream)
 
 // developer aid: attach a device buffer of 8 u64 per CTA that the NEXT static NTT launches fill with
 // {smid, t_start, t_after_each_pass (<=5), t_end} (globaltimer ns); pass nullptr to detach
+int b200_debug_ntt_stagger(int cycles)
+{
+#ifndef B200_EMU_HEADER
+    return g_ntt_stagger.exchange(cycles);
+#else
+    (void)cycles;
+    return 0;
+#endif
+}
 int b200_debug_ntt_variant(int variant)
 {
 #ifndef B200_EMU_HEADER
@@ -2081,6 +2149,104 @@ int b200_gather_scatter(b200_ctx *ctx, uint64_t *const *host_ptrs, uint64_t coun
     ctx->launches++;
     CU_TRY(cudaFreeAsync(dptrs, s));
     CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+// Same, with the pointer table already in device-ACCESSIBLE memory (e.g. pinned host memory, which kernels read directly under
+// unified addressing): no staging copy, no allocation — the combining layer's per-batch cost is then one launch.
+int b200_gather_scatter_table(b200_ctx *ctx, uint64_t *const *table, uint64_t count, uint64_t *slab, uint64_t words, int gather,
+                              void *stream)
+{
+    if (!ctx || !table || !slab)
+        return fail(B200_E_NULL, "null argument");
+    if (count == 0 || words == 0)
+        return 0;
+    if (count > 65535)
+        return fail(B200_E_INVALID, "at most 65535 items per gather/scatter");
+    dim3 grid((unsigned)std::min<long long>(64, (long long)(words + 255) / 256), (unsigned)count);
+    B200_LAUNCH(gather_scatter_kernel, grid, 256, 0, (cudaStream_t)stream, (u64 *const *)table, (u64 *)slab, (long long)words, gather);
+    ctx->launches++;
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+// ---- CUDA graphs for fixed launch sequences (the combining layer of the SEAL-named ABI replays one graph per batch) ----
+// Everything enqueued on `stream` between begin and end becomes a graph: kernels with their parameters BY VALUE and the
+// stream-ordered allocations / frees as memory nodes, so a replay touches the same addresses.  The caller guarantees that
+// the captured sequence only reads its varying inputs through fixed locations (pinned pointer tables).
+int b200_capture_begin(b200_ctx *ctx, void *stream)
+{
+#ifdef B200_EMU_HEADER
+    (void)ctx;
+    (void)stream;
+    return fail(B200_E_LOGIC, "graphs are not available in the emulation build");
+#else
+    if (!ctx || !stream)
+        return fail(B200_E_NULL, "null argument");
+    if (trace_on())
+        return fail(B200_E_LOGIC, "no graph capture while tracing");
+    CU_TRY(cudaStreamBeginCapture((cudaStream_t)stream, cudaStreamCaptureModeRelaxed));
+    return 0;
+#endif
+}
+int b200_capture_end(b200_ctx *ctx, void *stream, void **graph_exec)
+{
+#ifdef B200_EMU_HEADER
+    (void)ctx;
+    (void)stream;
+    (void)graph_exec;
+    return fail(B200_E_LOGIC, "graphs are not available in the emulation build");
+#else
+    if (!ctx || !stream || !graph_exec)
+        return fail(B200_E_NULL, "null argument");
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture((cudaStream_t)stream, &g);
+    if (e != cudaSuccess || !g)
+    {
+        cudaGetLastError();
+        return fail(B200_E_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+    }
+    cudaGraphExec_t x = nullptr;
+    e = cudaGraphInstantiate(&x, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess)
+        return fail(B200_E_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+    *graph_exec = x;
+    return 0;
+#endif
+}
+int b200_graph_launch(b200_ctx *ctx, void *graph_exec, void *stream)
+{
+#ifdef B200_EMU_HEADER
+    (void)ctx;
+    (void)graph_exec;
+    (void)stream;
+    return fail(B200_E_LOGIC, "graphs are not available in the emulation build");
+#else
+    if (!ctx || !graph_exec)
+        return fail(B200_E_NULL, "null argument");
+    CU_TRY(cudaGraphLaunch((cudaGraphExec_t)graph_exec, (cudaStream_t)stream));
+    ctx->launches++;
+    return 0;
+#endif
+}
+int b200_graph_destroy(b200_ctx *ctx, void *graph_exec)
+{
+#ifndef B200_EMU_HEADER
+    if (ctx && graph_exec)
+        cudaGraphExecDestroy((cudaGraphExec_t)graph_exec);
+#else
+    (void)ctx;
+    (void)graph_exec;
+#endif
+    return 0;
+}
+
+// stream-ordered allocation usable by work enqueued on `stream` after this call (no host synchronisation)
+int b200_malloc_async(b200_ctx *ctx, size_t bytes, void **dptr, void *stream)
+{
+    if (!ctx || !dptr)
+        return fail(B200_E_NULL, "null argument");
+    CU_TRY(cudaMallocFromPoolAsync(dptr, bytes ? bytes : 8, ctx->mempool, (cudaStream_t)stream));
     return 0;
 }
 

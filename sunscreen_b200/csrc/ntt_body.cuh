@@ -54,6 +54,9 @@ struct NttJob
     int prefetch_dist;         // >0: each CTA prefetches (L2) the input of CTA blockIdx + prefetch_dist
     unsigned long long *timeline; // developer aid (B200_NTT_TIMELINE): per CTA {smid, t_start, t_after_pass_1..4, t_end} in ns
     int slot_major;            // block order (static FP kernel): 1 = all items of slot 0, then slot 1, ...
+    int stagger;               // streaming FP kernel: CTA of resident slot s (blockIdx / #SMs) starts s * stagger clock cycles late,
+                               // so that the CTAs sharing an SM are in different phases (one moving data while the others compute)
+    int sm_count;
     // fused tensor source (FP64 static inverse kernel only): instead of reading `src`, slot (m, row) computes
     // D_m[row] = sum_{r+s=m} A_r[row] * B_s[row] on the fly from the NTT-form operands at `tsrc`
     // ([item][sa+sb (or sa when squaring)][trows][n]); 0 = off, 1 = product, 2 = square of a size-2 ciphertext

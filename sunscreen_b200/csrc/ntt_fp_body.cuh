@@ -235,11 +235,14 @@ B200_HD int fp_elem_index(int pbase, int base, int j, int logs)
 template <int L, bool FWD, bool SRC_GLOBAL, bool DST_GLOBAL, bool TW16 = false, bool RENORM = true, bool REDUCE = true, bool PRELOADED = false,
           bool RAW_IN = false /* shared memory holds the raw input words (landed by cp.async): convert on read */,
           bool TW_PRE = false /* the group's twiddles were prefetched by the caller (twpre) */,
-          int TWSRC = 0 /* fp_load_tw_src */, int ABL = 0 /* developer ablations: 1 cheap product, 2 no global I/O */>
+          int TWSRC = 0 /* fp_load_tw_src */, int ABL = 0 /* developer ablations: 1 cheap product, 2 no global loads, 4 no global stores */,
+          bool REFILL = false /* streaming kernel, last inverse pass: once this group's inputs have been consumed, the NEXT
+                                 polynomial's words for the same slots are requested (cp.async) from `refill` */>
 B200_HD void ntt_fp_group(double *sm, const u64 *__restrict__ gsrc, u64 *__restrict__ gdst, int g, int logs, int logn, int M,
                           const NttPrimeFp &P, bool renorm, bool last_inv, bool reduce_input, u64 pint, u64 ratio1,
                           const u64 *pre = nullptr /* PRELOADED: the group's 2^L raw input words, already in registers */,
-                          const double *twpre = nullptr, const double *stw = nullptr /* TWSRC == 1: shared-memory table */)
+                          const double *twpre = nullptr, const double *stw = nullptr /* TWSRC == 1: shared-memory table */,
+                          const u64 *refill = nullptr)
 {
     constexpr int R = 1 << L;
     const int s = 1 << logs;
@@ -280,7 +283,14 @@ B200_HD void ntt_fp_group(double *sm, const u64 *__restrict__ gsrc, u64 *__restr
 #endif
         }
         else
-            x[j] = sm[fp_elem_index(pbase, base, j, logs)];
+        {
+#if defined(__CUDA_ARCH__)
+            if (PRELOADED) // shared-memory pass with the group's values fetched one group ahead by the caller (bit patterns)
+                x[j] = __longlong_as_double((long long)pre[j]);
+            else
+#endif
+                x[j] = sm[fp_elem_index(pbase, base, j, logs)];
+        }
         if (RENORM && renorm)
             x[j] = fp_renorm_x(x[j], p, P.pinv);
     }
@@ -291,17 +301,36 @@ B200_HD void ntt_fp_group(double *sm, const u64 *__restrict__ gsrc, u64 *__restr
         fp_stage<L, 2, FWD, ABL>(x, tws, P, last_inv);
     if constexpr (L > 3)
         fp_stage<L, 3, FWD, ABL>(x, tws, P, last_inv);
+#if defined(__CUDA_ARCH__)
+    if (REFILL && !SRC_GLOBAL && refill)
+    {
+        // the slots this thread has just read are free (their values are in registers and have been used): land the next
+        // polynomial's words in them while this one is finished and written out
+#pragma unroll
+        for (int j = 0; j < R; j++)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(sm + fp_elem_index(pbase, base, j, logs))),
+                         "l"(refill + base + (j << logs))
+                         : "memory");
+    }
+#endif
 #pragma unroll
     for (int j = 0; j < R; j++)
     {
-        if (DST_GLOBAL && (ABL & 2))
+        if (DST_GLOBAL && (ABL & 4))
         {
             const u64 v = fp_to_canonical<true>(x[j], p, P.pinv);
             if (v == 0xFFFFFFFFFFFFFFFFULL) // never: keeps the value live without the store traffic
                 gdst[base + (j << logs)] = v;
         }
         else if (DST_GLOBAL)
-            gdst[base + (j << logs)] = fp_to_canonical<true>(x[j], p, P.pinv);
+        {
+#if defined(__CUDA_ARCH__)
+            if (ABL & 8)
+                __stcs(gdst + base + (j << logs), fp_to_canonical<true>(x[j], p, P.pinv));
+            else
+#endif
+                gdst[base + (j << logs)] = fp_to_canonical<true>(x[j], p, P.pinv);
+        }
         else
             sm[fp_elem_index(pbase, base, j, logs)] = x[j];
     }
@@ -426,7 +455,7 @@ template <int LOGN, int NT, bool FWD, int STEP /*0..NP-1 in execution order*/, i
 struct NttFpStaticPass
 {
     static __device__ __forceinline__ void run(const NttJob &job, const NttPrimeFp &P, const NttPrime &PI_, const u64 *src, u64 *dst,
-                                               double *smd, int tid, long long item, int slot)
+                                               double *smd, int tid, long long item, int slot, const u64 *nsrc = nullptr)
     {
 #if defined(__CUDA_ARCH__)
         constexpr int N = 1 << LOGN;
@@ -450,10 +479,13 @@ struct NttFpStaticPass
         // input through cp.async instead (B200_NTT_DIRECT_IN=0) measures the same within noise (0.72 vs 0.71 ms for
         // 16384 polynomials): the per-CTA timeline (tools/ntt_timeline.py) shows the copy-in itself takes only 2.6 us of
         // a CTA's 18.4 us; the kernel is co-limited by the FP64 pipe (52 %) and the shared-memory pipe (55-58 %).
-        constexpr bool SG = EDGE_IN && LOGS >= 5 && B200_NTT_DIRECT_IN, DG = EDGE_OUT && LOGS >= 5;
+        // VAR & 16: streaming (persistent) kernel — the polynomial's raw words are ALREADY on their way into shared memory when a
+        // pass sequence starts (requested during the previous polynomial's last pass, into slots that pass had finished with)
+        constexpr bool STREAM = (VAR & 16) != 0;
+        constexpr bool SG = EDGE_IN && LOGS >= 5 && B200_NTT_DIRECT_IN && !STREAM, DG = EDGE_OUT && LOGS >= 5 && !(VAR & 128); // 128: always stage the output
         constexpr bool TW16 = (L == 4 && LOGS == 0);
         constexpr int TWSRC = (VAR & 2) ? 2 : ((VAR & 1) && !TW16 && (1 << (DONE + L)) <= B200_NTT_TWS_ENTRIES) ? 1 : 0;
-        constexpr int ABL = ((VAR & 4) ? 1 : 0) | ((VAR & 8) ? 2 : 0);
+        constexpr int ABL = ((VAR & 4) ? 1 : 0) | ((VAR & (8 | 32)) ? 2 : 0) | ((VAR & (8 | 64)) ? 4 : 0) | ((VAR & 512) ? 8 : 0); // 32 / 64: loads / stores only; 512: streaming (evict-first) hints
         double *stw = smd + ntt_smem_words(N); // VAR & 1: B200_NTT_TWS_ENTRIES doubles behind the polynomial
         if (STEP == 0 && (VAR & 1))
         {
@@ -510,6 +542,8 @@ struct NttFpStaticPass
                     smd[ptid + it * PNT] = acc; // lazy, |acc| < 4p: the first pass renormalises if its bound needs it
                 }
             }
+            else if (STREAM)
+                asm volatile("cp.async.wait_all;" ::: "memory"); // requested by the kernel prologue / the previous polynomial's last pass
             else
             {
                 // asynchronous copy (LDGSTS): no registers are held, so all N/NT requests of a thread are in flight at
@@ -543,7 +577,36 @@ struct NttFpStaticPass
         // renormalisation / input reduction are block-uniform run-time flags: branch ONCE to a compile-time variant
         // (as predicated code they cost 12 FP64 ops and ~10 IMADs per element whether needed or not)
         auto groups = [&](auto RN, auto RD) {
-            if constexpr (SG && NGROUPS % NT == 0 && ITERS > 1)
+            if constexpr (STREAM && FWD && EDGE_OUT && !DG)
+            {
+                // streaming forward transform, last (sub-stride-1) pass: the 32 groups a warp handles in one iteration are one
+                // contiguous region of 32 R elements that no other warp touches in this pass, so the region is written out
+                // (coalesced, canonical) by the warp itself as soon as its groups are done — no block-wide barrier — and
+                // the NEXT polynomial's words for the same region are requested into the slots just read
+                constexpr int R = 1 << L;
+                static_assert(NGROUPS % NT == 0, "whole iterations");
+                const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+                for (int it = 0; it < ITERS; it++)
+                {
+                    const int g = tid + it * NT;
+                    ntt_fp_group<L, FWD, false, false, TW16, decltype(RN)::value, false, false, false, false, TWSRC, ABL>(
+                        smd, src, dst, g, LOGS, LOGN, M, P, true, false, true, PI_.p, PI_.ratio1, nullptr, nullptr, stw);
+                    __syncwarp();
+                    const int e0 = ((warp << 5) + it * NT) << L;
+#pragma unroll
+                    for (int r = 0; r < R; r++)
+                    {
+                        const int e = e0 + lane + 32 * r;
+                        const int pe = ntt_pad(e);
+                        dst[e] = fp_to_canonical<true>(smd[pe], P.p, P.pinv);
+                        if (nsrc)
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smd + pe)), "l"(nsrc + e)
+                                         : "memory");
+                    }
+                }
+            }
+            else if constexpr (SG && NGROUPS % NT == 0 && ITERS > 1)
             {
                 // direct first pass, software-pipelined: the raw words of group it+1 are requested before group `it` is
                 // transformed, so one DRAM latency is exposed per polynomial instead of one per group
@@ -554,7 +617,7 @@ struct NttFpStaticPass
                     const int b0 = (i0 << (LOGS + L)) + o0;
 #pragma unroll
                     for (int j = 0; j < R; j++)
-                        cur[j] = (ABL & 2) ? (u64)(b0 + j) : src[b0 + (j << LOGS)];
+                        cur[j] = (ABL & 2) ? (u64)(b0 + j) : (ABL & 8) ? __ldcs(src + b0 + (j << LOGS)) : src[b0 + (j << LOGS)];
                 }
 #pragma unroll
                 for (int it = 0; it < ITERS; it++)
@@ -566,7 +629,7 @@ struct NttFpStaticPass
                         const int bn = (in_ << (LOGS + L)) + on;
 #pragma unroll
                         for (int j = 0; j < R; j++)
-                            nxt[j] = (ABL & 2) ? (u64)(bn + j) : src[bn + (j << LOGS)];
+                            nxt[j] = (ABL & 2) ? (u64)(bn + j) : (ABL & 8) ? __ldcs(src + bn + (j << LOGS)) : src[bn + (j << LOGS)];
                     }
                     ntt_fp_group<L, FWD, SG, DG, TW16, decltype(RN)::value, decltype(RD)::value, true, false, false, TWSRC, ABL>(
                         smd, src, dst, g, LOGS, LOGN, M, P, true, !FWD && EDGE_OUT, true, PI_.p, PI_.ratio1, cur, nullptr, stw);
@@ -578,7 +641,35 @@ struct NttFpStaticPass
             else
             {
                 auto run = [&](auto RAWF) {
-                    if constexpr (L <= 3 && NGROUPS % NT == 0 && ITERS > 1 && B200_NTT_TW_PREFETCH && TWSRC == 0)
+                    if constexpr ((VAR & 1024) != 0 && L <= 3 && NGROUPS % NT == 0 && ITERS > 1 && !decltype(RAWF)::value)
+                    {
+                        // VAR & 1024: the DATA of group it+1 is read from shared memory before group `it` is transformed (instead of
+                        // prefetching twiddles): hides the shared-memory latency / queueing behind the butterflies
+                        constexpr int R = 1 << L;
+                        u64 xc[R], xn[R];
+                        auto fetch = [&](u64(&dstv)[R], int g) {
+                            const int i_ = g >> LOGS, o_ = g & ((1 << LOGS) - 1);
+                            const int b_ = (i_ << (LOGS + L)) + o_;
+                            const int pb_ = ntt_pad(b_);
+#pragma unroll
+                            for (int j = 0; j < R; j++)
+                                dstv[j] = (u64)__double_as_longlong(smd[fp_elem_index(pb_, b_, j, LOGS)]);
+                        };
+                        fetch(xc, tid);
+#pragma unroll
+                        for (int it = 0; it < ITERS; it++)
+                        {
+                            const int g = tid + it * NT;
+                            if (it + 1 < ITERS)
+                                fetch(xn, g + NT);
+                            ntt_fp_group<L, FWD, false, DG, TW16, decltype(RN)::value, false, true, false, false, TWSRC, ABL, STREAM && !FWD && DG>(
+                                smd, src, dst, g, LOGS, LOGN, M, P, true, !FWD && EDGE_OUT, true, PI_.p, PI_.ratio1, xc, nullptr, stw, nsrc);
+#pragma unroll
+                            for (int j = 0; j < R; j++)
+                                xc[j] = xn[j];
+                        }
+                    }
+                    else if constexpr (L <= 3 && NGROUPS % NT == 0 && ITERS > 1 && B200_NTT_TW_PREFETCH && TWSRC == 0)
                     {
                         // the twiddles of group it+1 are requested before group `it` is transformed: their L1/L2 latency
                         // (the largest stall reason of the kernel, profiles/r1_ncu_ntt_v6.txt) overlaps the butterflies
@@ -592,8 +683,9 @@ struct NttFpStaticPass
                             const int g = tid + it * NT;
                             if (it + 1 < ITERS)
                                 fp_load_group_tw<L, FWD, false>(twn, twt, g + NT, (g + NT) >> LOGS, LOGS, LOGN, M, 0, P, !FWD && EDGE_OUT);
-                            ntt_fp_group<L, FWD, SG, DG, TW16, decltype(RN)::value, decltype(RD)::value, false, decltype(RAWF)::value, true, 0, ABL>(
-                                smd, src, dst, g, LOGS, LOGN, M, P, true, !FWD && EDGE_OUT, true, PI_.p, PI_.ratio1, nullptr, twc);
+                            ntt_fp_group<L, FWD, SG, DG, TW16, decltype(RN)::value, decltype(RD)::value, false, decltype(RAWF)::value, true, 0, ABL,
+                                         STREAM && !FWD && DG>(
+                                smd, src, dst, g, LOGS, LOGN, M, P, true, !FWD && EDGE_OUT, true, PI_.p, PI_.ratio1, nullptr, twc, nullptr, nsrc);
 #pragma unroll
                             for (int j = 0; j < R - 1; j++)
                                 twc[j] = twn[j];
@@ -606,8 +698,9 @@ struct NttFpStaticPass
                         {
                             const int g = tid + it * NT;
                             if (NGROUPS % NT == 0 || g < NGROUPS)
-                                ntt_fp_group<L, FWD, SG, DG, TW16, decltype(RN)::value, decltype(RD)::value, false, decltype(RAWF)::value, false, TWSRC, ABL>(
-                                    smd, src, dst, g, LOGS, LOGN, M, P, true, !FWD && EDGE_OUT, true, PI_.p, PI_.ratio1, nullptr, nullptr, stw);
+                                ntt_fp_group<L, FWD, SG, DG, TW16, decltype(RN)::value, decltype(RD)::value, false, decltype(RAWF)::value, false, TWSRC, ABL,
+                                             STREAM && !FWD && DG>(
+                                    smd, src, dst, g, LOGS, LOGN, M, P, true, !FWD && EDGE_OUT, true, PI_.p, PI_.ratio1, nullptr, nullptr, stw, nsrc);
                         }
                     }
                 };
@@ -636,25 +729,38 @@ struct NttFpStaticPass
             else
                 groups(std::false_type{}, std::false_type{});
         }
-        __syncthreads();
+        if (!(STREAM && EDGE_OUT)) // (the streaming kernel's next polynomial starts with wait_all + barrier)
+            __syncthreads();
         if (job.timeline && tid == 0)
         {
             unsigned long long t;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
             job.timeline[(unsigned long long)blockIdx.x * 8 + 2 + STEP] = t;
         }
-        if (EDGE_OUT && !DG)
+        if (EDGE_OUT && !DG && !(STREAM && FWD))
         { // coalesced copy-out: lazy double -> canonical u64
+            if constexpr ((VAR & 256) != 0)
+            { // two adjacent words per thread: one 128-bit store (the pair never straddles a pad: even index, runs of 16)
+#pragma unroll
+                for (int it = 0; it < N / (2 * NT); it++)
+                {
+                    const int e = 2 * (tid + it * NT);
+                    const int pe = ntt_pad(e);
+                    const u64 v0 = fp_to_canonical<true>(smd[pe], P.p, P.pinv), v1 = fp_to_canonical<true>(smd[pe + 1], P.p, P.pinv);
+                    __stcs(reinterpret_cast<ulonglong2 *>(dst + e), make_ulonglong2(v0, v1));
+                }
+            }
+            else
 #pragma unroll
             for (int it = 0; it < N / NT; it++)
             {
                 const u64 v = fp_to_canonical<true>(smd[ptid + it * PNT], P.p, P.pinv);
-                if (!(ABL & 2) || v == 0xFFFFFFFFFFFFFFFFULL)
+                if (!(ABL & 4) || v == 0xFFFFFFFFFFFFFFFFULL)
                     dst[tid + it * NT] = v;
             }
         }
         if (STEP + 1 < NP)
-            NttFpStaticPass<LOGN, NT, FWD, (STEP + 1 < NP ? STEP + 1 : STEP), VAR>::run(job, P, PI_, src, dst, smd, tid, item, slot);
+            NttFpStaticPass<LOGN, NT, FWD, (STEP + 1 < NP ? STEP + 1 : STEP), VAR>::run(job, P, PI_, src, dst, smd, tid, item, slot, nsrc);
 #endif
     }
 };

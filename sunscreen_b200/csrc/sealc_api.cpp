@@ -157,52 +157,146 @@ static void combine_run_one(Context_ *c, CombineReq &r)
 static void combine_run_batch(Context_ *c, std::vector<CombineReq *> &batch)
 {
     const size_t N = batch.size();
-    if (N == 1)
+    if (N == 1 && !c->use_graphs)
         return combine_run_one(c, *batch[0]);
     CombineReq &r0 = *batch[0];
     try
     {
         OpScope scope(c);
+        Context_::Lane &lane = *scope.lane;
         const int lv = r0.lv;
         const u64 k = (u64)c->level_k[lv], n = c->parms.n;
         const u64 in_polys = r0.kind == 1 ? 3 : 2, out_polys = r0.kind == 0 ? 3 : 2;
         const u64 win = in_polys * k * n, wout = out_polys * k * n;
         const size_t operands = r0.kind == 0 ? 2 : 1;
-        // gather: all first operands, then (multiply) all second operands, in ONE launch
-        std::vector<u64 *> ptrs(operands * N);
-        for (size_t i = 0; i < N; i++)
+        // With graphs the batch is padded to a power of two (the pad items repeat item 0 and write to a scratch destination):
+        // far fewer distinct graph shapes per lane, at the price of a few wasted items in a latency-bound launch sequence.
+        size_t NP = N;
+        if (c->use_graphs)
+            for (NP = 1; NP < N; NP <<= 1)
+                ;
+        // Everything that varies from call to call goes through the lane's pinned tables (addresses fixed for the lane's
+        // lifetime, read directly by the kernels): operand pointers, destination pointers, transparent-result flags.
+        u64 **tab = lane.hptrs, **dtab = tab + 2 * Context_::COMBINE_MAX;
+        uint32_t *flags = lane.hflag;
+        for (size_t i = 0; i < NP; i++)
         {
-            ptrs[i] = const_cast<u64 *>(batch[i]->a->dev_ptr(c));
+            const size_t src = i < N ? i : 0;
+            tab[i] = const_cast<u64 *>(batch[src]->a->dev_ptr(c));
             if (operands == 2)
-                ptrs[N + i] = const_cast<u64 *>(batch[i]->b->dev_ptr(c));
+                tab[NP + i] = const_cast<u64 *>(batch[src]->b->dev_ptr(c));
         }
-        void *pin = nullptr, *pout = nullptr;
-        dev_check(b200_malloc(c->dev, operands * N * win * sizeof(u64), &pin));
-        struct Free
+        if (NP > N && lane.pad_words < wout)
         {
-            Context_ *c;
-            void *p;
-            ~Free() { b200_free_async(c->dev, p, cur_stream()); }
-        } f_in{ c, pin };
-        dev_check(b200_malloc(c->dev, N * wout * sizeof(u64), &pout));
-        Free f_out{ c, pout };
-        u64 *in = (u64 *)pin, *out = (u64 *)pout;
-        dev_check(b200_gather_scatter(c->dev, ptrs.data(), operands * N, in, win, 1, cur_stream()));
-        if (r0.kind == 0)
-            dev_check(b200_multiply(c->dev, lv, in, 2, in + N * win, 2, out, N, cur_stream()));
-        else
-            dev_check(b200_relinearize(c->dev, lv, in, r0.keys->flat_dev(c, 0, (int)k), out, N, cur_stream()));
-        // scatter into the destinations (gathered above, so a destination may alias an operand)
-        std::vector<u64 *> dptrs(N);
-        for (size_t i = 0; i < N; i++)
-            dptrs[i] = batch[i]->dst->prepare_output(c, c->ids[lv], out_polys, k);
-        dev_check(b200_gather_scatter(c->dev, dptrs.data(), N, out, wout, 0, cur_stream()));
-        uint32_t *flags = scope.lane->hflag;
+            if (lane.pad_out)
+                b200_free_async(c->dev, lane.pad_out, cur_stream());
+            void *pp = nullptr;
+            dev_check(b200_malloc(c->dev, wout * sizeof(u64), &pp));
+            lane.pad_out = (u64 *)pp;
+            lane.pad_words = wout;
+        }
+        // destinations are only written by the final scatter, after every operand has been gathered: aliasing is harmless.
+        // An operand that IS a destination keeps its buffer (prepare_output reuses it when the capacity suffices); when the
+        // shapes differ the old buffer is released in stream order, after the gather that reads it.
+        const u64 *key = r0.kind == 1 ? r0.keys->flat_dev(c, 0, (int)k) : nullptr;
+        auto enqueue = [&]() {
+            void *pin = nullptr, *pout = nullptr;
+            dev_check(b200_malloc_async(c->dev, operands * NP * win * sizeof(u64), &pin, cur_stream()));
+            dev_check(b200_malloc_async(c->dev, NP * wout * sizeof(u64), &pout, cur_stream()));
+            u64 *in = (u64 *)pin, *out = (u64 *)pout;
+            int rc = b200_gather_scatter_table(c->dev, tab, operands * NP, in, win, 1, cur_stream());
+            if (!rc)
+                rc = r0.kind == 0 ? b200_multiply(c->dev, lv, in, 2, in + NP * win, 2, out, NP, cur_stream())
+                                  : b200_relinearize(c->dev, lv, in, key, out, NP, cur_stream());
+            if (!rc)
+                rc = b200_gather_scatter_table(c->dev, dtab, NP, out, wout, 0, cur_stream());
+            if (!rc && c->check_transparent)
+                rc = b200_any_nonzero(c->dev, lv, out, (int)out_polys, flags, NP, cur_stream());
+            b200_free_async(c->dev, pin, cur_stream());
+            b200_free_async(c->dev, pout, cur_stream());
+            return rc;
+        };
+        // the gather must read an aliased operand before prepare_output may release its buffer: when a destination is also
+        // an operand of DIFFERENT shape, fall back to the order gather -> prepare (no graph for that rare batch)
+        bool reshaped_alias = false;
+        for (size_t i = 0; i < N && !reshaped_alias; i++)
+            for (size_t j = 0; j < N; j++)
+                if ((batch[i]->dst == batch[j]->a || batch[i]->dst == batch[j]->b) && batch[i]->dst->dev_words < wout)
+                    reshaped_alias = true;
         if (c->check_transparent)
-        {
-            for (size_t i = 0; i < N; i++)
+            for (size_t i = 0; i < NP; i++)
                 ((volatile uint32_t *)flags)[i] = 0;
-            dev_check(b200_any_nonzero(c->dev, lv, out, (int)out_polys, flags, N, cur_stream()));
+        if (reshaped_alias || !c->use_graphs)
+        {
+            if (NP != N) // (this branch runs unpadded: second operands sit right behind the first N)
+                for (size_t i = 0; i < N && operands == 2; i++)
+                    tab[N + i] = const_cast<u64 *>(batch[i]->b->dev_ptr(c));
+            void *pin = nullptr, *pout = nullptr;
+            dev_check(b200_malloc_async(c->dev, operands * N * win * sizeof(u64), &pin, cur_stream()));
+            dev_check(b200_malloc_async(c->dev, N * wout * sizeof(u64), &pout, cur_stream()));
+            u64 *in = (u64 *)pin, *out = (u64 *)pout;
+            int rc = b200_gather_scatter_table(c->dev, tab, operands * N, in, win, 1, cur_stream());
+            if (!rc)
+                rc = r0.kind == 0 ? b200_multiply(c->dev, lv, in, 2, in + N * win, 2, out, N, cur_stream())
+                                  : b200_relinearize(c->dev, lv, in, key, out, N, cur_stream());
+            for (size_t i = 0; i < N; i++)
+                dtab[i] = batch[i]->dst->prepare_output(c, c->ids[lv], out_polys, k);
+            if (!rc)
+                rc = b200_gather_scatter_table(c->dev, dtab, N, out, wout, 0, cur_stream());
+            if (!rc && c->check_transparent)
+                rc = b200_any_nonzero(c->dev, lv, out, (int)out_polys, flags, N, cur_stream());
+            b200_free_async(c->dev, pin, cur_stream());
+            b200_free_async(c->dev, pout, cur_stream());
+            dev_check(rc);
+        }
+        else
+        {
+            for (size_t i = 0; i < NP; i++)
+                dtab[i] = i < N ? batch[i]->dst->prepare_output(c, c->ids[lv], out_polys, k) : lane.pad_out;
+            Context_::Lane::Graph *g = nullptr;
+            for (auto &e : lane.graphs)
+                if ((e.kind == r0.kind || e.kind == -1 - r0.kind) && e.lv == lv && e.n == NP && e.key == (const void *)key)
+                    g = &e;
+            if (!g)
+            { // first sight of this shape on this lane: run it kernel by kernel (this also warms every cache the sequence touches)
+                if ((int)lane.graphs.size() >= Context_::GRAPHS_PER_LANE)
+                {
+                    size_t old = 0;
+                    for (size_t i = 1; i < lane.graphs.size(); i++)
+                        if (lane.graphs[i].stamp < lane.graphs[old].stamp)
+                            old = i;
+                    if (lane.graphs[old].exec)
+                        b200_graph_destroy(c->dev, lane.graphs[old].exec);
+                    lane.graphs.erase(lane.graphs.begin() + (long)old);
+                }
+                lane.graphs.push_back({ r0.kind, lv, NP, (const void *)key, nullptr, ++lane.clock });
+                dev_check(enqueue());
+            }
+            else
+            {
+                g->stamp = ++lane.clock;
+                if (!g->exec)
+                { // second use: capture the sequence; from now on one graph launch replaces its ~10 kernel launches
+                    if (g->kind >= 0 && b200_capture_begin(c->dev, cur_stream()) == 0)
+                    {
+                        const int rc = enqueue();
+                        void *exec = nullptr;
+                        const int rc2 = b200_capture_end(c->dev, cur_stream(), &exec);
+                        if (rc || rc2)
+                        { // not capturable here: this shape keeps the kernel-by-kernel path (nothing was executed yet)
+                            if (exec)
+                                b200_graph_destroy(c->dev, exec);
+                            exec = nullptr;
+                            g->kind = -1 - r0.kind;
+                        }
+                        g->exec = exec;
+                    }
+                }
+                if (g->exec)
+                    dev_check(b200_graph_launch(c->dev, g->exec, cur_stream()));
+                else
+                    dev_check(enqueue());
+            }
         }
         scope.wait();
         if (c->check_transparent)
@@ -223,34 +317,36 @@ static void combine_submit(Context_ *c, CombineReq &req)
     Context_::Combiner &cb = c->comb[req.kind];
     std::unique_lock<std::mutex> lk(cb.m);
     cb.pending.push_back(&req);
+    bool mine_pending = true; // still in cb.pending (nobody has taken it yet)
     while (!req.done)
     {
-        if (cb.busy)
-        {
+        if (mine_pending)
+            mine_pending = std::find(cb.pending.begin(), cb.pending.end(), &req) != cb.pending.end();
+        if (!mine_pending || cb.active >= c->combine_leaders)
+        { // in flight with another leader, or all leaders busy: requests pile up and leave together with the next free leader
             cb.cv.wait(lk);
             continue;
         }
-        cb.busy = true; // leader
-        while (!cb.pending.empty() && !req.done)
+        // lead: my request and every compatible one that is waiting, as one batch, on a lane of its own
+        cb.active++;
+        std::vector<CombineReq *> batch{ &req }, rest;
+        for (auto *r : cb.pending)
         {
-            std::vector<CombineReq *> batch, rest;
-            for (auto *r : cb.pending)
-            {
-                if ((int)batch.size() < Context_::COMBINE_MAX && (batch.empty() || r->compatible(*batch[0])))
-                    batch.push_back(r);
-                else
-                    rest.push_back(r);
-            }
-            cb.pending.swap(rest);
-            lk.unlock();
-            combine_run_batch(c, batch);
-            lk.lock();
-            for (auto *r : batch)
-                r->done = true;
-            cb.cv.notify_all();
+            if (r == &req)
+                continue;
+            if ((int)batch.size() < Context_::COMBINE_MAX && r->compatible(req))
+                batch.push_back(r);
+            else
+                rest.push_back(r);
         }
-        cb.busy = false;
-        cb.cv.notify_all(); // a waiter whose request is still pending takes over
+        cb.pending.swap(rest);
+        lk.unlock();
+        combine_run_batch(c, batch);
+        lk.lock();
+        for (auto *r : batch)
+            r->done = true;
+        cb.active--;
+        cb.cv.notify_all();
     }
     lk.unlock();
     if (req.err)
@@ -770,6 +866,9 @@ long SEALContext_Create(void *parms, bool expand_mod_chain, int sec_level, void 
     const char *nt = getenv("B200_SKIP_TRANSPARENT_CHECK");
     c->check_transparent = !(nt && nt[0] == '1');
     c->combine = !std::getenv("B200_NO_COMBINE");
+    if (const char *cl = std::getenv("B200_COMBINE_LEADERS"))
+        c->combine_leaders = std::max(1, std::min(4, atoi(cl)));
+    c->use_graphs = !std::getenv("B200_NO_GRAPHS") && !std::getenv("B200_TRACE");
     // validation (S/context.cpp:135-420): anything failing leaves parameters_set = false, it is not an error here
     bool ok = e->n >= 2 && e->n <= 131072 && !(e->n & (e->n - 1)) && !e->coeff.empty() && e->plain >= 2;
     if (ok)
@@ -1851,11 +1950,9 @@ struct BatchSlab
     Context_ *c;
     void *p = nullptr;
     BatchSlab(Context_ *ctx, size_t words) : c(ctx) { dev_check(b200_malloc(c->dev, std::max<size_t>(words, 1) * 8, &p)); }
-    ~BatchSlab()
-    {
-        b200_stream_synchronize(c->dev, cur_stream());
-        b200_free(c->dev, p);
-    }
+    // freed in stream order (every use of the slab is on the operation's stream): no host synchronisation here, so the
+    // context mutex is never held while the GPU works — batches of different caller threads overlap their copies and kernels
+    ~BatchSlab() { b200_free_async(c->dev, p, cur_stream()); }
     u64 *w() const { return (u64 *)p; }
     BatchSlab(const BatchSlab &) = delete;
 };
@@ -1905,7 +2002,7 @@ void batch_scatter(Context_ *c, uint64_t count, void **dsts, const BatchSlab &sl
         std::vector<uint32_t> h(count);
         dev_check(b200_is_transparent(c->dev, level, slab.w(), 2, (uint32_t *)flags.p, count, cur_stream()));
         dev_check(b200_memcpy_d2h(c->dev, h.data(), flags.p, count * 4, cur_stream()));
-        dev_check(b200_stream_synchronize(c->dev, cur_stream()));
+        tl_scope->wait(); // releases the context mutex while the batch completes
         for (uint32_t f : h)
             if (f)
                 throw LogicErr("result ciphertext is transparent");
@@ -1950,6 +2047,7 @@ long B200_Ciphertext_SetWordsBatch(void *context, uint64_t count, void **cts, ui
             ct->is_ntt_form = ntt;
         }
         dev_check(b200_gather_scatter(c->dev, ptrs.data(), count, S.w(), w, 0, cur_stream()));
+        scope.wait(); // the caller may reuse `words` when the call returns; context mutex released while the copy runs
     });
 }
 // all handles must have the same shape; `words` receives [count][size][k][n]
@@ -1981,7 +2079,7 @@ long B200_Ciphertext_GetWordsBatch(void *context, uint64_t count, void **cts, ui
         BatchSlab S(c, count * w);
         dev_check(b200_gather_scatter(c->dev, ptrs.data(), count, S.w(), w, 1, cur_stream()));
         dev_check(b200_memcpy_d2h(c->dev, words, S.p, count * w * sizeof(u64), cur_stream()));
-        dev_check(b200_stream_synchronize(c->dev, cur_stream()));
+        scope.wait(); // context mutex released while the copy runs
     });
 }
 
@@ -2068,7 +2166,7 @@ long B200_Evaluator_PlainBatch(void *p, int which, uint64_t count, void **encs, 
             dev_check(b200_sub_plain(c->dev, lv, A.w(), 2, P.w(), count, O.w(), count, cur_stream()));
         else
             dev_check(b200_multiply_plain(c->dev, lv, A.w(), 2, P.w(), count, O.w(), count, cur_stream()));
-        dev_check(b200_stream_synchronize(c->dev, cur_stream())); // `host` is read by the copy above
+        tl_scope->wait(); // `host` is read by the copy above
         batch_scatter(c, count, dsts, O, ((Ciphertext_ *)encs[0])->parms_id, k, lv);
     });
 }

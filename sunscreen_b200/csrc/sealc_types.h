@@ -125,7 +125,24 @@ struct Context_
         bool ready = false;
         void *stream = nullptr;
         uint32_t *hflag = nullptr;    // transparent-result flag: pinned host memory the check kernel writes directly
+        u64 **hptrs = nullptr;        // pinned pointer table of the combining layer: 3 * COMBINE_MAX entries the kernels read directly
+        // CUDA graphs of the combining layer's launch sequences, one per (kind, level, batch size, key): every varying input
+        // reaches the kernels through `hptrs` / `hflag`, whose addresses never change, so a graph is replayed as it is
+        struct Graph
+        {
+            int kind, lv;
+            size_t n;
+            const void *key;
+            void *exec;   // nullptr: seen once (caches are warm), capture on the next use
+            uint64_t stamp;
+        };
+        std::vector<Graph> graphs;
+        uint64_t clock = 0;
+        u64 *pad_out = nullptr; // scratch destination of the pad items of a batch rounded up to a power of two
+        size_t pad_words = 0;
     };
+    static const int GRAPHS_PER_LANE = 48;
+    bool use_graphs = true; // B200_NO_GRAPHS=1: enqueue the kernels one by one
     static const int NLANE = 8;
     Lane lanes[NLANE];
     // Flat combining of concurrent per-handle calls (sealc_api.cpp: combine_submit): calls of the same kind that arrive
@@ -151,8 +168,9 @@ struct Context_
         std::mutex m;
         std::condition_variable cv;
         std::vector<CombineReq *> pending;
-        bool busy = false;
+        int active = 0; // leaders currently executing a batch
     };
+    int combine_leaders = 3; // per kind: a caller that finds fewer leaders busy runs at once, on its own lane (B200_COMBINE_LEADERS)
     static const int NCOMB = 3;       // multiply (2,2) | relinearize (3 -> 2) | apply_galois
     static const int COMBINE_MAX = 64; // items per combined batch (= entries of a lane's pinned flag array)
     Combiner comb[NCOMB];
@@ -176,6 +194,13 @@ struct Context_
                     b200_stream_destroy(dev, l.stream);
                 if (l.hflag)
                     b200_free_host(l.hflag);
+                if (l.hptrs)
+                    b200_free_host(l.hptrs);
+                for (auto &g : l.graphs)
+                    if (g.exec)
+                        b200_graph_destroy(dev, g.exec);
+                if (l.pad_out)
+                    b200_free(dev, l.pad_out);
             }
             if (!owner)
                 b200_ctx_destroy(dev);
@@ -259,6 +284,9 @@ struct OpScope
             void *h = nullptr;
             dev_check(b200_malloc_host(sizeof(uint32_t) * Context_::COMBINE_MAX, &h));
             lane->hflag = (uint32_t *)h;
+            h = nullptr;
+            dev_check(b200_malloc_host(sizeof(u64 *) * 3 * Context_::COMBINE_MAX, &h));
+            lane->hptrs = (u64 **)h;
         }
         tl_scope = this;
     }

@@ -18,7 +18,8 @@
 // (S/c/ciphertext.cpp:472-577): E_INVALIDARG for a too-small buffer or an unsupported compression mode,
 // COR_E_INVALIDOPERATION for malformed / invalid data, COR_E_IO for a truncated buffer.
 //
-// Compression: zlib comes from the system libz; Zstandard is bound at run time from the system libzstd.so.1 (no
+// Compression: zlib comes from the system libz; Zstandard is compiled in (1.4.5, the reference's vendored version) when its
+// sources are present at build time, else bound at run time from the system libzstd.so.1 (no
 // headers in this image).  A Zstandard frame written here is a valid frame for the reference's decoder and vice
 // versa, but the compressed BYTES are those of the system library version, not of the zstd 1.4.5 the reference
 // vendors; only compr_mode none is byte-identical (tests/sealc_checks.py::wire_format).
@@ -76,7 +77,25 @@ struct In
     }
 };
 
-// ---- Zstandard through dlopen (stable API subset; prototypes restated from the public zstd.h) ----
+// ---- Zstandard (stable API subset; prototypes restated from the public zstd.h) ----
+// B200_VENDORED_ZSTD (csrc/Makefile, set when the Zstandard 1.4.5 sources the reference vendors are available at build
+// time): the library is compiled INTO this shared object with hidden visibility, so compressed streams are byte-identical
+// with the reference's (seal_fhe's `deterministic` test hashes them, seal_fhe/src/encryptor_decryptor.rs:919-932).
+// Otherwise the system libzstd.so.1 is bound at run time: interchangeable streams, but that version's bytes.
+#ifdef B200_VENDORED_ZSTD
+extern "C" {
+size_t ZSTD_compressBound(size_t);
+size_t ZSTD_compress(void *, size_t, const void *, size_t, int);
+unsigned ZSTD_isError(size_t);
+void *ZSTD_createDStream(void);
+size_t ZSTD_freeDStream(void *);
+size_t ZSTD_initDStream(void *);
+struct ZSTD_outBuffer_s;
+struct ZSTD_inBuffer_s;
+size_t ZSTD_decompressStream(void *, struct ZSTD_outBuffer_s *, struct ZSTD_inBuffer_s *);
+unsigned ZSTD_versionNumber(void);
+}
+#endif
 struct ZBuf
 {
     const void *src;
@@ -99,6 +118,17 @@ struct Zstd
     bool ok = false;
     Zstd()
     {
+#ifdef B200_VENDORED_ZSTD
+        compressBound = ZSTD_compressBound;
+        compress = ZSTD_compress;
+        isError = ZSTD_isError;
+        createDStream = ZSTD_createDStream;
+        freeDStream = ZSTD_freeDStream;
+        initDStream = ZSTD_initDStream;
+        decompressStream = reinterpret_cast<size_t (*)(void *, ZOut *, ZBuf *)>(ZSTD_decompressStream);
+        ok = true;
+        return;
+#endif
         void *h = dlopen("libzstd.so.1", RTLD_NOW | RTLD_LOCAL);
         if (!h)
             return;
@@ -120,6 +150,18 @@ struct Zstd
     }
 };
 
+} // namespace
+namespace b200c {
+int vendored_zstd()
+{
+#ifdef B200_VENDORED_ZSTD
+    return 1;
+#else
+    return 0;
+#endif
+}
+} // namespace b200c
+namespace {
 bool compr_supported(uint8_t mode)
 {
     return mode == COMPR_NONE || mode == COMPR_ZLIB || (mode == COMPR_ZSTD && Zstd::get().ok);
@@ -667,6 +709,10 @@ long load_impl(uint8_t *inptr, uint64_t size, int64_t *in_bytes, LoadF members)
 } // namespace
 
 extern "C" {
+
+// 1 when Zstandard 1.4.5 (the version the reference vendors) is compiled into this library: compressed streams are then
+// byte-identical with the reference's; 0 when the system libzstd is bound at run time (interchangeable streams only)
+long B200_VendoredZstd(void) { return b200c::vendored_zstd(); }
 
 // ---- Ciphertext (S/c/ciphertext.cpp:472-577) ----
 long Ciphertext_SaveSize(void *p, uint8_t compr_mode, int64_t *result)

@@ -50,6 +50,13 @@ _SIGS = {
     "b200_memcpy_d2d": [vp, vp, vp, C.c_size_t, vp],
     "b200_memzero": [vp, vp, C.c_size_t, vp],
     "b200_debug_ntt_variant": [C.c_int],
+    "b200_debug_ntt_stagger": [C.c_int],
+    "b200_gather_scatter_table": [vp, vp, u64, vp, u64, C.c_int, vp],
+    "b200_malloc_async": [vp, C.c_size_t, C.POINTER(vp), vp],
+    "b200_capture_begin": [vp, vp],
+    "b200_capture_end": [vp, vp, C.POINTER(vp)],
+    "b200_graph_launch": [vp, vp, vp],
+    "b200_graph_destroy": [vp, vp],
     "b200_stream_synchronize": [vp, vp],
     "b200_ntt_forward": [vp, C.c_int, vp, u64, vp],
     "b200_ntt_inverse": [vp, C.c_int, vp, u64, vp],

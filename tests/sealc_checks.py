@@ -761,6 +761,15 @@ def seal_fhe_golden_fixture(S, golden_dir):
     assert _siphash13(len(zref).to_bytes(8, "little") + zref) == 9942548233613012008
     zour = OL.save("Ciphertext", results[1][3], COMPR_ZSTD)
     assert RL.save("Ciphertext", RL.load("Ciphertext", zour), 0) == results[0][2]
+    # a build that compiled the Zstandard 1.4.5 the reference vendors into the library (csrc/Makefile: B200_VENDORED_ZSTD)
+    # emits the reference's bytes exactly: the crate's own `deterministic` test would then see its golden hash
+    has = getattr(S.lib, "B200_VendoredZstd", None)
+    if has is not None and has() == 1:
+        assert zour == zref, "vendored Zstandard 1.4.5: compressed ciphertext bytes differ from the reference's"
+        assert _siphash13(len(zour).to_bytes(8, "little") + zour) == 9942548233613012008
+        for kind, idx in (("PublicKey", 0), ("SecretKey", 1)):
+            ro, oo = (L.load(kind, results[i][idx]) for i, L in ((0, RL), (1, OL)))
+            assert RL.save(kind, ro, COMPR_ZSTD) == OL.save(kind, oo, COMPR_ZSTD), f"{kind}: Zstandard bytes differ"
 
 
 def single_prime_context(S, n, moduli, t):

@@ -3,6 +3,7 @@
 
   VAR 0  the shipping kernel with twiddles from global memory
   VAR 1  first 512 twiddles of the table in shared memory            (results checked against VAR 0)
+  VAR 16 streaming: persistent CTAs, next polynomial requested during the last pass (results checked against VAR 0)
   VAR 2 / 4 / 8 and sums: ABLATIONS — no twiddle loads / one-DMUL products / no global traffic.  Their results are
   meaningless; they measure what each component of the kernel costs (which is what bounds it).
 """
@@ -16,7 +17,7 @@ from bench import MODULI, PLAIN, N_POLY
 
 items = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
-variants = [int(v) for v in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0, 1, 2, 4, 6, 8, 14]
+variants = sys.argv[3].split(",") if len(sys.argv) > 3 else [0, 1, 16, 2, 4, 6, 8, 14]
 lib = B200Lib.default()
 ctx = B200Context(N_POLY, MODULI, PLAIN)
 k = ctx.k()
@@ -40,7 +41,11 @@ def timed(fn):
 
 
 ref_f = ref_i = None
-for var in variants:
+# "16:6000" = variant 16 with a start-up stagger of 6000 clock cycles per resident CTA slot
+for spec in variants:
+    var, _, stag = str(spec).partition(":")
+    var = int(var)
+    lib.lib.b200_debug_ntt_stagger(int(stag or 0))
     lib.lib.b200_debug_ntt_variant(var)
     x = x0.clone()
     ctx.ntt_forward(x, items, stream=s)
@@ -52,12 +57,13 @@ for var in variants:
     if var == 0:
         ref_f = fwd_out
         assert torch.equal(x, x0), "round trip"
-    elif var == 1:
+    elif var in (1, 16):
         note = "  forward == VAR 0: %s, round trip: %s" % (torch.equal(fwd_out, ref_f), torch.equal(x, x0))
     for _ in range(2):
         ctx.ntt_forward(x, items, stream=s)
         ctx.ntt_inverse(x, items, stream=s)
     f = timed(lambda: ctx.ntt_forward(x, items, stream=s))
     i_ = timed(lambda: ctx.ntt_inverse(x, items, stream=s))
-    print(f"VAR {var:2d}: fwd {f:.3f} ms {bytes_ / f / 1e6:6.0f} GB/s | inv {i_:.3f} ms {bytes_ / i_ / 1e6:6.0f} GB/s{note}", flush=True)
+    print(f"VAR {str(spec):>8s}: fwd {f:.3f} ms {bytes_ / f / 1e6:6.0f} GB/s | inv {i_:.3f} ms {bytes_ / i_ / 1e6:6.0f} GB/s{note}", flush=True)
 lib.lib.b200_debug_ntt_variant(0)
+lib.lib.b200_debug_ntt_stagger(0)
