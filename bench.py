@@ -340,6 +340,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--quick", action="store_true", help="device-resident loop + rooflines only (for runs under ncu)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -418,87 +419,93 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     value = world * B * args.steps / (ms / 1000.0)
 
-    # ---- e2e legs (host buffers; H2D + compute + D2H inside the timed region) ----
     ct_bytes = 2 * k * n * 8
-    ah = torch.empty((B, 2, k, n), dtype=torch.int64).pin_memory()
-    bh = torch.empty((B, 2, k, n), dtype=torch.int64).pin_memory()
-    oh = torch.empty((B, 2, k, n), dtype=torch.int64).pin_memory()
-    ah.copy_(a)
-    bh.copy_(b)
-    e2e_steps = max(2, min(args.steps, 5))
-
-    def wall_max(seconds):
-        if dist is None:
-            return seconds
-        ts = torch.tensor([seconds], device=dev, dtype=torch.float64)
-        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
-        return float(ts.item())
-
-    # the link's own ceiling for this box: one pinned 1 GiB copy each way (the e2e legs move 1 MiB in + 0.5 MiB out per op)
-    link = {}
-    for name, dst_t, src_t in (("h2d", a, ah), ("d2h", oh, out)):
-        dst_t.copy_(src_t, non_blocking=True)
-        torch.cuda.synchronize()
-        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        c0.record()
-        dst_t.copy_(src_t, non_blocking=True)
-        c1.record()
-        torch.cuda.synchronize()
-        link[name + "_gbs"] = dst_t.numel() * 8 / (c0.elapsed_time(c1) / 1000.0) / 1e9
-    ah.copy_(a)  # (a was only overwritten with its own contents; keep the pinned copy authoritative)
-    link["bound_ops_per_s"] = min(link["h2d_gbs"] * 1e9 / (2 * ct_bytes), link["d2h_gbs"] * 1e9 / ct_bytes)
-
-    # (a) layer-1 host-slab entry point
-    ctx.multiply_relin_host(ah, bh, rlk, oh, B)  # warm
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        ctx.multiply_relin_host(ah, bh, rlk, oh, B)
-    torch.cuda.synchronize()
-    slab_s = wall_max(time.perf_counter() - t0)
-    slab_value = world * B * e2e_steps / slab_s
-    slab_same = bool(torch.equal(oh.to(dev), out))
-    pack_num = 6 if (max(MODULI[:k]) < 2 ** 48 and os.environ.get("B200_HOST_PACK", "0") not in ("", "0")) else 8
-
-    # (b) the plugin calls (SEAL-named C ABI): handles, batch seam, bulk word access
-    os.environ["B200_DEVICE"] = str(local)  # the SEAL-named layer creates its own device context: same GPU as this rank
-    plug = PluginLegs(ctx, local, k, n, rlk)
-    oh.zero_()
-    plug.batch_step(ah, bh, oh, B)  # warm (allocates the handles' device buffers)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        plug.batch_step(ah, bh, oh, B)
-    plug_s = wall_max(time.perf_counter() - t0)
-    e2e_value = world * B * e2e_steps / plug_s
-    same = bool(torch.equal(oh.to(dev), out))
-    # (c) per-handle calls from 8 threads, handles device-resident
-    ph_threads = int(os.environ.get("B200_BENCH_PH_THREADS", "8"))
-    ph_pairs = min(B, 1024)
-    plug.per_handle_prepare(ah, bh, ph_pairs)
-    plug.per_handle_run(ph_threads, ph_pairs)  # warm
-    barrier()
-    native = plug.per_handle_native(ph_threads, ph_pairs) is not None  # also warms the native harness
-    ph_scaling = {}
-    if native:
-        barrier()
-        for tcount in (1, 2, 4, 8, 16, 32):
-            for _ in range(3):  # warm: the batch shapes this thread count produces get their graphs instantiated here
-                plug.per_handle_native(tcount, ph_pairs)
-            ph_scaling[str(tcount)] = ph_pairs / min(plug.per_handle_native(tcount, ph_pairs) for _ in range(3))
-        barrier()
-        plug.per_handle_native(ph_threads, ph_pairs)
-        ph_s = wall_max(min(plug.per_handle_native(ph_threads, ph_pairs) for _ in range(3)))
-        ph1_value = ph_scaling["1"]
+    e2e_value = slab_value = ph_value = ph1_value = None
+    if args.quick:
+        quick_line = {"metric": "ciphertext mul+relin/sec", "value": value, "unit": "ops/s", "n_gpus": world, "steps": args.steps,
+                      "ms_per_step": ms / args.steps, "gpu_launches": int(launches), "quick": True}
     else:
+        # ---- e2e legs (host buffers; H2D + compute + D2H inside the timed region) ----
+        ct_bytes = 2 * k * n * 8
+        ah = torch.empty((B, 2, k, n), dtype=torch.int64).pin_memory()
+        bh = torch.empty((B, 2, k, n), dtype=torch.int64).pin_memory()
+        oh = torch.empty((B, 2, k, n), dtype=torch.int64).pin_memory()
+        ah.copy_(a)
+        bh.copy_(b)
+        e2e_steps = max(2, min(args.steps, 5))
+
+        def wall_max(seconds):
+            if dist is None:
+                return seconds
+            ts = torch.tensor([seconds], device=dev, dtype=torch.float64)
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+            return float(ts.item())
+
+        # the link's own ceiling for this box: one pinned 1 GiB copy each way (the e2e legs move 1 MiB in + 0.5 MiB out per op)
+        link = {}
+        for name, dst_t, src_t in (("h2d", a, ah), ("d2h", oh, out)):
+            dst_t.copy_(src_t, non_blocking=True)
+            torch.cuda.synchronize()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            dst_t.copy_(src_t, non_blocking=True)
+            c1.record()
+            torch.cuda.synchronize()
+            link[name + "_gbs"] = dst_t.numel() * 8 / (c0.elapsed_time(c1) / 1000.0) / 1e9
+        ah.copy_(a)  # (a was only overwritten with its own contents; keep the pinned copy authoritative)
+        link["bound_ops_per_s"] = min(link["h2d_gbs"] * 1e9 / (2 * ct_bytes), link["d2h_gbs"] * 1e9 / ct_bytes)
+
+        # (a) layer-1 host-slab entry point
+        ctx.multiply_relin_host(ah, bh, rlk, oh, B)  # warm
+        barrier()
         t0 = time.perf_counter()
-        plug.per_handle_run(ph_threads, ph_pairs)
-        ph_s = wall_max(time.perf_counter() - t0)
+        for _ in range(e2e_steps):
+            ctx.multiply_relin_host(ah, bh, rlk, oh, B)
+        torch.cuda.synchronize()
+        slab_s = wall_max(time.perf_counter() - t0)
+        slab_value = world * B * e2e_steps / slab_s
+        slab_same = bool(torch.equal(oh.to(dev), out))
+        pack_num = 6 if (max(MODULI[:k]) < 2 ** 48 and os.environ.get("B200_HOST_PACK", "0") not in ("", "0")) else 8
+
+        # (b) the plugin calls (SEAL-named C ABI): handles, batch seam, bulk word access
+        os.environ["B200_DEVICE"] = str(local)  # the SEAL-named layer creates its own device context: same GPU as this rank
+        plug = PluginLegs(ctx, local, k, n, rlk)
+        oh.zero_()
+        plug.batch_step(ah, bh, oh, B)  # warm (allocates the handles' device buffers)
+        barrier()
         t0 = time.perf_counter()
-        plug.per_handle_run(1, min(ph_pairs, 64))
-        ph1_value = min(ph_pairs, 64) / (time.perf_counter() - t0)
-    ph_value = world * ph_pairs / ph_s
-    ph_same = plug.per_handle_check(out, ph_pairs)
+        for _ in range(e2e_steps):
+            plug.batch_step(ah, bh, oh, B)
+        plug_s = wall_max(time.perf_counter() - t0)
+        e2e_value = world * B * e2e_steps / plug_s
+        same = bool(torch.equal(oh.to(dev), out))
+        # (c) per-handle calls from 8 threads, handles device-resident
+        ph_threads = int(os.environ.get("B200_BENCH_PH_THREADS", "8"))
+        ph_pairs = min(B, 1024)
+        plug.per_handle_prepare(ah, bh, ph_pairs)
+        plug.per_handle_run(ph_threads, ph_pairs)  # warm
+        barrier()
+        native = plug.per_handle_native(ph_threads, ph_pairs) is not None  # also warms the native harness
+        ph_scaling = {}
+        if native:
+            barrier()
+            for tcount in (1, 2, 4, 8, 16, 32):
+                for _ in range(3):  # warm: the batch shapes this thread count produces get their graphs instantiated here
+                    plug.per_handle_native(tcount, ph_pairs)
+                ph_scaling[str(tcount)] = ph_pairs / min(plug.per_handle_native(tcount, ph_pairs) for _ in range(3))
+            barrier()
+            plug.per_handle_native(ph_threads, ph_pairs)
+            ph_s = wall_max(min(plug.per_handle_native(ph_threads, ph_pairs) for _ in range(3)))
+            ph1_value = ph_scaling["1"]
+        else:
+            t0 = time.perf_counter()
+            plug.per_handle_run(ph_threads, ph_pairs)
+            ph_s = wall_max(time.perf_counter() - t0)
+            t0 = time.perf_counter()
+            plug.per_handle_run(1, min(ph_pairs, 64))
+            ph1_value = min(ph_pairs, 64) / (time.perf_counter() - t0)
+        ph_value = world * ph_pairs / ph_s
+        ph_same = plug.per_handle_check(out, ph_pairs)
 
     # ---- north-star multi-GPU split (N > 1): rank 0 holds the whole batch, NCCL scatter -> compute -> NCCL gather ----
     sharded = None
@@ -641,7 +648,10 @@ def main():
                 cpu = {"value": None, "unit": "ops/s", "cores": os.cpu_count(), "kind": "reference",
                        "sample": f"unavailable: {ex}"}
 
-    if rank == 0:
+    if rank == 0 and args.quick:
+        quick_line.update({"roofline": roof, "roofline_keyswitch": roof_ks, "sharded": sharded, "clocks": clocks})
+        print(json.dumps(quick_line))
+    elif rank == 0:
         line = {
             "metric": "ciphertext mul+relin/sec", "value": value, "unit": "ops/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",

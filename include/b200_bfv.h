@@ -175,6 +175,8 @@ int b200_capture_begin(b200_ctx *ctx, void *stream);
 int b200_capture_end(b200_ctx *ctx, void *stream, void **graph_exec);
 int b200_graph_launch(b200_ctx *ctx, void *graph_exec, void *stream);
 int b200_graph_destroy(b200_ctx *ctx, void *graph_exec);
+/* make the context's GPU the calling thread's current device (new host threads start on device 0) */
+int b200_bind_thread(b200_ctx *ctx);
 /* stream-ordered allocation for work enqueued on `stream` afterwards (release with b200_free_async on the same stream) */
 int b200_malloc_async(b200_ctx *ctx, size_t bytes, void **dptr, void *stream);
 

@@ -2027,14 +2027,14 @@ int b200_memcpy_h2d(b200_ctx *ctx, void *dst, const void *src, size_t bytes, voi
 {
     if (!ctx)
         return fail(B200_E_NULL, "null argument");
-    CU_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    CU_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
     return 0;
 }
 int b200_memcpy_d2h(b200_ctx *ctx, void *dst, const void *src, size_t bytes, void *stream)
 {
     if (!ctx)
         return fail(B200_E_NULL, "null argument");
-    CU_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CU_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
     return 0;
 }
 int b200_memcpy_d2d(b200_ctx *ctx, void *dst, const void *src, size_t bytes, void *stream)
@@ -2241,6 +2241,15 @@ int b200_graph_destroy(b200_ctx *ctx, void *graph_exec)
     return 0;
 }
 
+// make the context's GPU the calling thread's current device (a new host thread starts on device 0: the SEAL-named layer
+// calls this at the start of every operation, so worker threads of a multi-GPU process need no CUDA calls of their own)
+int b200_bind_thread(b200_ctx *ctx)
+{
+    if (!ctx)
+        return fail(B200_E_NULL, "null argument");
+    CU_TRY(cudaSetDevice(ctx->device)); // (a no-op when it already is the current device)
+    return 0;
+}
 // stream-ordered allocation usable by work enqueued on `stream` after this call (no host synchronisation)
 int b200_malloc_async(b200_ctx *ctx, size_t bytes, void **dptr, void *stream)
 {

@@ -170,7 +170,7 @@ struct Context_
         std::vector<CombineReq *> pending;
         int active = 0; // leaders currently executing a batch
     };
-    int combine_leaders = 3; // per kind: a caller that finds fewer leaders busy runs at once, on its own lane (B200_COMBINE_LEADERS)
+    int combine_leaders = 4; // per kind: a caller that finds fewer leaders busy runs at once, on its own lane (B200_COMBINE_LEADERS)
     static const int NCOMB = 3;       // multiply (2,2) | relinearize (3 -> 2) | apply_galois
     static const int COMBINE_MAX = 64; // items per combined batch (= entries of a lane's pinned flag array)
     Combiner comb[NCOMB];
@@ -257,6 +257,7 @@ struct OpScope
     OpScope *outer;
     explicit OpScope(Context_ *ctx) : c(ctx), outer(tl_scope)
     {
+        dev_check(b200_bind_thread(ctx->dev)); // worker threads of the caller never called cudaSetDevice themselves
         if (outer && outer->c == ctx)
         { // nested helper inside an operation of the same context: share its lane and its lock
             lane = outer->lane;

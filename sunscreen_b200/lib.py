@@ -53,6 +53,7 @@ _SIGS = {
     "b200_debug_ntt_stagger": [C.c_int],
     "b200_gather_scatter_table": [vp, vp, u64, vp, u64, C.c_int, vp],
     "b200_malloc_async": [vp, C.c_size_t, C.POINTER(vp), vp],
+    "b200_bind_thread": [vp],
     "b200_capture_begin": [vp, vp],
     "b200_capture_end": [vp, vp, C.POINTER(vp)],
     "b200_graph_launch": [vp, vp, vp],

@@ -21,7 +21,7 @@ inline const char *cudaGetErrorString(cudaError_t) { return "emu error"; }
 typedef void *cudaStream_t;
 typedef void *cudaEvent_t;
 typedef void *cudaMemPool_t;
-enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
+enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
 enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaFuncAttributeMaxDynamicSharedMemorySize = 8,
        cudaMemPoolReuseAllowInternalDependencies = 3, cudaMemPoolAttrReleaseThreshold = 4 };
 struct cudaDeviceProp { int multiProcessorCount = 1; size_t sharedMemPerBlockOptin = 232448; };
