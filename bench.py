@@ -194,7 +194,10 @@ def run_reference(args):
                    "parallelism": f"{cores} host threads, one memory pool each (oracle/_ref = unmodified reference)"},
         "cpu_baseline": {"value": rate, "unit": "ops/s", "cores": cores, "kind": "reference",
                          "sample": f"{args.steps} steps x {cores} threads x {iters} multiply+relinearize_inplace, "
-                                   "uniform-random ciphertext words"},
+                                   "uniform-random ciphertext words",
+                         # threads used vs what the lease really grants (a CPU-quota'd 1-GPU lease gives ~16 cores' worth)
+                         "box": cpu_quota(),
+                         "build": "unmodified reference sources, -O3, Intel HEXL off (not buildable offline)"},
         "e2e": {"value": rate, "unit": "ops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -216,8 +219,8 @@ class PluginLegs:
         self.k, self.n = k, n
         key = rlk_dev.cpu().numpy().view(np.uint64)  # (k, 2, K, n) key-level NTT-form words
         self.rlk = self.O.new_ksk({0: key})
-        self.threads = int(os.environ.get("B200_BENCH_E2E_THREADS", "4"))
-        self.chunk = int(os.environ.get("B200_BENCH_E2E_CHUNK", "128"))
+        self.threads = int(os.environ.get("B200_BENCH_E2E_THREADS", "8"))
+        self.chunk = int(os.environ.get("B200_BENCH_E2E_CHUNK", "64"))
         self.pool = {}
 
     def _handles(self, tag, count):
@@ -445,13 +448,18 @@ def main():
         link = {}
         for name, dst_t, src_t in (("h2d", a, ah), ("d2h", oh, out)):
             dst_t.copy_(src_t, non_blocking=True)
-            torch.cuda.synchronize()
+            barrier()  # every rank copies at the same time: GPUs that share a host link / PCIe switch share its bandwidth
             c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             c0.record()
-            dst_t.copy_(src_t, non_blocking=True)
+            for _ in range(2):
+                dst_t.copy_(src_t, non_blocking=True)
             c1.record()
             torch.cuda.synchronize()
-            link[name + "_gbs"] = dst_t.numel() * 8 / (c0.elapsed_time(c1) / 1000.0) / 1e9
+            link[name + "_gbs"] = 2 * dst_t.numel() * 8 / (c0.elapsed_time(c1) / 1000.0) / 1e9
+            if dist is not None:
+                tot = torch.tensor([link[name + "_gbs"]], device=dev, dtype=torch.float64)
+                dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+                link[name + "_all_ranks_concurrent_gbs"] = float(tot.item())
         ah.copy_(a)  # (a was only overwritten with its own contents; keep the pinned copy authoritative)
         link["bound_ops_per_s"] = min(link["h2d_gbs"] * 1e9 / (2 * ct_bytes), link["d2h_gbs"] * 1e9 / ct_bytes)
 
@@ -669,8 +677,10 @@ def main():
                     "host_numa_node": numa_node, "pcie_gbs": 3 * B * ct_bytes * e2e_steps / plug_s / 1e9,
                     "roofline": {"bound": "pcie", "h2d_peak_gbs": link["h2d_gbs"], "d2h_peak_gbs": link["d2h_gbs"],
                                  "bound_ops_per_s_per_gpu": link["bound_ops_per_s"],
+                                 "h2d_all_ranks_concurrent_gbs": link.get("h2d_all_ranks_concurrent_gbs"),
+                                 "d2h_all_ranks_concurrent_gbs": link.get("d2h_all_ranks_concurrent_gbs"),
                                  "frac": e2e_value / world / link["bound_ops_per_s"],
-                                 "note": "1 MiB in + 0.5 MiB out per multiply+relinearize: the end-to-end rate is the host link's, not the kernels'"}},
+                                 "note": "1 MiB in + 0.5 MiB out per multiply+relinearize: the end-to-end rate is the host link's, not the kernels'; the peaks are measured with every rank copying at once (GPUs behind one PCIe switch share its uplink)"}},
             "e2e_host_slab": {"value": slab_value, "unit": "ops/s", "path": "b200_multiply_relin_host (layer-1 C ABI, include/b200_bfv.h)",
                               "h2d_bytes_per_step": 2 * B * ct_bytes * pack_num // 8, "d2h_bytes_per_step": B * ct_bytes * pack_num // 8,
                               "transfer": "6-byte packed residues" if pack_num == 6 else "8-byte words",

@@ -418,6 +418,51 @@ __global__ void ksmoddown_kernel(const PrimeDev *primes, int special_idx, const 
     ksmoddown_coeff<K>(primes, SP, inv_qsp, acc, n, base, d, c);
 }
 
+// the same, two adjacent coefficients per thread: 128-bit loads / stores (the kernel is a pure stream of 2(k+1) + k rows in,
+// 2k rows out per item)
+template <int K>
+__global__ void ksmoddown_kernel_v2(const PrimeDev *primes, int special_idx, const u64 *inv_qsp, const u64 *ks2,
+                                    const u64 *base0, long long base0_stride, const u64 *base1, long long base1_stride,
+                                    u64 *dst, long long dst_item_stride, long long n, long long total)
+{
+    const long long idx = GLOBAL_IDX();
+    if (idx >= total)
+        return;
+    const long long hn = n >> 1;
+    const long long c = (idx % hn) * 2;
+    const long long t = idx / hn;
+    const int comp = (int)(t & 1);
+    const long long item = t >> 1;
+    const PrimeDev SP = ld_prime(&primes[special_idx]);
+    const u64 *acc = ks2 + ((item * 2 + comp) * (K + 1)) * n + c;
+    const u64 *base = comp == 0 ? (base0 ? base0 + item * base0_stride : nullptr) : (base1 ? base1 + item * base1_stride : nullptr);
+    u64 *d = dst + item * dst_item_stride + (long long)comp * K * n + c;
+    const u64 half = SP.p >> 1;
+    const b200_u64x2 sp = ldg2(acc + (long long)K * n);
+    u64 s0 = sp.x + half, s1 = sp.y + half;
+    s0 = s0 >= SP.p ? s0 - SP.p : s0;
+    s1 = s1 >= SP.p ? s1 - SP.p : s1;
+#pragma unroll
+    for (int i = 0; i < K; i++)
+    {
+        const PrimeDev Q = ld_prime(&primes[i]);
+        const u64 h = barrett64(half, Q.p, Q.r1);
+        const u64 w = B200_LDG(&inv_qsp[2 * i]), wq = B200_LDG(&inv_qsp[2 * i + 1]);
+        const b200_u64x2 a = ldg2(acc + (long long)i * n);
+        u64 v0 = a.x + (Q.p - barrett64(s0, Q.p, Q.r1)) + h; // (a - r + h) mod q without underflow: < 3q
+        u64 v1 = a.y + (Q.p - barrett64(s1, Q.p, Q.r1)) + h;
+        v0 = shoup_mul(v0, w, wq, Q.p);
+        v1 = shoup_mul(v1, w, wq, Q.p);
+        if (base)
+        {
+            const b200_u64x2 b = ldg2(base + c + (long long)i * n);
+            v0 = add_mod(v0, b.x, Q.p);
+            v1 = add_mod(v1, b.y, Q.p);
+        }
+        stg2(d + (long long)i * n, v0, v1);
+    }
+}
+
 template <int K>
 __global__ void modswitch_kernel(const PrimeDev *primes, const u64 *inv_qlast, const u64 *src, u64 *dst, long long n,
                                  long long total)
@@ -1277,7 +1322,9 @@ static int launch_ntt(b200_ctx *ctx, const JobDesc &jd, const u64 *src, long lon
         // n = 8192: 256 threads x 3 CTAs/SM is the throughput configuration; a launch that cannot fill the SMs anyway (the
         // per-handle path: at most 36 polynomials) is latency-bound and finishes sooner with 512 threads per polynomial
         static const int nt_env = std::getenv("B200_NTT_NT") ? atoi(std::getenv("B200_NTT_NT")) : 0;
-        const int var_env = g_ntt_var.load(std::memory_order_relaxed);
+        int var_env = g_ntt_var.load(std::memory_order_relaxed);
+        if (var_env < 0) // automatic: the streaming (persistent) variant where it measured faster — the n = 16384 inverse transform,
+            var_env = (ctx->logn == 14 && !FWD) ? 16 : 0; // whose single CTA per SM has no neighbour to hide its input wait (profiles/r2_ntt_variants.txt)
         const int nt13 = nt_env ? nt_env : (blocks <= 2LL * ctx->sm_count ? 512 : 256);
         const int nt = ctx->logn == 12 ? 256 : ctx->logn == 13 ? (nt13 == 256 ? 256 : 512) : 1024;
         int var = ta && ta->mode ? (var_env & 1) : var_env; // the fused-tensor copy-in exists in the plain variants only
@@ -1717,8 +1764,8 @@ static int keyswitch_core(b200_ctx *ctx, int level, const u64 *d, long long d_st
             return rc;
     }
     {
-        const long long total = batch * 2 * n;
-        DISPATCH_K(k, B200_LAUNCH(ksmoddown_kernel<KK>, blocks_for(total, EB), EB, 0, s, ctx->d_primes, special, ctx->d_inv_qsp, ks2,
+        const long long total = batch * 2 * (n >> 1);
+        DISPATCH_K(k, B200_LAUNCH(ksmoddown_kernel_v2<KK>, blocks_for(total, EB), EB, 0, s, ctx->d_primes, special, ctx->d_inv_qsp, ks2,
                                                                                 base0, base0_stride, base1, base1_stride,
                                                                                 dst, dst_stride, n, total));
         ctx->launches++;

@@ -14,5 +14,5 @@ int b200_ntt_fp_setup(int smem_optin);
 #endif
 // variant launched when B200_NTT_VAR is not set
 #ifndef B200_NTT_DEFAULT_VAR
-#define B200_NTT_DEFAULT_VAR 0
+#define B200_NTT_DEFAULT_VAR (-1) /* automatic choice per size and direction (launch_ntt) */
 #endif

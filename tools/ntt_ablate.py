@@ -65,5 +65,5 @@ for spec in variants:
     f = timed(lambda: ctx.ntt_forward(x, items, stream=s))
     i_ = timed(lambda: ctx.ntt_inverse(x, items, stream=s))
     print(f"VAR {str(spec):>8s}: fwd {f:.3f} ms {bytes_ / f / 1e6:6.0f} GB/s | inv {i_:.3f} ms {bytes_ / i_ / 1e6:6.0f} GB/s{note}", flush=True)
-lib.lib.b200_debug_ntt_variant(0)
+lib.lib.b200_debug_ntt_variant(-1)
 lib.lib.b200_debug_ntt_stagger(0)
