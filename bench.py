@@ -236,8 +236,10 @@ class PluginLegs:
     def _ptr(self, t):
         return self.C.cast(t.data_ptr(), self.C.POINTER(self.u64))
 
-    def batch_step(self, ah, bh, oh, B):
-        """host words -> handles -> MultiplyRelinBatch -> host words, chunks of the batch driven by worker threads"""
+    def batch_step(self, abh, oh, B):
+        """host words -> handles -> MultiplyRelinBatch -> host words, chunks of the batch driven by worker threads.
+        abh: pinned (chunks, 2, chunk, 2, k, n) — per chunk the first operands, then the second operands, so that ONE
+        B200_Ciphertext_SetWordsBatch call (one transfer) loads both operand sets of a chunk."""
         S, O, u64, C = self.S, self.O, self.u64, self.C
         chunks = [(lo, min(lo + self.chunk, B)) for lo in range(0, B, self.chunk)]
         errs = []
@@ -247,12 +249,11 @@ class PluginLegs:
                 for ci in range(tid, len(chunks), self.threads):
                     lo, hi = chunks[ci]
                     cnt = hi - lo
-                    A = self._arr(self._handles(("a", ci), cnt))
-                    Bh = self._arr(self._handles(("b", ci), cnt))
+                    ha, hb = self._handles(("a", ci), cnt), self._handles(("b", ci), cnt)
                     D = self._arr(self._handles(("d", ci), cnt))
-                    S.call("B200_Ciphertext_SetWordsBatch", O.ctx, u64(cnt), A, O.first_id, u64(2), C.c_bool(False), self._ptr(ah[lo]))
-                    S.call("B200_Ciphertext_SetWordsBatch", O.ctx, u64(cnt), Bh, O.first_id, u64(2), C.c_bool(False), self._ptr(bh[lo]))
-                    S.call("B200_Evaluator_MultiplyRelinBatch", O.ev, u64(cnt), A, Bh, self.rlk, D)
+                    S.call("B200_Ciphertext_SetWordsBatch", O.ctx, u64(2 * cnt), self._arr(ha + hb), O.first_id, u64(2), C.c_bool(False),
+                           self._ptr(abh[ci]))
+                    S.call("B200_Evaluator_MultiplyRelinBatch", O.ev, u64(cnt), self._arr(ha), self._arr(hb), self.rlk, D)
                     S.call("B200_Ciphertext_GetWordsBatch", O.ctx, u64(cnt), D, self._ptr(oh[lo]), u64(cnt * 2 * self.k * self.n))
             except Exception as ex:  # surfaced by the caller
                 errs.append(ex)
@@ -496,11 +497,16 @@ def main():
         os.environ["B200_DEVICE"] = str(local)  # the SEAL-named layer creates its own device context: same GPU as this rank
         plug = PluginLegs(ctx, local, k, n, rlk)
         oh.zero_()
-        plug.batch_step(ah, bh, oh, B)  # warm (allocates the handles' device buffers)
+        assert B % plug.chunk == 0, "batch must be a multiple of the e2e chunk"
+        # the caller's host layout: per chunk, its first operands followed by its second operands (one transfer per chunk)
+        abh = torch.empty((B // plug.chunk, 2, plug.chunk, 2, k, n), dtype=torch.int64).pin_memory()
+        abh[:, 0].copy_(ah.view(B // plug.chunk, plug.chunk, 2, k, n))
+        abh[:, 1].copy_(bh.view(B // plug.chunk, plug.chunk, 2, k, n))
+        plug.batch_step(abh, oh, B)  # warm (allocates the handles' device buffers)
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            plug.batch_step(ah, bh, oh, B)
+            plug.batch_step(abh, oh, B)
         plug_s = wall_max(time.perf_counter() - t0)
         e2e_value = world * B * e2e_steps / plug_s
         same = bool(torch.equal(oh.to(dev), out))

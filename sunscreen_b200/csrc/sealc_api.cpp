@@ -138,6 +138,7 @@ using CombineReq = Context_::CombineReq;
 
 void multiply_direct(Context_ *c, Ciphertext_ &a, Ciphertext_ &b, Ciphertext_ &dst, bool square, int lv);
 void relinearize_direct(Context_ *c, Ciphertext_ &a, KSwitchKeys_ &keys, Ciphertext_ &dst, int lv);
+void op_galois(Context_ *c, Ciphertext_ &a, uint32_t elt, KSwitchKeys_ &keys, Ciphertext_ &dst);
 
 static void combine_run_one(Context_ *c, CombineReq &r)
 {
@@ -145,8 +146,13 @@ static void combine_run_one(Context_ *c, CombineReq &r)
     {
         if (r.kind == 0)
             multiply_direct(c, *r.a, *r.b, *r.dst, false, r.lv);
-        else
+        else if (r.kind == 1)
             relinearize_direct(c, *r.a, *r.keys, *r.dst, r.lv);
+        else
+        {
+            OpScope scope(c);
+            op_galois(c, *r.a, r.elt, *r.keys, *r.dst);
+        }
     }
     catch (...)
     {
@@ -198,7 +204,7 @@ static void combine_run_batch(Context_ *c, std::vector<CombineReq *> &batch)
         // destinations are only written by the final scatter, after every operand has been gathered: aliasing is harmless.
         // An operand that IS a destination keeps its buffer (prepare_output reuses it when the capacity suffices); when the
         // shapes differ the old buffer is released in stream order, after the gather that reads it.
-        const u64 *key = r0.kind == 1 ? r0.keys->flat_dev(c, 0, (int)k) : nullptr;
+        const u64 *key = r0.kind == 0 ? nullptr : r0.keys->flat_dev(c, r0.kind == 1 ? 0 : r0.key_index, (int)k);
         auto enqueue = [&]() {
             void *pin = nullptr, *pout = nullptr;
             dev_check(b200_malloc_async(c->dev, operands * NP * win * sizeof(u64), &pin, cur_stream()));
@@ -206,8 +212,9 @@ static void combine_run_batch(Context_ *c, std::vector<CombineReq *> &batch)
             u64 *in = (u64 *)pin, *out = (u64 *)pout;
             int rc = b200_gather_scatter_table(c->dev, tab, operands * NP, in, win, 1, cur_stream());
             if (!rc)
-                rc = r0.kind == 0 ? b200_multiply(c->dev, lv, in, 2, in + NP * win, 2, out, NP, cur_stream())
-                                  : b200_relinearize(c->dev, lv, in, key, out, NP, cur_stream());
+                rc = r0.kind == 0   ? b200_multiply(c->dev, lv, in, 2, in + NP * win, 2, out, NP, cur_stream())
+                     : r0.kind == 1 ? b200_relinearize(c->dev, lv, in, key, out, NP, cur_stream())
+                                    : b200_apply_galois(c->dev, lv, in, r0.elt, key, out, NP, cur_stream());
             if (!rc)
                 rc = b200_gather_scatter_table(c->dev, dtab, NP, out, wout, 0, cur_stream());
             if (!rc && c->check_transparent)
@@ -237,8 +244,9 @@ static void combine_run_batch(Context_ *c, std::vector<CombineReq *> &batch)
             u64 *in = (u64 *)pin, *out = (u64 *)pout;
             int rc = b200_gather_scatter_table(c->dev, tab, operands * N, in, win, 1, cur_stream());
             if (!rc)
-                rc = r0.kind == 0 ? b200_multiply(c->dev, lv, in, 2, in + N * win, 2, out, N, cur_stream())
-                                  : b200_relinearize(c->dev, lv, in, key, out, N, cur_stream());
+                rc = r0.kind == 0   ? b200_multiply(c->dev, lv, in, 2, in + N * win, 2, out, N, cur_stream())
+                     : r0.kind == 1 ? b200_relinearize(c->dev, lv, in, key, out, N, cur_stream())
+                                    : b200_apply_galois(c->dev, lv, in, r0.elt, key, out, N, cur_stream());
             for (size_t i = 0; i < N; i++)
                 dtab[i] = batch[i]->dst->prepare_output(c, c->ids[lv], out_polys, k);
             if (!rc)
@@ -255,7 +263,7 @@ static void combine_run_batch(Context_ *c, std::vector<CombineReq *> &batch)
                 dtab[i] = i < N ? batch[i]->dst->prepare_output(c, c->ids[lv], out_polys, k) : lane.pad_out;
             Context_::Lane::Graph *g = nullptr;
             for (auto &e : lane.graphs)
-                if ((e.kind == r0.kind || e.kind == -1 - r0.kind) && e.lv == lv && e.n == NP && e.key == (const void *)key)
+                if ((e.kind == r0.kind || e.kind == -1 - r0.kind) && e.lv == lv && e.n == NP && e.key == (const void *)key && e.elt == r0.elt)
                     g = &e;
             if (!g)
             { // first sight of this shape on this lane: run it kernel by kernel (this also warms every cache the sequence touches)
@@ -269,7 +277,7 @@ static void combine_run_batch(Context_ *c, std::vector<CombineReq *> &batch)
                         b200_graph_destroy(c->dev, lane.graphs[old].exec);
                     lane.graphs.erase(lane.graphs.begin() + (long)old);
                 }
-                lane.graphs.push_back({ r0.kind, lv, NP, (const void *)key, nullptr, ++lane.clock });
+                lane.graphs.push_back({ r0.kind, lv, NP, (const void *)key, nullptr, ++lane.clock, r0.elt });
                 dev_check(enqueue());
             }
             else
@@ -513,6 +521,37 @@ std::vector<int> naf(int value)
             res.push_back((sign ? -zi : zi) * (1 << i));
     }
     return res;
+}
+
+// One application of a Galois automorphism whose key is present, through the combiner (same checks, same errors as op_galois);
+// false: not combinable here (combining off, nested call) — the caller takes the direct path.
+bool galois_combined(Context_ *c, Ciphertext_ &a, uint32_t elt, KSwitchKeys_ &keys, Ciphertext_ &dst)
+{
+    if (!c->combine || tl_scope)
+        return false;
+    int lv = data_level(c, a, "encrypted is not valid for encryption parameters");
+    if (keys.parms_id != c->ids[0])
+        throw InvalidArg("galois_keys is not valid for encryption parameters");
+    if (!(elt & 1) || elt >= 2 * c->parms.n)
+        throw InvalidArg("Galois element is not valid");
+    if (a.size > 2)
+        throw InvalidArg("encrypted size must be 2");
+    const size_t index = (elt - 1) >> 1;
+    if (index >= keys.keys.size() || keys.keys[index].empty())
+        throw InvalidArg("Galois key not present");
+    check_keys(c, keys, index);
+    if (keys.keys[index].size() < (size_t)a.k || a.is_ntt_form)
+        return false; // let the direct path report it
+    CombineReq r;
+    r.kind = 2;
+    r.a = &a;
+    r.dst = &dst;
+    r.keys = &keys;
+    r.key_index = index;
+    r.elt = elt;
+    r.lv = lv;
+    combine_submit(c, r);
+    return true;
 }
 
 void op_rotate(Context_ *c, Ciphertext_ &a, int steps, KSwitchKeys_ &keys, Ciphertext_ &dst)
@@ -1921,8 +1960,19 @@ long Evaluator_RotateRows(void *p, void *a, int steps, void *keys, void *dst, vo
     NULLRET(dst);
     auto *c = ((Evaluator_ *)p)->ctx;
     return guard([&] {
+        auto &K = *(KSwitchKeys_ *)keys;
+        if (c->combine && c->using_batching && K.parms_id == c->ids[0] && steps != 0)
+        { // a rotation whose key is present is one key switch: concurrent ones are combined like multiply / relinearize
+            uint32_t elt = 0;
+            if (b200_galois_elt_from_step(c->dev, steps, &elt) == 0)
+            {
+                const size_t idx = (elt - 1) >> 1;
+                if (idx < K.keys.size() && !K.keys[idx].empty() && galois_combined(c, *(Ciphertext_ *)a, elt, K, *(Ciphertext_ *)dst))
+                    return;
+            }
+        }
         OpScope scope(c);
-        op_rotate(c, *(Ciphertext_ *)a, steps, *(KSwitchKeys_ *)keys, *(Ciphertext_ *)dst);
+        op_rotate(c, *(Ciphertext_ *)a, steps, K, *(Ciphertext_ *)dst);
     });
 }
 long Evaluator_RotateColumns(void *p, void *a, void *keys, void *dst, void *)
@@ -1933,9 +1983,11 @@ long Evaluator_RotateColumns(void *p, void *a, void *keys, void *dst, void *)
     NULLRET(dst);
     auto *c = ((Evaluator_ *)p)->ctx;
     return guard([&] {
-        OpScope scope(c);
         if (!c->using_batching)
             throw LogicErr("encryption parameters do not support batching");
+        if (galois_combined(c, *(Ciphertext_ *)a, (uint32_t)(2 * c->parms.n - 1), *(KSwitchKeys_ *)keys, *(Ciphertext_ *)dst))
+            return;
+        OpScope scope(c);
         op_galois(c, *(Ciphertext_ *)a, (uint32_t)(2 * c->parms.n - 1), *(KSwitchKeys_ *)keys, *(Ciphertext_ *)dst);
     });
 }

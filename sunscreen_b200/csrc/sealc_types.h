@@ -135,6 +135,7 @@ struct Context_
             const void *key;
             void *exec;   // nullptr: seen once (caches are warm), capture on the next use
             uint64_t stamp;
+            uint32_t elt; // Galois element (rotations)
         };
         std::vector<Graph> graphs;
         uint64_t clock = 0;

@@ -1151,11 +1151,16 @@ def concurrent_evaluator_calls(S, n, moduli, t, threads=8, rounds=6):
     cts = [OL.load("Ciphertext", RL.save("Ciphertext", R.encrypt(enc, R.new_pt(rng.integers(0, t, size=16, dtype=np.uint64))), 0)) for _ in range(4)]
     orlk = OL.load("KSwitchKeys", RL.save("KSwitchKeys", rlk, 0))
     pl = O.new_pt(rng.integers(1, t, size=9, dtype=np.uint64))
+    batching = t % (2 * n) == 1
+    glk = R.galois_keys_steps(kg, [1, 2]) if batching else None
+    oglk = OL.load("KSwitchKeys", RL.save("KSwitchKeys", glk, 0)) if batching else None
 
     def work(i):
         a, b = cts[i % 4], cts[(i + 1) % 4]
         m = O.relinearize(O.multiply(a, b), orlk)
         s = O.add(m, a)
+        if batching:  # rotations with a present key go through the combiner too (two different steps -> two batch groups)
+            s = O.rotate_rows(s, 1 + (i & 1), oglk)
         p = O.multiply_plain(s, pl)
         return OL.save("Ciphertext", O.sub(p, b), 0)
 
@@ -1184,7 +1189,10 @@ def concurrent_evaluator_calls(S, n, moduli, t, threads=8, rounds=6):
     rpl = R.new_pt(O.pt_coeffs(pl))
     for i in range(threads):
         a, b = rcts[i % 4], rcts[(i + 1) % 4]
-        exp = R.sub(R.multiply_plain(R.add(R.relinearize(R.multiply(a, b), rlk), a), rpl), b)
+        e1 = R.add(R.relinearize(R.multiply(a, b), rlk), a)
+        if batching:
+            e1 = R.rotate_rows(e1, 1 + (i & 1), glk)
+        exp = R.sub(R.multiply_plain(e1, rpl), b)
         assert RL.save("Ciphertext", exp, 0) == serial[i]
 
 

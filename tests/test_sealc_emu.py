@@ -88,6 +88,7 @@ def test_context_validation_sweep(S, ref):
 
 def test_concurrent_evaluator_calls(S, ref):
     sc.concurrent_evaluator_calls(S, *PARAMS["n4096"], threads=6, rounds=3)
+    sc.concurrent_evaluator_calls(S, *PARAMS["n8192"], threads=4, rounds=2)  # batching plain modulus: rotations too
 
 
 def test_combined_calls_isolation(S, ref):
