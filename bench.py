@@ -678,7 +678,7 @@ def main():
                        # a CPU-quota'd lease shows up here: threads >> the cores' worth of time the box grants
                        "box": quota, "parallel_speedup_over_one_thread": rate / rate1 if rate1 else None,
                        "build": "unmodified reference sources, -O3, Intel HEXL off (not buildable offline), one MemoryPool per thread",
-                       "full_node_reference": "round-1 SCALE run, same arm on an unquota'd 8-GPU node (128 threads): 3509 ops/s"}
+                       "full_node_reference": "the same arm on an 8-GPU lease (96-core cgroup quota, 128 threads): 3654 ops/s (profiles/r2_bench_reference_arm_fullnode.json)"}
             except Exception as ex:  # reference .so missing on this box
                 cpu = {"value": None, "unit": "ops/s", "cores": os.cpu_count(), "kind": "reference",
                        "sample": f"unavailable: {ex}"}

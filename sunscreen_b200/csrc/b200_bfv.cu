@@ -1,7 +1,7 @@
 // b200_bfv.cu — CUDA kernels (sm_100a), device context and the layer-1 C ABI (include/b200_bfv.h).
 //
 // One process drives one GPU.  All work is enqueued on the caller's stream; temporaries come from the
-// stream-ordered allocator (cudaMallocAsync), so back-to-back calls never synchronise with the host.
+// context-private stream-ordered pool (cudaMallocFromPoolAsync), so back-to-back calls never synchronise with the host.
 // There is deliberately no CPU execution path in this library: if CUDA is unavailable every entry point
 // returns B200_E_CUDA.
 #include "../../include/b200_bfv.h"

@@ -205,12 +205,14 @@ static void combine_run_batch(Context_ *c, std::vector<CombineReq *> &batch)
         // An operand that IS a destination keeps its buffer (prepare_output reuses it when the capacity suffices); when the
         // shapes differ the old buffer is released in stream order, after the gather that reads it.
         const u64 *key = r0.kind == 0 ? nullptr : r0.keys->flat_dev(c, r0.kind == 1 ? 0 : r0.key_index, (int)k);
-        auto enqueue = [&]() {
+        auto enqueue = [&]() -> int { // never throws: it also runs inside a stream capture, which must always be ended
             void *pin = nullptr, *pout = nullptr;
-            dev_check(b200_malloc_async(c->dev, operands * NP * win * sizeof(u64), &pin, cur_stream()));
-            dev_check(b200_malloc_async(c->dev, NP * wout * sizeof(u64), &pout, cur_stream()));
+            int rc = b200_malloc_async(c->dev, operands * NP * win * sizeof(u64), &pin, cur_stream());
+            if (!rc)
+                rc = b200_malloc_async(c->dev, NP * wout * sizeof(u64), &pout, cur_stream());
             u64 *in = (u64 *)pin, *out = (u64 *)pout;
-            int rc = b200_gather_scatter_table(c->dev, tab, operands * NP, in, win, 1, cur_stream());
+            if (!rc)
+                rc = b200_gather_scatter_table(c->dev, tab, operands * NP, in, win, 1, cur_stream());
             if (!rc)
                 rc = r0.kind == 0   ? b200_multiply(c->dev, lv, in, 2, in + NP * win, 2, out, NP, cur_stream())
                      : r0.kind == 1 ? b200_relinearize(c->dev, lv, in, key, out, NP, cur_stream())
@@ -219,8 +221,10 @@ static void combine_run_batch(Context_ *c, std::vector<CombineReq *> &batch)
                 rc = b200_gather_scatter_table(c->dev, dtab, NP, out, wout, 0, cur_stream());
             if (!rc && c->check_transparent)
                 rc = b200_any_nonzero(c->dev, lv, out, (int)out_polys, flags, NP, cur_stream());
-            b200_free_async(c->dev, pin, cur_stream());
-            b200_free_async(c->dev, pout, cur_stream());
+            if (pin)
+                b200_free_async(c->dev, pin, cur_stream());
+            if (pout)
+                b200_free_async(c->dev, pout, cur_stream());
             return rc;
         };
         // the gather must read an aliased operand before prepare_output may release its buffer: when a destination is also

@@ -55,6 +55,43 @@ def test_batched_multiply_relin_seam(S, ref):
         assert np.array_equal(O.ct_words(d), e)
 
 
+def test_bulk_word_access_with_device_buffers(S, ref):
+    """B200_Ciphertext_{Set,Get}WordsBatch accept device-resident buffers too (the multi-GPU split hands each rank its
+    slice as an NCCL-scattered device tensor, tools/chi_sq_sharded.py): same words as the host-buffer form, and the result
+    of MultiplyRelinBatch read back into a device tensor equals the reference's."""
+    import numpy as np
+    import refseal
+    import torch
+    n, moduli, t = PARAMS["n8192"]
+    R = refseal.RefContext(n, moduli, t)
+    O = S.context(n, moduli, t)
+    inp = refseal.appendix_b_inputs(n, moduli, t)
+    rng = np.random.default_rng(8)
+    cnt = 3
+    A = np.stack([np.stack([rng.integers(0, moduli[r], size=(2, n), dtype=np.uint64) for r in range(O.k)], axis=1) for _ in range(cnt)])
+    B = np.stack([np.stack([rng.integers(0, moduli[r], size=(2, n), dtype=np.uint64) for r in range(O.k)], axis=1) for _ in range(cnt)])
+    vp, u64 = C.c_void_p, C.c_uint64
+    arr = lambda hs: (vp * len(hs))(*hs)
+    dptr = lambda tsr: C.cast(tsr.data_ptr(), C.POINTER(u64))
+    dA = torch.from_numpy(A.view(np.int64)).cuda()
+    dB = torch.from_numpy(B.view(np.int64)).cuda()
+    torch.cuda.synchronize()
+    ha, hb, hd = ([O._dst() for _ in range(cnt)] for _ in range(3))
+    S.call("B200_Ciphertext_SetWordsBatch", O.ctx, u64(cnt), arr(ha), O.first_id, u64(2), C.c_bool(False), dptr(dA))
+    S.call("B200_Ciphertext_SetWordsBatch", O.ctx, u64(cnt), arr(hb), O.first_id, u64(2), C.c_bool(False), dptr(dB))
+    for i in range(cnt):
+        assert np.array_equal(O.ct_words(ha[i]), A[i]) and np.array_equal(O.ct_words(hb[i]), B[i])
+    rlk = O.new_ksk({0: inp["rlk"]})
+    S.call("B200_Evaluator_MultiplyRelinBatch", O.ev, u64(cnt), arr(ha), arr(hb), rlk, arr(hd))
+    out = torch.zeros((cnt, 2, O.k, n), dtype=torch.int64, device="cuda")
+    S.call("B200_Ciphertext_GetWordsBatch", O.ctx, u64(cnt), arr(hd), dptr(out), u64(out.numel()))
+    got = out.cpu().numpy().view(np.uint64)
+    rrlk = R.new_ksk({0: inp["rlk"]})
+    for i in range(cnt):
+        exp = R.ct_words(R.relinearize(R.multiply(R.new_ct(A[i]), R.new_ct(B[i])), rrlk))
+        assert np.array_equal(got[i], exp), f"item {i}"
+
+
 @pytest.mark.parametrize("name", ["n4096", "n8192"])
 def test_seeded_encryption_matches_reference(S, ref, name):
     sc.seeded_encryption_parity(S, *PARAMS[name])
