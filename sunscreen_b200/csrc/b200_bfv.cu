@@ -1323,8 +1323,16 @@ static int launch_ntt(b200_ctx *ctx, const JobDesc &jd, const u64 *src, long lon
         // per-handle path: at most 36 polynomials) is latency-bound and finishes sooner with 512 threads per polynomial
         static const int nt_env = std::getenv("B200_NTT_NT") ? atoi(std::getenv("B200_NTT_NT")) : 0;
         int var_env = g_ntt_var.load(std::memory_order_relaxed);
-        if (var_env < 0) // automatic: the streaming (persistent) variant where it measured faster — the n = 16384 inverse transform,
-            var_env = (ctx->logn == 14 && !FWD) ? 16 : 0; // whose single CTA per SM has no neighbour to hide its input wait (profiles/r2_ntt_variants.txt)
+        if (var_env < 0)
+        { // automatic: what measured fastest per size and direction (profiles/r2_ntt_variants.txt).  2048 = warp(-group)-private
+          // sub-transforms, +1 = first 512 twiddles in shared memory, +16 = streaming (persistent) kernel
+            if (ctx->logn == 14)
+                var_env = FWD ? 2049 : 2064;
+            else if (ctx->logn == 13)
+                var_env = FWD ? 2048 : 2049;
+            else
+                var_env = 2048;
+        }
         const int nt13 = nt_env ? nt_env : (blocks <= 2LL * ctx->sm_count ? 512 : 256);
         const int nt = ctx->logn == 12 ? 256 : ctx->logn == 13 ? (nt13 == 256 ? 256 : 512) : 1024;
         int var = ta && ta->mode ? (var_env & 1) : var_env; // the fused-tensor copy-in exists in the plain variants only

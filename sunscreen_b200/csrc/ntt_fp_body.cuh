@@ -482,6 +482,24 @@ struct NttFpStaticPass
         // VAR & 16: streaming (persistent) kernel — the polynomial's raw words are ALREADY on their way into shared memory when a
         // pass sequence starts (requested during the previous polynomial's last pass, into slots that pass had finished with)
         constexpr bool STREAM = (VAR & 16) != 0;
+        // VAR & 2048: warp-private sub-transforms.  After the first forward pass (radix 2^L0) the polynomial falls apart into 2^L0
+        // independent blocks of N >> L0 points; with the blocks divided evenly among the warps each warp owns its block(s) for the remaining passes, so
+        // those passes (and the write-out of the block) need only __syncwarp — one block-wide barrier per polynomial instead of
+        // four — and the block's early-pass twiddles are warp-uniform.  The inverse mirrors it (warp-private until the last pass).
+        // With more warps than blocks (n = 16384: 32 warps, 8 blocks) a block belongs to a GROUP of warps that synchronises on its
+        // own named barrier: eight independent four-warp groups inside the one CTA an SM can hold.
+        constexpr int WP_BLOCKS = 1 << NttSchedL<LOGN, 0>::value, WP_WARPS = NT / 32;
+        constexpr int WP_TG = WP_WARPS > WP_BLOCKS ? 32 * (WP_WARPS / WP_BLOCKS) : 32; // threads of one group
+        constexpr int WP_NG = NT / WP_TG;                                               // groups in the CTA (<= 15 named barriers)
+        constexpr bool WP = (VAR & 2048) != 0 && (WP_BLOCKS % WP_NG) == 0 && WP_NG <= 15 && !(STREAM && FWD);
+        constexpr bool WPSTEP = WP && (FWD ? STEP >= 1 : STEP + 1 < NP); // this pass runs group-private
+        const int wlane = tid % WP_TG, wwarp = tid / WP_TG;                // position inside the group, group index
+        auto wp_sync = [&]() {
+            if constexpr (WP_TG == 32)
+                __syncwarp();
+            else
+                asm volatile("bar.sync %0, %1;" ::"r"(1 + wwarp), "r"(WP_TG) : "memory");
+        };
         constexpr bool SG = EDGE_IN && LOGS >= 5 && B200_NTT_DIRECT_IN && !STREAM, DG = EDGE_OUT && LOGS >= 5 && !(VAR & 128); // 128: always stage the output
         constexpr bool TW16 = (L == 4 && LOGS == 0);
         constexpr int TWSRC = (VAR & 2) ? 2 : ((VAR & 1) && !TW16 && (1 << (DONE + L)) <= B200_NTT_TWS_ENTRIES) ? 1 : 0;
@@ -555,6 +573,19 @@ struct NttFpStaticPass
                     for (int it = 0; it < N / NT; it++)
                         smd[ptid + it * PNT] = __longlong_as_double((long long)(tid + it * NT));
                 }
+                else if (WP && !FWD && !STREAM)
+                { // warp-private: the warp lands its OWN block (the first passes of the inverse stay inside it)
+                    constexpr int BS = N / WP_NG;
+#pragma unroll
+                    for (int r = 0; r < BS / WP_TG; r++)
+                    {
+                        const int e = wwarp * BS + wlane + WP_TG * r;
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smd + ntt_pad(e))), "l"(src + e)
+                                     : "memory");
+                    }
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                }
                 else
                 {
 #pragma unroll
@@ -565,7 +596,10 @@ struct NttFpStaticPass
                     asm volatile("cp.async.wait_group 0;" ::: "memory");
                 }
             }
-            __syncthreads();
+            if (WP && !FWD && !STREAM && !job.tensor_mode && !(ABL & 2)) // (streaming: the block was requested by other threads)
+                wp_sync();
+            else
+                __syncthreads();
             if (job.timeline && tid == 0)
             {
                 unsigned long long t;
@@ -576,6 +610,8 @@ struct NttFpStaticPass
         constexpr bool RAW = EDGE_IN && !SG; // (the tensor-fused copy-in writes doubles: handled by the run-time flag below)
         // renormalisation / input reduction are block-uniform run-time flags: branch ONCE to a compile-time variant
         // (as predicated code they cost 12 FP64 ops and ~10 IMADs per element whether needed or not)
+        // group handled by this thread in iteration `it`: block-strided by default, inside the warp's own block when warp-private
+        auto gidx = [&](int it) { return WPSTEP ? wwarp * (NGROUPS / WP_NG) + wlane + WP_TG * it : tid + it * NT; };
         auto groups = [&](auto RN, auto RD) {
             if constexpr (STREAM && FWD && EDGE_OUT && !DG)
             {
@@ -655,13 +691,13 @@ struct NttFpStaticPass
                             for (int j = 0; j < R; j++)
                                 dstv[j] = (u64)__double_as_longlong(smd[fp_elem_index(pb_, b_, j, LOGS)]);
                         };
-                        fetch(xc, tid);
+                        fetch(xc, gidx(0));
 #pragma unroll
                         for (int it = 0; it < ITERS; it++)
                         {
-                            const int g = tid + it * NT;
+                            const int g = gidx(it);
                             if (it + 1 < ITERS)
-                                fetch(xn, g + NT);
+                                fetch(xn, gidx(it + 1));
                             ntt_fp_group<L, FWD, false, DG, TW16, decltype(RN)::value, false, true, false, false, TWSRC, ABL, STREAM && !FWD && DG>(
                                 smd, src, dst, g, LOGS, LOGN, M, P, true, !FWD && EDGE_OUT, true, PI_.p, PI_.ratio1, xc, nullptr, stw, nsrc);
 #pragma unroll
@@ -676,13 +712,13 @@ struct NttFpStaticPass
                         constexpr int R = 1 << L;
                         const double *__restrict__ twt = FWD ? P.fwd : P.inv;
                         double twc[R - 1], twn[R - 1];
-                        fp_load_group_tw<L, FWD, false>(twc, twt, tid, tid >> LOGS, LOGS, LOGN, M, 0, P, !FWD && EDGE_OUT);
+                        fp_load_group_tw<L, FWD, false>(twc, twt, gidx(0), gidx(0) >> LOGS, LOGS, LOGN, M, 0, P, !FWD && EDGE_OUT);
 #pragma unroll
                         for (int it = 0; it < ITERS; it++)
                         {
-                            const int g = tid + it * NT;
+                            const int g = gidx(it);
                             if (it + 1 < ITERS)
-                                fp_load_group_tw<L, FWD, false>(twn, twt, g + NT, (g + NT) >> LOGS, LOGS, LOGN, M, 0, P, !FWD && EDGE_OUT);
+                                fp_load_group_tw<L, FWD, false>(twn, twt, gidx(it + 1), gidx(it + 1) >> LOGS, LOGS, LOGN, M, 0, P, !FWD && EDGE_OUT);
                             ntt_fp_group<L, FWD, SG, DG, TW16, decltype(RN)::value, decltype(RD)::value, false, decltype(RAWF)::value, true, 0, ABL,
                                          STREAM && !FWD && DG>(
                                 smd, src, dst, g, LOGS, LOGN, M, P, true, !FWD && EDGE_OUT, true, PI_.p, PI_.ratio1, nullptr, twc, nullptr, nsrc);
@@ -696,7 +732,7 @@ struct NttFpStaticPass
 #pragma unroll
                         for (int it = 0; it < ITERS; it++)
                         {
-                            const int g = tid + it * NT;
+                            const int g = gidx(it);
                             if (NGROUPS % NT == 0 || g < NGROUPS)
                                 ntt_fp_group<L, FWD, SG, DG, TW16, decltype(RN)::value, decltype(RD)::value, false, decltype(RAWF)::value, false, TWSRC, ABL,
                                              STREAM && !FWD && DG>(
@@ -729,7 +765,9 @@ struct NttFpStaticPass
             else
                 groups(std::false_type{}, std::false_type{});
         }
-        if (!(STREAM && EDGE_OUT)) // (the streaming kernel's next polynomial starts with wait_all + barrier)
+        if (WPSTEP && (FWD || STEP + 2 < NP))
+            wp_sync(); // the next pass (or the write-out) of this group touches only the group's own block(s)
+        else if (!(STREAM && EDGE_OUT)) // (the streaming kernel's next polynomial starts with wait_all + barrier)
             __syncthreads();
         if (job.timeline && tid == 0)
         {
@@ -748,6 +786,16 @@ struct NttFpStaticPass
                     const int pe = ntt_pad(e);
                     const u64 v0 = fp_to_canonical<true>(smd[pe], P.p, P.pinv), v1 = fp_to_canonical<true>(smd[pe + 1], P.p, P.pinv);
                     __stcs(reinterpret_cast<ulonglong2 *>(dst + e), make_ulonglong2(v0, v1));
+                }
+            }
+            else if constexpr (WP)
+            { // the warp writes its own block out as soon as its last pass is done (no block-wide barrier before this)
+                constexpr int BS = N / WP_NG;
+#pragma unroll
+                for (int r = 0; r < BS / WP_TG; r++)
+                {
+                    const int e = wwarp * BS + wlane + WP_TG * r;
+                    dst[e] = fp_to_canonical<true>(smd[ntt_pad(e)], P.p, P.pinv);
                 }
             }
             else

@@ -115,7 +115,9 @@ __global__ void __launch_bounds__(NT, (LOGN <= 13 ? (NT <= 256 ? 3 : 2) : 1)) nt
     X(13, 256, 0) X(13, 256, 1) X(13, 512, 0) X(13, 512, 1)                                                            \
     X(14, 1024, 0) X(14, 1024, 1)                                                                                      \
     /* developer ablations (tools/ntt_ablate.py), n = 8192 throughput configuration only */                            \
-    X(13, 256, 2) X(13, 256, 4) X(13, 256, 6) X(13, 256, 8) X(13, 256, 14) X(13, 256, 32) X(13, 256, 64) X(13, 256, 128) X(13, 256, 256) X(13, 256, 384) X(13, 256, 512) X(13, 256, 896) X(13, 256, 1024) X(13, 256, 1025)                                             \
+    X(13, 256, 2) X(13, 256, 4) X(13, 256, 6) X(13, 256, 8) X(13, 256, 14) X(13, 256, 32) X(13, 256, 64) X(13, 256, 128) X(13, 256, 256) X(13, 256, 384) X(13, 256, 512) X(13, 256, 896) X(13, 256, 1024) X(13, 256, 1025)                                                                           \
+    /* warp-private sub-transforms (+ streaming inverse) */                                                             \
+    X(12, 256, 2048) X(12, 256, 2049) X(13, 512, 2048) X(13, 512, 2049) X(13, 256, 2048) X(13, 256, 2064) X(13, 256, 2049) X(14, 1024, 2048) X(14, 1024, 2049) X(14, 1024, 2064)                                             \
     /* streaming (persistent) variant */                                                                               \
     X(12, 256, 16) X(13, 256, 16) X(14, 1024, 16)
 
