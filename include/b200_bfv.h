@@ -175,6 +175,9 @@ int b200_capture_begin(b200_ctx *ctx, void *stream);
 int b200_capture_end(b200_ctx *ctx, void *stream, void **graph_exec);
 int b200_graph_launch(b200_ctx *ctx, void *graph_exec, void *stream);
 int b200_graph_destroy(b200_ctx *ctx, void *graph_exec);
+/* wait for `stream` without spinning (blocking-sync event cached in *event_slot; release it with b200_event_destroy) */
+int b200_stream_synchronize_blocking(b200_ctx *ctx, void *stream, void **event_slot);
+int b200_event_destroy(b200_ctx *ctx, void *event);
 /* make the context's GPU the calling thread's current device (new host threads start on device 0) */
 int b200_bind_thread(b200_ctx *ctx);
 /* stream-ordered allocation for work enqueued on `stream` afterwards (release with b200_free_async on the same stream) */

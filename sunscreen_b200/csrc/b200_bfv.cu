@@ -2296,6 +2296,30 @@ int b200_graph_destroy(b200_ctx *ctx, void *graph_exec)
     return 0;
 }
 
+// Wait for `stream` WITHOUT spinning: the calling thread sleeps on a blocking-sync event until the work is done.  For waits of
+// milliseconds (the batch seams: transfers of tens of MiB) — many caller threads that spin in cudaStreamSynchronize burn one core each,
+// and on a CPU-quota'd host that gets the whole process throttled.  `*event_slot` caches the event (created on first use).
+int b200_stream_synchronize_blocking(b200_ctx *ctx, void *stream, void **event_slot)
+{
+    if (!ctx || !event_slot)
+        return fail(B200_E_NULL, "null argument");
+    cudaEvent_t ev = (cudaEvent_t)*event_slot;
+    if (!ev)
+    {
+        CU_TRY(cudaEventCreateWithFlags(&ev, cudaEventBlockingSync | cudaEventDisableTiming));
+        *event_slot = ev;
+    }
+    CU_TRY(cudaEventRecord(ev, (cudaStream_t)stream));
+    CU_TRY(cudaEventSynchronize(ev));
+    return 0;
+}
+int b200_event_destroy(b200_ctx *ctx, void *event)
+{
+    (void)ctx;
+    if (event)
+        cudaEventDestroy((cudaEvent_t)event);
+    return 0;
+}
 // make the context's GPU the calling thread's current device (a new host thread starts on device 0: the SEAL-named layer
 // calls this at the start of every operation, so worker threads of a multi-GPU process need no CUDA calls of their own)
 int b200_bind_thread(b200_ctx *ctx)

@@ -2091,6 +2091,7 @@ long B200_Ciphertext_SetWordsBatch(void *context, uint64_t count, void **cts, ui
             return;
         batch_handles(count, { cts });
         OpScope scope(c);
+        scope.blocking = count >= 8; // long waits: sleep, do not spin (many caller threads on a CPU-quota'd host)
         const u64 k = (u64)c->level_k[lv];
         const u64 w = size * k * c->parms.n;
         BatchSlab S(c, count * w);
@@ -2122,6 +2123,7 @@ long B200_Ciphertext_GetWordsBatch(void *context, uint64_t count, void **cts, ui
         if (cap < count * w)
             throw InvalidArg("capacity too small");
         OpScope scope(c);
+        scope.blocking = count >= 8; // long waits: sleep, do not spin (many caller threads on a CPU-quota'd host)
         std::vector<u64 *> ptrs(count);
         for (uint64_t i = 0; i < count; i++)
         {
@@ -2153,6 +2155,7 @@ long B200_Evaluator_MultiplyRelinBatch(void *p, uint64_t count, void **e1, void 
             return;
         batch_handles(count, { e1, e2, dsts });
         OpScope scope(c);
+        scope.blocking = count >= 8; // long waits: sleep, do not spin (many caller threads on a CPU-quota'd host)
         const u64 w = batch_item_words(c, e1);
         BatchSlab A(c, count * w), B(c, count * w), D(c, count * w);
         u64 k = 0, kb = 0;
@@ -2176,6 +2179,7 @@ long B200_Evaluator_AddSubBatch(void *p, uint64_t count, void **e1, void **e2, b
             return;
         batch_handles(count, { e1, e2, dsts });
         OpScope scope(c);
+        scope.blocking = count >= 8; // long waits: sleep, do not spin (many caller threads on a CPU-quota'd host)
         const u64 w = batch_item_words(c, e1);
         BatchSlab A(c, count * w), B(c, count * w);
         u64 k = 0, kb = 0;
@@ -2201,6 +2205,7 @@ long B200_Evaluator_PlainBatch(void *p, int which, uint64_t count, void **encs, 
             return;
         batch_handles(count, { encs, plains, dsts });
         OpScope scope(c);
+        scope.blocking = count >= 8; // long waits: sleep, do not spin (many caller threads on a CPU-quota'd host)
         const size_t n = c->parms.n;
         const u64 w = batch_item_words(c, encs);
         BatchSlab A(c, count * w), O(c, count * w), P(c, count * n);
@@ -2242,6 +2247,7 @@ long B200_Evaluator_RotateRowsBatch(void *p, uint64_t count, void **encs, int st
             throw LogicErr("encryption parameters do not support batching");
         batch_handles(count, { encs, dsts });
         OpScope scope(c);
+        scope.blocking = count >= 8; // long waits: sleep, do not spin (many caller threads on a CPU-quota'd host)
         const u64 w = batch_item_words(c, encs);
         BatchSlab A(c, count * w), O(c, count * w);
         u64 k = 0;

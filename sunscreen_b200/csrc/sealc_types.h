@@ -139,6 +139,7 @@ struct Context_
         };
         std::vector<Graph> graphs;
         uint64_t clock = 0;
+        void *ev = nullptr;     // blocking-sync event of the batch seams' waits (b200_stream_synchronize_blocking)
         u64 *pad_out = nullptr; // scratch destination of the pad items of a batch rounded up to a power of two
         size_t pad_words = 0;
     };
@@ -202,6 +203,8 @@ struct Context_
                         b200_graph_destroy(dev, g.exec);
                 if (l.pad_out)
                     b200_free(dev, l.pad_out);
+                if (l.ev)
+                    b200_event_destroy(dev, l.ev);
             }
             if (!owner)
                 b200_ctx_destroy(dev);
@@ -256,6 +259,7 @@ struct OpScope
     Context_::Lane *lane = nullptr;
     std::unique_lock<std::mutex> lane_lk, ctx_lk;
     OpScope *outer;
+    bool blocking = false; // sleep instead of spinning while the GPU works (set by the batch seams: their waits are milliseconds)
     explicit OpScope(Context_ *ctx) : c(ctx), outer(tl_scope)
     {
         dev_check(b200_bind_thread(ctx->dev)); // worker threads of the caller never called cudaSetDevice themselves
@@ -302,7 +306,7 @@ struct OpScope
         const bool held = root->ctx_lk.owns_lock();
         if (held)
             root->ctx_lk.unlock();
-        int rc = b200_stream_synchronize(c->dev, lane->stream);
+        int rc = blocking ? b200_stream_synchronize_blocking(c->dev, lane->stream, &lane->ev) : b200_stream_synchronize(c->dev, lane->stream);
         if (held)
             root->ctx_lk.lock();
         dev_check(rc);
@@ -314,7 +318,10 @@ struct OpScope
             return;
         if (ctx_lk.owns_lock())
             ctx_lk.unlock();
-        b200_stream_synchronize(c->dev, lane->stream); // the operation is complete when the call returns
+        if (blocking)
+            b200_stream_synchronize_blocking(c->dev, lane->stream, &lane->ev);
+        else
+            b200_stream_synchronize(c->dev, lane->stream); // the operation is complete when the call returns
     }
     OpScope(const OpScope &) = delete;
 };

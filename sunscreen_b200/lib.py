@@ -54,6 +54,8 @@ _SIGS = {
     "b200_gather_scatter_table": [vp, vp, u64, vp, u64, C.c_int, vp],
     "b200_malloc_async": [vp, C.c_size_t, C.POINTER(vp), vp],
     "b200_bind_thread": [vp],
+    "b200_stream_synchronize_blocking": [vp, vp, C.POINTER(vp)],
+    "b200_event_destroy": [vp, vp],
     "b200_capture_begin": [vp, vp],
     "b200_capture_end": [vp, vp, C.POINTER(vp)],
     "b200_graph_launch": [vp, vp, vp],

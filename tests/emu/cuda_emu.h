@@ -22,7 +22,7 @@ typedef void *cudaStream_t;
 typedef void *cudaEvent_t;
 typedef void *cudaMemPool_t;
 enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
-enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaFuncAttributeMaxDynamicSharedMemorySize = 8,
+enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaEventBlockingSync = 1, cudaFuncAttributeMaxDynamicSharedMemorySize = 8,
        cudaMemPoolReuseAllowInternalDependencies = 3, cudaMemPoolAttrReleaseThreshold = 4 };
 struct cudaDeviceProp { int multiProcessorCount = 1; size_t sharedMemPerBlockOptin = 232448; };
 struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
