@@ -219,8 +219,11 @@ class PluginLegs:
         self.k, self.n = k, n
         key = rlk_dev.cpu().numpy().view(np.uint64)  # (k, 2, K, n) key-level NTT-form words
         self.rlk = self.O.new_ksk({0: key})
-        self.threads = int(os.environ.get("B200_BENCH_E2E_THREADS", "8"))
-        self.chunk = int(os.environ.get("B200_BENCH_E2E_CHUNK", "64"))
+        # worker threads spin while their call completes: with many ranks on one host keep their total below the cores the lease
+        # grants (8 ranks x 8 spinning threads on a 96-core quota was seen to get the whole job throttled)
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.threads = int(os.environ.get("B200_BENCH_E2E_THREADS", "8" if world <= 4 else "4"))
+        self.chunk = int(os.environ.get("B200_BENCH_E2E_CHUNK", "64" if world <= 4 else "128"))
         self.pool = {}
 
     def _handles(self, tag, count):

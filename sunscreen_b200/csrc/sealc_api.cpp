@@ -909,6 +909,7 @@ long SEALContext_Create(void *parms, bool expand_mod_chain, int sec_level, void 
     const char *nt = getenv("B200_SKIP_TRANSPARENT_CHECK");
     c->check_transparent = !(nt && nt[0] == '1');
     c->combine = !std::getenv("B200_NO_COMBINE");
+    c->blocking_waits = std::getenv("B200_BLOCKING_WAITS") != nullptr;
     if (const char *cl = std::getenv("B200_COMBINE_LEADERS"))
         c->combine_leaders = std::max(1, std::min(4, atoi(cl)));
     c->use_graphs = !std::getenv("B200_NO_GRAPHS") && !std::getenv("B200_TRACE");
@@ -2091,7 +2092,7 @@ long B200_Ciphertext_SetWordsBatch(void *context, uint64_t count, void **cts, ui
             return;
         batch_handles(count, { cts });
         OpScope scope(c);
-        scope.blocking = count >= 8; // long waits: sleep, do not spin (many caller threads on a CPU-quota'd host)
+        scope.blocking = c->blocking_waits; // B200_BLOCKING_WAITS=1: sleep instead of spinning while the batch completes
         const u64 k = (u64)c->level_k[lv];
         const u64 w = size * k * c->parms.n;
         BatchSlab S(c, count * w);
@@ -2123,7 +2124,7 @@ long B200_Ciphertext_GetWordsBatch(void *context, uint64_t count, void **cts, ui
         if (cap < count * w)
             throw InvalidArg("capacity too small");
         OpScope scope(c);
-        scope.blocking = count >= 8; // long waits: sleep, do not spin (many caller threads on a CPU-quota'd host)
+        scope.blocking = c->blocking_waits; // B200_BLOCKING_WAITS=1: sleep instead of spinning while the batch completes
         std::vector<u64 *> ptrs(count);
         for (uint64_t i = 0; i < count; i++)
         {
@@ -2155,7 +2156,7 @@ long B200_Evaluator_MultiplyRelinBatch(void *p, uint64_t count, void **e1, void 
             return;
         batch_handles(count, { e1, e2, dsts });
         OpScope scope(c);
-        scope.blocking = count >= 8; // long waits: sleep, do not spin (many caller threads on a CPU-quota'd host)
+        scope.blocking = c->blocking_waits; // B200_BLOCKING_WAITS=1: sleep instead of spinning while the batch completes
         const u64 w = batch_item_words(c, e1);
         BatchSlab A(c, count * w), B(c, count * w), D(c, count * w);
         u64 k = 0, kb = 0;
@@ -2179,7 +2180,7 @@ long B200_Evaluator_AddSubBatch(void *p, uint64_t count, void **e1, void **e2, b
             return;
         batch_handles(count, { e1, e2, dsts });
         OpScope scope(c);
-        scope.blocking = count >= 8; // long waits: sleep, do not spin (many caller threads on a CPU-quota'd host)
+        scope.blocking = c->blocking_waits; // B200_BLOCKING_WAITS=1: sleep instead of spinning while the batch completes
         const u64 w = batch_item_words(c, e1);
         BatchSlab A(c, count * w), B(c, count * w);
         u64 k = 0, kb = 0;
@@ -2205,7 +2206,7 @@ long B200_Evaluator_PlainBatch(void *p, int which, uint64_t count, void **encs, 
             return;
         batch_handles(count, { encs, plains, dsts });
         OpScope scope(c);
-        scope.blocking = count >= 8; // long waits: sleep, do not spin (many caller threads on a CPU-quota'd host)
+        scope.blocking = c->blocking_waits; // B200_BLOCKING_WAITS=1: sleep instead of spinning while the batch completes
         const size_t n = c->parms.n;
         const u64 w = batch_item_words(c, encs);
         BatchSlab A(c, count * w), O(c, count * w), P(c, count * n);
@@ -2247,7 +2248,7 @@ long B200_Evaluator_RotateRowsBatch(void *p, uint64_t count, void **encs, int st
             throw LogicErr("encryption parameters do not support batching");
         batch_handles(count, { encs, dsts });
         OpScope scope(c);
-        scope.blocking = count >= 8; // long waits: sleep, do not spin (many caller threads on a CPU-quota'd host)
+        scope.blocking = c->blocking_waits; // B200_BLOCKING_WAITS=1: sleep instead of spinning while the batch completes
         const u64 w = batch_item_words(c, encs);
         BatchSlab A(c, count * w), O(c, count * w);
         u64 k = 0;
