@@ -1915,6 +1915,7 @@ int b200_ctx_create(uint64_t n, const uint64_t *coeff_modulus, uint64_t count, u
     return 0;
 }
 
+static void host_pool_destroy(b200_ctx *ctx);
 void b200_ctx_destroy(b200_ctx *ctx)
 {
     if (!ctx)
@@ -1933,8 +1934,7 @@ void b200_ctx_destroy(b200_ctx *ctx)
             cudaFree(ctx->dpk_b[i]);
             cudaFree(ctx->dpk_o[i]);
         }
-    delete ctx->pool;
-    ctx->pool = nullptr;
+    host_pool_destroy(ctx); // (HostPool is defined further down: deleting it here would delete an incomplete type)
     for (int i = 0; i < b200_ctx::NBUF; i++)
         if (ctx->hp_a[i])
         {
@@ -3150,6 +3150,11 @@ struct HostPool
     }
 };
 
+static void host_pool_destroy(b200_ctx *ctx)
+{
+    delete ctx->pool;
+    ctx->pool = nullptr;
+}
 static HostPool *host_pool(b200_ctx *ctx)
 {
     if (!ctx->pool)
