@@ -523,7 +523,7 @@ B200_HD void lift_coeff_fp(const LiftFpC<K> &L, const u64 *__restrict__ src, u64
             double acc = fp_mulmod(rc, L.qm[2 * j], L.qm[2 * j + 1], p);
 #pragma unroll
             for (int i = 0; i < K; i++)
-                acc = B200_DADD(acc, fp_mulmod(y[i], L.mat[2 * (j * K + i)], L.mat[2 * (j * K + i) + 1], p));
+                acc = B200_DADD(acc, fp_mulmod_term(i, y[i], L.mat[2 * (j * K + i)], L.mat[2 * (j * K + i) + 1], p));
             dst[j * n + c] = fp_to_canonical(acc, p, pinv);
         }
     }
@@ -589,7 +589,7 @@ B200_HD void scale_coeff_fp(const ScaleFpC<K> &L, const u64 *__restrict__ src, u
             double acc = fp_mulmod(fp_from_u64(src[(K + j) * n + c]), L.tq[2 * j], L.tq[2 * j + 1], p);
 #pragma unroll
             for (int i = 0; i < K; i++)
-                acc = B200_DADD(acc, fp_mulmod(y[i], L.mat[2 * (j * K + i)], L.mat[2 * (j * K + i) + 1], p));
+                acc = B200_DADD(acc, fp_mulmod_term(i, y[i], L.mat[2 * (j * K + i)], L.mat[2 * (j * K + i) + 1], p));
             // canonical w_j
             double w = fp_renorm(acc, p, pinv);
             w = fp_canon(w, p);
@@ -612,7 +612,7 @@ B200_HD void scale_coeff_fp(const ScaleFpC<K> &L, const u64 *__restrict__ src, u
 #pragma unroll
     for (int b = 0; b < K + 1; b++)
         if (b < L.nB)
-            alpha = B200_DADD(alpha, fp_mulmod(yb[b], L.sk_mat_msk[2 * b], L.sk_mat_msk[2 * b + 1], ms));
+            alpha = B200_DADD(alpha, fp_mulmod_term(b, yb[b], L.sk_mat_msk[2 * b], L.sk_mat_msk[2 * b + 1], ms));
     alpha = fp_canon(fp_renorm(alpha, ms, msinv), ms);
     const bool neg = alpha > B200_DMUL(ms, 0.5); // m_sk odd: alpha > floor(m_sk/2)  <=>  alpha > m_sk/2
     const double mag = neg ? B200_DADD(ms, -alpha) : alpha;
@@ -626,7 +626,7 @@ B200_HD void scale_coeff_fp(const ScaleFpC<K> &L, const u64 *__restrict__ src, u
 #pragma unroll
         for (int b = 0; b < K + 1; b++)
             if (b < L.nB)
-                acc = B200_DADD(acc, fp_mulmod(yb[b], L.sk_mat_q[2 * (i * (K + 1) + b)], L.sk_mat_q[2 * (i * (K + 1) + b) + 1], q));
+                acc = B200_DADD(acc, fp_mulmod_term(b, yb[b], L.sk_mat_q[2 * (i * (K + 1) + b)], L.sk_mat_q[2 * (i * (K + 1) + b) + 1], q));
         dst[i * n + c] = fp_to_canonical(acc, q, qinv);
     }
 }

@@ -69,6 +69,24 @@ B200_HD double fp_mulmod(double y, double w, double wp, double p)
     const double q = B200_DADD(B200_DFMA(y, wp, B200_MAGIC), -B200_MAGIC);
     return B200_DADD(B200_DFMA(-q, p, h), l);
 }
+// the same with the rounding on the XU pipe (DMUL + FRND.F64 instead of DFMA + DADD): one FP64 slot less, one XU slot more.
+// The BEHZ kernels alternate the two forms term by term (B200_BEHZ_XU_MIX): routing ALL their roundings through the 16-lane
+// XU pipe measured slower, none leaves that pipe idle (ncu: 2-6 %) while the FP64 pipe and the issue slots are the bound.
+B200_HD double fp_mulmod_x(double y, double w, double wp, double p)
+{
+    const double h = B200_DMUL(y, w);
+    const double l = B200_DFMA(y, w, -h);
+    const double q = B200_RINT(B200_DMUL(y, wp));
+    return B200_DADD(B200_DFMA(-q, p, h), l);
+}
+#ifndef B200_BEHZ_XU_MIX
+#define B200_BEHZ_XU_MIX 1
+#endif
+// term `i` of an inner product: odd terms round on the XU pipe
+B200_HD double fp_mulmod_term(int i, double y, double w, double wp, double p)
+{
+    return (B200_BEHZ_XU_MIX && (i & 1)) ? fp_mulmod_x(y, w, wp, p) : fp_mulmod(y, w, wp, p);
+}
 // general product a*b mod p for |a|,|b| < 2^47 (no precomputed quotient): result in (-p, p)
 B200_HD double fp_mulmod2(double a, double b, double p, double pinv)
 {
